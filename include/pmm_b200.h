@@ -1,0 +1,155 @@
+/*
+ * pmm_b200.h -- C ABI of the B200-native PMM likelihood / EM engine.
+ *
+ * The reference (raphael-group/LAML v1.0.5) is pure Python and has no FFI; its
+ * extension point for this path is the solver-class protocol
+ * (laml_libs/Virtual_solver.py:5-17) implemented by EM_solver
+ * (laml_libs/EM_solver.py:18-527).  Each entry point below replaces the named
+ * method(s) of that class at array level; laml_b200/solver.py is the Python
+ * class that binds them behind the reference's method names, and
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on
+ *     error, and pmm_last_error() returns a human-readable message.
+ *   - host pointers unless the name ends in _dev; the caller owns all host
+ *     buffers, the handle owns all device memory.
+ *   - a handle is bound to one CUDA device and one stream; it is not
+ *     thread-safe.  One handle per GPU (one process per GPU under torchrun).
+ *   - node ids: leaves 0..n_leaves-1, internal nodes n_leaves..n_nodes-1
+ *     (the reference's own array convention, laml_libs/fastEM_solver.py:82-134);
+ *     trees are binary (EM_solver binarises in its constructor, EM_solver.py:26-43);
+ *     several roots = a forest (ML_solver.py:26-32).
+ *   - state codes: 0 unedited; a >= 1 the 1-based rank of the edited state in the
+ *     site's prior; -1 '?' (missing); -2 a literal -1 = known silenced
+ *     (ML_solver.py:137-142).
+ *   - there is NO CPU fallback: every compute entry point fails if no CUDA
+ *     device is usable.
+ */
+#ifndef PMM_B200_H
+#define PMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmm_handle pmm_handle;
+
+/* Library / ABI version (bumped when a signature changes). */
+int pmm_abi_version(void);
+
+/* Message for the last failure on this handle (or for a failed pmm_create when
+ * h == NULL).  Valid until the next call on the same handle. */
+const char *pmm_last_error(const pmm_handle *h);
+
+/*
+ * Replaces ML_solver.__init__'s data model (ML_solver.py:19-86): uploads the
+ * integer-coded character matrix and the normalised per-site prior.
+ *   site_ptr[n_sites+1] : CSR offsets of the sites' edited alphabets
+ *   prior[nnz]          : normalised prior q (ML_solver.py:70-74), by state rank
+ *   codes[n_leaves*n_sites] : row-major by leaf id
+ *   device              : CUDA device ordinal
+ *   mem_budget_bytes    : device memory the handle may use for the per-node
+ *                         state vectors (0 = 85% of what is free); if the problem
+ *                         needs more, sites are processed in several chunks.
+ */
+int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const double *prior,
+               const int32_t *codes, int32_t device, size_t mem_budget_bytes, pmm_handle **out);
+
+void pmm_destroy(pmm_handle *h);
+
+/* Run the handle's kernels on this cudaStream_t (default: a stream it creates). */
+int pmm_set_stream(pmm_handle *h, void *cuda_stream);
+
+/*
+ * Replaces the tree the solver walks (treeswift objects, ML_solver.py:26-32):
+ * the topology as arrays; the level schedules (height-ordered for the inside
+ * pass, depth-ordered for the outside pass) are derived here.
+ */
+int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const int32_t *left,
+                 const int32_t *right);
+
+/*
+ * EM_solver.lineage_llh / Estep_in_llh (EM_solver.py:91-141): inside pass.
+ *   d[n_nodes] branch lengths (node.edge_length), nu, phi (self.params)
+ *   site_llh[n_sites] (optional, may be NULL): per-site log-likelihood summed over trees
+ *   llh: sum over trees and sites of log P(D)
+ */
+int pmm_inside(pmm_handle *h, const double *d, double nu, double phi, double *site_llh, double *llh);
+
+/*
+ * EM_solver.Estep (EM_solver.py:302-305) reduced to what Mstep consumes
+ * (EM_solver.py:318-348): S[v*5+k] = sum over sites of S_k for the branch above
+ * node v; Rtilde = sum over leaves and '?' entries of 1-exp(post1) (:323);
+ * llh as pmm_inside.  site_llh optional.
+ */
+int pmm_estep(pmm_handle *h, const double *d, double nu, double phi, double *S, double *Rtilde,
+              double *llh, double *site_llh);
+
+/*
+ * Per-(node,site) posteriors for the annotation writer (runner.py:391-435),
+ * the only caller that needs them: post0/post1 = log P(node state 0 / silenced | D)
+ * (EM_solver.py:276-277), each [n_nodes*n_sites] row-major by node, NULL to skip.
+ */
+int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double *post0, double *post1);
+
+/*
+ * EM_solver.Mstep without the ultrametric equalities (EM_solver.py:307-459 with
+ * ultra_constr_cache=None): phi closed form (:318-326), statistics clamp and
+ * rescale (:342-346), per-branch maximisation of (:351-357) over [dmin,dmax]
+ * with nu fixed, then the 1-D problem in nu (:394-407).
+ *   S[n*5], Rtilde: from pmm_estep;  R = number of non-'?' leaf entries (:322)
+ *   free_mask[n]: 1 = branch enters the program (not polytomy-marked, not mark_fixed)
+ *   d in/out; nu, phi in/out.
+ */
+int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n_cells,
+              const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi, double dmin,
+              double dmax, double eps_s, double eps_nu, double *d, double *nu, double *phi);
+
+/*
+ * EM_solver.EM_optimization (EM_solver.py:461-512), ultra_constr=False, fully on
+ * the device: E-step, M-step and the convergence test |dllh/llh| < conv_eps.
+ * status: 0 = "optimal".  iters = em_iter as the reference counts it.
+ */
+int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask,
+           int32_t optimize_nu, int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax,
+           double conv_eps, int32_t max_iter, double *nllh, int32_t *iters, int32_t *status);
+
+/* ---- device-resident variants (multi-GPU site sharding; see laml_b200/dist.py) ----
+ * The statistics buffer is [S(n*5) | Rtilde | llh] fp64 on the device; the host
+ * layer all-reduces it in place over NCCL between pmm_estep_dev and pmm_mstep_dev. */
+/* When the handle holds a site shard, the M-step rescales statistics to the site count
+ * of the WHOLE problem (self.numsites, EM_solver.py:345); default = the handle's own. */
+int pmm_set_total_sites(pmm_handle *h, int32_t n_sites_total);
+int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi);
+int pmm_download_params(pmm_handle *h, double *d, double *nu, double *phi);
+int pmm_estep_dev(pmm_handle *h);                 /* params on device -> stats on device */
+int pmm_inside_dev(pmm_handle *h);                /* params on device -> llh slot of stats */
+void *pmm_stats_dev_ptr(pmm_handle *h);           /* device pointer, (5*n_nodes+2) doubles */
+int64_t pmm_stats_len(const pmm_handle *h);
+int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu,
+                  int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu);
+int pmm_sync(pmm_handle *h);
+
+/* ---- introspection for benchmarks ------------------------------------------------- */
+typedef struct {
+    int64_t n_nodes, n_leaves, n_sites;
+    int64_t slots_per_node;      /* W = sum over sites of (A_s + 2): the algorithmic state slots */
+    int64_t row_stride;          /* W plus tile padding, largest chunk */
+    int64_t n_chunks, n_tiles, tile_slots;
+    int64_t inside_levels, outside_levels;
+    int64_t device_bytes;        /* allocated by the handle */
+    int64_t kernel_launches;     /* launched by this handle so far */
+} pmm_info;
+int pmm_get_info(const pmm_handle *h, pmm_info *info);
+
+/* Timing of the last pmm_estep / pmm_inside on the handle's stream (CUDA events), ms. */
+int pmm_last_timing(const pmm_handle *h, double *inside_ms, double *outside_ms, double *total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,222 @@
+"""ctypes binding of the C ABI in ``include/pmm_b200.h`` (``libpmm_b200.so``).
+
+This is deliberately thin: numpy arrays in, numpy arrays out, every error from
+the library raised as :class:`PMMError`.  There is no fallback of any kind -- if
+the shared library is missing or no CUDA device is usable the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmm_b200.so")
+
+#: every symbol ``include/pmm_b200.h`` declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "pmm_abi_version", "pmm_last_error", "pmm_create", "pmm_destroy", "pmm_set_stream", "pmm_set_tree",
+    "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
+    "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
+    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing",
+]
+
+
+class PMMError(RuntimeError):
+    pass
+
+
+class PMMInfo(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in (
+        "n_nodes", "n_leaves", "n_sites", "slots_per_node", "row_stride", "n_chunks", "n_tiles", "tile_slots",
+        "inside_levels", "outside_levels", "device_bytes", "kernel_launches")]
+
+
+_lib = None
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PMMError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). The PMM engine has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f64, i64 = C.c_void_p, C.c_int32, C.c_double, C.c_int64
+    P = C.POINTER
+    L.pmm_abi_version.restype = C.c_int
+    L.pmm_last_error.restype = C.c_char_p
+    L.pmm_last_error.argtypes = [vp]
+    L.pmm_create.argtypes = [i32, i32, vp, vp, vp, i32, C.c_size_t, P(vp)]
+    L.pmm_destroy.argtypes = [vp]
+    L.pmm_destroy.restype = None
+    L.pmm_set_stream.argtypes = [vp, vp]
+    L.pmm_set_tree.argtypes = [vp, i32, vp, vp, vp]
+    L.pmm_inside.argtypes = [vp, vp, f64, f64, vp, P(f64)]
+    L.pmm_estep.argtypes = [vp, vp, f64, f64, vp, P(f64), P(f64), vp]
+    L.pmm_posteriors.argtypes = [vp, vp, f64, f64, vp, vp]
+    L.pmm_mstep.argtypes = [vp, vp, f64, f64, i32, vp, i32, i32, f64, f64, f64, f64, vp, P(f64), P(f64)]
+    L.pmm_em.argtypes = [vp, vp, P(f64), P(f64), vp, i32, i32, f64, i32, f64, f64, f64, i32, P(f64), P(i32), P(i32)]
+    L.pmm_set_total_sites.argtypes = [vp, i32]
+    L.pmm_upload_params.argtypes = [vp, vp, f64, f64]
+    L.pmm_download_params.argtypes = [vp, vp, P(f64), P(f64)]
+    L.pmm_estep_dev.argtypes = [vp]
+    L.pmm_inside_dev.argtypes = [vp]
+    L.pmm_stats_dev_ptr.argtypes = [vp]
+    L.pmm_stats_dev_ptr.restype = vp
+    L.pmm_stats_len.argtypes = [vp]
+    L.pmm_stats_len.restype = i64
+    L.pmm_mstep_dev.argtypes = [vp, f64, i32, vp, i32, i32, f64, f64, f64, f64]
+    L.pmm_sync.argtypes = [vp]
+    L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
+    L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
+    _lib = L
+    return L
+
+
+class Engine:
+    """One handle = one GPU, one data set (or site shard), one current tree."""
+
+    def __init__(self, n_leaves: int, qptr, qval, codes, device: int = 0, mem_budget_bytes: int = 0):
+        L = load_library()
+        self._L = L
+        self._h = C.c_void_p()
+        qptr = _i32(qptr)
+        qval = _f64(qval) if len(qval) else np.zeros(1)
+        codes = _i32(codes)
+        if codes.ndim != 2 or codes.shape[0] != n_leaves:
+            raise PMMError("codes must be (n_leaves, n_sites) in leaf-id order")
+        self.n_leaves, self.n_sites = int(n_leaves), int(codes.shape[1])
+        rc = L.pmm_create(self.n_leaves, self.n_sites, qptr.ctypes.data, qval.ctypes.data, codes.ctypes.data,
+                          int(device), int(mem_budget_bytes), C.byref(self._h))
+        if rc:
+            raise PMMError(L.pmm_last_error(None).decode())
+        self.n_nodes = 0
+        self.device = int(device)
+
+    # -- plumbing -----------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise PMMError(self._L.pmm_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.pmm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self._L.pmm_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_tree(self, parent, left, right):
+        parent, left, right = _i32(parent), _i32(left), _i32(right)
+        self._ck(self._L.pmm_set_tree(self._h, parent.shape[0], parent.ctypes.data, left.ctypes.data, right.ctypes.data))
+        self.n_nodes = int(parent.shape[0])
+
+    def set_total_sites(self, k: int):
+        self._ck(self._L.pmm_set_total_sites(self._h, int(k)))
+
+    # -- host-buffer entry points --------------------------------------------
+    def inside(self, d, nu, phi, want_site_llh=False):
+        d = _f64(d)
+        llh = C.c_double()
+        site = np.empty(self.n_sites) if want_site_llh else None
+        self._ck(self._L.pmm_inside(self._h, d.ctypes.data, float(nu), float(phi),
+                                    site.ctypes.data if want_site_llh else None, C.byref(llh)))
+        return (llh.value, site) if want_site_llh else llh.value
+
+    def estep(self, d, nu, phi, want_site_llh=False):
+        d = _f64(d)
+        S = np.empty((self.n_nodes, 5))
+        rt, llh = C.c_double(), C.c_double()
+        site = np.empty(self.n_sites) if want_site_llh else None
+        self._ck(self._L.pmm_estep(self._h, d.ctypes.data, float(nu), float(phi), S.ctypes.data, C.byref(rt),
+                                   C.byref(llh), site.ctypes.data if want_site_llh else None))
+        out = {"S": S, "Rtilde": rt.value, "llh": llh.value}
+        if want_site_llh:
+            out["site_llh"] = site
+        return out
+
+    def posteriors(self, d, nu, phi):
+        d = _f64(d)
+        p0 = np.empty((self.n_nodes, self.n_sites)); p1 = np.empty((self.n_nodes, self.n_sites))
+        self._ck(self._L.pmm_posteriors(self._h, d.ctypes.data, float(nu), float(phi), p0.ctypes.data, p1.ctypes.data))
+        return p0, p1
+
+    def mstep(self, S, Rtilde, R, n_cells, d, nu, phi, free_mask=None, optimize_nu=True, optimize_phi=True,
+              dmin=0.005, dmax=10.0, eps_s=1e-6, eps_nu=1e-5):
+        S = _f64(S); d = np.array(d, np.float64, copy=True)
+        fm = np.ascontiguousarray(free_mask, np.uint8) if free_mask is not None else None
+        nu_c, phi_c = C.c_double(nu), C.c_double(phi)
+        self._ck(self._L.pmm_mstep(self._h, S.ctypes.data, float(Rtilde), float(R), int(n_cells),
+                                   fm.ctypes.data if fm is not None else None, int(optimize_nu), int(optimize_phi),
+                                   dmin, dmax, eps_s, eps_nu, d.ctypes.data, C.byref(nu_c), C.byref(phi_c)))
+        return d, nu_c.value, phi_c.value
+
+    def em(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
+           conv_eps=1e-8, max_iter=1000):
+        d = np.array(d, np.float64, copy=True)
+        fm = np.ascontiguousarray(free_mask, np.uint8) if free_mask is not None else None
+        nu_c, phi_c, nllh = C.c_double(nu), C.c_double(phi), C.c_double()
+        iters, status = C.c_int32(), C.c_int32()
+        self._ck(self._L.pmm_em(self._h, d.ctypes.data, C.byref(nu_c), C.byref(phi_c),
+                                fm.ctypes.data if fm is not None else None, int(optimize_nu), int(optimize_phi),
+                                float(R), int(n_cells), dmin, dmax, conv_eps, int(max_iter), C.byref(nllh),
+                                C.byref(iters), C.byref(status)))
+        return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
+                "status": "optimal" if status.value == 0 else "failed"}
+
+    # -- device-resident entry points ----------------------------------------
+    def upload_params(self, d, nu, phi):
+        d = _f64(d)
+        self._ck(self._L.pmm_upload_params(self._h, d.ctypes.data, float(nu), float(phi)))
+
+    def download_params(self):
+        d = np.empty(self.n_nodes)
+        nu, phi = C.c_double(), C.c_double()
+        self._ck(self._L.pmm_download_params(self._h, d.ctypes.data, C.byref(nu), C.byref(phi)))
+        return d, nu.value, phi.value
+
+    def estep_dev(self):
+        self._ck(self._L.pmm_estep_dev(self._h))
+
+    def inside_dev(self):
+        self._ck(self._L.pmm_inside_dev(self._h))
+
+    def mstep_dev(self, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
+                  eps_s=1e-6, eps_nu=1e-5):
+        fm = np.ascontiguousarray(free_mask, np.uint8) if free_mask is not None else None
+        self._ck(self._L.pmm_mstep_dev(self._h, float(R), int(n_cells), fm.ctypes.data if fm is not None else None,
+                                       int(optimize_nu), int(optimize_phi), dmin, dmax, eps_s, eps_nu))
+
+    def stats_ptr(self):
+        return int(self._L.pmm_stats_dev_ptr(self._h)), int(self._L.pmm_stats_len(self._h))
+
+    def sync(self):
+        self._ck(self._L.pmm_sync(self._h))
+
+    def info(self) -> dict:
+        inf = PMMInfo()
+        self._ck(self._L.pmm_get_info(self._h, C.byref(inf)))
+        return {k: int(getattr(inf, k)) for k, _ in PMMInfo._fields_}
+
+    def last_timing(self):
+        a, b, t = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._L.pmm_last_timing(self._h, C.byref(a), C.byref(b), C.byref(t)))
+        return {"inside_ms": a.value, "outside_ms": b.value, "total_ms": t.value}

@@ -1,0 +1,646 @@
+// pmm_engine.cu -- host side of the C ABI declared in include/pmm_b200.h.
+//
+// Owns device memory, derives the level schedules, builds the tiled slot
+// layout, and launches the kernels in pmm_kernels.cuh.  No torch types, no CPU
+// fallback: if CUDA is unusable every entry point fails with an error string.
+#include "../../include/pmm_b200.h"
+#include "pmm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pmm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Chunk {
+    int site0 = 0, K = 0, W = 0, Wp = 0, ntiles = 0;
+    int *d_site_off = nullptr, *d_site_len = nullptr, *d_tile_site = nullptr, *d_tile_off = nullptr;
+    double *d_q = nullptr;
+};
+
+}  // namespace
+
+struct pmm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // data
+    int n_leaves = 0, K = 0;
+    int K_total = 0;                // sites of the whole problem when this handle holds a shard
+    std::vector<int> site_ptr;      // host copy
+    std::vector<double> prior;
+    int *d_codes = nullptr;
+    int64_t W = 0;                  // algorithmic slots per node
+    int TS = 2048, G = 8;
+    size_t budget = 0;
+    std::vector<Chunk> chunks;
+    int maxWp = 0, maxK = 0, max_tiles = 0;
+    // tree
+    int n = 0, n_int = 0, n_roots = 0;
+    std::vector<int> parent, left, right;
+    int *d_parent = nullptr, *d_left = nullptr, *d_right = nullptr, *d_root_index = nullptr, *d_roots = nullptr;
+    std::vector<std::vector<int>> in_levels, out_levels;   // host copies (sizes)
+    int *d_in_nodes = nullptr, *d_out_nodes = nullptr;
+    std::vector<int> in_ptr, out_ptr;
+    // state
+    double *d_X = nullptr, *d_O = nullptr;
+    int *d_iexp = nullptr, *d_oexp = nullptr;
+    double *d_rootLm = nullptr, *d_root_site_llh = nullptr;
+    int *d_rootLe = nullptr;
+    double *d_Spart = nullptr, *d_Rpart = nullptr, *d_Rnode = nullptr;
+    double *d_site_llh = nullptr;   // [K]
+    double *d_bc = nullptr, *d_d = nullptr, *d_params = nullptr;
+    double *d_stats = nullptr;      // [5n | Rtilde | llh]
+    double *d_Snorm = nullptr;
+    unsigned char *d_free = nullptr;
+    double *d_post0 = nullptr, *d_post1 = nullptr;
+    size_t device_bytes = 0;
+    int64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float t_inside = 0, t_outside = 0, t_total = 0;
+    bool timing_valid = false;
+};
+
+namespace {
+
+int fail(pmm_handle *h, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> int dalloc(pmm_handle *h, T **p, size_t count) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e != cudaSuccess) return fail(h, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    h->device_bytes += bytes;
+    return 0;
+}
+template <class T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+void free_chunks(pmm_handle *h) {
+    for (auto &c : h->chunks) { dfree(c.d_site_off); dfree(c.d_site_len); dfree(c.d_tile_site); dfree(c.d_tile_off); dfree(c.d_q); }
+    h->chunks.clear();
+}
+
+void free_tree_state(pmm_handle *h) {
+    dfree(h->d_parent); dfree(h->d_left); dfree(h->d_right); dfree(h->d_root_index); dfree(h->d_roots);
+    dfree(h->d_in_nodes); dfree(h->d_out_nodes);
+    dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_oexp);
+    dfree(h->d_rootLm); dfree(h->d_rootLe); dfree(h->d_root_site_llh);
+    dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
+    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free);
+    dfree(h->d_post0); dfree(h->d_post1);
+    free_chunks(h);
+}
+
+// Tiled slot layout of the sites [s_lo, s_hi): see the header of pmm_kernels.cuh.
+int build_chunk(pmm_handle *h, int s_lo, int s_hi, Chunk &c) {
+    const int K = s_hi - s_lo;
+    std::vector<int> site_off(K), site_len(K), tile_site{0}, tile_off{0};
+    int off = 0, cur = 0;
+    for (int s = 0; s < K; s++) {
+        int len = h->site_ptr[s_lo + s + 1] - h->site_ptr[s_lo + s] + 2;
+        if (cur > 0 && cur + len > h->TS) {
+            off = (off + 1) & ~1;
+            tile_site.push_back(s);
+            tile_off.push_back(off);
+            cur = 0;
+        }
+        site_off[s] = off;
+        site_len[s] = len;
+        off += len;
+        cur += len;
+    }
+    off = (off + 1) & ~1;
+    tile_site.push_back(K);
+    tile_off.push_back(off);
+    c.site0 = s_lo; c.K = K; c.Wp = off; c.ntiles = (int)tile_site.size() - 1;
+    c.W = h->site_ptr[s_hi] - h->site_ptr[s_lo] + 2 * K;
+    std::vector<double> q((size_t)std::max(off, 1), 0.0);
+    for (int s = 0; s < K; s++) {
+        int A = site_len[s] - 2;
+        for (int a = 0; a < A; a++) q[site_off[s] + 2 + a] = h->prior[h->site_ptr[s_lo + s] + a];
+    }
+    if (dalloc(h, &c.d_site_off, K) || dalloc(h, &c.d_site_len, K) || dalloc(h, &c.d_tile_site, tile_site.size()) ||
+        dalloc(h, &c.d_tile_off, tile_off.size()) || dalloc(h, &c.d_q, q.size()))
+        return 1;
+    CK(cudaMemcpy(c.d_site_off, site_off.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_site_len, site_len.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_tile_site, tile_site.data(), sizeof(int) * tile_site.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_tile_off, tile_off.data(), sizeof(int) * tile_off.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_q, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Split the sites into chunks whose rows fit the memory budget, balanced by slots.
+int plan_chunks(pmm_handle *h) {
+    free_chunks(h);
+    const int K = h->K;
+    const double per_slot = 16.0 * std::max(h->n_int, 1);            // X + O rows, bytes per slot column
+    const double per_site = 8.0 * std::max(h->n_int, 1);             // iexp + oexp
+    double total = per_slot * (double)(h->W + 2 * K / std::max(h->TS / 64, 1)) + per_site * K;
+    size_t budget = h->budget;
+    if (budget == 0) {
+        size_t fr = 0, tot = 0;
+        cudaError_t e = cudaMemGetInfo(&fr, &tot);
+        if (e != cudaSuccess) return fail(h, "cudaMemGetInfo failed: %s", cudaGetErrorString(e));
+        budget = (size_t)(0.85 * (double)fr);
+    }
+    int forced = env_int("PMM_CHUNKS", 0);
+    int nch = forced > 0 ? forced : (int)std::ceil(total / (double)budget);
+    nch = std::max(1, std::min(nch, std::max(K, 1)));
+    // contiguous ranges with ~equal slot counts
+    std::vector<int> bounds{0};
+    int64_t acc = 0;
+    for (int s = 0; s < K; s++) {
+        acc += h->site_ptr[s + 1] - h->site_ptr[s] + 2;
+        int want = (int)bounds.size();
+        if (want < nch && acc * nch >= (int64_t)want * h->W) bounds.push_back(s + 1);
+    }
+    if (bounds.back() != K) bounds.push_back(K);
+    h->chunks.resize(bounds.size() - 1);
+    h->maxWp = h->maxK = h->max_tiles = 0;
+    for (size_t c = 0; c + 1 < bounds.size(); c++) {
+        if (build_chunk(h, bounds[c], bounds[c + 1], h->chunks[c])) return 1;
+        h->maxWp = std::max(h->maxWp, h->chunks[c].Wp);
+        h->maxK = std::max(h->maxK, h->chunks[c].K);
+        h->max_tiles = std::max(h->max_tiles, h->chunks[c].ntiles);
+    }
+    return 0;
+}
+
+KParams make_params(pmm_handle *h, const Chunk &c, bool with_post) {
+    KParams P;
+    P.site_off = c.d_site_off; P.site_len = c.d_site_len; P.tile_site = c.d_tile_site; P.tile_off = c.d_tile_off;
+    P.q = c.d_q; P.K = c.K; P.Wp = c.Wp; P.ntiles = c.ntiles;
+    P.codes = h->d_codes; P.codes_stride = h->K; P.site0 = c.site0;
+    P.left = h->d_left; P.right = h->d_right; P.parent = h->d_parent; P.root_index = h->d_root_index;
+    P.n_leaves = h->n_leaves; P.n_nodes = h->n;
+    P.params = h->d_params; P.bc = h->d_bc;
+    P.X = h->d_X; P.O = h->d_O; P.iexp = h->d_iexp; P.oexp = h->d_oexp;
+    P.rootLm = h->d_rootLm; P.rootLe = h->d_rootLe; P.root_site_llh = h->d_root_site_llh;
+    P.Spart = h->d_Spart; P.Rpart = h->d_Rpart;
+    P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
+    P.K_total = h->K;
+    return P;
+}
+
+size_t smem_inside(int TS) { return (size_t)2 * TS * 8 + 64; }
+size_t smem_outside(int TS, int G) { return (size_t)3 * TS * 8 + 16 + (size_t)(NT / G) * 11 * 8 + 64; }
+
+template <int G> int set_attrs(pmm_handle *h) {
+    CK(cudaFuncSetAttribute(pmm_inside_level<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inside(h->TS)));
+    CK(cudaFuncSetAttribute(pmm_outside_level<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outside(h->TS, G)));
+    return 0;
+}
+
+template <int G> int launch_inside(pmm_handle *h, const KParams &P) {
+    const int nl = (int)h->in_ptr.size() - 1;
+    for (int l = 0; l < nl; l++) {
+        int cnt = h->in_ptr[l + 1] - h->in_ptr[l];
+        if (!cnt) continue;
+        pmm_inside_level<G><<<(unsigned)((size_t)cnt * P.ntiles), NT, smem_inside(h->TS), h->stream>>>(P, h->d_in_nodes + h->in_ptr[l], h->TS);
+        h->launches++;
+    }
+    pmm_root_llh<G><<<(unsigned)(h->n_roots * P.ntiles), NT, 0, h->stream>>>(P, h->d_roots);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int G> int launch_outside(pmm_handle *h, const KParams &P) {
+    const int nl = (int)h->out_ptr.size() - 1;
+    for (int l = 0; l < nl; l++) {
+        int cnt = h->out_ptr[l + 1] - h->out_ptr[l];
+        if (!cnt) continue;
+        pmm_outside_level<G><<<(unsigned)((size_t)cnt * P.ntiles), NT, smem_outside(h->TS, G), h->stream>>>(P, h->d_out_nodes + h->out_ptr[l], h->TS);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+#define DISPATCH_G(h, fn, ...)                                            \
+    ((h)->G == 4 ? fn<4>(__VA_ARGS__) : (h)->G == 8 ? fn<8>(__VA_ARGS__) : \
+     (h)->G == 16 ? fn<16>(__VA_ARGS__) : fn<32>(__VA_ARGS__))
+
+int check_ready(pmm_handle *h) {
+    if (!h) return 1;
+    if (h->n == 0) return fail(h, "pmm_set_tree has not been called");
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+// inside (+ optionally outside/counts) over all chunks, parameters already on the device
+int run_passes(pmm_handle *h, bool outside, bool with_post) {
+    const int n = h->n;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    pmm_branch_consts<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_d, h->d_params, n, h->d_bc);
+    h->launches++;
+    double *d_llh = h->d_stats + (size_t)5 * n + 1;
+    double *d_Rt = h->d_stats + (size_t)5 * n;
+    float acc_in = 0, acc_out = 0;
+    for (size_t ci = 0; ci < h->chunks.size(); ci++) {
+        const Chunk &c = h->chunks[ci];
+        KParams P = make_params(h, c, with_post);
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        if (DISPATCH_G(h, launch_inside, h, P)) return 1;
+        pmm_site_llh<<<(c.K + 255) / 256, 256, 0, h->stream>>>(h->d_root_site_llh, h->n_roots, c.K, h->d_site_llh + c.site0);
+        pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_site_llh + c.site0, c.K, d_llh, ci > 0);
+        h->launches += 2;
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        if (outside) {
+            if (DISPATCH_G(h, launch_outside, h, P)) return 1;
+            pmm_reduce_S<<<(5 * n + 255) / 256, 256, 0, h->stream>>>(h->d_Spart, c.ntiles, 5 * n, h->d_stats, ci > 0);
+            pmm_reduce_S<<<(h->n_int + 255) / 256, 256, 0, h->stream>>>(h->d_Rpart, c.ntiles, h->n_int, h->d_Rnode, 0);
+            pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Rnode, h->n_int, d_Rt, ci > 0);
+            h->launches += 3;
+        }
+        CK(cudaEventRecord(h->ev[3], h->stream));
+        if (h->chunks.size() > 1) {
+            // several chunks: accumulate phase times chunk by chunk (costs a sync per chunk)
+            CK(cudaEventSynchronize(h->ev[3]));
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, h->ev[1], h->ev[2]);
+            cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
+            acc_in += a; acc_out += b;
+        }
+    }
+    CK(cudaGetLastError());
+    h->t_inside = acc_in; h->t_outside = acc_out;
+    h->timing_valid = false;     // resolved lazily in pmm_last_timing after a sync
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================== C ABI
+extern "C" {
+
+int pmm_abi_version(void) { return 1; }
+
+const char *pmm_last_error(const pmm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const double *prior, const int32_t *codes,
+               int32_t device, size_t mem_budget_bytes, pmm_handle **out) {
+    if (!out) return fail(nullptr, "pmm_create: out is NULL");
+    *out = nullptr;
+    if (n_leaves < 2 || n_sites < 1 || !site_ptr || !codes) return fail(nullptr, "pmm_create: need >=2 leaves, >=1 site, non-NULL arrays");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "pmm_create: no usable CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, "pmm_create: device %d out of range (%d visible)", device, ndev);
+    pmm_handle *h = new pmm_handle();
+    h->device = device;
+    auto bail = [&](int) { g_create_error = h->err; pmm_destroy(h); return 1; };
+    if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(1); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(1); }
+    h->own_stream = true;
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    h->n_leaves = n_leaves; h->K = n_sites; h->budget = mem_budget_bytes;
+    h->site_ptr.assign(site_ptr, site_ptr + n_sites + 1);
+    if (h->site_ptr[0] != 0) { h->err = "site_ptr[0] must be 0"; return bail(1); }
+    int maxlen = 0;
+    for (int s = 0; s < n_sites; s++) {
+        int A = site_ptr[s + 1] - site_ptr[s];
+        if (A < 0) { h->err = "site_ptr must be non-decreasing"; return bail(1); }
+        maxlen = std::max(maxlen, A + 2);
+    }
+    const int nnz = site_ptr[n_sites];
+    h->prior.assign(prior, prior + nnz);
+    for (int i = 0; i < nnz; i++)
+        if (!(h->prior[i] >= 0.0)) { h->err = "prior entries must be non-negative numbers"; return bail(1); }
+    h->W = (int64_t)nnz + 2 * (int64_t)n_sites;
+    h->TS = env_int("PMM_TILE_SLOTS", 2048);
+    h->TS = std::max((h->TS + 1) & ~1, (maxlen + 1) & ~1);
+    if (h->TS > 9000) { h->err = "an alphabet is too large for one shared-memory tile (limit ~9000 states)"; return bail(1); }
+    double mean_len = (double)h->W / n_sites;
+    h->G = env_int("PMM_GROUP", mean_len < 12 ? 4 : (mean_len < 48 ? 8 : 16));
+    if (h->G != 4 && h->G != 8 && h->G != 16 && h->G != 32) { h->err = "PMM_GROUP must be 4, 8, 16 or 32"; return bail(1); }
+    // validate codes against the alphabets, then upload
+    for (int64_t r = 0; r < n_leaves; r++)
+        for (int s = 0; s < n_sites; s++) {
+            int c = codes[r * n_sites + s];
+            if (c < -2 || c > site_ptr[s + 1] - site_ptr[s]) {
+                char b[160];
+                snprintf(b, sizeof b, "code %d of leaf %lld at site %d is outside the site's alphabet (%d states)", c, (long long)r, s,
+                         site_ptr[s + 1] - site_ptr[s]);
+                h->err = b;
+                return bail(1);
+            }
+        }
+    if (dalloc(h, &h->d_codes, (size_t)n_leaves * n_sites) || dalloc(h, &h->d_params, 2)) return bail(1);
+    if (cudaMemcpy(h->d_codes, codes, sizeof(int) * (size_t)n_leaves * n_sites, cudaMemcpyHostToDevice) != cudaSuccess) {
+        h->err = "uploading codes failed";
+        return bail(1);
+    }
+    int rc = DISPATCH_G(h, set_attrs, h);
+    if (rc) return bail(1);
+    *out = h;
+    return 0;
+}
+
+void pmm_destroy(pmm_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_tree_state(h);
+    dfree(h->d_codes); dfree(h->d_params);
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int pmm_set_stream(pmm_handle *h, void *cuda_stream) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return 0;
+}
+
+int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const int32_t *left, const int32_t *right) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    const int N = h->n_leaves, n = n_nodes;
+    if (n <= N || n > 2 * N - 1 || !parent || !left || !right)
+        return fail(h, "pmm_set_tree: a binary forest over %d leaf nodes has between %d and %d nodes (got %d)", N, N + 1, 2 * N - 1, n);
+    // validate: leaves first, binary, consistent parent links
+    int n_roots = 0;
+    for (int v = 0; v < n; v++) {
+        bool leaf = left[v] < 0;
+        if (leaf != (right[v] < 0)) return fail(h, "node %d has exactly one child; trees must be binary", v);
+        if (leaf != (v < N)) return fail(h, "node ids must list the %d leaves first (node %d violates this)", N, v);
+        if (!leaf) {
+            if (left[v] >= n || right[v] >= n || left[v] == right[v]) return fail(h, "node %d has invalid children", v);
+            if (parent[left[v]] != v || parent[right[v]] != v) return fail(h, "parent/child arrays disagree at node %d", v);
+        }
+        if (parent[v] < 0) { n_roots++; if (leaf) return fail(h, "a single-leaf tree has no likelihood recursion"); }
+        else if (parent[v] >= n) return fail(h, "node %d has an invalid parent", v);
+    }
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));
+    size_t keep_bytes = h->device_bytes;
+    free_tree_state(h);
+    h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;
+    (void)keep_bytes;
+    h->n = n; h->n_int = n - N; h->n_roots = n_roots;
+    h->parent.assign(parent, parent + n); h->left.assign(left, left + n); h->right.assign(right, right + n);
+    // depth (root = 0) and height (leaf = 0) without recursion
+    std::vector<int> depth(n, -1), height(n, 0), order;
+    order.reserve(n);
+    std::vector<int> roots;
+    for (int v = 0; v < n; v++) if (parent[v] < 0) { roots.push_back(v); depth[v] = 0; order.push_back(v); }
+    for (size_t i = 0; i < order.size(); i++) {
+        int v = order[i];
+        if (left[v] >= 0) {
+            for (int c : {left[v], right[v]}) {
+                if (depth[c] >= 0) return fail(h, "node %d is reachable twice; not a forest", c);
+                depth[c] = depth[v] + 1;
+                order.push_back(c);
+            }
+        }
+    }
+    if ((int)order.size() != n) return fail(h, "tree arrays contain a cycle or unreachable nodes");
+    std::vector<int> root_index(n, 0);
+    for (size_t i = 0; i < roots.size(); i++) root_index[roots[i]] = (int)i;
+    for (int v : order) if (parent[v] >= 0) root_index[v] = root_index[parent[v]];
+    for (int i = n - 1; i >= 0; i--) {
+        int v = order[i];
+        if (left[v] >= 0) height[v] = 1 + std::max(height[left[v]], height[right[v]]);
+    }
+    int H = 0, D = 0;
+    for (int v = N; v < n; v++) { H = std::max(H, height[v]); D = std::max(D, depth[v]); }
+    // inside schedule: internal nodes by height 1..H; outside: internal nodes by depth 0..D
+    std::vector<std::vector<int>> inl(H), outl(D + 1);
+    for (int v = N; v < n; v++) { inl[height[v] - 1].push_back(v); outl[depth[v]].push_back(v); }
+    std::vector<int> in_nodes, out_nodes;
+    h->in_ptr.assign(1, 0); h->out_ptr.assign(1, 0);
+    for (auto &L : inl) { in_nodes.insert(in_nodes.end(), L.begin(), L.end()); h->in_ptr.push_back((int)in_nodes.size()); }
+    for (auto &L : outl) { out_nodes.insert(out_nodes.end(), L.begin(), L.end()); h->out_ptr.push_back((int)out_nodes.size()); }
+
+    if (dalloc(h, &h->d_parent, n) || dalloc(h, &h->d_left, n) || dalloc(h, &h->d_right, n) || dalloc(h, &h->d_root_index, n) ||
+        dalloc(h, &h->d_roots, roots.size()) || dalloc(h, &h->d_in_nodes, in_nodes.size()) || dalloc(h, &h->d_out_nodes, out_nodes.size()))
+        return 1;
+    CK(cudaMemcpy(h->d_parent, parent, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_left, left, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_right, right, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_root_index, root_index.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_roots, roots.data(), sizeof(int) * roots.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_in_nodes, in_nodes.data(), sizeof(int) * in_nodes.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_out_nodes, out_nodes.data(), sizeof(int) * out_nodes.size(), cudaMemcpyHostToDevice));
+
+    // small per-node buffers first, then the chunk plan against what is left
+    if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
+        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_Rnode, h->n_int) ||
+        dalloc(h, &h->d_site_llh, h->K))
+        return 1;
+    if (plan_chunks(h)) return 1;
+    const size_t rows = (size_t)h->n_int;
+    if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxK) ||
+        dalloc(h, &h->d_oexp, rows * h->maxK) || dalloc(h, &h->d_rootLm, (size_t)n_roots * h->maxK) ||
+        dalloc(h, &h->d_rootLe, (size_t)n_roots * h->maxK) || dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
+        dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
+        return 1;
+    // rows start as zeros so that tile pad slots stay clean
+    CK(cudaMemsetAsync(h->d_X, 0, sizeof(double) * rows * h->maxWp, h->stream));
+    CK(cudaMemsetAsync(h->d_O, 0, sizeof(double) * rows * h->maxWp, h->stream));
+    CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pmm_set_total_sites(pmm_handle *h, int32_t n_sites_total) {
+    if (!h) return 1;
+    if (n_sites_total < h->K) return fail(h, "total sites (%d) cannot be below this handle's sites (%d)", n_sites_total, h->K);
+    h->K_total = n_sites_total;
+    return 0;
+}
+
+int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi) {
+    if (check_ready(h)) return 1;
+    if (!(nu >= 0.0) || !(phi >= 0.0) || phi > 1.0) return fail(h, "need nu >= 0 and 0 <= phi <= 1 (got nu=%g phi=%g)", nu, phi);
+    for (int v = 0; v < h->n; v++)
+        if (!(d[v] >= 0.0) || !std::isfinite(d[v])) return fail(h, "branch length of node %d is %g; need finite, non-negative", v, d[v]);
+    double p[2] = {nu, phi};
+    CK(cudaMemcpyAsync(h->d_d, d, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_params, p, sizeof p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // p lives on this stack frame
+    return 0;
+}
+
+int pmm_download_params(pmm_handle *h, double *d, double *nu, double *phi) {
+    if (check_ready(h)) return 1;
+    double p[2];
+    if (d) CK(cudaMemcpyAsync(d, h->d_d, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(p, h->d_params, sizeof p, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (nu) *nu = p[0];
+    if (phi) *phi = p[1];
+    return 0;
+}
+
+int pmm_inside_dev(pmm_handle *h) {
+    if (check_ready(h)) return 1;
+    return run_passes(h, false, false);
+}
+
+int pmm_estep_dev(pmm_handle *h) {
+    if (check_ready(h)) return 1;
+    return run_passes(h, true, false);
+}
+
+void *pmm_stats_dev_ptr(pmm_handle *h) { return h ? (void *)h->d_stats : nullptr; }
+int64_t pmm_stats_len(const pmm_handle *h) { return h ? (int64_t)5 * h->n + 2 : 0; }
+
+int pmm_sync(pmm_handle *h) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pmm_inside(pmm_handle *h, const double *d, double nu, double phi, double *site_llh, double *llh) {
+    if (pmm_upload_params(h, d, nu, phi)) return 1;
+    if (run_passes(h, false, false)) return 1;
+    if (llh) CK(cudaMemcpyAsync(llh, h->d_stats + (size_t)5 * h->n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (site_llh) CK(cudaMemcpyAsync(site_llh, h->d_site_llh, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pmm_estep(pmm_handle *h, const double *d, double nu, double phi, double *S, double *Rtilde, double *llh, double *site_llh) {
+    if (pmm_upload_params(h, d, nu, phi)) return 1;
+    if (run_passes(h, true, false)) return 1;
+    const size_t n5 = (size_t)5 * h->n;
+    if (S) CK(cudaMemcpyAsync(S, h->d_stats, sizeof(double) * n5, cudaMemcpyDeviceToHost, h->stream));
+    if (Rtilde) CK(cudaMemcpyAsync(Rtilde, h->d_stats + n5, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (llh) CK(cudaMemcpyAsync(llh, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (site_llh) CK(cudaMemcpyAsync(site_llh, h->d_site_llh, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double *post0, double *post1) {
+    if (pmm_upload_params(h, d, nu, phi)) return 1;
+    const size_t cnt = (size_t)h->n * h->K;
+    if (!h->d_post0) { if (dalloc(h, &h->d_post0, cnt) || dalloc(h, &h->d_post1, cnt)) return 1; }
+    if (run_passes(h, true, true)) return 1;
+    if (post0) CK(cudaMemcpyAsync(post0, h->d_post0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    if (post1) CK(cudaMemcpyAsync(post1, h->d_post1, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi,
+                  double dmin, double dmax, double eps_s, double eps_nu) {
+    if (check_ready(h)) return 1;
+    const int n = h->n;
+    if (free_mask) CK(cudaMemcpyAsync(h->d_free, free_mask, n, cudaMemcpyHostToDevice, h->stream));
+    const int K_total = h->K_total > 0 ? h->K_total : h->K;
+    pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
+                                                               dmin, dmax, eps_s, eps_nu);
+    pmm_mstep_globals<<<1, 1024, 0, h->stream>>>(h->d_stats, h->d_free, n, h->d_Snorm, h->d_d, h->d_params, R,
+                                                 (double)K_total * (double)n_cells, optimize_nu, optimize_phi);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu,
+              int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu, double *d, double *nu, double *phi) {
+    if (pmm_upload_params(h, d, *nu, *phi)) return 1;
+    const size_t n5 = (size_t)5 * h->n;
+    CK(cudaMemcpyAsync(h->d_stats, S, sizeof(double) * n5, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_stats + n5, &Rtilde, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (pmm_mstep_dev(h, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax, eps_s, eps_nu)) return 1;
+    return pmm_download_params(h, d, nu, phi);
+}
+
+int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi,
+           double R, int32_t n_cells, double dmin, double dmax, double conv_eps, int32_t max_iter, double *nllh, int32_t *iters,
+           int32_t *status) {
+    if (pmm_upload_params(h, d, *nu, *phi)) return 1;
+    const int n = h->n;
+    const size_t n5 = (size_t)5 * n;
+    if (free_mask) CK(cudaMemcpyAsync(h->d_free, free_mask, n, cudaMemcpyHostToDevice, h->stream));
+    double pre = 0, cur = 0;
+    // EM_solver.py:467 pre_llh, then per iteration E, M, llh (:475-505).  The inside pass that
+    // yields llh(p_k) is the same one the next E-step needs, so it is run once per iteration.
+    if (run_passes(h, true, false)) return 1;
+    CK(cudaMemcpyAsync(&pre, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cur = pre;
+    int it = 1;
+    while (it <= max_iter) {
+        if (pmm_mstep_dev(h, R, n_cells, nullptr, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
+        if (run_passes(h, true, false)) return 1;
+        CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (std::fabs((cur - pre) / pre) < conv_eps) break;
+        pre = cur;
+        it++;
+    }
+    if (nllh) *nllh = -cur;
+    if (iters) *iters = it;
+    if (status) *status = 0;
+    return pmm_download_params(h, d, nu, phi);
+}
+
+int pmm_get_info(const pmm_handle *h, pmm_info *info) {
+    if (!h || !info) return 1;
+    info->n_nodes = h->n; info->n_leaves = h->n_leaves; info->n_sites = h->K;
+    info->slots_per_node = h->W; info->row_stride = h->maxWp;
+    info->n_chunks = (int64_t)h->chunks.size(); info->n_tiles = h->max_tiles; info->tile_slots = h->TS;
+    info->inside_levels = (int64_t)h->in_ptr.size() - 1; info->outside_levels = (int64_t)h->out_ptr.size() - 1;
+    info->device_bytes = (int64_t)h->device_bytes; info->kernel_launches = h->launches;
+    return 0;
+}
+
+int pmm_last_timing(const pmm_handle *hc, double *inside_ms, double *outside_ms, double *total_ms) {
+    pmm_handle *h = const_cast<pmm_handle *>(hc);
+    if (!h || h->n == 0) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev[3]));
+    float a = h->t_inside, b = h->t_outside, tot = 0;
+    if (h->chunks.size() == 1) {
+        cudaEventElapsedTime(&a, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
+    }
+    cudaEventElapsedTime(&tot, h->ev[0], h->ev[3]);
+    if (inside_ms) *inside_ms = a;
+    if (outside_ms) *outside_ms = b;
+    if (total_ms) *total_ms = tot;
+    return 0;
+}
+
+}  // extern "C"

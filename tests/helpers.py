@@ -84,3 +84,29 @@ def assert_close_loginf(a, b, rtol, atol, what=""):
     ia, ib = np.isneginf(a), np.isneginf(b)
     assert (ia == ib).all(), "%s: -inf pattern differs at %s" % (what, np.argwhere(ia != ib)[:5])
     np.testing.assert_allclose(a[~ia], b[~ib], rtol=rtol, atol=atol, err_msg=what)
+
+
+def make_engine(case, device=0, **kw):
+    """Engine for a :class:`Case` (codes re-ordered to leaf-id order)."""
+    from laml_b200.capi import Engine
+    eng = Engine(case.forest.n_leaves, case.enc.qptr, case.enc.qval, case.enc.codes[case.leaf_row], device=device, **kw)
+    eng.set_tree(case.forest.parent, case.forest.left, case.forest.right)
+    return eng
+
+
+class env_override:
+    """temporarily set environment variables read by pmm_create / pmm_set_tree"""
+
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -1,0 +1,126 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against
+(1) the reference's own outputs (golden fixtures), (2) the reference's
+known-answer tests, (3) the C oracle on seeded synthetic inputs.
+
+Tolerances are BASELINE.json's: total nllh 1e-9 relative, per-branch expected
+counts 1e-8 relative (absolute floor 1e-10*K: S1 and S3 are differences in the
+reference, EM_solver.py:299-300)."""
+import numpy as np
+import pytest
+
+from helpers import (NPZ_CASES, env_override, json_case, load_json, load_npz_case, make_engine)
+
+pytestmark = pytest.mark.gpu
+
+KAT = load_json("kat_likelihood.json")
+PROP = load_json("outside_cases.json")
+
+
+def check_against_golden(case, z, eng):
+    out = eng.estep(case.d, case.nu, case.phi, want_site_llh=True)
+    nllh = float(z["nllh"])
+    K = case.enc.n_sites
+    assert abs(-out["llh"] - nllh) <= 1e-9 * abs(nllh)
+    np.testing.assert_allclose(out["site_llh"], z["site_llh"], rtol=1e-9, atol=1e-10)
+    ids = case.ids(z["labels"], z["tree_of"])
+    np.testing.assert_allclose(out["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * K)
+    assert abs(out["Rtilde"] - float(z["Rtilde"])) <= 1e-8 * max(1.0, float(z["Rtilde"]))
+    llh_only = eng.inside(case.d, case.nu, case.phi)
+    assert llh_only == out["llh"]          # same kernels, same order: bit-identical
+    return out
+
+
+@pytest.mark.parametrize("name", NPZ_CASES)
+def test_reference_dumps(name):
+    case, z = load_npz_case(name)
+    eng = make_engine(case)
+    check_against_golden(case, z, eng)
+    eng.close()
+
+
+@pytest.mark.parametrize("rec", KAT, ids=["test_%d" % r["no"] for r in KAT])
+def test_known_answer_likelihood(rec):
+    case = json_case(rec)
+    eng = make_engine(case)
+    llh = eng.inside(case.d, case.nu, case.phi)
+    assert abs(-llh - rec["true_nllh"]) < 5e-6                      # the reference's own assertion (places=5)
+    assert abs(-llh - rec["ref_nllh"]) <= 1e-9 * max(1.0, abs(rec["ref_nllh"]))
+    eng.close()
+
+
+@pytest.mark.parametrize("rec", PROP, ids=["test_%d" % r["no"] for r in PROP])
+def test_outside_cases(rec):
+    """unit tests 21-44: per-branch counts and posteriors against the reference dump"""
+    from helpers import unjson, assert_close_loginf
+    case = json_case(rec)
+    eng = make_engine(case)
+    out = eng.estep(case.d, case.nu, case.phi)
+    ids = case.ids(rec["labels"])
+    assert abs(-out["llh"] - rec["nllh"]) <= 1e-9 * max(1.0, abs(rec["nllh"]))
+    for k in range(5):
+        np.testing.assert_allclose(out["S"][ids, k], unjson(rec["S%d" % k]).sum(axis=1), rtol=1e-8, atol=1e-10)
+    p0, p1 = eng.posteriors(case.d, case.nu, case.phi)
+    assert_close_loginf(p0[ids], unjson(rec["post0"]), 1e-8, 1e-9, "post0")
+    assert_close_loginf(p1[ids], unjson(rec["post1"]), 1e-8, 1e-9, "post1")
+    eng.close()
+
+
+@pytest.mark.parametrize("ts,group,chunks", [(64, 4, 1), (128, 8, 1), (256, 16, 2), (512, 32, 3), (2048, 8, 1)])
+def test_layout_variants(ts, group, chunks):
+    """tile size, lane-group width and site chunking must not change results"""
+    case, z = load_npz_case("ref_rand_ragged")
+    with env_override(PMM_TILE_SLOTS=ts, PMM_GROUP=group, PMM_CHUNKS=chunks):
+        eng = make_engine(case)
+        info = eng.info()
+        assert info["n_chunks"] == chunks
+        check_against_golden(case, z, eng)
+        eng.close()
+    case, z = load_npz_case("ref_test45_test1")
+    with env_override(PMM_TILE_SLOTS=ts, PMM_GROUP=group, PMM_CHUNKS=chunks):
+        eng = make_engine(case)
+        check_against_golden(case, z, eng)
+        eng.close()
+
+
+@pytest.mark.parametrize("cfg,seed", [("config2_1k_x_30", 1), ("config2_1k_x_30", 2)])
+def test_synthetic_vs_oracle(cfg, seed):
+    from laml_b200.capi import Engine
+    from laml_b200.synth import CONFIGS, make_workload
+    from oracle.pmm_oracle import OracleProblem
+    w = make_workload(seed=seed, **CONFIGS[cfg])
+    N = w.forest.n_leaves
+    orc = OracleProblem(w.forest, np.arange(N, dtype=np.int32), w.codes, w.qptr, w.qval)
+    ref = orc.estep(w.d, w.nu, w.phi, nthreads=4)
+    eng = Engine(N, w.qptr, w.qval, w.codes)
+    eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    out = eng.estep(w.d, w.nu, w.phi, want_site_llh=True)
+    K = w.codes.shape[1]
+    assert abs(out["llh"] - ref["llh"]) <= 1e-9 * abs(ref["llh"])
+    np.testing.assert_allclose(out["site_llh"], ref["site_llh"], rtol=1e-9)
+    np.testing.assert_allclose(out["S"], ref["S"].T, rtol=1e-8, atol=1e-10 * K)
+    assert abs(out["Rtilde"] - ref["Rtilde"]) <= 1e-8 * ref["Rtilde"]
+    # size-independent property: the five counts and the silenced-stays-silenced mass
+    # partition each site, so every branch's counts sum to at most K
+    assert (out["S"].sum(axis=1) <= K * (1 + 1e-9)).all() and (out["S"] >= -1e-9).all()
+    eng.close()
+
+
+def test_mstep_and_em_vs_oracle():
+    case, z = load_npz_case("ref_test4_zero")
+    orc = case.oracle()
+    eng = make_engine(case)
+    est = eng.estep(case.d, 0.1, 0.1)
+    R = orc.R()
+    d1, nu1, phi1 = eng.mstep(est["S"], est["Rtilde"], R, orc.n_cells, case.d, 0.1, 0.1)
+    d0, nu0, phi0, _ = orc.mstep(est["S"].T.copy(), est["Rtilde"], case.d, 0.1)
+    np.testing.assert_allclose(d1, d0, rtol=1e-12, atol=1e-14)
+    assert abs(nu1 - nu0) <= 1e-12 and abs(phi1 - phi0) <= 1e-14
+    # full EM from the reference's starting lengths
+    d_init = np.maximum(case.d, 0.01)
+    got = eng.em(d_init, 0.1, 0.1, R, orc.n_cells)
+    ref = orc.em(d_init, 0.1, 0.1)
+    assert got["iters"] == ref["iters"]
+    assert abs(got["nllh"] - ref["nllh"]) <= 1e-9 * ref["nllh"]
+    np.testing.assert_allclose(got["d"], ref["d"], rtol=1e-5, atol=1e-7)
+    assert abs(got["nu"] - ref["nu"]) <= 1e-5 and abs(got["phi"] - ref["phi"]) <= 1e-5
+    eng.close()
