@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the PMM EM hot path (BASELINE.json metric) -- see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A *step* is one EM iteration on the whole synthetic workload: E-step (inside pass,
+outside pass + expected counts), the all-reduce of the statistics when N > 1, and the
+M-step.  Under torchrun every rank holds a contiguous site shard of the SAME workload
+(strong scaling); rank 0 prints ONE JSON line.
+
+``--impl reference`` times the reference's own algorithm on the host cores: the
+reference is pure Python and cannot travel to the GPU box, so this arm runs its C
+restatement (oracle/, pinned against the reference's golden vectors) with every
+host thread, on a bounded site sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(PEAKS_FILE))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_spec(name):
+    from laml_b200.synth import CONFIGS
+    if name not in CONFIGS:
+        raise SystemExit("unknown workload %r; choose from %s" % (name, sorted(CONFIGS)))
+    return dict(CONFIGS[name])
+
+
+def build_inputs(spec, sites, device):
+    """tree, branch lengths and priors of the whole workload + simulated codes of ``sites``"""
+    from laml_b200.synth import lognormal_branch_lengths, random_priors, random_tree, simulate_codes
+    seed = 1
+    forest = random_tree(spec["n_leaves"], seed=seed)
+    d = lognormal_branch_lengths(forest, seed=seed + 1)
+    qptr, qval = random_priors(spec["n_sites"], spec["a_lo"], spec["a_hi"], seed=seed + 4,
+                               uniform=spec.get("uniform_prior", False))
+    codes = simulate_codes(forest, d, qptr, qval, spec["nu"], spec["phi"], seed=seed + 6, device=device, sites=sites)
+    return forest, d, qptr, qval, codes
+
+
+def shard_prior(qptr, qval, lo, hi):
+    return (qptr[lo:hi + 1] - qptr[lo]).astype(np.int32), qval[qptr[lo]:qptr[hi]].copy()
+
+
+def cpu_reference_step(orc, d, nu, phi, sites, nthreads, with_mstep=True):
+    """one EM iteration of the reference's algorithm (oracle port) on a site sample"""
+    t0 = time.perf_counter()
+    est = orc.estep(d, nu, phi, sites=sites, nthreads=nthreads)
+    if with_mstep:
+        orc.mstep(est["S"], est["Rtilde"], d, nu)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from __graft_entry__ import build
+    build()
+    from oracle.pmm_oracle import OracleProblem, num_threads
+    spec = workload_spec(args.workload)
+    threads = num_threads()
+    n_sample = min(spec["n_sites"], args.cpu_sample_sites or max(8, 2 * threads))
+    forest, d, qptr, qval, codes = build_inputs(spec, (0, n_sample), "cpu")
+    q2, v2 = shard_prior(qptr, qval, 0, n_sample)
+    N = forest.n_leaves
+    orc = OracleProblem(forest, np.arange(N, dtype=np.int32), codes, q2, v2)
+    for _ in range(args.warmup):
+        cpu_reference_step(orc, d, spec["nu"], spec["phi"], (0, n_sample), threads)
+    t = [cpu_reference_step(orc, d, spec["nu"], spec["phi"], (0, n_sample), threads) for _ in range(args.steps)]
+    dt = float(np.sum(t)) / args.steps
+    value = N * n_sample / dt
+    sample = "%d of %d sites, full %d-cell tree, %d threads; cell*site/s scales linearly in sites" % (
+        n_sample, spec["n_sites"], N, threads)
+    line = {
+        "impl": "reference", "metric": "em_iteration_cell_site_per_s", "value": value, "unit": "cell*site/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.workload, spec, qptr, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "cell*site/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell*site/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "em_iter_per_s_full_workload": value / (N * spec["n_sites"]),
+        "note": "reference is pure Python (cannot travel); this arm is its C restatement oracle/pmm_oracle.c, "
+                "pinned to the reference's golden vectors (tests/test_oracle_golden.py)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(name, spec, qptr, gpus):
+    W = int(qptr[-1]) + 2 * (len(qptr) - 1)
+    return {"workload": name, "cells": spec["n_leaves"], "sites": spec["n_sites"],
+            "alphabet": "%d..%d states/site" % (spec["a_lo"], spec["a_hi"]), "nu": spec["nu"], "phi": spec["phi"],
+            "state_slots_per_node_W": W, "nodes": 2 * spec["n_leaves"] - 1,
+            "parallelism": "site-shard x%d" % gpus}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from laml_b200.capi import Engine
+    from laml_b200.dist import ShardedEngine, partition_sites
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PMM engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    spec = workload_spec(args.workload)
+    Ktot, N = spec["n_sites"], spec["n_leaves"]
+    # priors are cheap: build them first to partition by state slots
+    from laml_b200.synth import random_priors
+    qptr_all, _ = random_priors(Ktot, spec["a_lo"], spec["a_hi"], seed=5, uniform=spec.get("uniform_prior", False))
+    lo, hi = partition_sites(qptr_all, world)[rank]
+    forest, d, qptr, qval, codes = build_inputs(spec, (lo, hi), "cuda:%d" % local_rank)
+    assert (qptr == qptr_all).all()
+    q2, v2 = shard_prior(qptr, qval, lo, hi)
+    n = forest.n_nodes
+    eng = Engine(N, q2, v2, codes, device=local_rank)
+    eng.set_tree(forest.parent, forest.left, forest.right)
+    sh = ShardedEngine(eng, Ktot)
+    info = eng.info()
+    # R = number of non-'?' leaf entries (EM_solver.py:322) over ALL sites
+    Rt = torch.tensor([float((codes != -1).sum())], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if world > 1:
+        dist.all_reduce(Rt)
+    R = float(Rt.item())
+    nu0, phi0 = spec["nu"], spec["phi"]
+
+    def reset():
+        eng.upload_params(d, nu0, phi0)
+
+    def step_device():
+        sh.estep_dev()
+        eng.mstep_dev(R, N)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") --------------------------------------
+    reset()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = eng.info()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = np.zeros(3)
+    with torch.cuda.stream(sh.stream):
+        ev0.record()
+        for _ in range(args.steps):
+            step_device()
+            tm = eng.last_timing()          # CUDA events on the launching stream (syncs this step)
+            phase += (tm["inside_ms"], tm["outside_ms"], tm["total_ms"])
+        ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = eng.info()["kernel_launches"] - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda:%d" % local_rank)
+    ph = torch.tensor(phase / args.steps, dtype=torch.float64, device="cuda:%d" % local_rank)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    inside_ms, outside_ms, estep_ms = [float(x) for x in ph.tolist()]
+
+    # ---- end to end through the host-buffer API ("e2e") ----------------------------
+    d_pin = torch.from_numpy(d.copy()).pin_memory().numpy()
+    S_pin = torch.empty((n, 5), dtype=torch.float64).pin_memory().numpy()
+
+    def step_e2e(dcur, nu, phi):
+        if world == 1:
+            est = eng.estep(dcur, nu, phi, out_S=S_pin)
+            return eng.mstep(est["S"], est["Rtilde"], R, N, dcur, nu, phi)
+        est = sh.estep(dcur, nu, phi)
+        return eng.mstep(est["S"], est["Rtilde"], R, N, dcur, nu, phi)
+
+    cur = (d_pin, nu0, phi0)
+    for _ in range(max(1, args.warmup // 2)):
+        cur = step_e2e(*cur)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cur = step_e2e(*cur)
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    h2d = 8 * n + 16 + 8 * (5 * n + 1) + 8 * n + 16        # estep: d,nu,phi; mstep: S,Rtilde,d,nu,phi
+    d2h = 8 * (5 * n + 2) + 8 * n + 16                      # estep: S,Rtilde,llh; mstep: d,nu,phi
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (pmm_outside_level) -----------------------
+    peak, peak_src = hbm_peak()
+    W_shard_max = info["slots_per_node"]
+    n_roots = int((forest.parent < 0).sum())
+    # 20 bytes per (child node, state slot) for outside+counts, 16 for inside
+    out_bytes = 20.0 * W_shard_max * (n - n_roots)
+    in_bytes = 16.0 * W_shard_max * n
+    # bytes this design actually has to move (leaf rows are never materialised): DESIGN.md
+    n_int = n - N
+    out_moved = 8.0 * info["row_stride"] * ((n_int - n_roots) * 2 + (n_int - n_roots))
+    in_moved = 8.0 * info["row_stride"] * (n_int + (n_int - n_roots))
+    out_launches = info["outside_levels"] * info["n_chunks"]
+    ach = out_bytes / (outside_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "pmm_outside_level", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        "bytes_per_step_survey_figure": out_bytes, "launches_per_step": out_launches,
+        "avg_launch_ms": outside_ms / max(out_launches, 1),
+        "moved_bytes_design": out_moved, "achieved_moved_GBs": out_moved / (outside_ms * 1e-3) / 1e9,
+        "frac_moved": out_moved / (outside_ms * 1e-3) / 1e9 / peak,
+        "inside": {"kernel": "pmm_inside_level", "achieved": in_bytes / (inside_ms * 1e-3) / 1e9,
+                   "frac": in_bytes / (inside_ms * 1e-3) / 1e9 / peak, "ms": inside_ms,
+                   "achieved_moved_GBs": in_moved / (inside_ms * 1e-3) / 1e9,
+                   "frac_moved": in_moved / (inside_ms * 1e-3) / 1e9 / peak},
+        "estep": {"bytes_survey_figure": in_bytes + out_bytes, "ms": estep_ms,
+                  "frac": (in_bytes + out_bytes) / (estep_ms * 1e-3) / 1e9 / peak},
+        "note": "achieved uses SURVEY 8(d)'s per-unit figure (rank 0's shard); *_moved is what this design must "
+                "move: leaf vectors are synthesised from 4-byte codes and never stored",
+    }
+
+    # ---- CPU baseline beside it (N=1 only) -----------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.pmm_oracle import OracleProblem, num_threads
+        threads = num_threads()
+        n_sample = min(Ktot, args.cpu_sample_sites or max(8, 2 * threads))
+        qs, vs = shard_prior(qptr, qval, 0, n_sample)
+        orc = OracleProblem(forest, np.arange(N, dtype=np.int32), codes[:, :n_sample], qs, vs)
+        cpu_reference_step(orc, d, nu0, phi0, (0, n_sample), threads)
+        reps, t_acc = 0, 0.0
+        while reps < 3 or (t_acc < 10.0 and reps < 50):
+            t_acc += cpu_reference_step(orc, d, nu0, phi0, (0, n_sample), threads)
+            reps += 1
+        cpu = {"value": N * n_sample / (t_acc / reps), "unit": "cell*site/s", "cores": threads, "kind": "port",
+               "sample": "%d of %d sites, full %d-cell tree, %d reps, %d threads (oracle/pmm_oracle.c: the "
+                         "reference's algorithm in C)" % (n_sample, Ktot, N, reps, threads)}
+
+    value = N * Ktot / (ms_step * 1e-3)
+    line = {
+        "metric": "em_iteration_cell_site_per_s", "value": value, "unit": "cell*site/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(config_dict(args.workload, spec, qptr, world),
+                       l2="state rows far exceed L2: %.1f GB per pass per GPU" % (8e-9 * info["row_stride"] * n_int),
+                       site_chunks=info["n_chunks"], tile_slots=info["tile_slots"]),
+        "em_iter_per_s": 1e3 / ms_step, "estep_ms": estep_ms, "inside_ms": inside_ms, "outside_ms": outside_ms,
+        "estep_cell_site_per_s": N * Ktot / (estep_ms * 1e-3),
+        "node_site_per_s": n * Ktot / (estep_ms * 1e-3),
+        "e2e": {"value": N * Ktot / e2e_s, "unit": "cell*site/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "device_bytes": info["device_bytes"],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PMM_BENCH_WORKLOAD", "config4_100k_x_2k"))
+    ap.add_argument("--cpu-sample-sites", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -141,9 +141,10 @@ class Engine:
                                     site.ctypes.data if want_site_llh else None, C.byref(llh)))
         return (llh.value, site) if want_site_llh else llh.value
 
-    def estep(self, d, nu, phi, want_site_llh=False):
+    def estep(self, d, nu, phi, want_site_llh=False, out_S=None):
+        """``out_S``: optional caller-owned (n_nodes, 5) float64 buffer (e.g. pinned)."""
         d = _f64(d)
-        S = np.empty((self.n_nodes, 5))
+        S = np.empty((self.n_nodes, 5)) if out_S is None else out_S
         rt, llh = C.c_double(), C.c_double()
         site = np.empty(self.n_sites) if want_site_llh else None
         self._ck(self._L.pmm_estep(self._h, d.ctypes.data, float(nu), float(phi), S.ctypes.data, C.byref(rt),

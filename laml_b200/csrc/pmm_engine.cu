@@ -22,9 +22,10 @@ namespace {
 thread_local std::string g_create_error;
 
 struct Chunk {
-    int site0 = 0, K = 0, W = 0, Wp = 0, ntiles = 0;
+    int site0 = 0, K = 0, W = 0, Wp = 0, ntiles = 0, max_tile_sites = 0;
     int *d_site_off = nullptr, *d_site_len = nullptr, *d_tile_site = nullptr, *d_tile_off = nullptr;
-    double *d_q = nullptr;
+    int2 *d_ent = nullptr;
+    double *d_q = nullptr, *d_qsum = nullptr;
 };
 
 }  // namespace
@@ -41,10 +42,11 @@ struct pmm_handle {
     std::vector<double> prior;
     int *d_codes = nullptr;
     int64_t W = 0;                  // algorithmic slots per node
-    int TS = 2048, G = 8;
+    int TS = 1024;
+    int stages_in = 3, stages_out = 2, ctas_in = 1, ctas_out = 1, n_sms = 148;
     size_t budget = 0;
     std::vector<Chunk> chunks;
-    int maxWp = 0, maxK = 0, max_tiles = 0;
+    int maxWp = 0, maxK = 0, max_tiles = 0, max_tile_sites = 0;
     // tree
     int n = 0, n_int = 0, n_roots = 0;
     std::vector<int> parent, left, right;
@@ -54,9 +56,8 @@ struct pmm_handle {
     std::vector<int> in_ptr, out_ptr;
     // state
     double *d_X = nullptr, *d_O = nullptr;
-    int *d_iexp = nullptr, *d_oexp = nullptr;
-    double *d_rootLm = nullptr, *d_root_site_llh = nullptr;
-    int *d_rootLe = nullptr;
+    int *d_iexp = nullptr, *d_dexp = nullptr;
+    double *d_rootInvL = nullptr, *d_root_site_llh = nullptr;
     double *d_Spart = nullptr, *d_Rpart = nullptr, *d_Rnode = nullptr;
     double *d_site_llh = nullptr;   // [K]
     double *d_bc = nullptr, *d_d = nullptr, *d_params = nullptr;
@@ -104,15 +105,17 @@ int env_int(const char *name, int dflt) {
 }
 
 void free_chunks(pmm_handle *h) {
-    for (auto &c : h->chunks) { dfree(c.d_site_off); dfree(c.d_site_len); dfree(c.d_tile_site); dfree(c.d_tile_off); dfree(c.d_q); }
+    for (auto &c : h->chunks) {
+        dfree(c.d_site_off); dfree(c.d_site_len); dfree(c.d_tile_site); dfree(c.d_tile_off); dfree(c.d_ent); dfree(c.d_q); dfree(c.d_qsum);
+    }
     h->chunks.clear();
 }
 
 void free_tree_state(pmm_handle *h) {
     dfree(h->d_parent); dfree(h->d_left); dfree(h->d_right); dfree(h->d_root_index); dfree(h->d_roots);
     dfree(h->d_in_nodes); dfree(h->d_out_nodes);
-    dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_oexp);
-    dfree(h->d_rootLm); dfree(h->d_rootLe); dfree(h->d_root_site_llh);
+    dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp);
+    dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free);
     dfree(h->d_post0); dfree(h->d_post1);
@@ -125,9 +128,8 @@ int build_chunk(pmm_handle *h, int s_lo, int s_hi, Chunk &c) {
     std::vector<int> site_off(K), site_len(K), tile_site{0}, tile_off{0};
     int off = 0, cur = 0;
     for (int s = 0; s < K; s++) {
-        int len = h->site_ptr[s_lo + s + 1] - h->site_ptr[s_lo + s] + 2;
+        int len = (h->site_ptr[s_lo + s + 1] - h->site_ptr[s_lo + s] + 2 + 1) & ~1;   // padded to even
         if (cur > 0 && cur + len > h->TS) {
-            off = (off + 1) & ~1;
             tile_site.push_back(s);
             tile_off.push_back(off);
             cur = 0;
@@ -137,24 +139,44 @@ int build_chunk(pmm_handle *h, int s_lo, int s_hi, Chunk &c) {
         off += len;
         cur += len;
     }
-    off = (off + 1) & ~1;
     tile_site.push_back(K);
     tile_off.push_back(off);
     c.site0 = s_lo; c.K = K; c.Wp = off; c.ntiles = (int)tile_site.size() - 1;
     c.W = h->site_ptr[s_hi] - h->site_ptr[s_lo] + 2 * K;
-    std::vector<double> q((size_t)std::max(off, 1), 0.0);
+    std::vector<double> q((size_t)std::max(off, 1), 0.0), qsum((size_t)K, 0.0);
     for (int s = 0; s < K; s++) {
-        int A = site_len[s] - 2;
-        for (int a = 0; a < A; a++) q[site_off[s] + 2 + a] = h->prior[h->site_ptr[s_lo + s] + a];
+        int A = h->site_ptr[s_lo + s + 1] - h->site_ptr[s_lo + s];
+        double acc = 0.0;
+        for (int a = 0; a < A; a++) { double x = h->prior[h->site_ptr[s_lo + s] + a]; q[site_off[s] + 2 + a] = x; acc += x; }
+        qsum[s] = acc;
     }
+    // per tile: sites sorted by decreasing length, so that the lane groups of one warp (which take
+    // consecutive entries) run similar trip counts and the round-robin assignment is balanced
+    std::vector<int2> ent((size_t)K);
+    c.max_tile_sites = 0;
+    for (int t = 0; t < c.ntiles; t++) {
+        const int a = tile_site[t], b = tile_site[t + 1];
+        std::vector<int> idx(b - a);
+        for (int i = 0; i < b - a; i++) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return site_len[a + x] > site_len[a + y]; });
+        for (int i = 0; i < b - a; i++) {
+            const int ls = idx[i];
+            ent[a + i].x = (site_off[a + ls] - tile_off[t]) | (site_len[a + ls] << 16);
+            ent[a + i].y = ls;
+        }
+        c.max_tile_sites = std::max(c.max_tile_sites, b - a);
+    }
+    c.max_tile_sites = (c.max_tile_sites + 3) & ~3;
     if (dalloc(h, &c.d_site_off, K) || dalloc(h, &c.d_site_len, K) || dalloc(h, &c.d_tile_site, tile_site.size()) ||
-        dalloc(h, &c.d_tile_off, tile_off.size()) || dalloc(h, &c.d_q, q.size()))
+        dalloc(h, &c.d_tile_off, tile_off.size()) || dalloc(h, &c.d_q, q.size()) || dalloc(h, &c.d_qsum, K) || dalloc(h, &c.d_ent, K))
         return 1;
     CK(cudaMemcpy(c.d_site_off, site_off.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_site_len, site_len.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_tile_site, tile_site.data(), sizeof(int) * tile_site.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_tile_off, tile_off.data(), sizeof(int) * tile_off.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.d_q, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_qsum, qsum.data(), sizeof(double) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_ent, ent.data(), sizeof(int2) * K, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -185,12 +207,13 @@ int plan_chunks(pmm_handle *h) {
     }
     if (bounds.back() != K) bounds.push_back(K);
     h->chunks.resize(bounds.size() - 1);
-    h->maxWp = h->maxK = h->max_tiles = 0;
+    h->maxWp = h->maxK = h->max_tiles = h->max_tile_sites = 0;
     for (size_t c = 0; c + 1 < bounds.size(); c++) {
         if (build_chunk(h, bounds[c], bounds[c + 1], h->chunks[c])) return 1;
         h->maxWp = std::max(h->maxWp, h->chunks[c].Wp);
         h->maxK = std::max(h->maxK, h->chunks[c].K);
         h->max_tiles = std::max(h->max_tiles, h->chunks[c].ntiles);
+        h->max_tile_sites = std::max(h->max_tile_sites, h->chunks[c].max_tile_sites);
     }
     return 0;
 }
@@ -198,57 +221,84 @@ int plan_chunks(pmm_handle *h) {
 KParams make_params(pmm_handle *h, const Chunk &c, bool with_post) {
     KParams P;
     P.site_off = c.d_site_off; P.site_len = c.d_site_len; P.tile_site = c.d_tile_site; P.tile_off = c.d_tile_off;
-    P.q = c.d_q; P.K = c.K; P.Wp = c.Wp; P.ntiles = c.ntiles;
+    P.ent = c.d_ent; P.q = c.d_q; P.qsum = c.d_qsum;
+    P.K = c.K; P.Wp = c.Wp; P.ntiles = c.ntiles; P.max_tile_sites = h->max_tile_sites;
     P.codes = h->d_codes; P.codes_stride = h->K; P.site0 = c.site0;
     P.left = h->d_left; P.right = h->d_right; P.parent = h->d_parent; P.root_index = h->d_root_index;
     P.n_leaves = h->n_leaves; P.n_nodes = h->n;
     P.params = h->d_params; P.bc = h->d_bc;
-    P.X = h->d_X; P.O = h->d_O; P.iexp = h->d_iexp; P.oexp = h->d_oexp;
-    P.rootLm = h->d_rootLm; P.rootLe = h->d_rootLe; P.root_site_llh = h->d_root_site_llh;
+    P.X = h->d_X; P.O = h->d_O; P.iexp = h->d_iexp; P.dexp = h->d_dexp;
+    P.rootInvL = h->d_rootInvL; P.root_site_llh = h->d_root_site_llh;
     P.Spart = h->d_Spart; P.Rpart = h->d_Rpart;
     P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
     P.K_total = h->K;
+    P.TS = h->TS; P.stages = 0;
     return P;
 }
 
-size_t smem_inside(int TS) { return (size_t)2 * TS * 8 + 64; }
-size_t smem_outside(int TS, int G) { return (size_t)3 * TS * 8 + 16 + (size_t)(NT / G) * 11 * 8 + 64; }
-
-template <int G> int set_attrs(pmm_handle *h) {
-    CK(cudaFuncSetAttribute(pmm_inside_level<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inside(h->TS)));
-    CK(cudaFuncSetAttribute(pmm_outside_level<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outside(h->TS, G)));
+// Shared-memory ring depth and resident CTAs per SM for both level kernels, given the tile
+// geometry.  Called once the chunk plan (hence max_tile_sites) is known.
+int configure_kernels(pmm_handle *h) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->n_sms = prop.multiProcessorCount;
+    const size_t smem_cap = prop.sharedMemPerBlockOptin;       // 227 KB on sm_100
+    const int MS = h->max_tile_sites;
+    auto pick = [&](bool outside, int want_stages, int &stages) -> size_t {
+        for (int S = std::min(want_stages, MAX_STAGES); S >= 1; S--) {
+            size_t b = outside ? Plan<true>::total_bytes(h->TS, MS, S) : Plan<false>::total_bytes(h->TS, MS, S);
+            if (b <= smem_cap) { stages = S; return b; }
+        }
+        stages = 0;
+        return 0;
+    };
+    size_t bi = pick(false, env_int("PMM_STAGES_IN", 3), h->stages_in);
+    size_t bo = pick(true, env_int("PMM_STAGES_OUT", 3), h->stages_out);
+    if (!bi || !bo) return fail(h, "tile of %d slots does not fit in shared memory", h->TS);
+    CK(cudaFuncSetAttribute(pmm_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bi));
+    CK(cudaFuncSetAttribute(pmm_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bo));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_in, pmm_level<false>, NTHREADS, bi));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_out, pmm_level<true>, NTHREADS, bo));
+    if (h->ctas_in < 1 || h->ctas_out < 1) return fail(h, "level kernels cannot be resident (smem %zu / %zu bytes)", bi, bo);
+    h->ctas_in = std::min(h->ctas_in, env_int("PMM_CTAS_IN", 8));
+    h->ctas_out = std::min(h->ctas_out, env_int("PMM_CTAS_OUT", 8));
     return 0;
 }
 
-template <int G> int launch_inside(pmm_handle *h, const KParams &P) {
+// grid = (P, ntiles): P persistent CTAs per tile, sized to fill the SMs once
+template <bool OUTSIDE> void launch_level(pmm_handle *h, KParams P, const int *d_nodes, int cnt) {
+    const int resident = h->n_sms * (OUTSIDE ? h->ctas_out : h->ctas_in);
+    int per_tile = std::max(1, resident / std::max(P.ntiles, 1));
+    per_tile = std::min(per_tile, cnt);
+    P.stages = OUTSIDE ? h->stages_out : h->stages_in;
+    const size_t smem = OUTSIDE ? Plan<true>::total_bytes(h->TS, P.max_tile_sites, P.stages)
+                                : Plan<false>::total_bytes(h->TS, P.max_tile_sites, P.stages);
+    dim3 grid((unsigned)per_tile, (unsigned)P.ntiles);
+    pmm_level<OUTSIDE><<<grid, NTHREADS, smem, h->stream>>>(P, d_nodes, cnt);
+    h->launches++;
+}
+
+int launch_inside(pmm_handle *h, const KParams &P) {
     const int nl = (int)h->in_ptr.size() - 1;
     for (int l = 0; l < nl; l++) {
         int cnt = h->in_ptr[l + 1] - h->in_ptr[l];
-        if (!cnt) continue;
-        pmm_inside_level<G><<<(unsigned)((size_t)cnt * P.ntiles), NT, smem_inside(h->TS), h->stream>>>(P, h->d_in_nodes + h->in_ptr[l], h->TS);
-        h->launches++;
+        if (cnt) launch_level<false>(h, P, h->d_in_nodes + h->in_ptr[l], cnt);
     }
-    pmm_root_llh<G><<<(unsigned)(h->n_roots * P.ntiles), NT, 0, h->stream>>>(P, h->d_roots);
+    pmm_root_llh<<<(unsigned)(h->n_roots * P.ntiles), 256, 0, h->stream>>>(P, h->d_roots);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-template <int G> int launch_outside(pmm_handle *h, const KParams &P) {
+int launch_outside(pmm_handle *h, const KParams &P) {
     const int nl = (int)h->out_ptr.size() - 1;
     for (int l = 0; l < nl; l++) {
         int cnt = h->out_ptr[l + 1] - h->out_ptr[l];
-        if (!cnt) continue;
-        pmm_outside_level<G><<<(unsigned)((size_t)cnt * P.ntiles), NT, smem_outside(h->TS, G), h->stream>>>(P, h->d_out_nodes + h->out_ptr[l], h->TS);
-        h->launches++;
+        if (cnt) launch_level<true>(h, P, h->d_out_nodes + h->out_ptr[l], cnt);
     }
     CK(cudaGetLastError());
     return 0;
 }
-
-#define DISPATCH_G(h, fn, ...)                                            \
-    ((h)->G == 4 ? fn<4>(__VA_ARGS__) : (h)->G == 8 ? fn<8>(__VA_ARGS__) : \
-     (h)->G == 16 ? fn<16>(__VA_ARGS__) : fn<32>(__VA_ARGS__))
 
 int check_ready(pmm_handle *h) {
     if (!h) return 1;
@@ -270,13 +320,13 @@ int run_passes(pmm_handle *h, bool outside, bool with_post) {
         const Chunk &c = h->chunks[ci];
         KParams P = make_params(h, c, with_post);
         CK(cudaEventRecord(h->ev[1], h->stream));
-        if (DISPATCH_G(h, launch_inside, h, P)) return 1;
+        if (launch_inside(h, P)) return 1;
         pmm_site_llh<<<(c.K + 255) / 256, 256, 0, h->stream>>>(h->d_root_site_llh, h->n_roots, c.K, h->d_site_llh + c.site0);
         pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_site_llh + c.site0, c.K, d_llh, ci > 0);
         h->launches += 2;
         CK(cudaEventRecord(h->ev[2], h->stream));
         if (outside) {
-            if (DISPATCH_G(h, launch_outside, h, P)) return 1;
+            if (launch_outside(h, P)) return 1;
             pmm_reduce_S<<<(5 * n + 255) / 256, 256, 0, h->stream>>>(h->d_Spart, c.ntiles, 5 * n, h->d_stats, ci > 0);
             pmm_reduce_S<<<(h->n_int + 255) / 256, 256, 0, h->stream>>>(h->d_Rpart, c.ntiles, h->n_int, h->d_Rnode, 0);
             pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Rnode, h->n_int, d_Rt, ci > 0);
@@ -338,12 +388,9 @@ int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const
     for (int i = 0; i < nnz; i++)
         if (!(h->prior[i] >= 0.0)) { h->err = "prior entries must be non-negative numbers"; return bail(1); }
     h->W = (int64_t)nnz + 2 * (int64_t)n_sites;
-    h->TS = env_int("PMM_TILE_SLOTS", 2048);
+    h->TS = env_int("PMM_TILE_SLOTS", 1024);
     h->TS = std::max((h->TS + 1) & ~1, (maxlen + 1) & ~1);
-    if (h->TS > 9000) { h->err = "an alphabet is too large for one shared-memory tile (limit ~9000 states)"; return bail(1); }
-    double mean_len = (double)h->W / n_sites;
-    h->G = env_int("PMM_GROUP", mean_len < 12 ? 4 : (mean_len < 48 ? 8 : 16));
-    if (h->G != 4 && h->G != 8 && h->G != 16 && h->G != 32) { h->err = "PMM_GROUP must be 4, 8, 16 or 32"; return bail(1); }
+    if (h->TS > 8192) { h->err = "an alphabet is too large for one shared-memory tile (limit ~8000 states)"; return bail(1); }
     // validate codes against the alphabets, then upload
     for (int64_t r = 0; r < n_leaves; r++)
         for (int s = 0; s < n_sites; s++) {
@@ -361,8 +408,6 @@ int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const
         h->err = "uploading codes failed";
         return bail(1);
     }
-    int rc = DISPATCH_G(h, set_attrs, h);
-    if (rc) return bail(1);
     *out = h;
     return 0;
 }
@@ -408,10 +453,8 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         else if (parent[v] >= n) return fail(h, "node %d has an invalid parent", v);
     }
     if (h->stream) CK(cudaStreamSynchronize(h->stream));
-    size_t keep_bytes = h->device_bytes;
     free_tree_state(h);
-    h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;
-    (void)keep_bytes;
+    h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;   // what pmm_create holds
     h->n = n; h->n_int = n - N; h->n_roots = n_roots;
     h->parent.assign(parent, parent + n); h->left.assign(left, left + n); h->right.assign(right, right + n);
     // depth (root = 0) and height (leaf = 0) without recursion
@@ -464,15 +507,13 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
     if (plan_chunks(h)) return 1;
+    if (configure_kernels(h)) return 1;
     const size_t rows = (size_t)h->n_int;
     if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxK) ||
-        dalloc(h, &h->d_oexp, rows * h->maxK) || dalloc(h, &h->d_rootLm, (size_t)n_roots * h->maxK) ||
-        dalloc(h, &h->d_rootLe, (size_t)n_roots * h->maxK) || dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
+        dalloc(h, &h->d_dexp, rows * h->maxK) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxK) ||
+        dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
         dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
         return 1;
-    // rows start as zeros so that tile pad slots stay clean
-    CK(cudaMemsetAsync(h->d_X, 0, sizeof(double) * rows * h->maxWp, h->stream));
-    CK(cudaMemsetAsync(h->d_O, 0, sizeof(double) * rows * h->maxWp, h->stream));
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;

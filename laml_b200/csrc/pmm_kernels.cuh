@@ -2,36 +2,60 @@
 //
 // Model and formulas: SURVEY.md section 3.5 (full-state restatement of
 // laml_libs/EM_solver.py:91-300; verified against the reference in
-// tests/test_fullstate_model.py).  Design: DESIGN.md.
+// tests/test_fullstate_model.py).  Design notes: DESIGN.md.
 //
-// Data layout (per site chunk): every internal node owns one row of `Wp` fp64
-// slots.  A site s occupies `site_len[s] = A_s + 2` consecutive slots starting
-// at `site_off[s]`, ordered [x_0 (unedited), x_m (silenced), x_1 .. x_A].  Sites
-// are grouped into tiles of at most TS slots; every tile starts on an even slot
-// (16-byte aligned) so a tile of a row is one contiguous, aligned byte range
-// that a single 1-D TMA bulk copy (cp.async.bulk) moves between HBM and shared
-// memory.  Leaves own no row: their vectors are synthesised in shared memory
-// from 4-byte state codes.
+// Data layout (per site chunk): every INTERNAL node owns one row of `Wp` fp64
+// slots in X (inside vectors) and one in O (outside vectors).  A site s occupies
+// `len_s = roundup2(A_s + 2)` consecutive slots starting at the even offset
+// `site_off[s]`, ordered [x_0 (unedited), x_m (silenced), x_1 .. x_A, (pad)].
+// Sites are grouped into tiles of at most TS slots; a tile of a row is one
+// contiguous 16-byte-aligned byte range that a single 1-D TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) moves from HBM into shared memory.  Leaves own
+// no row: their messages are closed forms of a 4-byte state code.
+// Pad slots need no masking: their prior q is 0 and their outside value is 0 at
+// the root and stays 0 down the tree, so they drop out of every reduction.
 //
-// Scaling: rows are stored UNnormalised; whoever reads a row first finds the
-// largest exponent among a site's slots (integer max over the high words --
-// all values are non-negative) and multiplies by the exact power of two that
-// brings the maximum into [1,2).  The accumulated exponents live in int32
-// arrays (iexp / oexp), one entry per (internal node, site).  Power-of-two
-// scaling is exact, so the mantissas are those of an unscaled computation.
+// Scaling: rows are stored UNnormalised; whoever reads a row finds the largest
+// exponent among a site's slots (integer max over the high words -- all values
+// are non-negative) and multiplies by the exact power of two that brings the
+// maximum into [1,2).  Accumulated exponents are int32 per (internal node, site):
+//   iexp[u][s] : x_true[u] = X[u] * 2^iexp
+//   dexp[u][s] : D_u = oexp[u] + iexp[u] - Le  (Le = exponent of the site likelihood),
+//                which obeys D_child = D_u + e_out(u) - e_in(child), D_root = -e_in(root),
+//                so the outside pass never needs iexp again.
+// Power-of-two scaling is exact: mantissas are those of an unscaled computation.
+//
+// Execution: one launch per tree level.  grid = (P, ntiles); CTA (p, t) is
+// PERSISTENT over the level's nodes p, p+P, ... for tile t.  Warp NCW is the
+// producer: it stages the next nodes' child rows (TMA) and their per-site
+// metadata into an S-stage shared-memory ring, signalling `full` mbarriers;
+// NCW consumer warps (lane groups of G=8, one site per group, double2 per
+// lane => 128 contiguous bytes per group and iteration) compute and write their
+// results straight to global memory with 16-byte stores, then arrive on the
+// stage's `done` mbarrier.  The tile's prior q and site table stay resident in
+// shared memory for the whole launch.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace pmm {
 
-constexpr int NT = 256;          // threads per CTA
+constexpr int NCW = 8;                    // consumer warps per CTA
+constexpr int NTHREADS = (NCW + 1) * 32;  // + 1 producer warp
+constexpr int G = 8;                      // lanes per site group
+constexpr int NG = NCW * (32 / G);        // site groups per CTA
+constexpr int MAX_STAGES = 4;
 
 struct KParams {
     // chunk layout
-    const int *site_off, *site_len, *tile_site, *tile_off;
-    const double *q;             // [Wp] prior in slot layout (0 at x_0, x_m and pad slots)
-    int K, Wp, ntiles;
+    const int *site_off;         // [K]   slot offset of each site in a row (even)
+    const int *site_len;         // [K]   padded slot count (even)
+    const int *tile_site;        // [ntiles+1]
+    const int *tile_off;         // [ntiles+1]
+    const int2 *ent;             // [K]   per tile, sites sorted by length: x = off_in_tile | len<<16, y = site index in tile
+    const double *q;             // [Wp]  prior in slot layout (0 at x_0, x_m, pads)
+    const double *qsum;          // [K]   sum_a q_a
+    int K, Wp, ntiles, max_tile_sites;
     // data
     const int *codes;            // [n_leaves][codes_stride]
     int codes_stride, site0;
@@ -43,13 +67,14 @@ struct KParams {
     const double *bc;            // [n][4] = a, b, c, g per branch
     // state
     double *X, *O;               // [n_int][Wp] inside / outside rows
-    int *iexp, *oexp;            // [n_int][K] accumulated exponents of the stored rows
-    double *rootLm; int *rootLe; // [n_roots][K] site likelihood mantissa / exponent
+    int *iexp, *dexp;            // [n_int][K]
+    double *rootInvL;            // [n_roots][K] 1 / (normalised site likelihood)
     double *root_site_llh;       // [n_roots][K]
     double *Spart;               // [ntiles][n][5]
     double *Rpart;               // [ntiles][n_int]
     double *post0, *post1;       // optional [n][K_total] log posteriors (annotation path), or null
     int K_total;
+    int TS, stages;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -57,10 +82,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_arrive(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -80,14 +108,6 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// 1-D TMA bulk copy shared -> global
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- scalar helpers
 __device__ __forceinline__ unsigned hi32(double x) { return (unsigned)__double2hiint(x); }
@@ -99,37 +119,35 @@ __device__ __forceinline__ int expo_of_hi(unsigned hi) {
 __device__ __forceinline__ double pow2i(int e) {          // exact 2^e for e in [-1022,1023]
     return __hiloint2double((1023 + e) << 20, 0);
 }
-
-template <int G> __device__ __forceinline__ unsigned group_mask() {
-    if (G == 32) return 0xffffffffu;
+__device__ __forceinline__ unsigned group_mask() {
     unsigned lane = threadIdx.x & 31u;
     return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
 }
-template <int G> __device__ __forceinline__ double gsum(double x, unsigned m) {
+__device__ __forceinline__ double gsum(double x, unsigned m) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(m, x, o);
     return x;
 }
-template <int G> __device__ __forceinline__ unsigned gmax(unsigned x, unsigned m) {
+__device__ __forceinline__ unsigned gmax(unsigned x, unsigned m) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(m, x, o));
     return x;
 }
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 
-// Leaf state vector written into a shared-memory tile (EM_solver.py:103-116 in
-// full-state form): '?' -> (phi, 1, phi..), known silenced -> e_m,
-// 0 -> (1-phi) e_0, alpha -> (1-phi) e_alpha.
-template <int G>
-__device__ __forceinline__ void synth_leaf(double *x, int off, int len, int code, double phi, int gl, unsigned gm) {
-    double base = (code == -1) ? phi : 0.0;
-    for (int i = 2 + gl; i < len; i += G) x[off + i] = base;
-    __syncwarp(gm);
-    if (gl == 0) {
-        x[off] = (code == 0) ? 1.0 - phi : ((code == -1) ? phi : 0.0);
-        x[off + 1] = (code < 0) ? 1.0 : 0.0;
-        if (code > 0) x[off + 1 + code] = 1.0 - phi;
-    }
-    __syncwarp(gm);
+// Leaf state vector as a closed form of its code (EM_solver.py:103-116 in full-state
+// form): x_0, x_m, and x_alpha = xb + [alpha == hot] * dx.
+//   '?' (-1) -> (phi, 1, phi..)   known silenced (-2) -> e_m   0 -> (1-phi) e_0   a -> (1-phi) e_a
+struct Leaf { double x0, xm, xb, dx; int hot; };   // hot = slot index inside the site (1 + a) or -1
+__device__ __forceinline__ Leaf leaf_of(int code, double phi) {
+    Leaf L;
+    L.x0 = (code == 0) ? 1.0 - phi : ((code == -1) ? phi : 0.0);
+    L.xm = (code < 0) ? 1.0 : 0.0;
+    L.xb = (code == -1) ? phi : 0.0;
+    L.dx = (code > 0) ? 1.0 - phi : 0.0;
+    L.hot = (code > 0) ? 1 + code : -1;
+    return L;
 }
 
 // ---------------------------------------------------------------- K0: branch constants
@@ -150,161 +168,489 @@ __global__ void pmm_branch_consts(const double *__restrict__ d, const double *__
     reinterpret_cast<double4 *>(bc)[v] = r;
 }
 
-// ---------------------------------------------------------------- K1: inside, one level
-// One CTA per (internal node u of this level, tile).  Children rows are staged
-// in shared memory by TMA bulk copies (leaf children are synthesised), groups
-// of G lanes own one site each: pass 1 reduces sum(q x) and the exponent of the
-// maximum per child, pass 2 forms x_u = E_v .* E_w in place; one bulk store
-// writes the tile of row u.
-template <int G>
-__global__ void __launch_bounds__(NT) pmm_inside_level(KParams P, const int *__restrict__ nodes, int TS) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *xv = reinterpret_cast<double *>(smem_raw);
-    double *xw = xv + TS;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(xw + TS);
+// ---------------------------------------------------------------- shared-memory plan
+// [ q tile : TS doubles ][ qsum : MS doubles ][ ent : MS int2 ][ barriers ][ stage 0 ][ stage 1 ] ...
+// stage = [ NARR row tiles : NARR*TS doubles ][ invL : MS doubles (outside) ][ red : NCW*12 doubles (outside) ]
+//         [ mA, mB, mD : 3*MS ints ][ desc : 32 ints ]
+// MS = max sites per tile, rounded up to a multiple of 4.
+struct Desc { int u, v, w, valid; double4 cv, cw; };   // 80 bytes (stage reserves 128)
 
-    const int t = blockIdx.x % P.ntiles;
-    const int u = nodes[blockIdx.x / P.ntiles];
-    const int v = P.left[u], w = P.right[u];
-    const int N = P.n_leaves;
-    const bool v_int = v >= N, w_int = w >= N;
-    const int s0 = P.tile_site[t], s1 = P.tile_site[t + 1];
+template <bool OUTSIDE> struct Plan {
+    static constexpr int NARR = OUTSIDE ? 3 : 2;
+    __host__ __device__ static size_t stage_bytes(int TS, int MS) {
+        size_t b = (size_t)NARR * TS * 8;
+        if (OUTSIDE) b += (size_t)MS * 8 + (size_t)NCW * 12 * 8;
+        b += (size_t)3 * MS * 4 + 32 * 4;
+        return (b + 127) & ~(size_t)127;
+    }
+    __host__ __device__ static size_t fixed_bytes(int TS, int MS) {
+        return (size_t)TS * 8 + (size_t)MS * 8 + (size_t)MS * 8 + 2 * MAX_STAGES * 8 + 16;
+    }
+    __host__ __device__ static size_t total_bytes(int TS, int MS, int S) { return fixed_bytes(TS, MS) + S * stage_bytes(TS, MS) + 256; }
+};
+
+// ---------------------------------------------------------------- per-site work: inside
+// x_u = E_v .* E_w with E = child message (SURVEY 3.5 "edge transfer"):
+//   E_0 = a x_0 + b sum(q x) + g x_m,  E_alpha = c x_alpha + g x_m,  E_m = x_m.
+template <bool VI, bool WI>
+__device__ __forceinline__ void inside_site(const double *__restrict__ A, const double *__restrict__ B,
+                                            const double *__restrict__ sq, double qsum, int off, int len, int codeA_or_cum,
+                                            int codeB_or_cum, const double4 cv, const double4 cw, double phi,
+                                            double *__restrict__ gout, int *__restrict__ iexp_out, int gl, unsigned gm) {
+    double sv = 0.0, sw = 0.0;
+    unsigned mv = 0u, mw = 0u;
+    if (VI || WI) {
+        for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+            const double2 q2 = ld2(sq + off + i);
+            if (VI) {
+                const double2 a = ld2(A + off + i);
+                sv = fma(q2.x, a.x, sv); sv = fma(q2.y, a.y, sv);
+                mv = max(mv, max(hi32(a.x), hi32(a.y)));
+            }
+            if (WI) {
+                const double2 b = ld2(B + off + i);
+                sw = fma(q2.x, b.x, sw); sw = fma(q2.y, b.y, sw);
+                mw = max(mw, max(hi32(b.x), hi32(b.y)));
+            }
+        }
+    }
+    // child v: message constants  E0 (k0), Em, and E_alpha = cs * x + gmc  (internal)  or  Eb + [hot] dE (leaf)
+    double k0v, Emv, csv = 0.0, gmv = 0.0, Ebv = 0.0, dEv = 0.0; int cumv = 0, hv = -1;
+    if (VI) {
+        const double2 h = ld2(A + off);
+        sv = gsum(sv, gm);
+        mv = gmax(max(mv, max(hi32(h.x), hi32(h.y))), gm);
+        const int e = expo_of_hi(mv);
+        const double sc = pow2i(-e);
+        Emv = h.y * sc;
+        gmv = cv.w * Emv;
+        k0v = (cv.x * h.x + cv.y * sv) * sc + gmv;
+        csv = cv.z * sc;
+        cumv = codeA_or_cum + e;
+    } else {
+        const Leaf L = leaf_of(codeA_or_cum, phi);
+        hv = L.hot;
+        const double qh = (hv >= 0) ? sq[off + hv] : 0.0;
+        Emv = L.xm;
+        k0v = cv.x * L.x0 + cv.y * (L.xb * qsum + qh * L.dx) + cv.w * L.xm;
+        Ebv = cv.z * L.xb + cv.w * L.xm;
+        dEv = cv.z * L.dx;
+    }
+    double k0w, Emw, csw = 0.0, gmw = 0.0, Ebw = 0.0, dEw = 0.0; int cumw = 0, hw = -1;
+    if (WI) {
+        const double2 h = ld2(B + off);
+        sw = gsum(sw, gm);
+        mw = gmax(max(mw, max(hi32(h.x), hi32(h.y))), gm);
+        const int e = expo_of_hi(mw);
+        const double sc = pow2i(-e);
+        Emw = h.y * sc;
+        gmw = cw.w * Emw;
+        k0w = (cw.x * h.x + cw.y * sw) * sc + gmw;
+        csw = cw.z * sc;
+        cumw = codeB_or_cum + e;
+    } else {
+        const Leaf L = leaf_of(codeB_or_cum, phi);
+        hw = L.hot;
+        const double qh = (hw >= 0) ? sq[off + hw] : 0.0;
+        Emw = L.xm;
+        k0w = cw.x * L.x0 + cw.y * (L.xb * qsum + qh * L.dx) + cw.w * L.xm;
+        Ebw = cw.z * L.xb + cw.w * L.xm;
+        dEw = cw.z * L.dx;
+    }
+    for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+        double2 ev, ew;
+        if (VI) { const double2 a = ld2(A + off + i); ev.x = fma(csv, a.x, gmv); ev.y = fma(csv, a.y, gmv); }
+        else { ev.x = Ebv + ((i == hv) ? dEv : 0.0); ev.y = Ebv + ((i + 1 == hv) ? dEv : 0.0); }
+        if (WI) { const double2 b = ld2(B + off + i); ew.x = fma(csw, b.x, gmw); ew.y = fma(csw, b.y, gmw); }
+        else { ew.x = Ebw + ((i == hw) ? dEw : 0.0); ew.y = Ebw + ((i + 1 == hw) ? dEw : 0.0); }
+        st2(gout + off + i, ev.x * ew.x, ev.y * ew.y);
+    }
+    if (gl == 0) {
+        st2(gout + off, k0v * k0w, Emv * Emw);
+        *iexp_out = cumv + cumw;
+    }
+}
+
+// ---------------------------------------------------------------- per-site work: outside + counts
+// For node u with children v, w (EM_solver.py:143-300 in full-state form):
+//   T^v = out[u] .* E^w, out[v]_0 = a T_0, out[v]_a = b q_a T_0 + c T_a, out[v]_m = g (T_0 + sum_a T_a) + T_m
+//   S0 = T_0 a x_0 / L, S1 = T_0 b sum(q x) / L, S2 = T_0 g x_m / L, S3 = c sum_a T_a x_a / L, S4 = g x_m sum_a T_a / L.
+// All per-site reductions are taken on the raw rows in ONE pass:
+//   sum q xv, sum q xw, sum o, sum o xv, sum o xw, sum o xv xw   (only those an internal child needs).
+template <bool VI, bool WI>
+__device__ __forceinline__ void outside_site(const double *__restrict__ C, const double *__restrict__ A,
+                                             const double *__restrict__ B, const double *__restrict__ sq, double qsum,
+                                             int off, int len, int codeA, int codeB, int Du, double invL, const double4 cv,
+                                             const double4 cw, double phi, double *__restrict__ goutv,
+                                             double *__restrict__ goutw, int *__restrict__ dexp_v, int *__restrict__ dexp_w,
+                                             double *__restrict__ post, int gl, unsigned gm, double (&acc)[11]) {
+    double sv = 0, sw = 0, so = 0, sov = 0, sow = 0, sovw = 0;
+    unsigned mv = 0u, mw = 0u, mo = 0u;
+    for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+        const double2 o = ld2(C + off + i);
+        so += o.x; so += o.y;
+        mo = max(mo, max(hi32(o.x), hi32(o.y)));
+        double2 q2 = make_double2(0.0, 0.0);
+        if (VI || WI) q2 = ld2(sq + off + i);
+        double2 oa = make_double2(0.0, 0.0);
+        if (VI) {
+            const double2 a = ld2(A + off + i);
+            sv = fma(q2.x, a.x, sv); sv = fma(q2.y, a.y, sv);
+            oa.x = o.x * a.x; oa.y = o.y * a.y;
+            sov += oa.x; sov += oa.y;
+            mv = max(mv, max(hi32(a.x), hi32(a.y)));
+        }
+        if (WI) {
+            const double2 b = ld2(B + off + i);
+            sw = fma(q2.x, b.x, sw); sw = fma(q2.y, b.y, sw);
+            sow = fma(o.x, b.x, sow); sow = fma(o.y, b.y, sow);
+            if (VI) { sovw = fma(oa.x, b.x, sovw); sovw = fma(oa.y, b.y, sovw); }
+            mw = max(mw, max(hi32(b.x), hi32(b.y)));
+        }
+    }
+    const double2 oh = ld2(C + off);
+    so = gsum(so, gm);
+    mo = gmax(max(mo, max(hi32(oh.x), hi32(oh.y))), gm);
+    const int eo = expo_of_hi(mo);
+    const double sco = pow2i(-eo);
+    const double no0 = oh.x * sco, nom = oh.y * sco, So = so * sco;
+
+    // normalised child summaries: x_0, x_m, S = sum q x, So* = sum o x; e = exponent; hot (leaves)
+    double nx0v, nxmv, Sv, Sov, scv = 1.0; int ev = 0, hv = -1; double xbv = 0.0, dxv = 0.0;
+    if (VI) {
+        const double2 h = ld2(A + off);
+        sv = gsum(sv, gm); sov = gsum(sov, gm);
+        mv = gmax(max(mv, max(hi32(h.x), hi32(h.y))), gm);
+        ev = expo_of_hi(mv); scv = pow2i(-ev);
+        nx0v = h.x * scv; nxmv = h.y * scv; Sv = sv * scv; Sov = sov * sco * scv;
+    } else {
+        const Leaf L = leaf_of(codeA, phi);
+        hv = L.hot; xbv = L.xb; dxv = L.dx;
+        nx0v = L.x0; nxmv = L.xm;
+        const double qh = (hv >= 0) ? sq[off + hv] : 0.0;
+        const double ohv = (hv >= 0) ? C[off + hv] * sco : 0.0;
+        Sv = xbv * qsum + qh * dxv;
+        Sov = xbv * So + ohv * dxv;
+    }
+    double nx0w, nxmw, Sw, Sow, scw = 1.0; int ew = 0, hw = -1; double xbw = 0.0, dxw = 0.0;
+    if (WI) {
+        const double2 h = ld2(B + off);
+        sw = gsum(sw, gm); sow = gsum(sow, gm);
+        mw = gmax(max(mw, max(hi32(h.x), hi32(h.y))), gm);
+        ew = expo_of_hi(mw); scw = pow2i(-ew);
+        nx0w = h.x * scw; nxmw = h.y * scw; Sw = sw * scw; Sow = sow * sco * scw;
+    } else {
+        const Leaf L = leaf_of(codeB, phi);
+        hw = L.hot; xbw = L.xb; dxw = L.dx;
+        nx0w = L.x0; nxmw = L.xm;
+        const double qh = (hw >= 0) ? sq[off + hw] : 0.0;
+        const double ohw = (hw >= 0) ? C[off + hw] * sco : 0.0;
+        Sw = xbw * qsum + qh * dxw;
+        Sow = xbw * So + ohw * dxw;
+    }
+    double Sovw;                                    // sum_a o_a xv_a xw_a (normalised)
+    if (VI && WI) Sovw = gsum(sovw, gm) * sco * scv * scw;
+    else if (VI) Sovw = xbw * Sov + ((hw >= 0) ? dxw * (C[off + hw] * sco) * (A[off + hw] * scv) : 0.0);
+    else if (WI) Sovw = xbv * Sow + ((hv >= 0) ? dxv * (C[off + hv] * sco) * (B[off + hv] * scw) : 0.0);
+    else {
+        const double ohv = (hv >= 0) ? C[off + hv] * sco : 0.0, ohw = (hw >= 0) ? C[off + hw] * sco : 0.0;
+        Sovw = xbv * xbw * So + xbw * dxv * ohv + xbv * dxw * ohw + ((hv >= 0 && hv == hw) ? dxv * dxw * ohv : 0.0);
+    }
+    // sibling messages: E_0, E_alpha = c x + g x_m, E_m = x_m
+    const double gmv = cv.w * nxmv, gmw = cw.w * nxmw;
+    const double k0v = cv.x * nx0v + cv.y * Sv + gmv;
+    const double k0w = cw.x * nx0w + cw.y * Sw + gmw;
+    // top-of-branch vectors: T^v = out[u] .* E^w,  T^w = out[u] .* E^v
+    const double Tv0 = no0 * k0w, Tvm = nom * nxmw, sTv = cw.z * Sow + gmw * So;
+    const double Tw0 = no0 * k0v, Twm = nom * nxmv, sTw = cv.z * Sov + gmv * So;
+    const double sTvx = cw.z * Sovw + gmw * Sov;     // sum_a T^v_a x^v_a
+    const double sTwx = cv.z * Sovw + gmv * Sow;     // sum_a T^w_a x^w_a
+    const double outvm = cv.w * (Tv0 + sTv) + Tvm;
+    const double outwm = cw.w * (Tw0 + sTw) + Twm;
+
+    if (gl == 0) {
+        if (VI) { st2(goutv + off, cv.x * Tv0, outvm); *dexp_v = Du + eo - ev; }
+        if (WI) { st2(goutw + off, cw.x * Tw0, outwm); *dexp_w = Du + eo - ew; }
+        // expected counts (EM_solver.py:279-300): everything is relative to the site likelihood
+        const int delta = max(-1000, min(1000, Du + eo));
+        const double fac = scalbn(invL, delta);
+        acc[0] += Tv0 * cv.x * nx0v * fac;
+        acc[1] += Tv0 * cv.y * Sv * fac;
+        acc[2] += Tv0 * gmv * fac;
+        acc[3] += cv.z * sTvx * fac;
+        acc[4] += gmv * sTv * fac;
+        acc[5] += Tw0 * cw.x * nx0w * fac;
+        acc[6] += Tw0 * cw.y * Sw * fac;
+        acc[7] += Tw0 * gmw * fac;
+        acc[8] += cw.z * sTwx * fac;
+        acc[9] += gmw * sTw * fac;
+        // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
+        if (!VI && codeA == -1) acc[10] += 1.0 - outvm * nxmv * fac;
+        if (!WI && codeB == -1) acc[10] += 1.0 - outwm * nxmw * fac;
+        if (post) {
+            // post0 = log P(node in state 0 | D) = log(out_0 x_0 / L); post1 likewise for the
+            // silenced state (EM_solver.py:276-277); [0],[1] child v, [2],[3] child w
+            const double p0v = cv.x * Tv0 * nx0v * fac, p1v = outvm * nxmv * fac;
+            const double p0w = cw.x * Tw0 * nx0w * fac, p1w = outwm * nxmw * fac;
+            post[0] = (p0v > 0.0) ? log(p0v) : -INFINITY;
+            post[1] = (p1v > 0.0) ? log(p1v) : -INFINITY;
+            post[2] = (p0w > 0.0) ? log(p0w) : -INFINITY;
+            post[3] = (p1w > 0.0) ? log(p1w) : -INFINITY;
+        }
+    }
+    if (VI || WI) {
+        const double bv = cv.y * Tv0, bw = cw.y * Tw0;
+        const double cvo = cv.z * sco, cwo = cw.z * sco;
+        const double csv = cv.z * scv, csw = cw.z * scw;
+        const double Ebv = cv.z * xbv + gmv, dEv = cv.z * dxv;     // leaf forms of E^v, E^w
+        const double Ebw = cw.z * xbw + gmw, dEw = cw.z * dxw;
+        for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+            const double2 o = ld2(C + off + i);
+            const double2 q2 = ld2(sq + off + i);
+            double2 Ev, Ew;
+            if (VI) { const double2 a = ld2(A + off + i); Ev.x = fma(csv, a.x, gmv); Ev.y = fma(csv, a.y, gmv); }
+            else { Ev.x = Ebv + ((i == hv) ? dEv : 0.0); Ev.y = Ebv + ((i + 1 == hv) ? dEv : 0.0); }
+            if (WI) { const double2 b = ld2(B + off + i); Ew.x = fma(csw, b.x, gmw); Ew.y = fma(csw, b.y, gmw); }
+            else { Ew.x = Ebw + ((i == hw) ? dEw : 0.0); Ew.y = Ebw + ((i + 1 == hw) ? dEw : 0.0); }
+            if (VI) st2(goutv + off + i, fma(bv, q2.x, cvo * o.x * Ew.x), fma(bv, q2.y, cvo * o.y * Ew.y));
+            if (WI) st2(goutw + off + i, fma(bw, q2.x, cwo * o.x * Ev.x), fma(bw, q2.y, cwo * o.y * Ev.y));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K1 / K2: one tree level, persistent
+template <bool OUTSIDE>
+__global__ void __launch_bounds__(NTHREADS, 2)
+pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
+    using PL = Plan<OUTSIDE>;
+    constexpr int NARR = PL::NARR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int TS = P.TS, MS = P.max_tile_sites, S = P.stages;
+    double *s_q = reinterpret_cast<double *>(smem_raw);
+    double *s_qsum = s_q + TS;
+    int2 *s_ent = reinterpret_cast<int2 *>(s_qsum + MS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_ent + MS);
+    uint64_t *done = full + MAX_STAGES;
+    unsigned char *stage0 = reinterpret_cast<unsigned char *>(done + MAX_STAGES) + 16;
+    stage0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
+    const size_t stage_bytes = PL::stage_bytes(TS, MS);
+
+    const int t = blockIdx.y;
+    const int s0 = P.tile_site[t], nsites = P.tile_site[t + 1] - s0;
     const int off0 = P.tile_off[t];
     const int tlen = P.tile_off[t + 1] - off0;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = P.n_leaves;
+    const int n_items = (n_level - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (v_int || w_int) {
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t bytes = (uint32_t)tlen * 8u;
-            mbar_expect_tx(bar, bytes * ((v_int ? 1u : 0u) + (w_int ? 1u : 0u)));
-            if (v_int) bulk_load(xv, P.X + (size_t)(v - N) * P.Wp + off0, bytes, bar);
-            if (w_int) bulk_load(xw, P.X + (size_t)(w - N) * P.Wp + off0, bytes, bar);
-        }
-    }
-    const double phi = P.params[1];
-    const double4 cv = reinterpret_cast<const double4 *>(P.bc)[v];
-    const double4 cw = reinterpret_cast<const double4 *>(P.bc)[w];
-    const unsigned gm = group_mask<G>();
-    const int gl = tid & (G - 1);
-    const int grp = tid / G;
-    constexpr int NG = NT / G;
-
-    // leaf children: synthesise their vectors while the bulk loads are in flight
-    if (!v_int || !w_int) {
-        for (int s = s0 + grp; s < s1; s += NG) {
-            int off = P.site_off[s] - off0, len = P.site_len[s];
-            if (!v_int) synth_leaf<G>(xv, off, len, P.codes[(size_t)v * P.codes_stride + P.site0 + s], phi, gl, gm);
-            if (!w_int) synth_leaf<G>(xw, off, len, P.codes[(size_t)w * P.codes_stride + P.site0 + s], phi, gl, gm);
-        }
-        // the tile's tail pad slot (if any) travels with the bulk store of row u: keep it zero
-        if (tid == 0 && !v_int) {
-            const int real_end = P.site_off[s1 - 1] + P.site_len[s1 - 1] - off0;
-            if (real_end < tlen) xv[real_end] = 0.0;
-        }
-    }
-    if (v_int || w_int) mbar_wait(bar, 0);
-
-    int *iexp_u = P.iexp + (size_t)(u - N) * P.K;
-    const int *iexp_v = v_int ? P.iexp + (size_t)(v - N) * P.K : nullptr;
-    const int *iexp_w = w_int ? P.iexp + (size_t)(w - N) * P.K : nullptr;
-
-    for (int s = s0 + grp; s < s1; s += NG) {
-        const int goff = P.site_off[s];
-        const int off = goff - off0, len = P.site_len[s];
-        double sv = 0.0, sw = 0.0;
-        unsigned mv = 0u, mw = 0u;
-        for (int i = 2 + gl; i < len; i += G) {
-            double qi = __ldg(P.q + goff + i);
-            double a = xv[off + i], b = xw[off + i];
-            sv = fma(qi, a, sv);
-            sw = fma(qi, b, sw);
-            mv = max(mv, hi32(a));
-            mw = max(mw, hi32(b));
-        }
-        const double x0v = xv[off], xmv = xv[off + 1], x0w = xw[off], xmw = xw[off + 1];
-        mv = max(mv, max(hi32(x0v), hi32(xmv)));
-        mw = max(mw, max(hi32(x0w), hi32(xmw)));
-        sv = gsum<G>(sv, gm);
-        sw = gsum<G>(sw, gm);
-        mv = gmax<G>(mv, gm);
-        mw = gmax<G>(mw, gm);
-        const int ev = expo_of_hi(mv), ew = expo_of_hi(mw);
-        const double scv = pow2i(-ev), scw = pow2i(-ew);
-        // normalised child messages (SURVEY 3.5 "edge transfer")
-        const double xmv_n = xmv * scv, xmw_n = xmw * scw;
-        const double k0v = (cv.x * x0v + cv.y * sv) * scv + cv.w * xmv_n;
-        const double k0w = (cw.x * x0w + cw.y * sw) * scw + cw.w * xmw_n;
-        const double gmv = cv.w * xmv_n, gmw = cw.w * xmw_n;
-        const double csv = cv.z * scv, csw = cw.z * scw;
-        for (int i = 2 + gl; i < len; i += G)
-            xv[off + i] = fma(csv, xv[off + i], gmv) * fma(csw, xw[off + i], gmw);
-        if (gl == 0) {
-            xv[off] = k0v * k0w;
-            xv[off + 1] = xmv_n * xmw_n;
-            iexp_u[s] = (v_int ? iexp_v[s] : 0) + ev + (w_int ? iexp_w[s] : 0) + ew;
-        }
-    }
-    fence_async_smem();
-    __syncthreads();
+    // resident tile tables
+    for (int i = tid; i < tlen; i += NTHREADS) s_q[i] = P.q[off0 + i];
+    for (int i = tid; i < nsites; i += NTHREADS) { s_qsum[i] = P.qsum[s0 + i]; s_ent[i] = P.ent[s0 + i]; }
     if (tid == 0) {
-        bulk_store(P.X + (size_t)(u - N) * P.Wp + off0, xv, (uint32_t)tlen * 8u);
-        bulk_commit();
-        bulk_wait_read0();
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 2); mbar_init(&done[s], NCW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto stage_ptr = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
+    // stage field accessors
+    auto f_rows = [&](unsigned char *st) { return reinterpret_cast<double *>(st); };
+    auto f_invL = [&](unsigned char *st) { return reinterpret_cast<double *>(st) + (size_t)NARR * TS; };
+    auto f_red = [&](unsigned char *st) { return f_invL(st) + (OUTSIDE ? MS : 0); };
+    auto f_meta = [&](unsigned char *st) { return reinterpret_cast<int *>(f_red(st) + (OUTSIDE ? NCW * 12 : 0)); };
+    auto f_desc = [&](unsigned char *st) { return reinterpret_cast<Desc *>(f_meta(st) + 3 * MS); };
+
+    if (warp == NCW) {
+        // ======================= producer warp =======================
+        auto flush_counts = [&](unsigned char *st) {
+            // deterministic cross-warp sum of the per-warp partial counts of a finished item
+            const Desc dsc = *f_desc(st);
+            const double *red = f_red(st);
+            if (lane < 11) {
+                double sum = 0.0;
+                for (int wdx = 0; wdx < NCW; wdx++) sum += red[wdx * 12 + lane];
+                if (lane < 5) P.Spart[((size_t)t * P.n_nodes + dsc.v) * 5 + lane] = sum;
+                else if (lane < 10) P.Spart[((size_t)t * P.n_nodes + dsc.w) * 5 + (lane - 5)] = sum;
+                else P.Rpart[(size_t)t * (P.n_nodes - N) + (dsc.u - N)] = sum;
+            }
+            __syncwarp();
+        };
+        int nu_ = n_items > 0 ? nodes[blockIdx.x] : 0;
+        int nv_ = n_items > 0 ? P.left[nu_] : 0, nw_ = n_items > 0 ? P.right[nu_] : 0;
+        for (int k = 0; k < n_items; k++) {
+            const int s = k % S;
+            unsigned char *st = stage_ptr(s);
+            const int u = nu_, v = nv_, w = nw_;
+            if (k + 1 < n_items) {                                // ids of the next item, ahead of need
+                nu_ = nodes[blockIdx.x + (k + 1) * gridDim.x];
+                nv_ = P.left[nu_]; nw_ = P.right[nu_];
+            }
+            if (k >= S) {
+                mbar_wait(&done[s], ((k / S) - 1) & 1);          // consumers have finished item k-S
+                if (OUTSIDE) flush_counts(st);
+            }
+            const bool vi = v >= N, wi = w >= N;
+            double *rows = f_rows(st);
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)tlen * 8u;
+                const uint32_t nld = (vi ? 1u : 0u) + (wi ? 1u : 0u) + (OUTSIDE ? 1u : 0u);
+                mbar_expect_tx_arrive(&full[s], bytes * nld);
+                if (vi) bulk_load(rows, P.X + (size_t)(v - N) * P.Wp + off0, bytes, &full[s]);
+                if (wi) bulk_load(rows + TS, P.X + (size_t)(w - N) * P.Wp + off0, bytes, &full[s]);
+                if (OUTSIDE) bulk_load(rows + 2 * TS, P.O + (size_t)(u - N) * P.Wp + off0, bytes, &full[s]);
+            }
+            // per-site metadata: leaf codes or accumulated exponents; D_u and 1/L for the outside pass
+            int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
+            const int *srcA = vi ? (OUTSIDE ? nullptr : P.iexp + (size_t)(v - N) * P.K + s0)
+                                 : P.codes + (size_t)v * P.codes_stride + P.site0 + s0;
+            const int *srcB = wi ? (OUTSIDE ? nullptr : P.iexp + (size_t)(w - N) * P.K + s0)
+                                 : P.codes + (size_t)w * P.codes_stride + P.site0 + s0;
+            for (int i = lane; i < nsites; i += 32) {
+                if (srcA) mA[i] = srcA[i];
+                if (srcB) mB[i] = srcB[i];
+            }
+            if (OUTSIDE) {
+                const int *srcD = P.dexp + (size_t)(u - N) * P.K + s0;
+                const double *srcL = P.rootInvL + (size_t)P.root_index[u] * P.K + s0;
+                double *invL = f_invL(st);
+                for (int i = lane; i < nsites; i += 32) { mD[i] = srcD[i]; invL[i] = srcL[i]; }
+            }
+            if (lane == 0) {
+                Desc dd; dd.u = u; dd.v = v; dd.w = w; dd.valid = 1;
+                dd.cv = reinterpret_cast<const double4 *>(P.bc)[v];
+                dd.cw = reinterpret_cast<const double4 *>(P.bc)[w];
+                *f_desc(st) = dd;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        if (OUTSIDE) {
+            // drain: partial counts of the last min(S, n_items) items
+            for (int k = max(0, n_items - S); k < n_items; k++) {
+                const int s = k % S;
+                mbar_wait(&done[s], (k / S) & 1);
+                flush_counts(stage_ptr(s));
+            }
+        }
+        return;
+    }
+
+    // ======================= consumer warps =======================
+    const unsigned gm = group_mask();
+    const int gl = lane & (G - 1);
+    const int grp = warp * (32 / G) + lane / G;
+    const double phi = P.params[1];
+    for (int k = 0; k < n_items; k++) {
+        const int s = k % S;
+        unsigned char *st = stage_ptr(s);
+        mbar_wait(&full[s], (k / S) & 1);
+        const Desc dsc = *f_desc(st);
+        const int u = dsc.u, v = dsc.v, w = dsc.w;
+        const bool vi = v >= N, wi = w >= N;
+        const double4 cv = dsc.cv, cw = dsc.cw;
+        const double *A = f_rows(st), *B = A + TS, *C = B + TS;
+        const int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
+        if (!OUTSIDE) {
+            double *gout = P.X + (size_t)(u - N) * P.Wp + off0;
+            int *iexp_u = P.iexp + (size_t)(u - N) * P.K + s0;
+            for (int j = grp; j < nsites; j += NG) {
+                const int2 e = s_ent[j];
+                const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
+                if (vi && wi) inside_site<true, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                else if (vi) inside_site<true, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                else if (wi) inside_site<false, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                else inside_site<false, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+            }
+        } else {
+            double *goutv = vi ? P.O + (size_t)(v - N) * P.Wp + off0 : nullptr;
+            double *goutw = wi ? P.O + (size_t)(w - N) * P.Wp + off0 : nullptr;
+            int *dv = vi ? P.dexp + (size_t)(v - N) * P.K + s0 : nullptr;
+            int *dw = wi ? P.dexp + (size_t)(w - N) * P.K + s0 : nullptr;
+            const double *invL = f_invL(st);
+            double acc[11];
+#pragma unroll
+            for (int q = 0; q < 11; q++) acc[q] = 0.0;
+            for (int j = grp; j < nsites; j += NG) {
+                const int2 e = s_ent[j];
+                const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
+                double pst[4];
+                double *post = P.post0 ? pst : nullptr;
+                if (vi && wi) outside_site<true, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw + ls, post, gl, gm, acc);
+                else if (vi) outside_site<true, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw, post, gl, gm, acc);
+                else if (wi) outside_site<false, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv, dw + ls, post, gl, gm, acc);
+                else outside_site<false, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv, dw, post, gl, gm, acc);
+                if (post && gl == 0) {
+                    const size_t gs = (size_t)P.site0 + s0 + ls;
+                    P.post0[(size_t)v * P.K_total + gs] = pst[0]; P.post1[(size_t)v * P.K_total + gs] = pst[1];
+                    P.post0[(size_t)w * P.K_total + gs] = pst[2]; P.post1[(size_t)w * P.K_total + gs] = pst[3];
+                }
+            }
+            // warp-level sum over the warp's groups (only lane 0 of each group holds data), fixed order
+            double *red = f_red(st);
+#pragma unroll
+            for (int q = 0; q < 11; q++) {
+                double x = (gl == 0) ? acc[q] : 0.0;
+#pragma unroll
+                for (int o = G; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) red[warp * 12 + q] = x;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
     }
 }
 
 // ---------------------------------------------------------------- K1r: root likelihood
 // One CTA per (root, tile): site likelihood L_s = E[root]_0 (the root's own branch
-// starts in state 0, EM_solver.py:140), its log, and the expected counts of the
-// root branch (EM_solver.py:282-286).
-template <int G>
-__global__ void __launch_bounds__(NT) pmm_root_llh(KParams P, const int *__restrict__ roots) {
-    __shared__ double red[NT / G][3];
+// starts in state 0, EM_solver.py:140), its log, the expected counts of the root
+// branch (EM_solver.py:282-286), and the seeds of the outside pass: out[root]
+// (EM_solver.py:151-158), D_root and 1/L.
+__global__ void __launch_bounds__(256) pmm_root_llh(KParams P, const int *__restrict__ roots) {
+    constexpr int RG = 256 / G;
+    __shared__ double red[RG][3];
     const int t = blockIdx.x % P.ntiles;
     const int ri = blockIdx.x / P.ntiles;
     const int r = roots[ri];
     const int N = P.n_leaves;
     const int s0 = P.tile_site[t], s1 = P.tile_site[t + 1];
     const int tid = threadIdx.x;
-    const unsigned gm = group_mask<G>();
+    const unsigned gm = group_mask();
     const int gl = tid & (G - 1), grp = tid / G;
-    constexpr int NG = NT / G;
     const double4 cr = reinterpret_cast<const double4 *>(P.bc)[r];
     const double *x = P.X + (size_t)(r - N) * P.Wp;
+    double *o = P.O + (size_t)(r - N) * P.Wp;
     const int *iexp_r = P.iexp + (size_t)(r - N) * P.K;
+    int *dexp_r = P.dexp + (size_t)(r - N) * P.K;
     double acc0 = 0, acc1 = 0, acc2 = 0;
-    for (int s = s0 + grp; s < s1; s += NG) {
+    for (int s = s0 + grp; s < s1; s += RG) {
         const int goff = P.site_off[s], len = P.site_len[s];
         double sq = 0.0;
         unsigned mx = 0u;
         for (int i = 2 + gl; i < len; i += G) {
-            double a = x[goff + i];
-            sq = fma(__ldg(P.q + goff + i), a, sq);
+            const double a = x[goff + i], qi = P.q[goff + i];
+            sq = fma(qi, a, sq);
             mx = max(mx, hi32(a));
+            o[goff + i] = cr.y * qi;
         }
         const double x0 = x[goff], xm = x[goff + 1];
         mx = max(mx, max(hi32(x0), hi32(xm)));
-        sq = gsum<G>(sq, gm);
-        mx = gmax<G>(mx, gm);
+        sq = gsum(sq, gm);
+        mx = gmax(mx, gm);
         if (gl == 0) {
             const int e = expo_of_hi(mx);
             const double sc = pow2i(-e);
             const double t0 = cr.x * x0 * sc, t1 = cr.y * sq * sc, t2 = cr.w * xm * sc;
             const double L = t0 + t1 + t2;
             const int Le = iexp_r[s] + e;
-            P.rootLm[(size_t)ri * P.K + s] = L;
-            P.rootLe[(size_t)ri * P.K + s] = Le;
+            const double inv = (L > 0.0) ? 1.0 / L : 0.0;
+            o[goff] = cr.x; o[goff + 1] = cr.w;
+            dexp_r[s] = -e;
+            P.rootInvL[(size_t)ri * P.K + s] = inv;
             P.root_site_llh[(size_t)ri * P.K + s] = (L > 0.0) ? log(L) + (double)Le * 0.693147180559945309417232121458 : -INFINITY;
-            if (L > 0.0) {
-                const double inv = 1.0 / L;
-                acc0 += t0 * inv; acc1 += t1 * inv; acc2 += t2 * inv;
-            }
+            acc0 += t0 * inv; acc1 += t1 * inv; acc2 += t2 * inv;
             if (P.post0) {
-                // log P(root = 0 | D), log P(root silenced | D)  (EM_solver.py:276-277)
-                P.post0[(size_t)r * P.K_total + P.site0 + s] = (L > 0.0 && t0 > 0.0) ? log(t0 / L) : -INFINITY;
-                P.post1[(size_t)r * P.K_total + P.site0 + s] = (L > 0.0 && t2 > 0.0) ? log(t2 / L) : -INFINITY;
+                P.post0[(size_t)r * P.K_total + P.site0 + s] = (t0 * inv > 0.0) ? log(t0 * inv) : -INFINITY;
+                P.post1[(size_t)r * P.K_total + P.site0 + s] = (t2 * inv > 0.0) ? log(t2 * inv) : -INFINITY;
             }
         }
     }
@@ -312,205 +658,9 @@ __global__ void __launch_bounds__(NT) pmm_root_llh(KParams P, const int *__restr
     __syncthreads();
     if (tid < 5) {
         double sum = 0.0;
-        if (tid < 3) for (int g = 0; g < NG; g++) sum += red[g][tid];
+        if (tid < 3) for (int g = 0; g < RG; g++) sum += red[g][tid];
         P.Spart[((size_t)t * P.n_nodes + r) * 5 + tid] = sum;
     }
-}
-
-// ---------------------------------------------------------------- K2: outside + counts, one level
-// One CTA per (internal node u of this depth, tile).  Stages out[u] (or builds
-// the root's from the branch constants), x[v], x[w]; per site it forms the two
-// sibling messages, the top-of-branch vectors T_v = out[u] .* E_w and
-// T_w = out[u] .* E_v, writes out[v], out[w] (internal children only) and the
-// expected transition counts S0..S4 of both child branches
-// (EM_solver.py:143-300 in full-state form).  All six per-site
-// reductions are taken on the raw rows in ONE pass:
-//   sum q xv, sum q xw, sum o, sum o xv, sum o xw, sum o xv xw.
-template <int G>
-__global__ void __launch_bounds__(NT) pmm_outside_level(KParams P, const int *__restrict__ nodes, int TS) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *xo = reinterpret_cast<double *>(smem_raw);
-    double *xv = xo + TS;
-    double *xw = xv + TS;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(xw + TS);
-    constexpr int NG = NT / G;
-    double(*red)[11] = reinterpret_cast<double(*)[11]>(bar + 2);
-
-    const int t = blockIdx.x % P.ntiles;
-    const int u = nodes[blockIdx.x / P.ntiles];
-    const int v = P.left[u], w = P.right[u];
-    const int N = P.n_leaves;
-    const bool v_int = v >= N, w_int = w >= N;
-    const bool u_root = P.parent[u] < 0;
-    const int s0 = P.tile_site[t], s1 = P.tile_site[t + 1];
-    const int off0 = P.tile_off[t];
-    const int tlen = P.tile_off[t + 1] - off0;
-    const int tid = threadIdx.x;
-    const int nload = (v_int ? 1 : 0) + (w_int ? 1 : 0) + (u_root ? 0 : 1);
-
-    if (nload) {
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t bytes = (uint32_t)tlen * 8u;
-            mbar_expect_tx(bar, bytes * (uint32_t)nload);
-            if (!u_root) bulk_load(xo, P.O + (size_t)(u - N) * P.Wp + off0, bytes, bar);
-            if (v_int) bulk_load(xv, P.X + (size_t)(v - N) * P.Wp + off0, bytes, bar);
-            if (w_int) bulk_load(xw, P.X + (size_t)(w - N) * P.Wp + off0, bytes, bar);
-        }
-    }
-    const double phi = P.params[1];
-    const double4 cu = reinterpret_cast<const double4 *>(P.bc)[u];
-    const double4 cv = reinterpret_cast<const double4 *>(P.bc)[v];
-    const double4 cw = reinterpret_cast<const double4 *>(P.bc)[w];
-    const unsigned gm = group_mask<G>();
-    const int gl = tid & (G - 1), grp = tid / G;
-
-    if (!v_int || !w_int || u_root) {
-        for (int s = s0 + grp; s < s1; s += NG) {
-            const int goff = P.site_off[s];
-            const int off = goff - off0, len = P.site_len[s];
-            if (!v_int) synth_leaf<G>(xv, off, len, P.codes[(size_t)v * P.codes_stride + P.site0 + s], phi, gl, gm);
-            if (!w_int) synth_leaf<G>(xw, off, len, P.codes[(size_t)w * P.codes_stride + P.site0 + s], phi, gl, gm);
-            if (u_root) {
-                // out[root]: the root branch leaves a progenitor in state 0 (EM_solver.py:151-158)
-                for (int i = 2 + gl; i < len; i += G) xo[off + i] = cu.y * __ldg(P.q + goff + i);
-                if (gl == 0) { xo[off] = cu.x; xo[off + 1] = cu.w; }
-                __syncwarp(gm);
-            }
-        }
-    }
-    if (nload) mbar_wait(bar, 0);
-
-    const int ri = P.root_index[u];
-    const double *Lm = P.rootLm + (size_t)ri * P.K;
-    const int *Le = P.rootLe + (size_t)ri * P.K;
-    const int *iexp_u = P.iexp + (size_t)(u - N) * P.K;
-    const int *iexp_v = v_int ? P.iexp + (size_t)(v - N) * P.K : nullptr;
-    const int *iexp_w = w_int ? P.iexp + (size_t)(w - N) * P.K : nullptr;
-    const int *oexp_u = u_root ? nullptr : P.oexp + (size_t)(u - N) * P.K;
-    int *oexp_v = v_int ? P.oexp + (size_t)(v - N) * P.K : nullptr;
-    int *oexp_w = w_int ? P.oexp + (size_t)(w - N) * P.K : nullptr;
-
-    double acc[11];
-#pragma unroll
-    for (int k = 0; k < 11; k++) acc[k] = 0.0;
-
-    for (int s = s0 + grp; s < s1; s += NG) {
-        const int goff = P.site_off[s];
-        const int off = goff - off0, len = P.site_len[s];
-        double sv = 0, sw = 0, so = 0, sov = 0, sow = 0, sovw = 0;
-        unsigned mv = 0u, mw = 0u, mo = 0u;
-        for (int i = 2 + gl; i < len; i += G) {
-            const double qi = __ldg(P.q + goff + i);
-            const double a = xv[off + i], b = xw[off + i], o = xo[off + i];
-            const double oa = o * a;
-            sv = fma(qi, a, sv);
-            sw = fma(qi, b, sw);
-            so += o;
-            sov += oa;
-            sow = fma(o, b, sow);
-            sovw = fma(oa, b, sovw);
-            mv = max(mv, hi32(a));
-            mw = max(mw, hi32(b));
-            mo = max(mo, hi32(o));
-        }
-        const double x0v = xv[off], xmv = xv[off + 1], x0w = xw[off], xmw = xw[off + 1];
-        const double o0 = xo[off], om = xo[off + 1];
-        mv = max(mv, max(hi32(x0v), hi32(xmv)));
-        mw = max(mw, max(hi32(x0w), hi32(xmw)));
-        mo = max(mo, max(hi32(o0), hi32(om)));
-        sv = gsum<G>(sv, gm); sw = gsum<G>(sw, gm); so = gsum<G>(so, gm);
-        sov = gsum<G>(sov, gm); sow = gsum<G>(sow, gm); sovw = gsum<G>(sovw, gm);
-        mv = gmax<G>(mv, gm); mw = gmax<G>(mw, gm); mo = gmax<G>(mo, gm);
-        const int ev = expo_of_hi(mv), ew = expo_of_hi(mw), eo = expo_of_hi(mo);
-        const double scv = pow2i(-ev), scw = pow2i(-ew), sco = pow2i(-eo);
-        // normalised heads and sums
-        const double nx0v = x0v * scv, nxmv = xmv * scv, nx0w = x0w * scw, nxmw = xmw * scw;
-        const double no0 = o0 * sco, nom = om * sco;
-        const double Sv = sv * scv, Sw = sw * scw, So = so * sco;
-        const double Sov = sov * sco * scv, Sow = sow * sco * scw, Sovw = sovw * sco * scv * scw;
-        // sibling messages E: E_0, E_alpha = c x + g x_m, E_m = x_m
-        const double k0v = cv.x * nx0v + cv.y * Sv + cv.w * nxmv, gmv = cv.w * nxmv;
-        const double k0w = cw.x * nx0w + cw.y * Sw + cw.w * nxmw, gmw = cw.w * nxmw;
-        // top-of-branch vectors: T^v = out[u] .* E^w,  T^w = out[u] .* E^v
-        const double Tv0 = no0 * k0w, Tvm = nom * nxmw, sTv = cw.z * Sow + gmw * So;
-        const double Tw0 = no0 * k0v, Twm = nom * nxmv, sTw = cv.z * Sov + gmv * So;
-        const double sTvx = cw.z * Sovw + gmw * Sov;     // sum_a T^v_a x^v_a
-        const double sTwx = cv.z * Sovw + gmv * Sow;     // sum_a T^w_a x^w_a
-        // out rows of the children, in place: out[v] over xv, out[w] over xw
-        {
-            const double bv = cv.y * Tv0, bw = cw.y * Tw0;
-            const double cvo = cv.z * sco, cwo = cw.z * sco;
-            const double csv = cv.z * scv, csw = cw.z * scw;
-            for (int i = 2 + gl; i < len; i += G) {
-                const double qi = __ldg(P.q + goff + i);
-                const double a = xv[off + i], b = xw[off + i], o = xo[off + i];
-                const double Ew = fma(csw, b, gmw), Ev = fma(csv, a, gmv);
-                xv[off + i] = fma(bv, qi, cvo * o * Ew);
-                xw[off + i] = fma(bw, qi, cwo * o * Ev);
-            }
-        }
-        const double outvm = cv.w * (Tv0 + sTv) + Tvm;
-        const double outwm = cw.w * (Tw0 + sTw) + Twm;
-        if (gl == 0) {
-            xv[off] = cv.x * Tv0; xv[off + 1] = outvm;
-            xw[off] = cw.x * Tw0; xw[off + 1] = outwm;
-            const int cum_v = v_int ? iexp_v[s] : 0, cum_w = w_int ? iexp_w[s] : 0;
-            const int oe = (u_root ? 0 : oexp_u[s]) + eo;
-            if (v_int) oexp_v[s] = oe + cum_w + ew;
-            if (w_int) oexp_w[s] = oe + cum_v + ev;
-            // expected counts (EM_solver.py:279-300): everything is relative to the site likelihood
-            const double L = Lm[s];
-            int delta = oe + iexp_u[s] - Le[s];
-            delta = max(-1000, min(1000, delta));
-            const double fac = (L > 0.0) ? scalbn(1.0 / L, delta) : 0.0;
-            acc[0] += Tv0 * cv.x * nx0v * fac;
-            acc[1] += Tv0 * cv.y * Sv * fac;
-            acc[2] += Tv0 * cv.w * nxmv * fac;
-            acc[3] += cv.z * sTvx * fac;
-            acc[4] += cv.w * nxmv * sTv * fac;
-            acc[5] += Tw0 * cw.x * nx0w * fac;
-            acc[6] += Tw0 * cw.y * Sw * fac;
-            acc[7] += Tw0 * cw.w * nxmw * fac;
-            acc[8] += cw.z * sTwx * fac;
-            acc[9] += cw.w * nxmw * sTw * fac;
-            // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
-            if (!v_int && P.codes[(size_t)v * P.codes_stride + P.site0 + s] == -1) acc[10] += 1.0 - outvm * nxmv * fac;
-            if (!w_int && P.codes[(size_t)w * P.codes_stride + P.site0 + s] == -1) acc[10] += 1.0 - outwm * nxmw * fac;
-            if (P.post0) {
-                // post0 = log P(node in state 0 | D) = log(out_0 x_0 / L); post1 likewise for the
-                // silenced state (EM_solver.py:276-277)
-                const size_t gs = (size_t)P.site0 + s;
-                const double p0v = cv.x * Tv0 * nx0v * fac, p1v = outvm * nxmv * fac;
-                const double p0w = cw.x * Tw0 * nx0w * fac, p1w = outwm * nxmw * fac;
-                P.post0[(size_t)v * P.K_total + gs] = (p0v > 0.0) ? log(p0v) : -INFINITY;
-                P.post1[(size_t)v * P.K_total + gs] = (p1v > 0.0) ? log(p1v) : -INFINITY;
-                P.post0[(size_t)w * P.K_total + gs] = (p0w > 0.0) ? log(p0w) : -INFINITY;
-                P.post1[(size_t)w * P.K_total + gs] = (p1w > 0.0) ? log(p1w) : -INFINITY;
-            }
-        }
-    }
-    if (gl == 0) {
-#pragma unroll
-        for (int k = 0; k < 11; k++) red[grp][k] = acc[k];
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0 && (v_int || w_int)) {
-        if (v_int) bulk_store(P.O + (size_t)(v - N) * P.Wp + off0, xv, (uint32_t)tlen * 8u);
-        if (w_int) bulk_store(P.O + (size_t)(w - N) * P.Wp + off0, xw, (uint32_t)tlen * 8u);
-        bulk_commit();
-    }
-    if (tid >= 32 && tid < 32 + 11) {
-        const int k = tid - 32;
-        double sum = 0.0;
-        for (int g = 0; g < NG; g++) sum += red[g][k];
-        if (k < 5) P.Spart[((size_t)t * P.n_nodes + v) * 5 + k] = sum;
-        else if (k < 10) P.Spart[((size_t)t * P.n_nodes + w) * 5 + (k - 5)] = sum;
-        else P.Rpart[(size_t)t * (P.n_nodes - N) + (u - N)] = sum;
-    }
-    if (tid == 0 && (v_int || w_int)) bulk_wait_read0();
 }
 
 // ---------------------------------------------------------------- reductions

@@ -96,13 +96,15 @@ def random_priors(n_sites: int, a_lo: int, a_hi: int, seed: int = 5, uniform: bo
 
 @torch.no_grad()
 def simulate_codes(forest: FlatForest, d: np.ndarray, qptr: np.ndarray, qval: np.ndarray, nu: float, phi: float,
-                   seed: int = 7, device: str = "cpu", site_block: int = 512) -> np.ndarray:
-    """Leaf codes (n_leaves, K) int32 in the engine's coding (0, 1..A_s, -1 = '?')."""
+                   seed: int = 7, device: str = "cpu", site_block: int = 256, sites=None) -> np.ndarray:
+    """Leaf codes (n_leaves, K') int32 in the engine's coding (0, 1..A_s, -1 = '?')
+    for the sites ``[lo, hi)`` (default all).  Every block of ``site_block`` sites
+    has its own seeded stream, so a rank that simulates only its shard gets the
+    same columns as a rank that simulates everything."""
     K = len(qptr) - 1
+    lo, hi = (0, K) if sites is None else sites
     n, N = forest.n_nodes, forest.n_leaves
     dev = torch.device(device)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
     depth = torch.as_tensor(forest.depth, device=dev)
     parent = torch.as_tensor(forest.parent.astype(np.int64), device=dev)
     dt = torch.as_tensor(d, dtype=torch.float64, device=dev)
@@ -110,40 +112,42 @@ def simulate_codes(forest: FlatForest, d: np.ndarray, qptr: np.ndarray, qval: np
     stay0 = p ** (1.0 + nu)
     keep = p ** nu                       # not silenced on this branch
     levels = [torch.nonzero(depth == l).flatten() for l in range(int(forest.depth.max()) + 1)]
-    out = np.empty((N, K), np.int32)
+    levels = [(idx, parent[idx]) for idx in levels if idx.numel()]
+    out = np.empty((N, hi - lo), np.int32)
     Amax = int(np.max(np.diff(qptr))) if K else 0
     SIL = -3
-    for b0 in range(0, K, site_block):
-        b1 = min(K, b0 + site_block)
+    sil = torch.full((), SIL, dtype=torch.int16, device=dev)
+    zero = torch.zeros((), dtype=torch.int16, device=dev)
+    for blk in range(lo // site_block, (hi + site_block - 1) // site_block):
+        b0, b1 = blk * site_block, min(K, (blk + 1) * site_block)
         kb = b1 - b0
-        cdf = torch.ones((kb, Amax), dtype=torch.float64, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000003 + blk)
+        cdf = np.ones((kb, Amax), np.float64)
         for j, s in enumerate(range(b0, b1)):
-            q = torch.as_tensor(qval[qptr[s]:qptr[s + 1]], dtype=torch.float64, device=dev)
-            c = torch.cumsum(q, 0)
-            cdf[j, : q.numel()] = c / c[-1]
+            c = np.cumsum(qval[qptr[s]:qptr[s + 1]])
+            cdf[j, : c.shape[0]] = c / c[-1]
+        cdf = torch.as_tensor(cdf, device=dev)
         A_blk = torch.as_tensor(np.diff(qptr)[b0:b1].astype(np.int64), device=dev)
         state = torch.zeros((n, kb), dtype=torch.int16, device=dev)
-        for l, idx in enumerate(levels):
+        for idx, par in levels:
             m = idx.numel()
-            if m == 0:
-                continue
-            par = parent[idx]
-            pst = torch.where((par >= 0)[:, None], state[par.clamp(min=0)], torch.zeros((), dtype=torch.int16, device=dev))
+            pst = torch.where((par >= 0)[:, None], state[par.clamp(min=0)], zero)
             u = torch.rand((m, kb), dtype=torch.float64, device=dev, generator=gen)
             k_ = keep[idx][:, None]
             s0 = stay0[idx][:, None]
-            silenced = (pst == SIL) | (u >= k_)                     # u in [keep,1): silenced on this branch
+            silenced = (pst == SIL) | (u >= k_)                     # u in [p^nu, 1): silenced on this branch
             mutate = (pst == 0) & (u >= s0) & (u < k_)              # u in [p^(1+nu), p^nu): 0 -> alpha
             r = torch.rand((m, kb), dtype=torch.float64, device=dev, generator=gen)
             drawn = torch.searchsorted(cdf, r.t().contiguous()).t() + 1     # (m,kb) in 1..A
             drawn = torch.minimum(drawn, A_blk[None, :]).to(torch.int16)
             new = torch.where(mutate, drawn, pst)
-            new = torch.where(silenced, torch.full((), SIL, dtype=torch.int16, device=dev), new)
-            state[idx] = new
+            state[idx] = torch.where(silenced, sil, new)
         leaf = state[:N].to(torch.int32)
         drop = torch.rand((N, kb), dtype=torch.float64, device=dev, generator=gen) < phi
         leaf = torch.where((leaf == SIL) | drop, torch.full((), -1, dtype=torch.int32, device=dev), leaf)
-        out[:, b0:b1] = leaf.cpu().numpy()
+        c0, c1 = max(b0, lo), min(b1, hi)
+        out[:, c0 - lo:c1 - lo] = leaf[:, c0 - b0:c1 - b0].cpu().numpy()
     return out
 
 
@@ -164,11 +168,18 @@ class Workload:
 
 
 def make_workload(n_leaves: int, n_sites: int, a_lo: int, a_hi: int, nu: float, phi: float, seed: int = 1,
-                  uniform_prior: bool = False, device: str = "cpu", name: str = "", caterpillar_bias: float = 0.0) -> Workload:
+                  uniform_prior: bool = False, device: str = "cpu", name: str = "", caterpillar_bias: float = 0.0,
+                  sites=None) -> Workload:
+    """``sites=(lo,hi)`` restricts the simulated character matrix (and the returned
+    prior) to a contiguous site range of the same workload (site sharding)."""
     forest = random_tree(n_leaves, seed=seed, caterpillar_bias=caterpillar_bias)
     d = lognormal_branch_lengths(forest, seed=seed + 1)
     qptr, qval = random_priors(n_sites, a_lo, a_hi, seed=seed + 4, uniform=uniform_prior)
-    codes = simulate_codes(forest, d, qptr, qval, nu, phi, seed=seed + 6, device=device)
+    codes = simulate_codes(forest, d, qptr, qval, nu, phi, seed=seed + 6, device=device, sites=sites)
+    if sites is not None:
+        lo, hi = sites
+        qval = qval[qptr[lo]:qptr[hi]].copy()
+        qptr = (qptr[lo:hi + 1] - qptr[lo]).astype(np.int32)
     return Workload(forest, d, qptr, qval, codes, nu, phi, name)
 
 
