@@ -22,8 +22,9 @@ namespace {
 thread_local std::string g_create_error;
 
 struct Chunk {
-    int site0 = 0, K = 0, W = 0, Wp = 0, ntiles = 0, max_tile_sites = 0;
+    int site0 = 0, K = 0, Kp = 0, W = 0, Wp = 0, ntiles = 0, max_tile_sites = 0;
     int *d_site_off = nullptr, *d_site_len = nullptr, *d_tile_site = nullptr, *d_tile_off = nullptr;
+    int *d_tile_psite = nullptr, *d_site_pidx = nullptr, *d_codes = nullptr;
     int2 *d_ent = nullptr;
     double *d_q = nullptr, *d_qsum = nullptr;
 };
@@ -43,17 +44,20 @@ struct pmm_handle {
     int *d_codes = nullptr;
     int64_t W = 0;                  // algorithmic slots per node
     int TS = 1024;
-    int stages_in = 3, stages_out = 2, ctas_in = 1, ctas_out = 1, n_sms = 148;
+    int stages_in = 2, stages_out = 2, ctas_in[4] = {1, 1, 1, 1}, ctas_out[4] = {1, 1, 1, 1}, n_sms = 148;
+    size_t smem_in = 0, smem_out = 0;
     size_t budget = 0;
     std::vector<Chunk> chunks;
-    int maxWp = 0, maxK = 0, max_tiles = 0, max_tile_sites = 0;
+    int maxWp = 0, maxK = 0, maxKp = 0, max_tiles = 0, max_tile_sites = 0;
     // tree
     int n = 0, n_int = 0, n_roots = 0;
     std::vector<int> parent, left, right;
     int *d_parent = nullptr, *d_left = nullptr, *d_right = nullptr, *d_root_index = nullptr, *d_roots = nullptr;
-    std::vector<std::vector<int>> in_levels, out_levels;   // host copies (sizes)
-    int *d_in_nodes = nullptr, *d_out_nodes = nullptr;
-    std::vector<int> in_ptr, out_ptr;
+    // level schedules: items (u, v, w, root index) per level, sorted by node class
+    int4 *d_in_items = nullptr, *d_out_items = nullptr;
+    std::vector<int> in_ptr, out_ptr;              // level -> first item
+    std::vector<int> in_cls, out_cls;              // 3 class counts per level (II, IL, LL)
+    int spec_threshold = 1024;
     // state
     double *d_X = nullptr, *d_O = nullptr;
     int *d_iexp = nullptr, *d_dexp = nullptr;
@@ -107,13 +111,14 @@ int env_int(const char *name, int dflt) {
 void free_chunks(pmm_handle *h) {
     for (auto &c : h->chunks) {
         dfree(c.d_site_off); dfree(c.d_site_len); dfree(c.d_tile_site); dfree(c.d_tile_off); dfree(c.d_ent); dfree(c.d_q); dfree(c.d_qsum);
+        dfree(c.d_tile_psite); dfree(c.d_site_pidx); dfree(c.d_codes);
     }
     h->chunks.clear();
 }
 
 void free_tree_state(pmm_handle *h) {
     dfree(h->d_parent); dfree(h->d_left); dfree(h->d_right); dfree(h->d_root_index); dfree(h->d_roots);
-    dfree(h->d_in_nodes); dfree(h->d_out_nodes);
+    dfree(h->d_in_items); dfree(h->d_out_items);
     dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
@@ -167,6 +172,28 @@ int build_chunk(pmm_handle *h, int s_lo, int s_hi, Chunk &c) {
         c.max_tile_sites = std::max(c.max_tile_sites, b - a);
     }
     c.max_tile_sites = (c.max_tile_sites + 3) & ~3;
+    // padded site index space: every tile's sites start at a multiple of 4, so the tile's segment
+    // of a per-(node,site) int32/fp64 array is one aligned bulk copy
+    std::vector<int> tile_psite(c.ntiles + 1), site_pidx(K);
+    int pp = 0;
+    for (int t = 0; t < c.ntiles; t++) {
+        tile_psite[t] = pp;
+        for (int s2 = tile_site[t]; s2 < tile_site[t + 1]; s2++) site_pidx[s2] = pp + (s2 - tile_site[t]);
+        pp += (tile_site[t + 1] - tile_site[t] + 3) & ~3;
+    }
+    tile_psite[c.ntiles] = pp;
+    c.Kp = pp;
+    if (dalloc(h, &c.d_tile_psite, tile_psite.size()) || dalloc(h, &c.d_site_pidx, K) || dalloc(h, &c.d_codes, (size_t)h->n_leaves * c.Kp))
+        return 1;
+    CK(cudaMemcpy(c.d_tile_psite, tile_psite.data(), sizeof(int) * tile_psite.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.d_site_pidx, site_pidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+    CK(cudaMemset(c.d_codes, 0, sizeof(int) * (size_t)h->n_leaves * c.Kp));
+    {
+        const long long tot = (long long)h->n_leaves * K;
+        pmm_pad_codes<<<(unsigned)((tot + 255) / 256), 256>>>(h->d_codes, h->K, s_lo, K, c.d_site_pidx, c.Kp, h->n_leaves, c.d_codes);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
     if (dalloc(h, &c.d_site_off, K) || dalloc(h, &c.d_site_len, K) || dalloc(h, &c.d_tile_site, tile_site.size()) ||
         dalloc(h, &c.d_tile_off, tile_off.size()) || dalloc(h, &c.d_q, q.size()) || dalloc(h, &c.d_qsum, K) || dalloc(h, &c.d_ent, K))
         return 1;
@@ -207,11 +234,12 @@ int plan_chunks(pmm_handle *h) {
     }
     if (bounds.back() != K) bounds.push_back(K);
     h->chunks.resize(bounds.size() - 1);
-    h->maxWp = h->maxK = h->max_tiles = h->max_tile_sites = 0;
+    h->maxWp = h->maxK = h->maxKp = h->max_tiles = h->max_tile_sites = 0;
     for (size_t c = 0; c + 1 < bounds.size(); c++) {
         if (build_chunk(h, bounds[c], bounds[c + 1], h->chunks[c])) return 1;
         h->maxWp = std::max(h->maxWp, h->chunks[c].Wp);
         h->maxK = std::max(h->maxK, h->chunks[c].K);
+        h->maxKp = std::max(h->maxKp, h->chunks[c].Kp);
         h->max_tiles = std::max(h->max_tiles, h->chunks[c].ntiles);
         h->max_tile_sites = std::max(h->max_tile_sites, h->chunks[c].max_tile_sites);
     }
@@ -221,9 +249,10 @@ int plan_chunks(pmm_handle *h) {
 KParams make_params(pmm_handle *h, const Chunk &c, bool with_post) {
     KParams P;
     P.site_off = c.d_site_off; P.site_len = c.d_site_len; P.tile_site = c.d_tile_site; P.tile_off = c.d_tile_off;
+    P.tile_psite = c.d_tile_psite; P.site_pidx = c.d_site_pidx;
     P.ent = c.d_ent; P.q = c.d_q; P.qsum = c.d_qsum;
-    P.K = c.K; P.Wp = c.Wp; P.ntiles = c.ntiles; P.max_tile_sites = h->max_tile_sites;
-    P.codes = h->d_codes; P.codes_stride = h->K; P.site0 = c.site0;
+    P.K = c.K; P.Kp = c.Kp; P.Wp = c.Wp; P.ntiles = c.ntiles; P.max_tile_sites = h->max_tile_sites;
+    P.codes = c.d_codes; P.site0 = c.site0;
     P.left = h->d_left; P.right = h->d_right; P.parent = h->d_parent; P.root_index = h->d_root_index;
     P.n_leaves = h->n_leaves; P.n_nodes = h->n;
     P.params = h->d_params; P.bc = h->d_bc;
@@ -252,38 +281,50 @@ int configure_kernels(pmm_handle *h) {
         stages = 0;
         return 0;
     };
-    size_t bi = pick(false, env_int("PMM_STAGES_IN", 3), h->stages_in);
-    size_t bo = pick(true, env_int("PMM_STAGES_OUT", 3), h->stages_out);
+    size_t bi = pick(false, env_int("PMM_STAGES_IN", 2), h->stages_in);
+    size_t bo = pick(true, env_int("PMM_STAGES_OUT", 2), h->stages_out);
     if (!bi || !bo) return fail(h, "tile of %d slots does not fit in shared memory", h->TS);
-    CK(cudaFuncSetAttribute(pmm_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bi));
-    CK(cudaFuncSetAttribute(pmm_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bo));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_in, pmm_level<false>, NTHREADS, bi));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_out, pmm_level<true>, NTHREADS, bo));
-    if (h->ctas_in < 1 || h->ctas_out < 1) return fail(h, "level kernels cannot be resident (smem %zu / %zu bytes)", bi, bo);
-    h->ctas_in = std::min(h->ctas_in, env_int("PMM_CTAS_IN", 8));
-    h->ctas_out = std::min(h->ctas_out, env_int("PMM_CTAS_OUT", 8));
+    h->smem_in = bi; h->smem_out = bo;
+#define SETUP(OUT, CLS, smem, ctas)                                                                                        \
+    CK(cudaFuncSetAttribute(pmm_level<OUT, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));                \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(ctas), pmm_level<OUT, CLS>, NTHREADS, (smem)));                       \
+    if ((ctas) < 1) return fail(h, "level kernel cannot be resident (smem %zu bytes)", (size_t)(smem));
+    SETUP(false, CLS_II, bi, h->ctas_in[0]) SETUP(false, CLS_IL, bi, h->ctas_in[1]) SETUP(false, CLS_LL, bi, h->ctas_in[2])
+    SETUP(false, CLS_ANY, bi, h->ctas_in[3])
+    SETUP(true, CLS_II, bo, h->ctas_out[0]) SETUP(true, CLS_IL, bo, h->ctas_out[1]) SETUP(true, CLS_LL, bo, h->ctas_out[2])
+    SETUP(true, CLS_ANY, bo, h->ctas_out[3])
+#undef SETUP
+    const int cap_in = env_int("PMM_CTAS_IN", 8), cap_out = env_int("PMM_CTAS_OUT", 8);
+    for (int k = 0; k < 4; k++) { h->ctas_in[k] = std::min(h->ctas_in[k], cap_in); h->ctas_out[k] = std::min(h->ctas_out[k], cap_out); }
+    h->spec_threshold = env_int("PMM_SPEC_THRESHOLD", 1024);
     return 0;
 }
 
 // grid = (P, ntiles): P persistent CTAs per tile, sized to fill the SMs once
-template <bool OUTSIDE> void launch_level(pmm_handle *h, KParams P, const int *d_nodes, int cnt) {
-    const int resident = h->n_sms * (OUTSIDE ? h->ctas_out : h->ctas_in);
+template <bool OUTSIDE, int CLS> void launch_one(pmm_handle *h, KParams P, const int4 *d_items, int cnt) {
+    if (cnt <= 0) return;
+    const int resident = h->n_sms * (OUTSIDE ? h->ctas_out[CLS] : h->ctas_in[CLS]);
     int per_tile = std::max(1, resident / std::max(P.ntiles, 1));
     per_tile = std::min(per_tile, cnt);
     P.stages = OUTSIDE ? h->stages_out : h->stages_in;
-    const size_t smem = OUTSIDE ? Plan<true>::total_bytes(h->TS, P.max_tile_sites, P.stages)
-                                : Plan<false>::total_bytes(h->TS, P.max_tile_sites, P.stages);
     dim3 grid((unsigned)per_tile, (unsigned)P.ntiles);
-    pmm_level<OUTSIDE><<<grid, NTHREADS, smem, h->stream>>>(P, d_nodes, cnt);
+    pmm_level<OUTSIDE, CLS><<<grid, NTHREADS, OUTSIDE ? h->smem_out : h->smem_in, h->stream>>>(P, d_items, cnt);
     h->launches++;
+}
+
+// one tree level: big levels run one class-specialised launch per node class (the items are
+// sorted by class), small ones a single launch that reads the class per item
+template <bool OUTSIDE> void launch_level(pmm_handle *h, const KParams &P, const int4 *d_items, const int *cls_cnt) {
+    const int cnt = cls_cnt[0] + cls_cnt[1] + cls_cnt[2];
+    if (cnt < h->spec_threshold) { launch_one<OUTSIDE, CLS_ANY>(h, P, d_items, cnt); return; }
+    launch_one<OUTSIDE, CLS_II>(h, P, d_items, cls_cnt[0]);
+    launch_one<OUTSIDE, CLS_IL>(h, P, d_items + cls_cnt[0], cls_cnt[1]);
+    launch_one<OUTSIDE, CLS_LL>(h, P, d_items + cls_cnt[0] + cls_cnt[1], cls_cnt[2]);
 }
 
 int launch_inside(pmm_handle *h, const KParams &P) {
     const int nl = (int)h->in_ptr.size() - 1;
-    for (int l = 0; l < nl; l++) {
-        int cnt = h->in_ptr[l + 1] - h->in_ptr[l];
-        if (cnt) launch_level<false>(h, P, h->d_in_nodes + h->in_ptr[l], cnt);
-    }
+    for (int l = 0; l < nl; l++) launch_level<false>(h, P, h->d_in_items + h->in_ptr[l], &h->in_cls[3 * l]);
     pmm_root_llh<<<(unsigned)(h->n_roots * P.ntiles), 256, 0, h->stream>>>(P, h->d_roots);
     h->launches++;
     CK(cudaGetLastError());
@@ -292,10 +333,7 @@ int launch_inside(pmm_handle *h, const KParams &P) {
 
 int launch_outside(pmm_handle *h, const KParams &P) {
     const int nl = (int)h->out_ptr.size() - 1;
-    for (int l = 0; l < nl; l++) {
-        int cnt = h->out_ptr[l + 1] - h->out_ptr[l];
-        if (cnt) launch_level<true>(h, P, h->d_out_nodes + h->out_ptr[l], cnt);
-    }
+    for (int l = 0; l < nl; l++) launch_level<true>(h, P, h->d_out_items + h->out_ptr[l], &h->out_cls[3 * l]);
     CK(cudaGetLastError());
     return 0;
 }
@@ -482,24 +520,42 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     }
     int H = 0, D = 0;
     for (int v = N; v < n; v++) { H = std::max(H, height[v]); D = std::max(D, depth[v]); }
-    // inside schedule: internal nodes by height 1..H; outside: internal nodes by depth 0..D
+    // inside schedule: internal nodes by height 1..H; outside: internal nodes by depth 0..D.
+    // Within a level the items are sorted by node class (both children internal / one / none) and
+    // the children are ordered internal-first: the recursions are symmetric in the two children.
     std::vector<std::vector<int>> inl(H), outl(D + 1);
     for (int v = N; v < n; v++) { inl[height[v] - 1].push_back(v); outl[depth[v]].push_back(v); }
-    std::vector<int> in_nodes, out_nodes;
-    h->in_ptr.assign(1, 0); h->out_ptr.assign(1, 0);
-    for (auto &L : inl) { in_nodes.insert(in_nodes.end(), L.begin(), L.end()); h->in_ptr.push_back((int)in_nodes.size()); }
-    for (auto &L : outl) { out_nodes.insert(out_nodes.end(), L.begin(), L.end()); h->out_ptr.push_back((int)out_nodes.size()); }
+    auto build_items = [&](std::vector<std::vector<int>> &levels, std::vector<int4> &items, std::vector<int> &ptr, std::vector<int> &cls) {
+        ptr.assign(1, 0); cls.clear(); items.clear();
+        for (auto &L : levels) {
+            int cnt[3] = {0, 0, 0};
+            for (int pass = 0; pass < 3; pass++)
+                for (int u : L) {
+                    int a = left[u], b = right[u];
+                    if (a < N && b >= N) std::swap(a, b);
+                    const int c = (a >= N) ? ((b >= N) ? 0 : 1) : 2;
+                    if (c != pass) continue;
+                    items.push_back(make_int4(u, a, b, root_index[u]));
+                    cnt[c]++;
+                }
+            cls.insert(cls.end(), cnt, cnt + 3);
+            ptr.push_back((int)items.size());
+        }
+    };
+    std::vector<int4> in_items, out_items;
+    build_items(inl, in_items, h->in_ptr, h->in_cls);
+    build_items(outl, out_items, h->out_ptr, h->out_cls);
 
     if (dalloc(h, &h->d_parent, n) || dalloc(h, &h->d_left, n) || dalloc(h, &h->d_right, n) || dalloc(h, &h->d_root_index, n) ||
-        dalloc(h, &h->d_roots, roots.size()) || dalloc(h, &h->d_in_nodes, in_nodes.size()) || dalloc(h, &h->d_out_nodes, out_nodes.size()))
+        dalloc(h, &h->d_roots, roots.size()) || dalloc(h, &h->d_in_items, in_items.size()) || dalloc(h, &h->d_out_items, out_items.size()))
         return 1;
     CK(cudaMemcpy(h->d_parent, parent, sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_left, left, sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_right, right, sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_root_index, root_index.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_roots, roots.data(), sizeof(int) * roots.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_in_nodes, in_nodes.data(), sizeof(int) * in_nodes.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_out_nodes, out_nodes.data(), sizeof(int) * out_nodes.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_in_items, in_items.data(), sizeof(int4) * in_items.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_out_items, out_items.data(), sizeof(int4) * out_items.size(), cudaMemcpyHostToDevice));
 
     // small per-node buffers first, then the chunk plan against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
@@ -509,8 +565,8 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     if (plan_chunks(h)) return 1;
     if (configure_kernels(h)) return 1;
     const size_t rows = (size_t)h->n_int;
-    if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxK) ||
-        dalloc(h, &h->d_dexp, rows * h->maxK) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxK) ||
+    if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxKp) ||
+        dalloc(h, &h->d_dexp, rows * h->maxKp) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxKp) ||
         dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
         dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
         return 1;

@@ -40,7 +40,7 @@
 
 namespace pmm {
 
-constexpr int NCW = 8;                    // consumer warps per CTA
+constexpr int NCW = 7;                    // consumer warps per CTA
 constexpr int NTHREADS = (NCW + 1) * 32;  // + 1 producer warp
 constexpr int G = 8;                      // lanes per site group
 constexpr int NG = NCW * (32 / G);        // site groups per CTA
@@ -52,13 +52,15 @@ struct KParams {
     const int *site_len;         // [K]   padded slot count (even)
     const int *tile_site;        // [ntiles+1]
     const int *tile_off;         // [ntiles+1]
+    const int *tile_psite;       // [ntiles+1] first PADDED site index of each tile (multiple of 4)
+    const int *site_pidx;        // [K]   padded site index of each site
     const int2 *ent;             // [K]   per tile, sites sorted by length: x = off_in_tile | len<<16, y = site index in tile
     const double *q;             // [Wp]  prior in slot layout (0 at x_0, x_m, pads)
     const double *qsum;          // [K]   sum_a q_a
-    int K, Wp, ntiles, max_tile_sites;
-    // data
-    const int *codes;            // [n_leaves][codes_stride]
-    int codes_stride, site0;
+    int K, Kp, Wp, ntiles, max_tile_sites;
+    // data: per-(leaf,site) state codes in the padded site index space of this chunk
+    const int *codes;            // [n_leaves][Kp]
+    int site0;
     // tree
     const int *left, *right, *parent, *root_index;
     int n_leaves, n_nodes;
@@ -67,9 +69,9 @@ struct KParams {
     const double *bc;            // [n][4] = a, b, c, g per branch
     // state
     double *X, *O;               // [n_int][Wp] inside / outside rows
-    int *iexp, *dexp;            // [n_int][K]
-    double *rootInvL;            // [n_roots][K] 1 / (normalised site likelihood)
-    double *root_site_llh;       // [n_roots][K]
+    int *iexp, *dexp;            // [n_int][Kp]   (padded site index space: every tile's sites
+    double *rootInvL;            // [n_roots][Kp]  start at a multiple of 4, so a tile's segment of
+    double *root_site_llh;       // [n_roots][Kp]  any of these arrays is one aligned bulk copy)
     double *Spart;               // [ntiles][n][5]
     double *Rpart;               // [ntiles][n_int]
     double *post0, *post1;       // optional [n][K_total] log posteriors (annotation path), or null
@@ -173,7 +175,9 @@ __global__ void pmm_branch_consts(const double *__restrict__ d, const double *__
 // stage = [ NARR row tiles : NARR*TS doubles ][ invL : MS doubles (outside) ][ red : NCW*12 doubles (outside) ]
 //         [ mA, mB, mD : 3*MS ints ][ desc : 32 ints ]
 // MS = max sites per tile, rounded up to a multiple of 4.
-struct Desc { int u, v, w, valid; double4 cv, cw; };   // 80 bytes (stage reserves 128)
+struct Desc { int u, v, w, cls; double4 cv, cw; };   // 80 bytes (stage reserves 128); cv/cw arrive by TMA
+// node classes: both children internal / v internal, w leaf / both leaves / decided per item
+enum { CLS_II = 0, CLS_IL = 1, CLS_LL = 2, CLS_ANY = 3 };
 
 template <bool OUTSIDE> struct Plan {
     static constexpr int NARR = OUTSIDE ? 3 : 2;
@@ -419,9 +423,12 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
 }
 
 // ---------------------------------------------------------------- K1 / K2: one tree level, persistent
-template <bool OUTSIDE>
+// items[i] = (u, v, w) with the children ordered so that an internal child comes first
+// (the recursions are symmetric in the children).  CLS fixes the node class at compile
+// time for the big, class-sorted launches; CLS_ANY decides per item (small levels).
+template <bool OUTSIDE, int CLS>
 __global__ void __launch_bounds__(NTHREADS, 2)
-pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
+pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     using PL = Plan<OUTSIDE>;
     constexpr int NARR = PL::NARR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -437,6 +444,8 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
 
     const int t = blockIdx.y;
     const int s0 = P.tile_site[t], nsites = P.tile_site[t + 1] - s0;
+    const int ps0 = P.tile_psite[t];                       // padded site index of the tile's first site
+    const int nsp = (nsites + 3) & ~3;
     const int off0 = P.tile_off[t];
     const int tlen = P.tile_off[t + 1] - off0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -447,7 +456,7 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
     for (int i = tid; i < tlen; i += NTHREADS) s_q[i] = P.q[off0 + i];
     for (int i = tid; i < nsites; i += NTHREADS) { s_qsum[i] = P.qsum[s0 + i]; s_ent[i] = P.ent[s0 + i]; }
     if (tid == 0) {
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 2); mbar_init(&done[s], NCW); }
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], NCW); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -461,68 +470,59 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
     auto f_desc = [&](unsigned char *st) { return reinterpret_cast<Desc *>(f_meta(st) + 3 * MS); };
 
     if (warp == NCW) {
-        // ======================= producer warp =======================
+        // ======================= producer warp: everything it moves is an async bulk copy =======================
         auto flush_counts = [&](unsigned char *st) {
             // deterministic cross-warp sum of the per-warp partial counts of a finished item
-            const Desc dsc = *f_desc(st);
+            const Desc *dsc = f_desc(st);
+            const int du = dsc->u, dv = dsc->v, dw = dsc->w;
             const double *red = f_red(st);
             if (lane < 11) {
                 double sum = 0.0;
                 for (int wdx = 0; wdx < NCW; wdx++) sum += red[wdx * 12 + lane];
-                if (lane < 5) P.Spart[((size_t)t * P.n_nodes + dsc.v) * 5 + lane] = sum;
-                else if (lane < 10) P.Spart[((size_t)t * P.n_nodes + dsc.w) * 5 + (lane - 5)] = sum;
-                else P.Rpart[(size_t)t * (P.n_nodes - N) + (dsc.u - N)] = sum;
+                if (lane < 5) P.Spart[((size_t)t * P.n_nodes + dv) * 5 + lane] = sum;
+                else if (lane < 10) P.Spart[((size_t)t * P.n_nodes + dw) * 5 + (lane - 5)] = sum;
+                else P.Rpart[(size_t)t * (P.n_nodes - N) + (du - N)] = sum;
             }
             __syncwarp();
         };
-        int nu_ = n_items > 0 ? nodes[blockIdx.x] : 0;
-        int nv_ = n_items > 0 ? P.left[nu_] : 0, nw_ = n_items > 0 ? P.right[nu_] : 0;
+        int4 nxt = n_items > 0 ? items[blockIdx.x] : make_int4(0, 0, 0, 0);
         for (int k = 0; k < n_items; k++) {
             const int s = k % S;
             unsigned char *st = stage_ptr(s);
-            const int u = nu_, v = nv_, w = nw_;
-            if (k + 1 < n_items) {                                // ids of the next item, ahead of need
-                nu_ = nodes[blockIdx.x + (k + 1) * gridDim.x];
-                nv_ = P.left[nu_]; nw_ = P.right[nu_];
-            }
+            const int4 it = nxt;
+            if (k + 1 < n_items) nxt = items[blockIdx.x + (size_t)(k + 1) * gridDim.x];     // ahead of need
             if (k >= S) {
                 mbar_wait(&done[s], ((k / S) - 1) & 1);          // consumers have finished item k-S
                 if (OUTSIDE) flush_counts(st);
             }
-            const bool vi = v >= N, wi = w >= N;
-            double *rows = f_rows(st);
             if (lane == 0) {
-                const uint32_t bytes = (uint32_t)tlen * 8u;
-                const uint32_t nld = (vi ? 1u : 0u) + (wi ? 1u : 0u) + (OUTSIDE ? 1u : 0u);
-                mbar_expect_tx_arrive(&full[s], bytes * nld);
-                if (vi) bulk_load(rows, P.X + (size_t)(v - N) * P.Wp + off0, bytes, &full[s]);
-                if (wi) bulk_load(rows + TS, P.X + (size_t)(w - N) * P.Wp + off0, bytes, &full[s]);
-                if (OUTSIDE) bulk_load(rows + 2 * TS, P.O + (size_t)(u - N) * P.Wp + off0, bytes, &full[s]);
-            }
-            // per-site metadata: leaf codes or accumulated exponents; D_u and 1/L for the outside pass
-            int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
-            const int *srcA = vi ? (OUTSIDE ? nullptr : P.iexp + (size_t)(v - N) * P.K + s0)
-                                 : P.codes + (size_t)v * P.codes_stride + P.site0 + s0;
-            const int *srcB = wi ? (OUTSIDE ? nullptr : P.iexp + (size_t)(w - N) * P.K + s0)
-                                 : P.codes + (size_t)w * P.codes_stride + P.site0 + s0;
-            for (int i = lane; i < nsites; i += 32) {
-                if (srcA) mA[i] = srcA[i];
-                if (srcB) mB[i] = srcB[i];
-            }
-            if (OUTSIDE) {
-                const int *srcD = P.dexp + (size_t)(u - N) * P.K + s0;
-                const double *srcL = P.rootInvL + (size_t)P.root_index[u] * P.K + s0;
-                double *invL = f_invL(st);
-                for (int i = lane; i < nsites; i += 32) { mD[i] = srcD[i]; invL[i] = srcL[i]; }
-            }
-            if (lane == 0) {
-                Desc dd; dd.u = u; dd.v = v; dd.w = w; dd.valid = 1;
-                dd.cv = reinterpret_cast<const double4 *>(P.bc)[v];
-                dd.cw = reinterpret_cast<const double4 *>(P.bc)[w];
-                *f_desc(st) = dd;
+                const int u = it.x, v = it.y, w = it.z;
+                const bool vi = v >= N, wi = w >= N;
+                double *rows = f_rows(st);
+                int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
+                Desc *dsc = f_desc(st);
+                dsc->u = u; dsc->v = v; dsc->w = w; dsc->cls = vi ? (wi ? CLS_II : CLS_IL) : CLS_LL;
+                const uint32_t rb = (uint32_t)tlen * 8u, ib = (uint32_t)nsp * 4u, db = (uint32_t)nsp * 8u;
+                uint32_t tx = 64u;                                                 // cv, cw
+                tx += rb * ((vi ? 1u : 0u) + (wi ? 1u : 0u) + (OUTSIDE ? 1u : 0u));
+                tx += OUTSIDE ? (ib + db + ib * ((vi ? 0u : 1u) + (wi ? 0u : 1u))) : 2u * ib;
+                mbar_expect_tx_arrive(&full[s], tx);                               // release: orders the id stores above
+                bulk_load(&dsc->cv, P.bc + (size_t)4 * v, 32u, &full[s]);
+                bulk_load(&dsc->cw, P.bc + (size_t)4 * w, 32u, &full[s]);
+                if (vi) bulk_load(rows, P.X + (size_t)(v - N) * P.Wp + off0, rb, &full[s]);
+                if (wi) bulk_load(rows + TS, P.X + (size_t)(w - N) * P.Wp + off0, rb, &full[s]);
+                if (OUTSIDE) {
+                    bulk_load(rows + 2 * TS, P.O + (size_t)(u - N) * P.Wp + off0, rb, &full[s]);
+                    bulk_load(mD, P.dexp + (size_t)(u - N) * P.Kp + ps0, ib, &full[s]);
+                    bulk_load(f_invL(st), P.rootInvL + (size_t)it.w * P.Kp + ps0, db, &full[s]);
+                    if (!vi) bulk_load(mA, P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
+                    if (!wi) bulk_load(mB, P.codes + (size_t)w * P.Kp + ps0, ib, &full[s]);
+                } else {
+                    bulk_load(mA, vi ? P.iexp + (size_t)(v - N) * P.Kp + ps0 : P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
+                    bulk_load(mB, wi ? P.iexp + (size_t)(w - N) * P.Kp + ps0 : P.codes + (size_t)w * P.Kp + ps0, ib, &full[s]);
+                }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
         }
         if (OUTSIDE) {
             // drain: partial counts of the last min(S, n_items) items
@@ -544,28 +544,28 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
         const int s = k % S;
         unsigned char *st = stage_ptr(s);
         mbar_wait(&full[s], (k / S) & 1);
-        const Desc dsc = *f_desc(st);
-        const int u = dsc.u, v = dsc.v, w = dsc.w;
-        const bool vi = v >= N, wi = w >= N;
-        const double4 cv = dsc.cv, cw = dsc.cw;
+        const Desc *dsc = f_desc(st);
+        const int u = dsc->u, v = dsc->v, w = dsc->w;
+        const int cls = (CLS == CLS_ANY) ? dsc->cls : CLS;
+        const double4 cv = dsc->cv, cw = dsc->cw;
         const double *A = f_rows(st), *B = A + TS, *C = B + TS;
         const int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
         if (!OUTSIDE) {
             double *gout = P.X + (size_t)(u - N) * P.Wp + off0;
-            int *iexp_u = P.iexp + (size_t)(u - N) * P.K + s0;
+            int *iexp_u = P.iexp + (size_t)(u - N) * P.Kp + ps0;
             for (int j = grp; j < nsites; j += NG) {
                 const int2 e = s_ent[j];
                 const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
-                if (vi && wi) inside_site<true, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
-                else if (vi) inside_site<true, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
-                else if (wi) inside_site<false, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                if (cls == CLS_II) inside_site<true, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                else if (cls == CLS_IL) inside_site<true, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
                 else inside_site<false, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
             }
         } else {
+            const bool vi = cls != CLS_LL, wi = cls == CLS_II;
             double *goutv = vi ? P.O + (size_t)(v - N) * P.Wp + off0 : nullptr;
             double *goutw = wi ? P.O + (size_t)(w - N) * P.Wp + off0 : nullptr;
-            int *dv = vi ? P.dexp + (size_t)(v - N) * P.K + s0 : nullptr;
-            int *dw = wi ? P.dexp + (size_t)(w - N) * P.K + s0 : nullptr;
+            int *dv = vi ? P.dexp + (size_t)(v - N) * P.Kp + ps0 : nullptr;
+            int *dw = wi ? P.dexp + (size_t)(w - N) * P.Kp + ps0 : nullptr;
             const double *invL = f_invL(st);
             double acc[11];
 #pragma unroll
@@ -575,9 +575,8 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
                 const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
                 double pst[4];
                 double *post = P.post0 ? pst : nullptr;
-                if (vi && wi) outside_site<true, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw + ls, post, gl, gm, acc);
-                else if (vi) outside_site<true, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw, post, gl, gm, acc);
-                else if (wi) outside_site<false, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv, dw + ls, post, gl, gm, acc);
+                if (cls == CLS_II) outside_site<true, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw + ls, post, gl, gm, acc);
+                else if (cls == CLS_IL) outside_site<true, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw, post, gl, gm, acc);
                 else outside_site<false, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv, dw, post, gl, gm, acc);
                 if (post && gl == 0) {
                     const size_t gs = (size_t)P.site0 + s0 + ls;
@@ -600,6 +599,16 @@ pmm_level(KParams P, const int *__restrict__ nodes, int n_level) {
     }
 }
 
+// codes_p[r][site_pidx[s]] = raw[r][site0 + s]   (padded site index space of one chunk)
+__global__ void pmm_pad_codes(const int *__restrict__ raw, int raw_stride, int site0, int K, const int *__restrict__ site_pidx,
+                              int Kp, long long n_rows, int *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * K) return;
+    long long r = i / K;
+    int s = (int)(i - r * K);
+    out[r * Kp + site_pidx[s]] = raw[r * raw_stride + site0 + s];
+}
+
 // ---------------------------------------------------------------- K1r: root likelihood
 // One CTA per (root, tile): site likelihood L_s = E[root]_0 (the root's own branch
 // starts in state 0, EM_solver.py:140), its log, the expected counts of the root
@@ -619,8 +628,8 @@ __global__ void __launch_bounds__(256) pmm_root_llh(KParams P, const int *__rest
     const double4 cr = reinterpret_cast<const double4 *>(P.bc)[r];
     const double *x = P.X + (size_t)(r - N) * P.Wp;
     double *o = P.O + (size_t)(r - N) * P.Wp;
-    const int *iexp_r = P.iexp + (size_t)(r - N) * P.K;
-    int *dexp_r = P.dexp + (size_t)(r - N) * P.K;
+    const int *iexp_r = P.iexp + (size_t)(r - N) * P.Kp;
+    int *dexp_r = P.dexp + (size_t)(r - N) * P.Kp;
     double acc0 = 0, acc1 = 0, acc2 = 0;
     for (int s = s0 + grp; s < s1; s += RG) {
         const int goff = P.site_off[s], len = P.site_len[s];
@@ -641,11 +650,12 @@ __global__ void __launch_bounds__(256) pmm_root_llh(KParams P, const int *__rest
             const double sc = pow2i(-e);
             const double t0 = cr.x * x0 * sc, t1 = cr.y * sq * sc, t2 = cr.w * xm * sc;
             const double L = t0 + t1 + t2;
-            const int Le = iexp_r[s] + e;
+            const int ps = P.site_pidx[s];
+            const int Le = iexp_r[ps] + e;
             const double inv = (L > 0.0) ? 1.0 / L : 0.0;
             o[goff] = cr.x; o[goff + 1] = cr.w;
-            dexp_r[s] = -e;
-            P.rootInvL[(size_t)ri * P.K + s] = inv;
+            dexp_r[ps] = -e;
+            P.rootInvL[(size_t)ri * P.Kp + ps] = inv;
             P.root_site_llh[(size_t)ri * P.K + s] = (L > 0.0) ? log(L) + (double)Le * 0.693147180559945309417232121458 : -INFINITY;
             acc0 += t0 * inv; acc1 += t1 * inv; acc2 += t2 * inv;
             if (P.post0) {
