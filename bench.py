@@ -270,8 +270,9 @@ def run_ours(args, rank, local_rank, world):
     in_bytes = 16.0 * W_shard_max * n
     # bytes this design actually has to move (leaf rows are never materialised): DESIGN.md
     n_int = n - N
-    out_moved = 8.0 * info["row_stride"] * ((n_int - n_roots) * 2 + (n_int - n_roots))
-    in_moved = 8.0 * info["row_stride"] * (n_int + (n_int - n_roots))
+    Wrow = info["padded_slots_per_node"]     # slots per row incl. even-length padding, summed over site chunks
+    out_moved = 8.0 * Wrow * (n_int + 2 * (n_int - n_roots))      # read out[u]; read x[c], write out[c] for internal children
+    in_moved = 8.0 * Wrow * (n_int + (n_int - n_roots))           # write x[u]; read x[c] for internal children
     out_launches = info["outside_levels"] * info["n_chunks"]
     ach = out_bytes / (outside_ms * 1e-3) / 1e9
     roofline = {

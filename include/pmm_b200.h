@@ -138,7 +138,8 @@ int pmm_sync(pmm_handle *h);
 typedef struct {
     int64_t n_nodes, n_leaves, n_sites;
     int64_t slots_per_node;      /* W = sum over sites of (A_s + 2): the algorithmic state slots */
-    int64_t row_stride;          /* W plus tile padding, largest chunk */
+    int64_t row_stride;          /* slots per row (W plus even-length padding), largest chunk */
+    int64_t padded_slots_per_node; /* the same, summed over all site chunks */
     int64_t n_chunks, n_tiles, tile_slots;
     int64_t inside_levels, outside_levels;
     int64_t device_bytes;        /* allocated by the handle */

@@ -44,8 +44,8 @@ struct pmm_handle {
     int *d_codes = nullptr;
     int64_t W = 0;                  // algorithmic slots per node
     int TS = 1024;
-    int stages_in = 2, stages_out = 2, ctas_in[4] = {1, 1, 1, 1}, ctas_out[4] = {1, 1, 1, 1}, n_sms = 148;
-    size_t smem_in = 0, smem_out = 0;
+    int stages_in[4] = {2, 2, 2, 2}, stages_out[4] = {2, 2, 2, 2}, ctas_in[4] = {1, 1, 1, 1}, ctas_out[4] = {1, 1, 1, 1}, n_sms = 148;
+    size_t smem_in[4] = {0, 0, 0, 0}, smem_out[4] = {0, 0, 0, 0};
     size_t budget = 0;
     std::vector<Chunk> chunks;
     int maxWp = 0, maxK = 0, maxKp = 0, max_tiles = 0, max_tile_sites = 0;
@@ -57,7 +57,7 @@ struct pmm_handle {
     int4 *d_in_items = nullptr, *d_out_items = nullptr;
     std::vector<int> in_ptr, out_ptr;              // level -> first item
     std::vector<int> in_cls, out_cls;              // 3 class counts per level (II, IL, LL)
-    int spec_threshold = 1024;
+    int spec_threshold = 1 << 30;
     // state
     double *d_X = nullptr, *d_O = nullptr;
     int *d_iexp = nullptr, *d_dexp = nullptr;
@@ -272,31 +272,32 @@ int configure_kernels(pmm_handle *h) {
     CK(cudaGetDeviceProperties(&prop, h->device));
     h->n_sms = prop.multiProcessorCount;
     const size_t smem_cap = prop.sharedMemPerBlockOptin;       // 227 KB on sm_100
+    const size_t smem_sm = prop.sharedMemPerMultiprocessor;
     const int MS = h->max_tile_sites;
-    auto pick = [&](bool outside, int want_stages, int &stages) -> size_t {
-        for (int S = std::min(want_stages, MAX_STAGES); S >= 1; S--) {
-            size_t b = outside ? Plan<true>::total_bytes(h->TS, MS, S) : Plan<false>::total_bytes(h->TS, MS, S);
-            if (b <= smem_cap) { stages = S; return b; }
-        }
-        stages = 0;
-        return 0;
-    };
-    size_t bi = pick(false, env_int("PMM_STAGES_IN", 2), h->stages_in);
-    size_t bo = pick(true, env_int("PMM_STAGES_OUT", 2), h->stages_out);
-    if (!bi || !bo) return fail(h, "tile of %d slots does not fit in shared memory", h->TS);
-    h->smem_in = bi; h->smem_out = bo;
-#define SETUP(OUT, CLS, smem, ctas)                                                                                        \
-    CK(cudaFuncSetAttribute(pmm_level<OUT, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));                \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(ctas), pmm_level<OUT, CLS>, NTHREADS, (smem)));                       \
-    if ((ctas) < 1) return fail(h, "level kernel cannot be resident (smem %zu bytes)", (size_t)(smem));
-    SETUP(false, CLS_II, bi, h->ctas_in[0]) SETUP(false, CLS_IL, bi, h->ctas_in[1]) SETUP(false, CLS_LL, bi, h->ctas_in[2])
-    SETUP(false, CLS_ANY, bi, h->ctas_in[3])
-    SETUP(true, CLS_II, bo, h->ctas_out[0]) SETUP(true, CLS_IL, bo, h->ctas_out[1]) SETUP(true, CLS_LL, bo, h->ctas_out[2])
-    SETUP(true, CLS_ANY, bo, h->ctas_out[3])
+    const int want_in = env_int("PMM_STAGES_IN", 3), want_out = env_int("PMM_STAGES_OUT", 2);
+    const int want_ctas = env_int("PMM_CTAS", 2);
+    // per (pass, class): the deepest ring (<= wanted) that still leaves `want_ctas` CTAs resident per SM
+#define SETUP(OUT, CLS, IDX)                                                                                                  \
+    {                                                                                                                         \
+        int S = std::min(OUT ? want_out : want_in, MAX_STAGES);                                                               \
+        size_t b = 0;                                                                                                         \
+        for (; S >= 1; S--) {                                                                                                 \
+            b = Plan<OUT, CLS>::total_bytes(h->TS, MS, S);                                                                    \
+            if (b <= smem_cap && (S == 1 || (b + 1024) * want_ctas <= smem_sm)) break;                                        \
+        }                                                                                                                     \
+        if (S < 1) return fail(h, "tile of %d slots does not fit in shared memory", h->TS);                                   \
+        int ctas = 0;                                                                                                         \
+        CK(cudaFuncSetAttribute(pmm_level<OUT, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));                   \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, pmm_level<OUT, CLS>, NTHREADS, b));                           \
+        if (ctas < 1) return fail(h, "level kernel cannot be resident (smem %zu bytes)", b);                                  \
+        (OUT ? h->stages_out : h->stages_in)[IDX] = S;                                                                        \
+        (OUT ? h->smem_out : h->smem_in)[IDX] = b;                                                                            \
+        (OUT ? h->ctas_out : h->ctas_in)[IDX] = ctas;                                                                         \
+    }
+    SETUP(false, CLS_II, 0) SETUP(false, CLS_IL, 1) SETUP(false, CLS_LL, 2) SETUP(false, CLS_ANY, 3)
+    SETUP(true, CLS_II, 0) SETUP(true, CLS_IL, 1) SETUP(true, CLS_LL, 2) SETUP(true, CLS_ANY, 3)
 #undef SETUP
-    const int cap_in = env_int("PMM_CTAS_IN", 8), cap_out = env_int("PMM_CTAS_OUT", 8);
-    for (int k = 0; k < 4; k++) { h->ctas_in[k] = std::min(h->ctas_in[k], cap_in); h->ctas_out[k] = std::min(h->ctas_out[k], cap_out); }
-    h->spec_threshold = env_int("PMM_SPEC_THRESHOLD", 1024);
+    h->spec_threshold = env_int("PMM_SPEC_THRESHOLD", 1 << 30);   // measured: one class-agnostic launch per level wins
     return 0;
 }
 
@@ -306,9 +307,9 @@ template <bool OUTSIDE, int CLS> void launch_one(pmm_handle *h, KParams P, const
     const int resident = h->n_sms * (OUTSIDE ? h->ctas_out[CLS] : h->ctas_in[CLS]);
     int per_tile = std::max(1, resident / std::max(P.ntiles, 1));
     per_tile = std::min(per_tile, cnt);
-    P.stages = OUTSIDE ? h->stages_out : h->stages_in;
+    P.stages = OUTSIDE ? h->stages_out[CLS] : h->stages_in[CLS];
     dim3 grid((unsigned)per_tile, (unsigned)P.ntiles);
-    pmm_level<OUTSIDE, CLS><<<grid, NTHREADS, OUTSIDE ? h->smem_out : h->smem_in, h->stream>>>(P, d_items, cnt);
+    pmm_level<OUTSIDE, CLS><<<grid, NTHREADS, OUTSIDE ? h->smem_out[CLS] : h->smem_in[CLS], h->stream>>>(P, d_items, cnt);
     h->launches++;
 }
 
@@ -426,7 +427,7 @@ int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const
     for (int i = 0; i < nnz; i++)
         if (!(h->prior[i] >= 0.0)) { h->err = "prior entries must be non-negative numbers"; return bail(1); }
     h->W = (int64_t)nnz + 2 * (int64_t)n_sites;
-    h->TS = env_int("PMM_TILE_SLOTS", 1024);
+    h->TS = env_int("PMM_TILE_SLOTS", 1920);
     h->TS = std::max((h->TS + 1) & ~1, (maxlen + 1) & ~1);
     if (h->TS > 8192) { h->err = "an alphabet is too large for one shared-memory tile (limit ~8000 states)"; return bail(1); }
     // validate codes against the alphabets, then upload
@@ -717,6 +718,8 @@ int pmm_get_info(const pmm_handle *h, pmm_info *info) {
     if (!h || !info) return 1;
     info->n_nodes = h->n; info->n_leaves = h->n_leaves; info->n_sites = h->K;
     info->slots_per_node = h->W; info->row_stride = h->maxWp;
+    info->padded_slots_per_node = 0;
+    for (auto &c : h->chunks) info->padded_slots_per_node += c.Wp;
     info->n_chunks = (int64_t)h->chunks.size(); info->n_tiles = h->max_tiles; info->tile_slots = h->TS;
     info->inside_levels = (int64_t)h->in_ptr.size() - 1; info->outside_levels = (int64_t)h->out_ptr.size() - 1;
     info->device_bytes = (int64_t)h->device_bytes; info->kernel_launches = h->launches;

@@ -97,9 +97,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -179,8 +179,10 @@ struct Desc { int u, v, w, cls; double4 cv, cw; };   // 80 bytes (stage reserves
 // node classes: both children internal / v internal, w leaf / both leaves / decided per item
 enum { CLS_II = 0, CLS_IL = 1, CLS_LL = 2, CLS_ANY = 3 };
 
-template <bool OUTSIDE> struct Plan {
-    static constexpr int NARR = OUTSIDE ? 3 : 2;
+template <bool OUTSIDE, int CLS> struct Plan {
+    // row tiles a stage holds: the internal children's X rows (+ the node's O row for the outside pass)
+    static constexpr int NINT = (CLS == CLS_II || CLS == CLS_ANY) ? 2 : (CLS == CLS_IL ? 1 : 0);
+    static constexpr int NARR = NINT + (OUTSIDE ? 1 : 0);
     __host__ __device__ static size_t stage_bytes(int TS, int MS) {
         size_t b = (size_t)NARR * TS * 8;
         if (OUTSIDE) b += (size_t)MS * 8 + (size_t)NCW * 12 * 8;
@@ -188,9 +190,9 @@ template <bool OUTSIDE> struct Plan {
         return (b + 127) & ~(size_t)127;
     }
     __host__ __device__ static size_t fixed_bytes(int TS, int MS) {
-        return (size_t)TS * 8 + (size_t)MS * 8 + (size_t)MS * 8 + 2 * MAX_STAGES * 8 + 16;
+        return ((size_t)TS * 8 + (size_t)MS * 8 + (size_t)MS * 8 + 2 * MAX_STAGES * 8 + 127) & ~(size_t)127;
     }
-    __host__ __device__ static size_t total_bytes(int TS, int MS, int S) { return fixed_bytes(TS, MS) + S * stage_bytes(TS, MS) + 256; }
+    __host__ __device__ static size_t total_bytes(int TS, int MS, int S) { return fixed_bytes(TS, MS) + S * stage_bytes(TS, MS); }
 };
 
 // ---------------------------------------------------------------- per-site work: inside
@@ -201,9 +203,11 @@ __device__ __forceinline__ void inside_site(const double *__restrict__ A, const 
                                             const double *__restrict__ sq, double qsum, int off, int len, int codeA_or_cum,
                                             int codeB_or_cum, const double4 cv, const double4 cw, double phi,
                                             double *__restrict__ gout, int *__restrict__ iexp_out, int gl, unsigned gm) {
+    __builtin_assume(__isShared(A)); __builtin_assume(__isShared(B)); __builtin_assume(__isShared(sq));
     double sv = 0.0, sw = 0.0;
     unsigned mv = 0u, mw = 0u;
     if (VI || WI) {
+#pragma unroll 2
         for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
             const double2 q2 = ld2(sq + off + i);
             if (VI) {
@@ -261,6 +265,7 @@ __device__ __forceinline__ void inside_site(const double *__restrict__ A, const 
         Ebw = cw.z * L.xb + cw.w * L.xm;
         dEw = cw.z * L.dx;
     }
+#pragma unroll 2
     for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
         double2 ev, ew;
         if (VI) { const double2 a = ld2(A + off + i); ev.x = fma(csv, a.x, gmv); ev.y = fma(csv, a.y, gmv); }
@@ -288,8 +293,10 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
                                              const double4 cw, double phi, double *__restrict__ goutv,
                                              double *__restrict__ goutw, int *__restrict__ dexp_v, int *__restrict__ dexp_w,
                                              double *__restrict__ post, int gl, unsigned gm, double (&acc)[11]) {
+    __builtin_assume(__isShared(A)); __builtin_assume(__isShared(B)); __builtin_assume(__isShared(C)); __builtin_assume(__isShared(sq));
     double sv = 0, sw = 0, so = 0, sov = 0, sow = 0, sovw = 0;
     unsigned mv = 0u, mw = 0u, mo = 0u;
+#pragma unroll 2
     for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
         const double2 o = ld2(C + off + i);
         so += o.x; so += o.y;
@@ -408,6 +415,7 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
         const double csv = cv.z * scv, csw = cw.z * scw;
         const double Ebv = cv.z * xbv + gmv, dEv = cv.z * dxv;     // leaf forms of E^v, E^w
         const double Ebw = cw.z * xbw + gmw, dEw = cw.z * dxw;
+#pragma unroll 2
         for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
             const double2 o = ld2(C + off + i);
             const double2 q2 = ld2(sq + off + i);
@@ -429,7 +437,7 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
 template <bool OUTSIDE, int CLS>
 __global__ void __launch_bounds__(NTHREADS, 2)
 pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
-    using PL = Plan<OUTSIDE>;
+    using PL = Plan<OUTSIDE, CLS>;
     constexpr int NARR = PL::NARR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int TS = P.TS, MS = P.max_tile_sites, S = P.stages;
@@ -438,9 +446,8 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     int2 *s_ent = reinterpret_cast<int2 *>(s_qsum + MS);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_ent + MS);
     uint64_t *done = full + MAX_STAGES;
-    unsigned char *stage0 = reinterpret_cast<unsigned char *>(done + MAX_STAGES) + 16;
-    stage0 = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
-    const size_t stage_bytes = PL::stage_bytes(TS, MS);
+    unsigned char *stage0 = smem_raw + PL::fixed_bytes(TS, MS);       // pure pointer arithmetic keeps the
+    const size_t stage_bytes = PL::stage_bytes(TS, MS);               // shared address space visible to the compiler
 
     const int t = blockIdx.y;
     const int s0 = P.tile_site[t], nsites = P.tile_site[t + 1] - s0;
@@ -509,10 +516,11 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
                 mbar_expect_tx_arrive(&full[s], tx);                               // release: orders the id stores above
                 bulk_load(&dsc->cv, P.bc + (size_t)4 * v, 32u, &full[s]);
                 bulk_load(&dsc->cw, P.bc + (size_t)4 * w, 32u, &full[s]);
-                if (vi) bulk_load(rows, P.X + (size_t)(v - N) * P.Wp + off0, rb, &full[s]);
-                if (wi) bulk_load(rows + TS, P.X + (size_t)(w - N) * P.Wp + off0, rb, &full[s]);
+                double *rowA = rows + (OUTSIDE ? TS : 0), *rowB = rowA + TS;
+                if (vi) bulk_load(rowA, P.X + (size_t)(v - N) * P.Wp + off0, rb, &full[s]);
+                if (wi) bulk_load(rowB, P.X + (size_t)(w - N) * P.Wp + off0, rb, &full[s]);
                 if (OUTSIDE) {
-                    bulk_load(rows + 2 * TS, P.O + (size_t)(u - N) * P.Wp + off0, rb, &full[s]);
+                    bulk_load(rows, P.O + (size_t)(u - N) * P.Wp + off0, rb, &full[s]);
                     bulk_load(mD, P.dexp + (size_t)(u - N) * P.Kp + ps0, ib, &full[s]);
                     bulk_load(f_invL(st), P.rootInvL + (size_t)it.w * P.Kp + ps0, db, &full[s]);
                     if (!vi) bulk_load(mA, P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
@@ -548,7 +556,7 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
         const int u = dsc->u, v = dsc->v, w = dsc->w;
         const int cls = (CLS == CLS_ANY) ? dsc->cls : CLS;
         const double4 cv = dsc->cv, cw = dsc->cw;
-        const double *A = f_rows(st), *B = A + TS, *C = B + TS;
+        const double *C = f_rows(st), *A = C + (OUTSIDE ? TS : 0), *B = A + TS;
         const int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
         if (!OUTSIDE) {
             double *gout = P.X + (size_t)(u - N) * P.Wp + off0;
