@@ -752,59 +752,72 @@ __global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsig
     d[v] = res;
 }
 
-// single CTA: phi closed form and the nu bisection with deterministic block reductions
+// single CTA: phi closed form and the 1-D problem in nu.
+// g'(nu) = -sum (S0+S1+S3) d + sum (S2+S4) d / expm1(nu d) is convex and strictly decreasing on (0,1],
+// +inf at 0: safeguarded Newton (bracket kept, bisection fallback) reaches the root to the last
+// bits in ~10 evaluations; each evaluation is one deterministic block reduction over the branches.
 __global__ void __launch_bounds__(1024) pmm_mstep_globals(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask,
                                                            int n, const double *__restrict__ Snorm, const double *__restrict__ d,
                                                            double *__restrict__ params, double R, double cells_times_sites,
                                                            int optimize_nu, int optimize_phi) {
-    __shared__ double sh[1024];
-    __shared__ double bcast;
+    __shared__ double sh[1024], sh2[1024];
     const int tid = threadIdx.x;
-    auto block_sum = [&](double x) -> double {
-        sh[tid] = x;
+    // f = sum w d / expm1(x d),  fp = d f / d x   (w = S2 + S4)
+    auto eval = [&](double x, double &f, double &fp) {
+        double a = 0.0, b = 0.0;
+        for (int v = tid; v < n; v += 1024)
+            if (free_mask[v]) {
+                const double dv = d[v], w = Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
+                const double em = expm1(x * dv);
+                const double r = dv / em;
+                a += w * r;
+                b -= w * r * r * (em + 1.0);
+            }
+        sh[tid] = a; sh2[tid] = b;
         __syncthreads();
         for (int o = 512; o > 0; o >>= 1) {
-            if (tid < o) sh[tid] += sh[tid + o];
+            if (tid < o) { sh[tid] += sh[tid + o]; sh2[tid] += sh2[tid + o]; }
             __syncthreads();
         }
-        double r = sh[0];
+        f = sh[0]; fp = sh2[0];
         __syncthreads();
-        return r;
     };
     if (optimize_nu) {
-        double lin_p = 0.0;
+        double lin_p = 0.0, w_p = 0.0;
         for (int v = tid; v < n; v += 1024)
-            if (free_mask[v]) lin_p += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * d[v];
-        const double lin = block_sum(lin_p);
-        auto grad = [&](double x) -> double {
-            double g = 0.0;
-            for (int v = tid; v < n; v += 1024)
-                if (free_mask[v]) g += (Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4]) * d[v] / expm1(x * d[v]);
-            return block_sum(g) - lin;
-        };
-        double lo, hi = 1.0, res;
-        if (grad(hi) >= 0.0) res = 1.0;
-        else {
-            lo = 0.5;
-            bool zero = false;
-            for (;;) {
-                if (grad(lo) > 0.0) break;
-                hi = lo; lo *= 0.5;
-                if (lo < 1e-300) { zero = true; break; }
+            if (free_mask[v]) {
+                lin_p += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * d[v];
+                w_p += Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
             }
-            if (zero) res = 0.0;
-            else {
-                for (int it = 0; it < 200; it++) {
-                    double mid = 0.5 * (lo + hi);
-                    if (mid <= lo || mid >= hi) break;
-                    if (grad(mid) > 0.0) lo = mid; else hi = mid;
-                }
-                res = 0.5 * (lo + hi);
+        sh[tid] = lin_p; sh2[tid] = w_p;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if (tid < o) { sh[tid] += sh[tid + o]; sh2[tid] += sh2[tid + o]; }
+            __syncthreads();
+        }
+        const double lin = sh[0], wsum = sh2[0];
+        __syncthreads();
+        double f, fp, res;
+        eval(1.0, f, fp);
+        if (f - lin >= 0.0 || !(lin > 0.0)) res = 1.0;                   // upper bound active (EM_solver.py:402)
+        else {
+            double lo = 0.0, hi = 1.0;                                    // g'(lo) > 0 > g'(hi)
+            double x = fmin(0.5, wsum / lin);                             // 1/expm1(t) < 1/t  =>  root < wsum/lin
+            res = x;
+            for (int it = 0; it < 100; it++) {
+                eval(x, f, fp);
+                const double g = f - lin;
+                if (g > 0.0) lo = x; else hi = x;
+                res = x;
+                if (g == 0.0) break;
+                double xn = x - g / fp;
+                if (!(xn > lo && xn < hi)) xn = (lo > 0.0) ? 0.5 * (lo + hi) : 0.5 * hi;
+                if (fabs(xn - x) <= 4e-16 * x) { res = xn; break; }
+                if (xn < 1e-300) { res = 0.0; break; }
+                x = xn;
             }
         }
-        if (tid == 0) bcast = res;
-        __syncthreads();
-        if (tid == 0) params[0] = bcast;
+        if (tid == 0) params[0] = res;
     }
     if (optimize_phi && tid == 0) {
         const double Rt = stats[(size_t)n * 5];
