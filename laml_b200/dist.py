@@ -96,7 +96,7 @@ class ShardedEngine:
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
         with self._on_stream():
-            st = self.stats.cpu().numpy()
+            st = np.array(self.stats.cpu().numpy(), copy=True)
         n5 = 5 * self.n_nodes
         return {"S": st[:n5].reshape(self.n_nodes, 5), "Rtilde": float(st[n5]), "llh": float(st[n5 + 1])}
 

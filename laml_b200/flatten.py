@@ -48,20 +48,27 @@ class FlatForest:
                          for nd in self.nodes], dtype=np.float64)
 
 
-def flatten_trees(trees: Sequence) -> FlatForest:
+def flatten_trees(trees: Sequence, leaf_key=None) -> FlatForest:
     """Flatten tree objects (anything with ``traverse_postorder`` and nodes
     carrying ``children``/``parent``) into a :class:`FlatForest`.  All trees
-    must be binary (the solver binarises first, ``EM_solver.py:26-43``)."""
+    must be binary (the solver binarises first, ``EM_solver.py:26-43``).
+    ``leaf_key`` (label -> sortable) fixes the order of the leaf ids inside each
+    tree independently of the topology, so an engine that already holds the
+    character matrix in that order only needs ``set_tree`` for a new topology."""
     leaves, internals = [], []
     for tree in trees:
+        tree_leaves = []
         for nd in tree.traverse_postorder():
             k = len(nd.children)
             if k == 0:
-                leaves.append(nd)
+                tree_leaves.append(nd)
             elif k == 2:
                 internals.append(nd)
             else:
                 raise ValueError("PMM engine needs binary trees; found a node with %d children" % k)
+        if leaf_key is not None:
+            tree_leaves.sort(key=lambda nd: leaf_key[nd.label])
+        leaves.extend(tree_leaves)
     nodes = leaves + internals
     ids = {id(nd): i for i, nd in enumerate(nodes)}
     n = len(nodes)

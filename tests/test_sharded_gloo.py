@@ -1,0 +1,98 @@
+"""World-size-2 `gloo` test of the site-sharded E-step / EM host logic
+(laml_b200/dist.py) on CPU.  The CUDA engine cannot run here, so each rank
+drives ShardedEngine with a stand-in that answers the device-resident subset of
+the Engine API from the oracle; what is under test is the partitioning, the
+all-reduce of [S | Rtilde | llh] and the replicated M-step loop."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+class OracleBackedEngine:
+    """test double for laml_b200.capi.Engine (device-resident calls only)"""
+
+    def __init__(self, forest, codes, qptr, qval, n_cells):
+        from oracle.pmm_oracle import OracleProblem
+        N = forest.n_leaves
+        self.orc = OracleProblem(forest, np.arange(N, dtype=np.int32), codes, qptr, qval)
+        self.n_nodes, self.device, self.K_total = forest.n_nodes, 0, codes.shape[1]
+        self.stats = torch.zeros(5 * self.n_nodes + 2, dtype=torch.float64)
+        self.n_cells = n_cells
+
+    def set_total_sites(self, k):
+        self.K_total = k
+
+    def upload_params(self, d, nu, phi):
+        self.d, self.nu, self.phi = np.array(d, np.float64), nu, phi
+
+    def download_params(self):
+        return self.d, self.nu, self.phi
+
+    def estep_dev(self):
+        out = self.orc.estep(self.d, self.nu, self.phi)
+        self.stats[: 5 * self.n_nodes] = torch.from_numpy(out["S"].T.reshape(-1).copy())
+        self.stats[5 * self.n_nodes] = out["Rtilde"]
+        self.stats[5 * self.n_nodes + 1] = out["llh"]
+
+    def mstep_dev(self, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
+                  eps_s=1e-6, eps_nu=1e-5):
+        from oracle.pmm_oracle import lib
+        n = self.n_nodes
+        S = self.stats[: 5 * n].numpy().reshape(n, 5).T.copy()
+        fm = np.ones(n, np.uint8)
+        Sn = np.zeros_like(S)
+        phi_star = lib().oracle_mstep_stats(n, self.K_total, n_cells, S, fm, R, float(self.stats[5 * n]), eps_s, Sn)
+        d = self.d.copy()
+        lib().oracle_mstep_brlen(n, Sn, fm, self.nu, eps_nu, dmin, dmax, d)
+        self.nu = lib().oracle_mstep_nu(n, Sn, fm, d)
+        self.d, self.phi = d, phi_star
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laml_b200.dist import ShardedEngine, partition_sites
+    from laml_b200.synth import make_workload
+    w = make_workload(60, 18, 2, 12, 0.2, 0.15, seed=21)
+    lo, hi = partition_sites(w.qptr, world)[rank]
+    qptr = (w.qptr[lo:hi + 1] - w.qptr[lo]).astype(np.int32)
+    qval = w.qval[w.qptr[lo]:w.qptr[hi]]
+    eng = OracleBackedEngine(w.forest, w.codes[:, lo:hi], qptr, qval, 60)
+    sh = ShardedEngine(eng, 18, stats_tensor=eng.stats)
+    R = float((w.codes != -1).sum())
+    est = sh.estep(w.d, w.nu, w.phi)
+    em = sh.em(np.maximum(w.d, 0.01), 0.2, 0.15, R, 60, max_iter=6)
+    if rank == 0:
+        ret["S"], ret["llh"], ret["Rt"] = est["S"].copy(), est["llh"], est["Rtilde"]
+        ret["em"] = (em["nllh"], em["nu"], em["phi"], em["d"].copy(), em["iters"])
+    dist.destroy_process_group()
+
+
+def test_sharded_matches_unsharded():
+    from laml_b200.synth import make_workload
+    from oracle.pmm_oracle import OracleProblem
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    w = make_workload(60, 18, 2, 12, 0.2, 0.15, seed=21)
+    orc = OracleProblem(w.forest, np.arange(60, dtype=np.int32), w.codes, w.qptr, w.qval)
+    ref = orc.estep(w.d, w.nu, w.phi)
+    np.testing.assert_allclose(ret["S"], ref["S"].T, rtol=1e-11, atol=1e-12)
+    assert abs(ret["llh"] - ref["llh"]) < 1e-9 and abs(ret["Rt"] - ref["Rtilde"]) < 1e-10
+    ref_em = orc.em(np.maximum(w.d, 0.01), 0.2, 0.15, max_iter=6)
+    nllh, nu, phi, d, iters = ret["em"]
+    assert iters == ref_em["iters"] or iters == 7            # loop exits at max_iter + 1 like the reference
+    assert abs(nllh - ref_em["nllh"]) <= 1e-9 * ref_em["nllh"]
+    np.testing.assert_allclose(d, ref_em["d"], rtol=1e-9, atol=1e-11)
+    assert abs(nu - ref_em["nu"]) < 1e-10 and abs(phi - ref_em["phi"]) < 1e-12
