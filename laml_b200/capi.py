@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmm_b200.so")
+LIB_PATH = os.environ.get("PMM_LIB") or os.path.join(_HERE, "libpmm_b200.so")   # PMM_LIB: tuning builds only
 
 #: every symbol ``include/pmm_b200.h`` declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [

@@ -42,7 +42,10 @@ namespace pmm {
 
 constexpr int NCW = 7;                    // consumer warps per CTA
 constexpr int NTHREADS = (NCW + 1) * 32;  // + 1 producer warp
-constexpr int G = 8;                      // lanes per site group
+#ifndef PMM_G
+#define PMM_G 4
+#endif
+constexpr int G = PMM_G;                  // lanes per site group
 constexpr int NG = NCW * (32 / G);        // site groups per CTA
 constexpr int MAX_STAGES = 4;
 
