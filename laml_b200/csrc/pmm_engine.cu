@@ -46,6 +46,7 @@ struct pmm_handle {
     int TS = 1024;
     int stages_in[4] = {2, 2, 2, 2}, stages_out[4] = {2, 2, 2, 2}, ctas_in[4] = {1, 1, 1, 1}, ctas_out[4] = {1, 1, 1, 1}, n_sms = 148;
     size_t smem_in[4] = {0, 0, 0, 0}, smem_out[4] = {0, 0, 0, 0};
+    int ctas_post = 1;
     size_t budget = 0;
     std::vector<Chunk> chunks;
     int maxWp = 0, maxK = 0, maxKp = 0, max_tiles = 0, max_tile_sites = 0;
@@ -57,10 +58,11 @@ struct pmm_handle {
     int4 *d_in_items = nullptr, *d_out_items = nullptr;
     std::vector<int> in_ptr, out_ptr;              // level -> first item
     std::vector<int> in_cls, out_cls;              // 3 class counts per level (II, IL, LL)
-    int spec_threshold = 1 << 30;
+    int spec_threshold = 2000;
     // state
     double *d_X = nullptr, *d_O = nullptr;
-    int *d_iexp = nullptr, *d_dexp = nullptr;
+    int *d_iexp = nullptr, *d_dexp = nullptr, *d_eX = nullptr, *d_eO = nullptr;
+    double *d_sqX = nullptr;
     double *d_rootInvL = nullptr, *d_root_site_llh = nullptr;
     double *d_Spart = nullptr, *d_Rpart = nullptr, *d_Rnode = nullptr;
     double *d_site_llh = nullptr;   // [K]
@@ -119,7 +121,7 @@ void free_chunks(pmm_handle *h) {
 void free_tree_state(pmm_handle *h) {
     dfree(h->d_parent); dfree(h->d_left); dfree(h->d_right); dfree(h->d_root_index); dfree(h->d_roots);
     dfree(h->d_in_items); dfree(h->d_out_items);
-    dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp);
+    dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp); dfree(h->d_eX); dfree(h->d_eO); dfree(h->d_sqX);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free);
@@ -212,7 +214,7 @@ int plan_chunks(pmm_handle *h) {
     free_chunks(h);
     const int K = h->K;
     const double per_slot = 16.0 * std::max(h->n_int, 1);            // X + O rows, bytes per slot column
-    const double per_site = 8.0 * std::max(h->n_int, 1);             // iexp + oexp
+    const double per_site = 24.0 * std::max(h->n_int, 1);            // iexp, dexp, eX, eO (int32) + sqX (fp64)
     double total = per_slot * (double)(h->W + 2 * K / std::max(h->TS / 64, 1)) + per_site * K;
     size_t budget = h->budget;
     if (budget == 0) {
@@ -256,7 +258,7 @@ KParams make_params(pmm_handle *h, const Chunk &c, bool with_post) {
     P.left = h->d_left; P.right = h->d_right; P.parent = h->d_parent; P.root_index = h->d_root_index;
     P.n_leaves = h->n_leaves; P.n_nodes = h->n;
     P.params = h->d_params; P.bc = h->d_bc;
-    P.X = h->d_X; P.O = h->d_O; P.iexp = h->d_iexp; P.dexp = h->d_dexp;
+    P.X = h->d_X; P.O = h->d_O; P.iexp = h->d_iexp; P.dexp = h->d_dexp; P.eX = h->d_eX; P.eO = h->d_eO; P.sqX = h->d_sqX;
     P.rootInvL = h->d_rootInvL; P.root_site_llh = h->d_root_site_llh;
     P.Spart = h->d_Spart; P.Rpart = h->d_Rpart;
     P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
@@ -297,7 +299,10 @@ int configure_kernels(pmm_handle *h) {
     SETUP(false, CLS_II, 0) SETUP(false, CLS_IL, 1) SETUP(false, CLS_LL, 2) SETUP(false, CLS_ANY, 3)
     SETUP(true, CLS_II, 0) SETUP(true, CLS_IL, 1) SETUP(true, CLS_LL, 2) SETUP(true, CLS_ANY, 3)
 #undef SETUP
-    h->spec_threshold = env_int("PMM_SPEC_THRESHOLD", 1 << 30);   // measured: one class-agnostic launch per level wins
+    CK(cudaFuncSetAttribute(pmm_level<true, CLS_ANY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out[CLS_ANY]));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->ctas_post, pmm_level<true, CLS_ANY, true>, NTHREADS, h->smem_out[CLS_ANY]));
+    if (h->ctas_post < 1) return fail(h, "posterior kernel cannot be resident");
+    h->spec_threshold = env_int("PMM_SPEC_THRESHOLD", 2000);   // levels with fewer nodes take one class-agnostic launch
     return 0;
 }
 
@@ -317,6 +322,18 @@ template <bool OUTSIDE, int CLS> void launch_one(pmm_handle *h, KParams P, const
 // sorted by class), small ones a single launch that reads the class per item
 template <bool OUTSIDE> void launch_level(pmm_handle *h, const KParams &P, const int4 *d_items, const int *cls_cnt) {
     const int cnt = cls_cnt[0] + cls_cnt[1] + cls_cnt[2];
+    if (OUTSIDE && P.post0) {
+        // annotation path (runner.py:391-435): per-(node,site) posteriors; one class-agnostic launch
+        if (cnt <= 0) return;
+        KParams Q = P;
+        Q.stages = h->stages_out[CLS_ANY];
+        const int resident = h->n_sms * h->ctas_post;
+        int per_tile = std::min(std::max(1, resident / std::max(P.ntiles, 1)), cnt);
+        dim3 grid((unsigned)per_tile, (unsigned)P.ntiles);
+        pmm_level<true, CLS_ANY, true><<<grid, NTHREADS, h->smem_out[CLS_ANY], h->stream>>>(Q, d_items, cnt);
+        h->launches++;
+        return;
+    }
     if (cnt < h->spec_threshold) { launch_one<OUTSIDE, CLS_ANY>(h, P, d_items, cnt); return; }
     launch_one<OUTSIDE, CLS_II>(h, P, d_items, cls_cnt[0]);
     launch_one<OUTSIDE, CLS_IL>(h, P, d_items + cls_cnt[0], cls_cnt[1]);
@@ -567,7 +584,8 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     if (configure_kernels(h)) return 1;
     const size_t rows = (size_t)h->n_int;
     if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxKp) ||
-        dalloc(h, &h->d_dexp, rows * h->maxKp) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxKp) ||
+        dalloc(h, &h->d_dexp, rows * h->maxKp) || dalloc(h, &h->d_eX, rows * h->maxKp) || dalloc(h, &h->d_eO, rows * h->maxKp) ||
+        dalloc(h, &h->d_sqX, rows * h->maxKp) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxKp) ||
         dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
         dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
         return 1;

@@ -15,15 +15,20 @@
 // Pad slots need no masking: their prior q is 0 and their outside value is 0 at
 // the root and stays 0 down the tree, so they drop out of every reduction.
 //
-// Scaling: rows are stored UNnormalised; whoever reads a row finds the largest
-// exponent among a site's slots (integer max over the high words -- all values
-// are non-negative) and multiplies by the exact power of two that brings the
-// maximum into [1,2).  Accumulated exponents are int32 per (internal node, site):
-//   iexp[u][s] : x_true[u] = X[u] * 2^iexp
-//   dexp[u][s] : D_u = oexp[u] + iexp[u] - Le  (Le = exponent of the site likelihood),
-//                which obeys D_child = D_u + e_out(u) - e_in(child), D_root = -e_in(root),
-//                so the outside pass never needs iexp again.
-// Power-of-two scaling is exact: mantissas are those of an unscaled computation.
+// Scaling: rows are stored UNnormalised, and every row travels with a per-site SUMMARY that its
+// writer computes in the same sweep that produces the row:
+//   eX[u][s]  : exponent e of the largest slot of X[u] at site s (integer max over the high
+//               words -- all values are non-negative); a reader multiplies by the exact power of
+//               two 2^-e, which brings the maximum into [1,2)
+//   sqX[u][s] : sum_a q_a X[u]_a (raw) -- the one reduction a parent needs before it can start
+//   iexp[u][s]: accumulated exponent: x_true[u] = (X[u] 2^-e) 2^iexp
+//   eO[u][s]  : exponent of the largest slot of O[u] at site s
+//   dexp[u][s]: D_u = oexp[u] + iexp[u] - Le  (Le = exponent of the site likelihood), which obeys
+//               D_child = D_u + eO(u) - eX(child), D_root = -eX(root)
+// Because the summaries exist, both level kernels make ONE pass over a site's slots: every
+// coefficient of the output is known before the sweep starts, and the sweep accumulates what the
+// next reader (and the expected counts) need.  Power-of-two scaling is exact: mantissas are those
+// of an unscaled computation.
 //
 // Execution: one launch per tree level.  grid = (P, ntiles); CTA (p, t) is
 // PERSISTENT over the level's nodes p, p+P, ... for tile t.  Warp NCW is the
@@ -72,9 +77,10 @@ struct KParams {
     const double *bc;            // [n][4] = a, b, c, g per branch
     // state
     double *X, *O;               // [n_int][Wp] inside / outside rows
-    int *iexp, *dexp;            // [n_int][Kp]   (padded site index space: every tile's sites
-    double *rootInvL;            // [n_roots][Kp]  start at a multiple of 4, so a tile's segment of
-    double *root_site_llh;       // [n_roots][Kp]  any of these arrays is one aligned bulk copy)
+    int *iexp, *dexp, *eX, *eO;  // [n_int][Kp]   (padded site index space: every tile's sites
+    double *sqX;                 // [n_int][Kp]    start at a multiple of 4, so a tile's segment of
+    double *rootInvL;            // [n_roots][Kp]  any of these arrays is one aligned bulk copy)
+    double *root_site_llh;       // [n_roots][K]
     double *Spart;               // [ntiles][n][5]
     double *Rpart;               // [ntiles][n_int]
     double *post0, *post1;       // optional [n][K_total] log posteriors (annotation path), or null
@@ -175,8 +181,8 @@ __global__ void pmm_branch_consts(const double *__restrict__ d, const double *__
 
 // ---------------------------------------------------------------- shared-memory plan
 // [ q tile : TS doubles ][ qsum : MS doubles ][ ent : MS int2 ][ barriers ][ stage 0 ][ stage 1 ] ...
-// stage = [ NARR row tiles : NARR*TS doubles ][ invL : MS doubles (outside) ][ red : NCW*12 doubles (outside) ]
-//         [ mA, mB, mD : 3*MS ints ][ desc : 32 ints ]
+// stage = [ NARR row tiles : NARR*TS doubles ][ dA, dB, dL : 3*MS doubles ][ red : NCW*12 doubles (outside) ]
+//         [ mA, mB, mC, mD : 4*MS ints ][ desc : 32 ints ]
 // MS = max sites per tile, rounded up to a multiple of 4.
 struct Desc { int u, v, w, cls; double4 cv, cw; };   // 80 bytes (stage reserves 128); cv/cw arrive by TMA
 // node classes: both children internal / v internal, w leaf / both leaves / decided per item
@@ -188,8 +194,9 @@ template <bool OUTSIDE, int CLS> struct Plan {
     static constexpr int NARR = NINT + (OUTSIDE ? 1 : 0);
     __host__ __device__ static size_t stage_bytes(int TS, int MS) {
         size_t b = (size_t)NARR * TS * 8;
-        if (OUTSIDE) b += (size_t)MS * 8 + (size_t)NCW * 12 * 8;
-        b += (size_t)3 * MS * 4 + 32 * 4;
+        b += (size_t)3 * MS * 8;                       // fp64 metadata: sq_v, sq_w, 1/L
+        if (OUTSIDE) b += (size_t)(NCW + NG) * 12 * 8; // per-warp and per-group partial counts
+        b += (size_t)4 * MS * 4 + 32 * 4;              // int32 metadata x4, item descriptor
         return (b + 127) & ~(size_t)127;
     }
     __host__ __device__ static size_t fixed_bytes(int TS, int MS) {
@@ -201,45 +208,26 @@ template <bool OUTSIDE, int CLS> struct Plan {
 // ---------------------------------------------------------------- per-site work: inside
 // x_u = E_v .* E_w with E = child message (SURVEY 3.5 "edge transfer"):
 //   E_0 = a x_0 + b sum(q x) + g x_m,  E_alpha = c x_alpha + g x_m,  E_m = x_m.
+// iA/iB: leaf code, or eX of an internal child; cumA/cumB, sqA/sqB: its iexp and sqX.
 template <bool VI, bool WI>
 __device__ __forceinline__ void inside_site(const double *__restrict__ A, const double *__restrict__ B,
-                                            const double *__restrict__ sq, double qsum, int off, int len, int codeA_or_cum,
-                                            int codeB_or_cum, const double4 cv, const double4 cw, double phi,
-                                            double *__restrict__ gout, int *__restrict__ iexp_out, int gl, unsigned gm) {
+                                            const double *__restrict__ sq, double qsum, int off, int len, int iA, int iB,
+                                            int cumA, int cumB, double sqA, double sqB, const double4 cv, const double4 cw,
+                                            double phi, double *__restrict__ gout, int *__restrict__ eX_out,
+                                            int *__restrict__ iexp_out, double *__restrict__ sqX_out, int gl, unsigned gm) {
     __builtin_assume(__isShared(A)); __builtin_assume(__isShared(B)); __builtin_assume(__isShared(sq));
-    double sv = 0.0, sw = 0.0;
-    unsigned mv = 0u, mw = 0u;
-    if (VI || WI) {
-#pragma unroll 2
-        for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
-            const double2 q2 = ld2(sq + off + i);
-            if (VI) {
-                const double2 a = ld2(A + off + i);
-                sv = fma(q2.x, a.x, sv); sv = fma(q2.y, a.y, sv);
-                mv = max(mv, max(hi32(a.x), hi32(a.y)));
-            }
-            if (WI) {
-                const double2 b = ld2(B + off + i);
-                sw = fma(q2.x, b.x, sw); sw = fma(q2.y, b.y, sw);
-                mw = max(mw, max(hi32(b.x), hi32(b.y)));
-            }
-        }
-    }
-    // child v: message constants  E0 (k0), Em, and E_alpha = cs * x + gmc  (internal)  or  Eb + [hot] dE (leaf)
+    // message constants: E0 (k0), Em, and E_alpha = cs * x + gmc (internal)  or  Eb + [hot] dE (leaf)
     double k0v, Emv, csv = 0.0, gmv = 0.0, Ebv = 0.0, dEv = 0.0; int cumv = 0, hv = -1;
     if (VI) {
         const double2 h = ld2(A + off);
-        sv = gsum(sv, gm);
-        mv = gmax(max(mv, max(hi32(h.x), hi32(h.y))), gm);
-        const int e = expo_of_hi(mv);
-        const double sc = pow2i(-e);
+        const double sc = pow2i(-iA);
         Emv = h.y * sc;
         gmv = cv.w * Emv;
-        k0v = (cv.x * h.x + cv.y * sv) * sc + gmv;
+        k0v = (cv.x * h.x + cv.y * sqA) * sc + gmv;
         csv = cv.z * sc;
-        cumv = codeA_or_cum + e;
+        cumv = cumA;
     } else {
-        const Leaf L = leaf_of(codeA_or_cum, phi);
+        const Leaf L = leaf_of(iA, phi);
         hv = L.hot;
         const double qh = (hv >= 0) ? sq[off + hv] : 0.0;
         Emv = L.xm;
@@ -250,17 +238,14 @@ __device__ __forceinline__ void inside_site(const double *__restrict__ A, const 
     double k0w, Emw, csw = 0.0, gmw = 0.0, Ebw = 0.0, dEw = 0.0; int cumw = 0, hw = -1;
     if (WI) {
         const double2 h = ld2(B + off);
-        sw = gsum(sw, gm);
-        mw = gmax(max(mw, max(hi32(h.x), hi32(h.y))), gm);
-        const int e = expo_of_hi(mw);
-        const double sc = pow2i(-e);
+        const double sc = pow2i(-iB);
         Emw = h.y * sc;
         gmw = cw.w * Emw;
-        k0w = (cw.x * h.x + cw.y * sw) * sc + gmw;
+        k0w = (cw.x * h.x + cw.y * sqB) * sc + gmw;
         csw = cw.z * sc;
-        cumw = codeB_or_cum + e;
+        cumw = cumB;
     } else {
-        const Leaf L = leaf_of(codeB_or_cum, phi);
+        const Leaf L = leaf_of(iB, phi);
         hw = L.hot;
         const double qh = (hw >= 0) ? sq[off + hw] : 0.0;
         Emw = L.xm;
@@ -268,18 +253,31 @@ __device__ __forceinline__ void inside_site(const double *__restrict__ A, const 
         Ebw = cw.z * L.xb + cw.w * L.xm;
         dEw = cw.z * L.dx;
     }
+    // the single sweep: write x_u and accumulate its summary (sum q x_u, exponent of its maximum)
+    double su = 0.0;
+    unsigned mu = 0u;
 #pragma unroll 2
     for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+        const double2 q2 = ld2(sq + off + i);
         double2 ev, ew;
         if (VI) { const double2 a = ld2(A + off + i); ev.x = fma(csv, a.x, gmv); ev.y = fma(csv, a.y, gmv); }
         else { ev.x = Ebv + ((i == hv) ? dEv : 0.0); ev.y = Ebv + ((i + 1 == hv) ? dEv : 0.0); }
         if (WI) { const double2 b = ld2(B + off + i); ew.x = fma(csw, b.x, gmw); ew.y = fma(csw, b.y, gmw); }
         else { ew.x = Ebw + ((i == hw) ? dEw : 0.0); ew.y = Ebw + ((i + 1 == hw) ? dEw : 0.0); }
-        st2(gout + off + i, ev.x * ew.x, ev.y * ew.y);
+        const double x0 = ev.x * ew.x, x1 = ev.y * ew.y;
+        st2(gout + off + i, x0, x1);
+        su = fma(q2.x, x0, su); su = fma(q2.y, x1, su);
+        mu = max(mu, max(hi32(x0), hi32(x1)));
     }
+    const double xu0 = k0v * k0w, xum = Emv * Emw;
+    su = gsum(su, gm);
+    mu = gmax(max(mu, max(hi32(xu0), hi32(xum))), gm);
     if (gl == 0) {
-        st2(gout + off, k0v * k0w, Emv * Emw);
-        *iexp_out = cumv + cumw;
+        const int e = expo_of_hi(mu);
+        st2(gout + off, xu0, xum);
+        *eX_out = e;
+        *iexp_out = cumv + cumw + e;
+        *sqX_out = su;
     }
 }
 
@@ -287,82 +285,100 @@ __device__ __forceinline__ void inside_site(const double *__restrict__ A, const 
 // For node u with children v, w (EM_solver.py:143-300 in full-state form):
 //   T^v = out[u] .* E^w, out[v]_0 = a T_0, out[v]_a = b q_a T_0 + c T_a, out[v]_m = g (T_0 + sum_a T_a) + T_m
 //   S0 = T_0 a x_0 / L, S1 = T_0 b sum(q x) / L, S2 = T_0 g x_m / L, S3 = c sum_a T_a x_a / L, S4 = g x_m sum_a T_a / L.
-// All per-site reductions are taken on the raw rows in ONE pass:
-//   sum q xv, sum q xw, sum o, sum o xv, sum o xw, sum o xv xw   (only those an internal child needs).
-template <bool VI, bool WI>
+// Every coefficient of out[v]_a, out[w]_a is known from the row summaries before the sweep; the
+// sweep writes them and accumulates  sum o, sum o xv, sum o xw, sum o xv xw  for the counts and
+// the silenced slots, plus the exponents of the new rows' maxima.
+// iA/iB: leaf code, or eX of an internal child; sqA/sqB: its sqX; Du, eOu, invL: of node u.
+template <bool VI, bool WI, bool POST>
 __device__ __forceinline__ void outside_site(const double *__restrict__ C, const double *__restrict__ A,
                                              const double *__restrict__ B, const double *__restrict__ sq, double qsum,
-                                             int off, int len, int codeA, int codeB, int Du, double invL, const double4 cv,
-                                             const double4 cw, double phi, double *__restrict__ goutv,
-                                             double *__restrict__ goutw, int *__restrict__ dexp_v, int *__restrict__ dexp_w,
-                                             double *__restrict__ post, int gl, unsigned gm, double (&acc)[11]) {
+                                             int off, int len, int iA, int iB, double sqA, double sqB, int Du, int eOu,
+                                             double invL, const double4 cv, const double4 cw, double phi,
+                                             double *__restrict__ goutv, double *__restrict__ goutw, int *__restrict__ dexp_v,
+                                             int *__restrict__ dexp_w, int *__restrict__ eO_v, int *__restrict__ eO_w,
+                                             double *__restrict__ post, int gl, unsigned gm, double *__restrict__ acc) {
     __builtin_assume(__isShared(A)); __builtin_assume(__isShared(B)); __builtin_assume(__isShared(C)); __builtin_assume(__isShared(sq));
-    double sv = 0, sw = 0, so = 0, sov = 0, sow = 0, sovw = 0;
-    unsigned mv = 0u, mw = 0u, mo = 0u;
-#pragma unroll 2
-    for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
-        const double2 o = ld2(C + off + i);
-        so += o.x; so += o.y;
-        mo = max(mo, max(hi32(o.x), hi32(o.y)));
-        double2 q2 = make_double2(0.0, 0.0);
-        if (VI || WI) q2 = ld2(sq + off + i);
-        double2 oa = make_double2(0.0, 0.0);
-        if (VI) {
-            const double2 a = ld2(A + off + i);
-            sv = fma(q2.x, a.x, sv); sv = fma(q2.y, a.y, sv);
-            oa.x = o.x * a.x; oa.y = o.y * a.y;
-            sov += oa.x; sov += oa.y;
-            mv = max(mv, max(hi32(a.x), hi32(a.y)));
-        }
-        if (WI) {
-            const double2 b = ld2(B + off + i);
-            sw = fma(q2.x, b.x, sw); sw = fma(q2.y, b.y, sw);
-            sow = fma(o.x, b.x, sow); sow = fma(o.y, b.y, sow);
-            if (VI) { sovw = fma(oa.x, b.x, sovw); sovw = fma(oa.y, b.y, sovw); }
-            mw = max(mw, max(hi32(b.x), hi32(b.y)));
-        }
-    }
+    __builtin_assume(__isShared(acc));
     const double2 oh = ld2(C + off);
-    so = gsum(so, gm);
-    mo = gmax(max(mo, max(hi32(oh.x), hi32(oh.y))), gm);
-    const int eo = expo_of_hi(mo);
-    const double sco = pow2i(-eo);
-    const double no0 = oh.x * sco, nom = oh.y * sco, So = so * sco;
-
-    // normalised child summaries: x_0, x_m, S = sum q x, So* = sum o x; e = exponent; hot (leaves)
-    double nx0v, nxmv, Sv, Sov, scv = 1.0; int ev = 0, hv = -1; double xbv = 0.0, dxv = 0.0;
+    const double sco = pow2i(-eOu);
+    const double no0 = oh.x * sco, nom = oh.y * sco;
+    // normalised child summaries: x_0, x_m, S = sum q x; hot slot (leaves)
+    double nx0v, nxmv, Sv, scv = 1.0; int ev = 0, hv = -1; double xbv = 0.0, dxv = 0.0;
     if (VI) {
         const double2 h = ld2(A + off);
-        sv = gsum(sv, gm); sov = gsum(sov, gm);
-        mv = gmax(max(mv, max(hi32(h.x), hi32(h.y))), gm);
-        ev = expo_of_hi(mv); scv = pow2i(-ev);
-        nx0v = h.x * scv; nxmv = h.y * scv; Sv = sv * scv; Sov = sov * sco * scv;
+        ev = iA; scv = pow2i(-ev);
+        nx0v = h.x * scv; nxmv = h.y * scv; Sv = sqA * scv;
     } else {
-        const Leaf L = leaf_of(codeA, phi);
+        const Leaf L = leaf_of(iA, phi);
         hv = L.hot; xbv = L.xb; dxv = L.dx;
         nx0v = L.x0; nxmv = L.xm;
-        const double qh = (hv >= 0) ? sq[off + hv] : 0.0;
-        const double ohv = (hv >= 0) ? C[off + hv] * sco : 0.0;
-        Sv = xbv * qsum + qh * dxv;
-        Sov = xbv * So + ohv * dxv;
+        Sv = xbv * qsum + ((hv >= 0) ? sq[off + hv] : 0.0) * dxv;
     }
-    double nx0w, nxmw, Sw, Sow, scw = 1.0; int ew = 0, hw = -1; double xbw = 0.0, dxw = 0.0;
+    double nx0w, nxmw, Sw, scw = 1.0; int ew = 0, hw = -1; double xbw = 0.0, dxw = 0.0;
     if (WI) {
         const double2 h = ld2(B + off);
-        sw = gsum(sw, gm); sow = gsum(sow, gm);
-        mw = gmax(max(mw, max(hi32(h.x), hi32(h.y))), gm);
-        ew = expo_of_hi(mw); scw = pow2i(-ew);
-        nx0w = h.x * scw; nxmw = h.y * scw; Sw = sw * scw; Sow = sow * sco * scw;
+        ew = iB; scw = pow2i(-ew);
+        nx0w = h.x * scw; nxmw = h.y * scw; Sw = sqB * scw;
     } else {
-        const Leaf L = leaf_of(codeB, phi);
+        const Leaf L = leaf_of(iB, phi);
         hw = L.hot; xbw = L.xb; dxw = L.dx;
         nx0w = L.x0; nxmw = L.xm;
-        const double qh = (hw >= 0) ? sq[off + hw] : 0.0;
-        const double ohw = (hw >= 0) ? C[off + hw] * sco : 0.0;
-        Sw = xbw * qsum + qh * dxw;
-        Sow = xbw * So + ohw * dxw;
+        Sw = xbw * qsum + ((hw >= 0) ? sq[off + hw] : 0.0) * dxw;
     }
-    double Sovw;                                    // sum_a o_a xv_a xw_a (normalised)
+    // sibling messages: E_0, E_alpha = c x + g x_m, E_m = x_m;  T^v = out[u] .* E^w, T^w = out[u] .* E^v
+    const double gmv = cv.w * nxmv, gmw = cw.w * nxmw;
+    const double k0v = cv.x * nx0v + cv.y * Sv + gmv;
+    const double k0w = cw.x * nx0w + cw.y * Sw + gmw;
+    const double Tv0 = no0 * k0w, Tvm = nom * nxmw;
+    const double Tw0 = no0 * k0v, Twm = nom * nxmv;
+
+    double so = 0, sov = 0, sow = 0, sovw = 0;
+    unsigned mov = 0u, mow = 0u;
+    {
+        const double bv = cv.y * Tv0, bw = cw.y * Tw0;
+        const double cvo = cv.z * sco, cwo = cw.z * sco;
+        const double csv = cv.z * scv, csw = cw.z * scw;
+        const double Ebv = cv.z * xbv + gmv, dEv = cv.z * dxv;     // leaf forms of E^v, E^w
+        const double Ebw = cw.z * xbw + gmw, dEw = cw.z * dxw;
+#pragma unroll 1
+        for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
+            const double2 o = ld2(C + off + i);
+            so += o.x; so += o.y;
+            double2 Ev, Ew, oa = make_double2(0.0, 0.0);
+            if (VI) {
+                const double2 a = ld2(A + off + i);
+                Ev.x = fma(csv, a.x, gmv); Ev.y = fma(csv, a.y, gmv);
+                oa.x = o.x * a.x; oa.y = o.y * a.y;
+                sov += oa.x; sov += oa.y;
+            } else { Ev.x = Ebv + ((i == hv) ? dEv : 0.0); Ev.y = Ebv + ((i + 1 == hv) ? dEv : 0.0); }
+            if (WI) {
+                const double2 b = ld2(B + off + i);
+                Ew.x = fma(csw, b.x, gmw); Ew.y = fma(csw, b.y, gmw);
+                sow = fma(o.x, b.x, sow); sow = fma(o.y, b.y, sow);
+                if (VI) { sovw = fma(oa.x, b.x, sovw); sovw = fma(oa.y, b.y, sovw); }
+            } else { Ew.x = Ebw + ((i == hw) ? dEw : 0.0); Ew.y = Ebw + ((i + 1 == hw) ? dEw : 0.0); }
+            if (VI || WI) {
+                const double2 q2 = ld2(sq + off + i);
+                if (VI) {
+                    const double y0 = fma(bv, q2.x, cvo * o.x * Ew.x), y1 = fma(bv, q2.y, cvo * o.y * Ew.y);
+                    st2(goutv + off + i, y0, y1);
+                    mov = max(mov, max(hi32(y0), hi32(y1)));
+                }
+                if (WI) {
+                    const double y0 = fma(bw, q2.x, cwo * o.x * Ev.x), y1 = fma(bw, q2.y, cwo * o.y * Ev.y);
+                    st2(goutw + off + i, y0, y1);
+                    mow = max(mow, max(hi32(y0), hi32(y1)));
+                }
+            }
+        }
+    }
+    so = gsum(so, gm);
+    const double So = so * sco;
+    double Sov, Sow, Sovw;                            // sum_a o_a xv_a, sum_a o_a xw_a, sum_a o_a xv_a xw_a (normalised)
+    if (VI) Sov = gsum(sov, gm) * sco * scv;
+    else Sov = xbv * So + ((hv >= 0) ? C[off + hv] * sco : 0.0) * dxv;
+    if (WI) Sow = gsum(sow, gm) * sco * scw;
+    else Sow = xbw * So + ((hw >= 0) ? C[off + hw] * sco : 0.0) * dxw;
     if (VI && WI) Sovw = gsum(sovw, gm) * sco * scv * scw;
     else if (VI) Sovw = xbw * Sov + ((hw >= 0) ? dxw * (C[off + hw] * sco) * (A[off + hw] * scv) : 0.0);
     else if (WI) Sovw = xbv * Sow + ((hv >= 0) ? dxv * (C[off + hv] * sco) * (B[off + hv] * scw) : 0.0);
@@ -370,23 +386,18 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
         const double ohv = (hv >= 0) ? C[off + hv] * sco : 0.0, ohw = (hw >= 0) ? C[off + hw] * sco : 0.0;
         Sovw = xbv * xbw * So + xbw * dxv * ohv + xbv * dxw * ohw + ((hv >= 0 && hv == hw) ? dxv * dxw * ohv : 0.0);
     }
-    // sibling messages: E_0, E_alpha = c x + g x_m, E_m = x_m
-    const double gmv = cv.w * nxmv, gmw = cw.w * nxmw;
-    const double k0v = cv.x * nx0v + cv.y * Sv + gmv;
-    const double k0w = cw.x * nx0w + cw.y * Sw + gmw;
-    // top-of-branch vectors: T^v = out[u] .* E^w,  T^w = out[u] .* E^v
-    const double Tv0 = no0 * k0w, Tvm = nom * nxmw, sTv = cw.z * Sow + gmw * So;
-    const double Tw0 = no0 * k0v, Twm = nom * nxmv, sTw = cv.z * Sov + gmv * So;
+    const double sTv = cw.z * Sow + gmw * So, sTw = cv.z * Sov + gmv * So;      // sum_a T^v_a, sum_a T^w_a
     const double sTvx = cw.z * Sovw + gmw * Sov;     // sum_a T^v_a x^v_a
     const double sTwx = cv.z * Sovw + gmv * Sow;     // sum_a T^w_a x^w_a
-    const double outvm = cv.w * (Tv0 + sTv) + Tvm;
-    const double outwm = cw.w * (Tw0 + sTw) + Twm;
-
+    const double outv0 = cv.x * Tv0, outvm = cv.w * (Tv0 + sTv) + Tvm;
+    const double outw0 = cw.x * Tw0, outwm = cw.w * (Tw0 + sTw) + Twm;
+    if (VI) mov = gmax(max(mov, max(hi32(outv0), hi32(outvm))), gm);
+    if (WI) mow = gmax(max(mow, max(hi32(outw0), hi32(outwm))), gm);
     if (gl == 0) {
-        if (VI) { st2(goutv + off, cv.x * Tv0, outvm); *dexp_v = Du + eo - ev; }
-        if (WI) { st2(goutw + off, cw.x * Tw0, outwm); *dexp_w = Du + eo - ew; }
+        if (VI) { st2(goutv + off, outv0, outvm); *dexp_v = Du + eOu - ev; *eO_v = expo_of_hi(mov); }
+        if (WI) { st2(goutw + off, outw0, outwm); *dexp_w = Du + eOu - ew; *eO_w = expo_of_hi(mow); }
         // expected counts (EM_solver.py:279-300): everything is relative to the site likelihood
-        const int delta = max(-1000, min(1000, Du + eo));
+        const int delta = max(-1000, min(1000, Du + eOu));
         const double fac = scalbn(invL, delta);
         acc[0] += Tv0 * cv.x * nx0v * fac;
         acc[1] += Tv0 * cv.y * Sv * fac;
@@ -399,36 +410,17 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
         acc[8] += cw.z * sTwx * fac;
         acc[9] += gmw * sTw * fac;
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
-        if (!VI && codeA == -1) acc[10] += 1.0 - outvm * nxmv * fac;
-        if (!WI && codeB == -1) acc[10] += 1.0 - outwm * nxmw * fac;
-        if (post) {
+        if (!VI && iA == -1) acc[10] += 1.0 - outvm * nxmv * fac;
+        if (!WI && iB == -1) acc[10] += 1.0 - outwm * nxmw * fac;
+        if (POST) {
             // post0 = log P(node in state 0 | D) = log(out_0 x_0 / L); post1 likewise for the
             // silenced state (EM_solver.py:276-277); [0],[1] child v, [2],[3] child w
-            const double p0v = cv.x * Tv0 * nx0v * fac, p1v = outvm * nxmv * fac;
-            const double p0w = cw.x * Tw0 * nx0w * fac, p1w = outwm * nxmw * fac;
+            const double p0v = outv0 * nx0v * fac, p1v = outvm * nxmv * fac;
+            const double p0w = outw0 * nx0w * fac, p1w = outwm * nxmw * fac;
             post[0] = (p0v > 0.0) ? log(p0v) : -INFINITY;
             post[1] = (p1v > 0.0) ? log(p1v) : -INFINITY;
             post[2] = (p0w > 0.0) ? log(p0w) : -INFINITY;
             post[3] = (p1w > 0.0) ? log(p1w) : -INFINITY;
-        }
-    }
-    if (VI || WI) {
-        const double bv = cv.y * Tv0, bw = cw.y * Tw0;
-        const double cvo = cv.z * sco, cwo = cw.z * sco;
-        const double csv = cv.z * scv, csw = cw.z * scw;
-        const double Ebv = cv.z * xbv + gmv, dEv = cv.z * dxv;     // leaf forms of E^v, E^w
-        const double Ebw = cw.z * xbw + gmw, dEw = cw.z * dxw;
-#pragma unroll 2
-        for (int i = 2 + 2 * gl; i < len; i += 2 * G) {
-            const double2 o = ld2(C + off + i);
-            const double2 q2 = ld2(sq + off + i);
-            double2 Ev, Ew;
-            if (VI) { const double2 a = ld2(A + off + i); Ev.x = fma(csv, a.x, gmv); Ev.y = fma(csv, a.y, gmv); }
-            else { Ev.x = Ebv + ((i == hv) ? dEv : 0.0); Ev.y = Ebv + ((i + 1 == hv) ? dEv : 0.0); }
-            if (WI) { const double2 b = ld2(B + off + i); Ew.x = fma(csw, b.x, gmw); Ew.y = fma(csw, b.y, gmw); }
-            else { Ew.x = Ebw + ((i == hw) ? dEw : 0.0); Ew.y = Ebw + ((i + 1 == hw) ? dEw : 0.0); }
-            if (VI) st2(goutv + off + i, fma(bv, q2.x, cvo * o.x * Ew.x), fma(bv, q2.y, cvo * o.y * Ew.y));
-            if (WI) st2(goutw + off + i, fma(bw, q2.x, cwo * o.x * Ev.x), fma(bw, q2.y, cwo * o.y * Ev.y));
         }
     }
 }
@@ -437,7 +429,7 @@ __device__ __forceinline__ void outside_site(const double *__restrict__ C, const
 // items[i] = (u, v, w) with the children ordered so that an internal child comes first
 // (the recursions are symmetric in the children).  CLS fixes the node class at compile
 // time for the big, class-sorted launches; CLS_ANY decides per item (small levels).
-template <bool OUTSIDE, int CLS>
+template <bool OUTSIDE, int CLS, bool POST = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     using PL = Plan<OUTSIDE, CLS>;
@@ -474,10 +466,10 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     auto stage_ptr = [&](int s) { return stage0 + (size_t)s * stage_bytes; };
     // stage field accessors
     auto f_rows = [&](unsigned char *st) { return reinterpret_cast<double *>(st); };
-    auto f_invL = [&](unsigned char *st) { return reinterpret_cast<double *>(st) + (size_t)NARR * TS; };
-    auto f_red = [&](unsigned char *st) { return f_invL(st) + (OUTSIDE ? MS : 0); };
-    auto f_meta = [&](unsigned char *st) { return reinterpret_cast<int *>(f_red(st) + (OUTSIDE ? NCW * 12 : 0)); };
-    auto f_desc = [&](unsigned char *st) { return reinterpret_cast<Desc *>(f_meta(st) + 3 * MS); };
+    auto f_dmeta = [&](unsigned char *st) { return reinterpret_cast<double *>(st) + (size_t)NARR * TS; };   // dA, dB, dL
+    auto f_red = [&](unsigned char *st) { return f_dmeta(st) + 3 * MS; };
+    auto f_meta = [&](unsigned char *st) { return reinterpret_cast<int *>(f_red(st) + (OUTSIDE ? (NCW + NG) * 12 : 0)); };   // mA..mD
+    auto f_desc = [&](unsigned char *st) { return reinterpret_cast<Desc *>(f_meta(st) + 4 * MS); };
 
     if (warp == NCW) {
         // ======================= producer warp: everything it moves is an async bulk copy =======================
@@ -509,28 +501,40 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
                 const int u = it.x, v = it.y, w = it.z;
                 const bool vi = v >= N, wi = w >= N;
                 double *rows = f_rows(st);
-                int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
+                int *mA = f_meta(st), *mB = mA + MS, *mC = mB + MS, *mD = mC + MS;
+                double *dA = f_dmeta(st), *dB = dA + MS, *dL = dB + MS;
                 Desc *dsc = f_desc(st);
                 dsc->u = u; dsc->v = v; dsc->w = w; dsc->cls = vi ? (wi ? CLS_II : CLS_IL) : CLS_LL;
                 const uint32_t rb = (uint32_t)tlen * 8u, ib = (uint32_t)nsp * 4u, db = (uint32_t)nsp * 8u;
-                uint32_t tx = 64u;                                                 // cv, cw
-                tx += rb * ((vi ? 1u : 0u) + (wi ? 1u : 0u) + (OUTSIDE ? 1u : 0u));
-                tx += OUTSIDE ? (ib + db + ib * ((vi ? 0u : 1u) + (wi ? 0u : 1u))) : 2u * ib;
+                const uint32_t nint = (vi ? 1u : 0u) + (wi ? 1u : 0u);
+                uint32_t tx = 64u + rb * (nint + (OUTSIDE ? 1u : 0u));             // cv, cw + row tiles
+                // internal child: eX (+ iexp for the inside pass) and sqX; leaf child: its codes
+                tx += nint * (ib + db + (OUTSIDE ? 0u : ib)) + (2u - nint) * ib;
+                if (OUTSIDE) tx += 2u * ib + db;                                   // dexp, eO, 1/L of node u
                 mbar_expect_tx_arrive(&full[s], tx);                               // release: orders the id stores above
                 bulk_load(&dsc->cv, P.bc + (size_t)4 * v, 32u, &full[s]);
                 bulk_load(&dsc->cw, P.bc + (size_t)4 * w, 32u, &full[s]);
                 double *rowA = rows + (OUTSIDE ? TS : 0), *rowB = rowA + TS;
-                if (vi) bulk_load(rowA, P.X + (size_t)(v - N) * P.Wp + off0, rb, &full[s]);
-                if (wi) bulk_load(rowB, P.X + (size_t)(w - N) * P.Wp + off0, rb, &full[s]);
+                if (vi) {
+                    const size_t mo = (size_t)(v - N) * P.Kp + ps0;
+                    bulk_load(rowA, P.X + (size_t)(v - N) * P.Wp + off0, rb, &full[s]);
+                    bulk_load(mA, P.eX + mo, ib, &full[s]);
+                    bulk_load(dA, P.sqX + mo, db, &full[s]);
+                    if (!OUTSIDE) bulk_load(mC, P.iexp + mo, ib, &full[s]);
+                } else bulk_load(mA, P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
+                if (wi) {
+                    const size_t mo = (size_t)(w - N) * P.Kp + ps0;
+                    bulk_load(rowB, P.X + (size_t)(w - N) * P.Wp + off0, rb, &full[s]);
+                    bulk_load(mB, P.eX + mo, ib, &full[s]);
+                    bulk_load(dB, P.sqX + mo, db, &full[s]);
+                    if (!OUTSIDE) bulk_load(mD, P.iexp + mo, ib, &full[s]);
+                } else bulk_load(mB, P.codes + (size_t)w * P.Kp + ps0, ib, &full[s]);
                 if (OUTSIDE) {
+                    const size_t mo = (size_t)(u - N) * P.Kp + ps0;
                     bulk_load(rows, P.O + (size_t)(u - N) * P.Wp + off0, rb, &full[s]);
-                    bulk_load(mD, P.dexp + (size_t)(u - N) * P.Kp + ps0, ib, &full[s]);
-                    bulk_load(f_invL(st), P.rootInvL + (size_t)it.w * P.Kp + ps0, db, &full[s]);
-                    if (!vi) bulk_load(mA, P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
-                    if (!wi) bulk_load(mB, P.codes + (size_t)w * P.Kp + ps0, ib, &full[s]);
-                } else {
-                    bulk_load(mA, vi ? P.iexp + (size_t)(v - N) * P.Kp + ps0 : P.codes + (size_t)v * P.Kp + ps0, ib, &full[s]);
-                    bulk_load(mB, wi ? P.iexp + (size_t)(w - N) * P.Kp + ps0 : P.codes + (size_t)w * P.Kp + ps0, ib, &full[s]);
+                    bulk_load(mC, P.dexp + mo, ib, &full[s]);
+                    bulk_load(mD, P.eO + mo, ib, &full[s]);
+                    bulk_load(dL, P.rootInvL + (size_t)it.w * P.Kp + ps0, db, &full[s]);
                 }
             }
             __syncwarp();
@@ -560,16 +564,19 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
         const int cls = (CLS == CLS_ANY) ? dsc->cls : CLS;
         const double4 cv = dsc->cv, cw = dsc->cw;
         const double *C = f_rows(st), *A = C + (OUTSIDE ? TS : 0), *B = A + TS;
-        const int *mA = f_meta(st), *mB = mA + MS, *mD = mB + MS;
+        const int *mA = f_meta(st), *mB = mA + MS, *mC = mB + MS, *mD = mC + MS;
+        const double *dA = f_dmeta(st), *dB = dA + MS, *dL = dB + MS;
         if (!OUTSIDE) {
+            const size_t mo = (size_t)(u - N) * P.Kp + ps0;
             double *gout = P.X + (size_t)(u - N) * P.Wp + off0;
-            int *iexp_u = P.iexp + (size_t)(u - N) * P.Kp + ps0;
+            int *eX_u = P.eX + mo, *iexp_u = P.iexp + mo;
+            double *sqX_u = P.sqX + mo;
             for (int j = grp; j < nsites; j += NG) {
                 const int2 e = s_ent[j];
                 const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
-                if (cls == CLS_II) inside_site<true, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
-                else if (cls == CLS_IL) inside_site<true, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
-                else inside_site<false, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], cv, cw, phi, gout, iexp_u + ls, gl, gm);
+                if (cls == CLS_II) inside_site<true, true>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mC[ls], mD[ls], dA[ls], dB[ls], cv, cw, phi, gout, eX_u + ls, iexp_u + ls, sqX_u + ls, gl, gm);
+                else if (cls == CLS_IL) inside_site<true, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mC[ls], 0, dA[ls], 0.0, cv, cw, phi, gout, eX_u + ls, iexp_u + ls, sqX_u + ls, gl, gm);
+                else inside_site<false, false>(A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], 0, 0, 0.0, 0.0, cv, cw, phi, gout, eX_u + ls, iexp_u + ls, sqX_u + ls, gl, gm);
             }
         } else {
             const bool vi = cls != CLS_LL, wi = cls == CLS_II;
@@ -577,32 +584,38 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
             double *goutw = wi ? P.O + (size_t)(w - N) * P.Wp + off0 : nullptr;
             int *dv = vi ? P.dexp + (size_t)(v - N) * P.Kp + ps0 : nullptr;
             int *dw = wi ? P.dexp + (size_t)(w - N) * P.Kp + ps0 : nullptr;
-            const double *invL = f_invL(st);
-            double acc[11];
+            int *eov = vi ? P.eO + (size_t)(v - N) * P.Kp + ps0 : nullptr;
+            int *eow = wi ? P.eO + (size_t)(w - N) * P.Kp + ps0 : nullptr;
+            // expected-count accumulators live in shared memory (one 12-double slot per lane group):
+            // keeping 11 fp64 accumulators in registers across the site sweep costs spills
+            double *red = f_red(st);
+            double *acc = red + (size_t)(NCW + grp) * 12;
+            if (gl == 0) {
 #pragma unroll
-            for (int q = 0; q < 11; q++) acc[q] = 0.0;
+                for (int q = 0; q < 11; q++) acc[q] = 0.0;
+            }
             for (int j = grp; j < nsites; j += NG) {
                 const int2 e = s_ent[j];
                 const int off = e.x & 0xffff, len = e.x >> 16, ls = e.y;
                 double pst[4];
-                double *post = P.post0 ? pst : nullptr;
-                if (cls == CLS_II) outside_site<true, true>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw + ls, post, gl, gm, acc);
-                else if (cls == CLS_IL) outside_site<true, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw, post, gl, gm, acc);
-                else outside_site<false, false>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], mD[ls], invL[ls], cv, cw, phi, goutv, goutw, dv, dw, post, gl, gm, acc);
-                if (post && gl == 0) {
+                double *post = pst;
+                if (cls == CLS_II) outside_site<true, true, POST>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], dA[ls], dB[ls], mC[ls], mD[ls], dL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw + ls, eov + ls, eow + ls, post, gl, gm, acc);
+                else if (cls == CLS_IL) outside_site<true, false, POST>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], dA[ls], 0.0, mC[ls], mD[ls], dL[ls], cv, cw, phi, goutv, goutw, dv + ls, dw, eov + ls, eow, post, gl, gm, acc);
+                else outside_site<false, false, POST>(C, A, B, s_q, s_qsum[ls], off, len, mA[ls], mB[ls], 0.0, 0.0, mC[ls], mD[ls], dL[ls], cv, cw, phi, goutv, goutw, dv, dw, eov, eow, post, gl, gm, acc);
+                if (POST && gl == 0) {
                     const size_t gs = (size_t)P.site0 + s0 + ls;
                     P.post0[(size_t)v * P.K_total + gs] = pst[0]; P.post1[(size_t)v * P.K_total + gs] = pst[1];
                     P.post0[(size_t)w * P.K_total + gs] = pst[2]; P.post1[(size_t)w * P.K_total + gs] = pst[3];
                 }
             }
-            // warp-level sum over the warp's groups (only lane 0 of each group holds data), fixed order
-            double *red = f_red(st);
+            // warp-level sum over the warp's groups in a fixed order
+            __syncwarp();
+            if (lane < 11) {
+                const double *g0 = red + (size_t)(NCW + warp * (32 / G)) * 12 + lane;
+                double x = 0.0;
 #pragma unroll
-            for (int q = 0; q < 11; q++) {
-                double x = (gl == 0) ? acc[q] : 0.0;
-#pragma unroll
-                for (int o = G; o < 32; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == 0) red[warp * 12 + q] = x;
+                for (int g = 0; g < 32 / G; g++) x += g0[g * 12];
+                red[warp * 12 + lane] = x;
             }
         }
         __syncwarp();
@@ -637,35 +650,30 @@ __global__ void __launch_bounds__(256) pmm_root_llh(KParams P, const int *__rest
     const unsigned gm = group_mask();
     const int gl = tid & (G - 1), grp = tid / G;
     const double4 cr = reinterpret_cast<const double4 *>(P.bc)[r];
+    const size_t mo = (size_t)(r - N) * P.Kp;
     const double *x = P.X + (size_t)(r - N) * P.Wp;
     double *o = P.O + (size_t)(r - N) * P.Wp;
-    const int *iexp_r = P.iexp + (size_t)(r - N) * P.Kp;
-    int *dexp_r = P.dexp + (size_t)(r - N) * P.Kp;
     double acc0 = 0, acc1 = 0, acc2 = 0;
     for (int s = s0 + grp; s < s1; s += RG) {
         const int goff = P.site_off[s], len = P.site_len[s];
-        double sq = 0.0;
         unsigned mx = 0u;
-        for (int i = 2 + gl; i < len; i += G) {
-            const double a = x[goff + i], qi = P.q[goff + i];
-            sq = fma(qi, a, sq);
-            mx = max(mx, hi32(a));
-            o[goff + i] = cr.y * qi;
+        for (int i = 2 + gl; i < len; i += G) {              // out[root]_alpha = b q_alpha
+            const double y = cr.y * P.q[goff + i];
+            o[goff + i] = y;
+            mx = max(mx, hi32(y));
         }
-        const double x0 = x[goff], xm = x[goff + 1];
-        mx = max(mx, max(hi32(x0), hi32(xm)));
-        sq = gsum(sq, gm);
-        mx = gmax(mx, gm);
+        mx = gmax(max(mx, max(hi32(cr.x), hi32(cr.w))), gm);
         if (gl == 0) {
-            const int e = expo_of_hi(mx);
-            const double sc = pow2i(-e);
-            const double t0 = cr.x * x0 * sc, t1 = cr.y * sq * sc, t2 = cr.w * xm * sc;
-            const double L = t0 + t1 + t2;
             const int ps = P.site_pidx[s];
-            const int Le = iexp_r[ps] + e;
+            const int e = P.eX[mo + ps];
+            const double sc = pow2i(-e);
+            const double t0 = cr.x * x[goff] * sc, t1 = cr.y * P.sqX[mo + ps] * sc, t2 = cr.w * x[goff + 1] * sc;
+            const double L = t0 + t1 + t2;
+            const int Le = P.iexp[mo + ps];                  // accumulated exponent incl. e
             const double inv = (L > 0.0) ? 1.0 / L : 0.0;
             o[goff] = cr.x; o[goff + 1] = cr.w;
-            dexp_r[ps] = -e;
+            P.eO[mo + ps] = expo_of_hi(mx);
+            P.dexp[mo + ps] = -e;
             P.rootInvL[(size_t)ri * P.Kp + ps] = inv;
             P.root_site_llh[(size_t)ri * P.K + s] = (L > 0.0) ? log(L) + (double)Le * 0.693147180559945309417232121458 : -INFINITY;
             acc0 += t0 * inv; acc1 += t1 * inv; acc2 += t2 * inv;
