@@ -70,6 +70,8 @@ struct pmm_handle {
     double *d_stats = nullptr;      // [5n | Rtilde | llh]
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
+    NuState *d_nu_state = nullptr;
+    double *d_nu_partial = nullptr;
     double *d_post0 = nullptr, *d_post1 = nullptr;
     size_t device_bytes = 0;
     int64_t launches = 0;
@@ -124,7 +126,7 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp); dfree(h->d_eX); dfree(h->d_eO); dfree(h->d_sqX);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
-    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free);
+    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial);
     dfree(h->d_post0); dfree(h->d_post1);
     free_chunks(h);
 }
@@ -577,7 +579,7 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
 
     // small per-node buffers first, then the chunk plan against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
-        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_Rnode, h->n_int) ||
+        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 4) || dalloc(h, &h->d_Rnode, h->n_int) ||
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
     if (plan_chunks(h)) return 1;
@@ -684,9 +686,20 @@ int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_
     const int K_total = h->K_total > 0 ? h->K_total : h->K;
     pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
                                                                dmin, dmax, eps_s, eps_nu);
-    pmm_mstep_globals<<<1, 1024, 0, h->stream>>>(h->d_stats, h->d_free, n, h->d_Snorm, h->d_d, h->d_params, R,
-                                                 (double)K_total * (double)n_cells, optimize_nu, optimize_phi);
-    h->launches += 2;
+    h->launches += 1;
+    if (optimize_nu) {
+        // fixed launch count: the state stops changing once `done` is set (kernels return at once)
+        const int iters = env_int("PMM_NU_ITERS", 24);
+        for (int it = 0; it <= iters; it++) {
+            pmm_nu_eval<<<NU_BLOCKS, 256, 0, h->stream>>>(h->d_free, n, h->d_Snorm, h->d_d, h->d_nu_state, it == 0, h->d_nu_partial);
+            pmm_nu_step<<<1, NU_BLOCKS, 0, h->stream>>>(h->d_nu_partial, h->d_nu_state, it == 0, h->d_params);
+        }
+        h->launches += 2 * (iters + 1);
+    }
+    if (optimize_phi) {
+        pmm_phi_step<<<1, 1, 0, h->stream>>>(h->d_stats, n, h->d_params, R, (double)K_total * (double)n_cells);
+        h->launches += 1;
+    }
     CK(cudaGetLastError());
     return 0;
 }

@@ -763,79 +763,89 @@ __global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsig
     d[v] = res;
 }
 
-// single CTA: phi closed form and the 1-D problem in nu.
+// ---- the 1-D problem in nu (EM_solver.py:394-407) and phi (:318-326)
 // g'(nu) = -sum (S0+S1+S3) d + sum (S2+S4) d / expm1(nu d) is convex and strictly decreasing on (0,1],
-// +inf at 0: safeguarded Newton (bracket kept, bisection fallback) reaches the root to the last
-// bits in ~10 evaluations; each evaluation is one deterministic block reduction over the branches.
-__global__ void __launch_bounds__(1024) pmm_mstep_globals(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask,
-                                                           int n, const double *__restrict__ Snorm, const double *__restrict__ d,
-                                                           double *__restrict__ params, double R, double cells_times_sites,
-                                                           int optimize_nu, int optimize_phi) {
-    __shared__ double sh[1024], sh2[1024];
+// +inf at 0: safeguarded Newton (bracket kept, bisection fallback).  Each evaluation is a grid-wide
+// two-stage reduction in a fixed order (bit-reproducible, identical on every rank): NU_BLOCKS CTAs
+// write partial sums, one CTA combines them and takes the Newton step.  The host enqueues a fixed
+// number of (eval, step) pairs; once converged the state is a fixed point of the step.
+constexpr int NU_BLOCKS = 256;
+struct NuState { double x, lo, hi, lin, wsum; int done, iters; };
+
+// partial[b] = { sum w d / expm1(x d),  d/dx of it,  sum (S0+S1+S3) d,  sum w }   over this CTA's branches
+__global__ void __launch_bounds__(256) pmm_nu_eval(const unsigned char *__restrict__ free_mask, int n,
+                                                    const double *__restrict__ Snorm, const double *__restrict__ d,
+                                                    const NuState *__restrict__ st, int first, double *__restrict__ partial) {
+    __shared__ double sh[4][256];
     const int tid = threadIdx.x;
-    // f = sum w d / expm1(x d),  fp = d f / d x   (w = S2 + S4)
-    auto eval = [&](double x, double &f, double &fp) {
-        double a = 0.0, b = 0.0;
-        for (int v = tid; v < n; v += 1024)
-            if (free_mask[v]) {
-                const double dv = d[v], w = Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
-                const double em = expm1(x * dv);
-                const double r = dv / em;
-                a += w * r;
-                b -= w * r * r * (em + 1.0);
-            }
-        sh[tid] = a; sh2[tid] = b;
-        __syncthreads();
-        for (int o = 512; o > 0; o >>= 1) {
-            if (tid < o) { sh[tid] += sh[tid + o]; sh2[tid] += sh2[tid + o]; }
-            __syncthreads();
+    if (!first && st->done) return;
+    const double x = first ? 1.0 : st->x;
+    double f = 0.0, fp = 0.0, lin = 0.0, ws = 0.0;
+    for (int v = blockIdx.x * 256 + tid; v < n; v += NU_BLOCKS * 256)
+        if (free_mask[v]) {
+            const double dv = d[v], w = Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
+            const double em = expm1(x * dv);
+            const double r = dv / em;
+            f += w * r;
+            fp -= w * r * r * (em + 1.0);
+            if (first) { lin += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * dv; ws += w; }
         }
-        f = sh[0]; fp = sh2[0];
-        __syncthreads();
-    };
-    if (optimize_nu) {
-        double lin_p = 0.0, w_p = 0.0;
-        for (int v = tid; v < n; v += 1024)
-            if (free_mask[v]) {
-                lin_p += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * d[v];
-                w_p += Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
-            }
-        sh[tid] = lin_p; sh2[tid] = w_p;
-        __syncthreads();
-        for (int o = 512; o > 0; o >>= 1) {
-            if (tid < o) { sh[tid] += sh[tid + o]; sh2[tid] += sh2[tid + o]; }
-            __syncthreads();
+    sh[0][tid] = f; sh[1][tid] = fp; sh[2][tid] = lin; sh[3][tid] = ws;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
         }
-        const double lin = sh[0], wsum = sh2[0];
         __syncthreads();
-        double f, fp, res;
-        eval(1.0, f, fp);
-        if (f - lin >= 0.0 || !(lin > 0.0)) res = 1.0;                   // upper bound active (EM_solver.py:402)
+    }
+    if (tid < 4) partial[blockIdx.x * 4 + tid] = sh[tid][0];
+}
+
+__global__ void __launch_bounds__(NU_BLOCKS) pmm_nu_step(const double *__restrict__ partial, NuState *__restrict__ st, int first,
+                                                          double *__restrict__ params) {
+    __shared__ double sh[4][NU_BLOCKS];
+    const int tid = threadIdx.x;
+    if (!first && st->done) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) sh[k][tid] = partial[tid * 4 + k];
+    __syncthreads();
+    for (int o = NU_BLOCKS / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    const double f = sh[0][0], fp = sh[1][0];
+    NuState s = *st;
+    if (first) {
+        s.lin = sh[2][0]; s.wsum = sh[3][0]; s.iters = 0; s.done = 0;
+        if (f - s.lin >= 0.0 || !(s.lin > 0.0)) { s.x = 1.0; s.done = 1; }        // upper bound active (EM_solver.py:402)
+        else { s.lo = 0.0; s.hi = 1.0; s.x = fmin(0.5, s.wsum / s.lin); }           // 1/expm1(t) < 1/t  =>  root < wsum/lin
+    } else {
+        const double g = f - s.lin, x = s.x;
+        if (g > 0.0) s.lo = x; else s.hi = x;
+        s.iters++;
+        if (g == 0.0) s.done = 1;
         else {
-            double lo = 0.0, hi = 1.0;                                    // g'(lo) > 0 > g'(hi)
-            double x = fmin(0.5, wsum / lin);                             // 1/expm1(t) < 1/t  =>  root < wsum/lin
-            res = x;
-            for (int it = 0; it < 100; it++) {
-                eval(x, f, fp);
-                const double g = f - lin;
-                if (g > 0.0) lo = x; else hi = x;
-                res = x;
-                if (g == 0.0) break;
-                double xn = x - g / fp;
-                if (!(xn > lo && xn < hi)) xn = (lo > 0.0) ? 0.5 * (lo + hi) : 0.5 * hi;
-                if (fabs(xn - x) <= 4e-16 * x) { res = xn; break; }
-                if (xn < 1e-300) { res = 0.0; break; }
-                x = xn;
-            }
+            double xn = x - g / fp;
+            if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
+            if (fabs(xn - x) <= 4e-16 * x) s.done = 1;
+            if (xn < 1e-300) { xn = 0.0; s.done = 1; }
+            s.x = xn;
         }
-        if (tid == 0) params[0] = res;
     }
-    if (optimize_phi && tid == 0) {
-        const double Rt = stats[(size_t)n * 5];
-        double phi_star = Rt / (R + Rt);
-        if (fabs(phi_star) < 1.0 / cells_times_sites) phi_star = 0.0;
-        params[1] = phi_star;
-    }
+    *st = s;
+    params[0] = s.x;
+}
+
+__global__ void pmm_phi_step(const double *__restrict__ stats, int n, double *__restrict__ params, double R, double cells_times_sites) {
+    const double Rt = stats[(size_t)n * 5];
+    double phi_star = Rt / (R + Rt);
+    if (fabs(phi_star) < 1.0 / cells_times_sites) phi_star = 0.0;
+    params[1] = phi_star;
 }
 
 }  // namespace pmm
