@@ -297,6 +297,8 @@ int configure_kernels(pmm_handle *h) {
         (OUT ? h->stages_out : h->stages_in)[IDX] = S;                                                                        \
         (OUT ? h->smem_out : h->smem_in)[IDX] = b;                                                                            \
         (OUT ? h->ctas_out : h->ctas_in)[IDX] = ctas;                                                                         \
+        if (env_int("PMM_VERBOSE", 0))                                                                                        \
+            fprintf(stderr, "[pmm] %s class %d: TS=%d stages=%d smem=%zu B, %d CTA/SM\n", OUT ? "outside" : "inside", IDX, h->TS, S, b, ctas); \
     }
     SETUP(false, CLS_II, 0) SETUP(false, CLS_IL, 1) SETUP(false, CLS_LL, 2) SETUP(false, CLS_ANY, 3)
     SETUP(true, CLS_II, 0) SETUP(true, CLS_IL, 1) SETUP(true, CLS_LL, 2) SETUP(true, CLS_ANY, 3)
@@ -446,7 +448,7 @@ int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const
     for (int i = 0; i < nnz; i++)
         if (!(h->prior[i] >= 0.0)) { h->err = "prior entries must be non-negative numbers"; return bail(1); }
     h->W = (int64_t)nnz + 2 * (int64_t)n_sites;
-    h->TS = env_int("PMM_TILE_SLOTS", 1920);
+    h->TS = env_int("PMM_TILE_SLOTS", 1792);
     h->TS = std::max((h->TS + 1) & ~1, (maxlen + 1) & ~1);
     if (h->TS > 8192) { h->err = "an alphabet is too large for one shared-memory tile (limit ~8000 states)"; return bail(1); }
     // validate codes against the alphabets, then upload

@@ -195,12 +195,13 @@ template <bool OUTSIDE, int CLS> struct Plan {
     __host__ __device__ static size_t stage_bytes(int TS, int MS) {
         size_t b = (size_t)NARR * TS * 8;
         b += (size_t)3 * MS * 8;                       // fp64 metadata: sq_v, sq_w, 1/L
-        if (OUTSIDE) b += (size_t)(NCW + NG) * 12 * 8; // per-warp and per-group partial counts
+        if (OUTSIDE) b += (size_t)NCW * 12 * 8;        // per-warp partial counts of the item in this stage
         b += (size_t)4 * MS * 4 + 32 * 4;              // int32 metadata x4, item descriptor
         return (b + 127) & ~(size_t)127;
     }
     __host__ __device__ static size_t fixed_bytes(int TS, int MS) {
-        return ((size_t)TS * 8 + (size_t)MS * 8 + (size_t)MS * 8 + 2 * MAX_STAGES * 8 + 127) & ~(size_t)127;
+        // q tile, qsum, site table, barriers, (outside) one 12-double accumulator slot per lane group
+        return ((size_t)TS * 8 + (size_t)MS * 8 + (size_t)MS * 8 + 2 * MAX_STAGES * 8 + (OUTSIDE ? (size_t)NG * 12 * 8 : 0) + 127) & ~(size_t)127;
     }
     __host__ __device__ static size_t total_bytes(int TS, int MS, int S) { return fixed_bytes(TS, MS) + S * stage_bytes(TS, MS); }
 };
@@ -441,6 +442,7 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     int2 *s_ent = reinterpret_cast<int2 *>(s_qsum + MS);
     uint64_t *full = reinterpret_cast<uint64_t *>(s_ent + MS);
     uint64_t *done = full + MAX_STAGES;
+    double *s_gacc = reinterpret_cast<double *>(done + MAX_STAGES);   // [NG][12], outside pass only
     unsigned char *stage0 = smem_raw + PL::fixed_bytes(TS, MS);       // pure pointer arithmetic keeps the
     const size_t stage_bytes = PL::stage_bytes(TS, MS);               // shared address space visible to the compiler
 
@@ -468,7 +470,7 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
     auto f_rows = [&](unsigned char *st) { return reinterpret_cast<double *>(st); };
     auto f_dmeta = [&](unsigned char *st) { return reinterpret_cast<double *>(st) + (size_t)NARR * TS; };   // dA, dB, dL
     auto f_red = [&](unsigned char *st) { return f_dmeta(st) + 3 * MS; };
-    auto f_meta = [&](unsigned char *st) { return reinterpret_cast<int *>(f_red(st) + (OUTSIDE ? (NCW + NG) * 12 : 0)); };   // mA..mD
+    auto f_meta = [&](unsigned char *st) { return reinterpret_cast<int *>(f_red(st) + (OUTSIDE ? NCW * 12 : 0)); };   // mA..mD
     auto f_desc = [&](unsigned char *st) { return reinterpret_cast<Desc *>(f_meta(st) + 4 * MS); };
 
     if (warp == NCW) {
@@ -589,7 +591,7 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
             // expected-count accumulators live in shared memory (one 12-double slot per lane group):
             // keeping 11 fp64 accumulators in registers across the site sweep costs spills
             double *red = f_red(st);
-            double *acc = red + (size_t)(NCW + grp) * 12;
+            double *acc = s_gacc + (size_t)grp * 12;
             if (gl == 0) {
 #pragma unroll
                 for (int q = 0; q < 11; q++) acc[q] = 0.0;
@@ -611,12 +613,13 @@ pmm_level(KParams P, const int4 *__restrict__ items, int n_level) {
             // warp-level sum over the warp's groups in a fixed order
             __syncwarp();
             if (lane < 11) {
-                const double *g0 = red + (size_t)(NCW + warp * (32 / G)) * 12 + lane;
+                const double *g0 = s_gacc + (size_t)(warp * (32 / G)) * 12 + lane;
                 double x = 0.0;
 #pragma unroll
                 for (int g = 0; g < 32 / G; g++) x += g0[g * 12];
                 red[warp * 12 + lane] = x;
             }
+            __syncwarp();      // the group slots are zeroed again at the start of the warp's next item
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[s]);
