@@ -513,8 +513,14 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         else if (parent[v] >= n) return fail(h, "node %d has an invalid parent", v);
     }
     if (h->stream) CK(cudaStreamSynchronize(h->stream));
-    free_tree_state(h);
-    h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;   // what pmm_create holds
+    // a new topology over the same node / root counts (topology search: Topology_search.py:289-299 builds
+    // a fresh solver per candidate) keeps every device buffer and the chunk plan: only the tree arrays and
+    // the level schedules are replaced
+    const bool reuse = (h->n == n && h->n_roots == n_roots && h->d_X != nullptr);
+    if (!reuse) {
+        free_tree_state(h);
+        h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;   // what pmm_create holds
+    }
     h->n = n; h->n_int = n - N; h->n_roots = n_roots;
     h->parent.assign(parent, parent + n); h->left.assign(left, left + n); h->right.assign(right, right + n);
     // depth (root = 0) and height (leaf = 0) without recursion
@@ -568,8 +574,9 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     build_items(inl, in_items, h->in_ptr, h->in_cls);
     build_items(outl, out_items, h->out_ptr, h->out_cls);
 
-    if (dalloc(h, &h->d_parent, n) || dalloc(h, &h->d_left, n) || dalloc(h, &h->d_right, n) || dalloc(h, &h->d_root_index, n) ||
-        dalloc(h, &h->d_roots, roots.size()) || dalloc(h, &h->d_in_items, in_items.size()) || dalloc(h, &h->d_out_items, out_items.size()))
+    if (!reuse &&
+        (dalloc(h, &h->d_parent, n) || dalloc(h, &h->d_left, n) || dalloc(h, &h->d_right, n) || dalloc(h, &h->d_root_index, n) ||
+         dalloc(h, &h->d_roots, roots.size()) || dalloc(h, &h->d_in_items, in_items.size()) || dalloc(h, &h->d_out_items, out_items.size())))
         return 1;
     CK(cudaMemcpy(h->d_parent, parent, sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_left, left, sizeof(int) * n, cudaMemcpyHostToDevice));
@@ -579,6 +586,7 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     CK(cudaMemcpy(h->d_in_items, in_items.data(), sizeof(int4) * in_items.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_out_items, out_items.data(), sizeof(int4) * out_items.size(), cudaMemcpyHostToDevice));
 
+    if (reuse) return 0;
     // small per-node buffers first, then the chunk plan against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
         dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 4) || dalloc(h, &h->d_Rnode, h->n_int) ||

@@ -124,3 +124,30 @@ def test_mstep_and_em_vs_oracle():
     np.testing.assert_allclose(got["d"], ref["d"], rtol=1e-5, atol=1e-7)
     assert abs(got["nu"] - ref["nu"]) <= 1e-5 and abs(got["phi"] - ref["phi"]) <= 1e-5
     eng.close()
+
+
+def test_set_tree_reuse_matches_fresh_engine():
+    """pmm_set_tree on a live handle (topology search re-scores many trees over the same cells)
+    must give the same numbers as a fresh handle"""
+    from laml_b200.capi import Engine
+    from laml_b200.synth import make_workload, random_tree, lognormal_branch_lengths
+    w = make_workload(120, 20, 2, 25, 0.2, 0.2, seed=61)
+    eng = Engine(120, w.qptr, w.qval, w.codes)
+    eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    a0 = eng.estep(w.d, w.nu, w.phi)
+    launches0 = eng.info()["device_bytes"]
+    for seed in (62, 63):
+        f2 = random_tree(120, seed=seed)
+        d2 = lognormal_branch_lengths(f2, seed=seed + 100)
+        eng.set_tree(f2.parent, f2.left, f2.right)
+        got = eng.estep(d2, w.nu, w.phi)
+        fresh = Engine(120, w.qptr, w.qval, w.codes)
+        fresh.set_tree(f2.parent, f2.left, f2.right)
+        ref = fresh.estep(d2, w.nu, w.phi)
+        assert got["llh"] == ref["llh"] and (got["S"] == ref["S"]).all() and got["Rtilde"] == ref["Rtilde"]
+        fresh.close()
+    assert eng.info()["device_bytes"] == launches0        # nothing was reallocated
+    eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    a1 = eng.estep(w.d, w.nu, w.phi)
+    assert a1["llh"] == a0["llh"] and (a1["S"] == a0["S"]).all()
+    eng.close()
