@@ -134,6 +134,23 @@ int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_
                   int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu);
 int pmm_sync(pmm_handle *h);
 
+/*
+ * Batched scoring of NNI candidate trees: replaces, for many candidates at
+ * once, what Topology_search.apply_nni does one candidate at a time (Topology_search.py:242-322:
+ * rebuild a solver from newick strings, score_tree -> optimize with every branch fixed except the
+ * five around the move, nu and phi fixed).  Candidate i swaps child cand_k[i] (0 = left, 1 = right)
+ * of the internal non-root node cand_u[i] with u's sibling.  d[n] are the current branch lengths
+ * (the caller applies ini_brlens' max(2 dmin, .) clamp, ML_solver.py:195-203, if it wants the
+ * reference's starting point).  Outputs per candidate: nllh of the whole forest after the local
+ * EM (EM_solver.py:461-512 restricted to 5 free branches), the five optimised lengths in the order
+ * (v, u, moved child, other child, former sibling), the EM iteration count, and the node ids those
+ * lengths belong to.  Needs all sites resident on this handle (1 site chunk).
+ */
+int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k,
+                        const double *d, double nu, double phi, double dmin, double dmax, double conv_eps,
+                        int32_t max_iter, double *out_nllh, double *out_d5, int32_t *out_iters,
+                        int32_t *out_nodes);
+
 /* ---- introspection for benchmarks ------------------------------------------------- */
 typedef struct {
     int64_t n_nodes, n_leaves, n_sites;

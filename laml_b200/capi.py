@@ -20,7 +20,7 @@ SYMBOLS = [
     "pmm_abi_version", "pmm_last_error", "pmm_create", "pmm_destroy", "pmm_set_stream", "pmm_set_tree",
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
-    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing",
+    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library():
     L.pmm_stats_len.argtypes = [vp]
     L.pmm_stats_len.restype = i64
     L.pmm_mstep_dev.argtypes = [vp, f64, i32, vp, i32, i32, f64, f64, f64, f64]
+    L.pmm_score_nni_batch.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
     L.pmm_sync.argtypes = [vp]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
@@ -182,6 +183,17 @@ class Engine:
                                 C.byref(iters), C.byref(status)))
         return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
                 "status": "optimal" if status.value == 0 else "failed"}
+
+    def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000):
+        """Score NNI candidates (``Topology_search.apply_nni``, one local 5-branch EM each) in one call."""
+        cu, ck = _i32(cand_u), _i32(cand_k)
+        m = int(cu.shape[0])
+        d = _f64(d)
+        nllh = np.empty(m); d5 = np.empty((m, 5)); iters = np.empty(m, np.int32); nodes = np.empty((m, 5), np.int32)
+        self._ck(self._L.pmm_score_nni_batch(self._h, m, cu.ctypes.data, ck.ctypes.data, d.ctypes.data, float(nu), float(phi),
+                                             dmin, dmax, conv_eps, int(max_iter), nllh.ctypes.data, d5.ctypes.data,
+                                             iters.ctypes.data, nodes.ctypes.data))
+        return {"nllh": nllh, "d5": d5, "iters": iters, "nodes": nodes}
 
     # -- device-resident entry points ----------------------------------------
     def upload_params(self, d, nu, phi):

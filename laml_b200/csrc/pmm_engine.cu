@@ -5,6 +5,7 @@
 // fallback: if CUDA is unusable every entry point fails with an error string.
 #include "../../include/pmm_b200.h"
 #include "pmm_kernels.cuh"
+#include "pmm_nni.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -753,6 +754,92 @@ int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *fre
     if (iters) *iters = it;
     if (status) *status = 0;
     return pmm_download_params(h, d, nu, phi);
+}
+
+
+int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k, const double *d, double nu,
+                        double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh, double *out_d5,
+                        int32_t *out_iters, int32_t *out_nodes) {
+    if (n_cand <= 0) return 0;
+    if (pmm_upload_params(h, d, nu, phi)) return 1;
+    if (h->chunks.size() != 1) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk, have %zu)", h->chunks.size());
+    const int N = h->n_leaves, n = h->n;
+    std::vector<int> root_index(n, 0);
+    {   // root index per node (host copy of the tree)
+        std::vector<int> order; order.reserve(n);
+        int nr = 0;
+        for (int v = 0; v < n; v++) if (h->parent[v] < 0) { root_index[v] = nr++; order.push_back(v); }
+        for (size_t i = 0; i < order.size(); i++) {
+            const int v = order[i];
+            if (h->left[v] >= 0) for (int c : {h->left[v], h->right[v]}) { root_index[c] = root_index[v]; order.push_back(c); }
+        }
+    }
+    std::vector<NniCand> cands(n_cand);
+    std::vector<NniState> st(n_cand);
+    for (int i = 0; i < n_cand; i++) {
+        const int u = cand_u[i], k = cand_k[i];
+        if (u < N || u >= n || h->parent[u] < 0 || (k != 0 && k != 1))
+            return fail(h, "NNI candidate %d: node %d must be an internal, non-root node and k in {0,1}", i, u);
+        const int v = h->parent[u];
+        const int w = (h->left[v] == u) ? h->right[v] : h->left[v];
+        const int ck = k ? h->right[u] : h->left[u], co = k ? h->left[u] : h->right[u];
+        NniCand c;
+        c.v = v; c.u = u; c.A = co; c.B = w; c.C = ck;
+        c.g = h->parent[v];
+        c.s = (c.g >= 0) ? ((h->left[c.g] == v) ? h->right[c.g] : h->left[c.g]) : -1;
+        c.root = root_index[u];
+        cands[i] = c;
+        NniState z;
+        z.d[0] = d[v]; z.d[1] = d[u]; z.d[2] = d[ck]; z.d[3] = d[co]; z.d[4] = d[w];
+        z.llh_prev = z.llh_cur = 0.0; z.iters = 0; z.done = 0;
+        st[i] = z;
+        if (out_nodes) { int32_t *o = out_nodes + (size_t)5 * i; o[0] = v; o[1] = u; o[2] = ck; o[3] = co; o[4] = w; }
+    }
+    // caches of the current tree: one full E-step
+    if (run_passes(h, true, false)) return 1;
+    const Chunk &c0 = h->chunks[0];
+    KParams P = make_params(h, c0, false);
+    double llh_total = 0.0;
+    CK(cudaMemcpyAsync(&llh_total, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NniCand *d_c = nullptr; NniState *d_s = nullptr; double *d_part = nullptr, *d_rsum = nullptr; int *d_active = nullptr;
+    auto cleanup = [&]() { dfree(d_c); dfree(d_s); dfree(d_part); dfree(d_rsum); dfree(d_active); };
+    const size_t keep = h->device_bytes;
+    if (dalloc(h, &d_c, n_cand) || dalloc(h, &d_s, n_cand) || dalloc(h, &d_part, (size_t)n_cand * c0.ntiles * 26) ||
+        dalloc(h, &d_rsum, h->n_roots) || dalloc(h, &d_active, 1)) { cleanup(); h->device_bytes = keep; return 1; }
+    h->device_bytes = keep;     // scratch of this call only
+    cudaError_t e = cudaMemcpyAsync(d_c, cands.data(), sizeof(NniCand) * n_cand, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, st.data(), sizeof(NniState) * n_cand, cudaMemcpyHostToDevice, h->stream);
+    for (int r = 0; r < h->n_roots && e == cudaSuccess; r++)
+        pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_root_site_llh + (size_t)r * c0.K, c0.K, d_rsum + r, 0);
+    const size_t smem = (size_t)5 * h->TS * 8;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pmm_nni_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);          // llh_total is on the host now
+    const int K_total = h->K_total > 0 ? h->K_total : h->K;
+    const int check_every = std::max(1, env_int("PMM_NNI_CHECK_EVERY", 4));
+    int active = n_cand;
+    for (int it = 0; it <= max_iter + 1 && active > 0 && e == cudaSuccess; it++) {
+        if (it % check_every == 0) e = cudaMemsetAsync(d_active, 0, sizeof(int), h->stream);
+        dim3 grid((unsigned)n_cand, (unsigned)c0.ntiles);
+        pmm_nni_sweep<<<grid, NNI_THREADS, smem, h->stream>>>(P, d_c, d_s, d_part);
+        pmm_nni_mstep<<<(n_cand + 127) / 128, 128, 0, h->stream>>>(d_part, n_cand, c0.ntiles, d_c, d_rsum, llh_total, d_s, h->d_params,
+                                                                   K_total, dmin, dmax, 1e-6, 1e-5, conv_eps, max_iter, d_active);
+        h->launches += 2;
+        if (it % check_every == check_every - 1) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&active, d_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_s, sizeof(NniState) * n_cand, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, "pmm_score_nni_batch: %s", cudaGetErrorString(e));
+    for (int i = 0; i < n_cand; i++) {
+        if (out_nllh) out_nllh[i] = -st[i].llh_cur;
+        if (out_iters) out_iters[i] = st[i].iters;
+        if (out_d5) for (int b = 0; b < 5; b++) out_d5[(size_t)5 * i + b] = st[i].d[b];
+    }
+    return 0;
 }
 
 int pmm_get_info(const pmm_handle *h, pmm_info *info) {
