@@ -122,3 +122,34 @@ class ShardedEngine:
             it += 1
         d_out, nu_out, phi_out = self.eng.download_params()
         return {"nllh": -cur, "d": d_out, "nu": nu_out, "phi": phi_out, "iters": it, "status": "optimal"}
+
+
+def score_nni_sharded(engine, cand_u, cand_k, d, nu, phi, group=None, device=None, **kw):
+    """Candidate-sharded NNI scoring (BASELINE config 5): candidate trees are independent units, so
+    every rank -- each holding ALL sites of the data set -- scores the slice ``rank::world`` with
+    ``Engine.score_nni_batch`` and the per-candidate results are combined with one ``all_gather``
+    (2 + 5 fp64 and 6 int32 per candidate).  Returns the full result on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    cand_u, cand_k = np.asarray(cand_u, np.int32), np.asarray(cand_k, np.int32)
+    m = len(cand_u)
+    mine = np.arange(rank, m, world)
+    res = engine.score_nni_batch(cand_u[mine], cand_k[mine], d, nu, phi, **kw) if len(mine) else \\
+        {"nllh": np.empty(0), "d5": np.empty((0, 5)), "iters": np.empty(0, np.int32), "nodes": np.empty((0, 5), np.int32)}
+    if world == 1:
+        return res
+    per = (m + world - 1) // world
+    pack = np.zeros((per, 12))
+    k = len(mine)
+    pack[:k, 0] = res["nllh"]; pack[:k, 1:6] = res["d5"]; pack[:k, 6] = res["iters"]; pack[:k, 7:12] = res["nodes"]
+    dev = device if device is not None else ("cuda:%d" % engine.device if torch.cuda.is_available() else "cpu")
+    local = torch.as_tensor(pack, device=dev)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local, group=group)
+    full = np.zeros((m, 12))
+    for r, p in enumerate(parts):
+        idx = np.arange(r, m, world)
+        full[idx] = p.cpu().numpy()[: len(idx)]
+    return {"nllh": full[:, 0], "d5": full[:, 1:6], "iters": full[:, 6].astype(np.int32), "nodes": full[:, 7:12].astype(np.int32)}

@@ -96,3 +96,42 @@ def test_sharded_matches_unsharded():
     assert abs(nllh - ref_em["nllh"]) <= 1e-9 * ref_em["nllh"]
     np.testing.assert_allclose(d, ref_em["d"], rtol=1e-9, atol=1e-11)
     assert abs(nu - ref_em["nu"]) < 1e-10 and abs(phi - ref_em["phi"]) < 1e-12
+
+
+class _FakeNniEngine:
+    """answers score_nni_batch with a deterministic function of (u, k) so the candidate sharding /
+    all_gather / re-ordering logic can be checked on CPU"""
+    device = 0
+
+    def score_nni_batch(self, cu, ck, d, nu, phi, **kw):
+        cu = np.asarray(cu); ck = np.asarray(ck)
+        nllh = 1000.0 + cu * 2.0 + ck
+        d5 = np.stack([cu * 0.001 + j for j in range(5)], axis=1)
+        nodes = np.stack([cu + j for j in range(5)], axis=1).astype(np.int32)
+        return {"nllh": nllh, "d5": d5, "iters": (cu % 7).astype(np.int32), "nodes": nodes}
+
+
+def _nni_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laml_b200.dist import score_nni_sharded
+    cu = np.arange(40, 53, dtype=np.int32).repeat(2)[:-1]          # odd count: uneven shards
+    ck = np.tile(np.array([0, 1], np.int32), 13)[:-1]
+    out = score_nni_sharded(_FakeNniEngine(), cu, ck, None, 0.1, 0.1, device="cpu")
+    ret[rank] = (out["nllh"].copy(), out["d5"].copy(), out["iters"].copy(), out["nodes"].copy())
+    dist.destroy_process_group()
+
+
+def test_nni_candidate_sharding():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_nni_worker, args=(2, port, ret), nprocs=2, join=True)
+    cu = np.arange(40, 53, dtype=np.int32).repeat(2)[:-1]
+    ck = np.tile(np.array([0, 1], np.int32), 13)[:-1]
+    want = _FakeNniEngine().score_nni_batch(cu, ck, None, 0.1, 0.1)
+    for r in (0, 1):
+        nllh, d5, iters, nodes = ret[r]
+        np.testing.assert_array_equal(nllh, want["nllh"]); np.testing.assert_array_equal(d5, want["d5"])
+        np.testing.assert_array_equal(iters, want["iters"]); np.testing.assert_array_equal(nodes, want["nodes"])
