@@ -136,8 +136,10 @@ def score_nni_sharded(engine, cand_u, cand_k, d, nu, phi, group=None, device=Non
     cand_u, cand_k = np.asarray(cand_u, np.int32), np.asarray(cand_k, np.int32)
     m = len(cand_u)
     mine = np.arange(rank, m, world)
-    res = engine.score_nni_batch(cand_u[mine], cand_k[mine], d, nu, phi, **kw) if len(mine) else \\
-        {"nllh": np.empty(0), "d5": np.empty((0, 5)), "iters": np.empty(0, np.int32), "nodes": np.empty((0, 5), np.int32)}
+    if len(mine):
+        res = engine.score_nni_batch(cand_u[mine], cand_k[mine], d, nu, phi, **kw)
+    else:
+        res = {"nllh": np.empty(0), "d5": np.empty((0, 5)), "iters": np.empty(0, np.int32), "nodes": np.empty((0, 5), np.int32)}
     if world == 1:
         return res
     per = (m + world - 1) // world
