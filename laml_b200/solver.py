@@ -16,8 +16,8 @@ random initial points (``ML_solver.py:195-213``), fixed-branch marking by LCA
 constrained branch-length program (``EM_solver.py:349-366``), which receives the
 GPU-computed sufficient statistics.  The reference solves that program with
 cvxpy -> MOSEK (commercial; not installable here); this class solves the *same*
-program with scipy's SLSQP, following the reference's own scipy formulation
-(``EM_solver.py:368-385``).
+program exactly with a tree-structured barrier Newton method on node heights
+(``laml_b200/ultrametric.py``).
 """
 from __future__ import annotations
 
@@ -286,37 +286,39 @@ class GPU_EM_solver:
         return success, ("optimal" if success else "failed_d")
 
     def _host_brlen(self, S, fm, d, nu, eps_nu, eps_s, cache):
-        """argmax of EM_solver.py:351-357 subject to the box and ``M d = b``, by SLSQP
-        (the reference's own scipy formulation, EM_solver.py:368-385)."""
-        from scipy import optimize
-        M, b = cache
-        idx = np.nonzero(fm)[0]
-        s = np.maximum(S[idx], eps_s)
+        """argmax of EM_solver.py:351-357 subject to the box and the ultrametric equalities, from the
+        GPU's statistics: node-height re-parametrisation + tree-structured barrier Newton
+        (``laml_b200/ultrametric.py``; exact, O(n) memory).  ``cache`` is the topology-dependent
+        :class:`UltrametricProblem`."""
+        from . import ultrametric as um
+        s = np.maximum(S, eps_s)                                     # EM_solver.py:343-346
         s = s / s.sum(axis=1, keepdims=True) * self.numsites
-        S0, S1, S2, S3, S4 = s.T
-        use_nu = nu > eps_nu
+        H0 = getattr(self, "_H_prev", None)
+        d_new, H, info = um.solve(cache, s, nu, eps_nu=eps_nu, H0=H0)
+        if d_new is None:
+            return d, "infeasible"
+        self._H_prev = H
+        out = d.copy()
+        free = fm.astype(bool)
+        out[free] = d_new[free]
+        return out, info["status"]
 
-        def f(x):
-            val = -(nu + 1) * S0 @ x - nu * (S1 + S3) @ x + S1 @ np.log(-np.expm1(-x))
-            if use_nu:
-                val += (S2 + S4) @ np.log(-np.expm1(-nu * x))
-            return -val
-
-        def g(x):
-            grad = -(nu + 1) * S0 - nu * (S1 + S3) + S1 / np.expm1(x)
-            if use_nu:
-                grad = grad + nu * (S2 + S4) / np.expm1(nu * x)
-            return -grad
-
-        x0 = np.clip(d[idx], self.dmin, self.dmax)
-        cons = [{"type": "eq", "fun": lambda x: M @ x - b, "jac": lambda x: M}] if len(b) else []
-        out = optimize.minimize(f, x0, jac=g, method="SLSQP", bounds=[(self.dmin, self.dmax)] * len(idx), constraints=cons,
-                                options={"maxiter": 1000, "ftol": 1e-12})
-        d_new = d.copy()
-        d_new[idx] = out.x
-        if not out.success and "incompatible" in str(out.message).lower():
-            return d_new, "infeasible"
-        return d_new, ("optimal" if out.success else str(out.message))
+    def _ultrametric_problem(self, local_brlen_opt=True):
+        """edge kinds for the height re-parametrisation: free / fixed length / counts as zero (polytomy mark),
+        exactly the three cases of EM_solver.py:60-79"""
+        from . import ultrametric as um
+        self._ensure()
+        f = self._forest
+        kind = np.zeros(f.n_nodes, np.int8)
+        fixed_len = np.zeros(f.n_nodes)
+        for i, nd in enumerate(f.nodes):
+            if nd.polytomy_mark:
+                kind[i] = um.ZERO
+            elif nd.mark_fixed and local_brlen_opt:
+                kind[i] = um.FIXED
+                fixed_len[i] = float(nd.edge_length)
+        self._H_prev = None
+        return um.UltrametricProblem(f.parent, kind, fixed_len, self.dmin, self.dmax)
 
     # ------------------------------------------------------------------ EM
     def EM_optimization(self, verbose=1, optimize_phi=True, optimize_nu=True, ultra_constr=False, maxIter=1000):
@@ -334,7 +336,7 @@ class GPU_EM_solver:
         pre_llh = self.lineage_llh()
         if verbose >= 0:
             print("Initial phi: " + str(self.params.phi) + ". Initial nu: " + str(self.params.nu) + ". Initial nllh: " + str(-pre_llh))
-        cache = self.ultrametric_constr(local_brlen_opt=True)
+        cache = self._ultrametric_problem(local_brlen_opt=True)
         em_iter, converged, status, curr_llh = 1, False, "optimal", pre_llh
         while em_iter <= maxIter:
             self.Estep()

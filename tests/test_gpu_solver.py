@@ -76,6 +76,31 @@ def test_fixed_branches_and_fixed_params():
     s.close()
 
 
+def test_example1_ultrametric_em_reaches_published_optimum():
+    """BASELINE config 1 (examples/example1, the runner's default ultra_constr=True): EM from a random start on
+    the shipped starting tree reaches the published optimum (examples/out_example1/example1_params.txt:
+    nllh 6987.352449704049, phi 0.14378501771164973, nu 0.13359737967697907).  Tolerances are the spread of the
+    reference's own five random starts (examples/example1/LAML_output.log:11-36: 4.5e-4 in nllh, ~1.5e-4 in
+    phi, ~5e-4 in nu); the E-step runs on the GPU, the ultrametric M-step in laml_b200/ultrametric.py."""
+    case, z = load_npz_case("ref_example1_start")
+    ref = OPT["example1"]
+    s = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': 0.1, 'nu': 0.1})
+    for tree in s.trees:                                   # the shipped starting tree carries no lengths
+        for nd in tree.traverse_postorder():
+            nd.edge_length = None
+    nllh, status = s.optimize(initials=1, random_seeds=1984, verbose=-1, ultra_constr=True)
+    assert status == "optimal"
+    assert abs(nllh - ref["nllh"]) < 1e-3
+    assert abs(s.params.phi - ref["phi"]) < 3e-4 and abs(s.params.nu - ref["nu"]) < 1e-3
+    tree = s.trees[0]
+    dist = {}
+    for nd in tree.traverse_preorder():
+        dist[nd] = (dist[nd.parent] if nd.parent is not None else 0.0) + (nd.edge_length or 0.0)
+    tips = np.array([dist[nd] for nd in tree.traverse_leaves()])
+    assert np.ptp(tips) < 1e-6
+    s.close()
+
+
 def test_ultrametric_em():
     """ultra_constr=True (the runner's default, runner.py:91,287): host program on GPU statistics;
     the result must be ultrametric and not worse than the start"""
