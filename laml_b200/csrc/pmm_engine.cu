@@ -96,7 +96,10 @@ int fail(pmm_handle *h, const char *fmt, ...) {
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError(); /* do not leave a sticky error behind for the next caller */   \
+            return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
     } while (0)
 
 template <class T> int dalloc(pmm_handle *h, T **p, size_t count) {
@@ -518,12 +521,12 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     // a fresh solver per candidate) keeps every device buffer and the chunk plan: only the tree arrays and
     // the level schedules are replaced
     const bool reuse = (h->n == n && h->n_roots == n_roots && h->d_X != nullptr);
+    (void)cudaGetLastError();      // a stale error of another library in this process is not ours
     if (!reuse) {
         free_tree_state(h);
         h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;   // what pmm_create holds
+        h->n = 0;                  // "no tree" until this call has succeeded
     }
-    h->n = n; h->n_int = n - N; h->n_roots = n_roots;
-    h->parent.assign(parent, parent + n); h->left.assign(left, left + n); h->right.assign(right, right + n);
     // depth (root = 0) and height (leaf = 0) without recursion
     std::vector<int> depth(n, -1), height(n, 0), order;
     order.reserve(n);
@@ -540,6 +543,8 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         }
     }
     if ((int)order.size() != n) return fail(h, "tree arrays contain a cycle or unreachable nodes");
+    h->n_int = n - N; h->n_roots = n_roots;
+    h->parent.assign(parent, parent + n); h->left.assign(left, left + n); h->right.assign(right, right + n);
     std::vector<int> root_index(n, 0);
     for (size_t i = 0; i < roots.size(); i++) root_index[roots[i]] = (int)i;
     for (int v : order) if (parent[v] >= 0) root_index[v] = root_index[parent[v]];
@@ -604,6 +609,7 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         return 1;
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->n = n;
     return 0;
 }
 
