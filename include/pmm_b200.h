@@ -161,6 +161,10 @@ typedef struct {
     int64_t inside_levels, outside_levels;
     int64_t device_bytes;        /* allocated by the handle */
     int64_t kernel_launches;     /* launched by this handle so far */
+    /* lumped-state engine (the default E-step path; PMM_ENGINE=fullstate selects the row engine) */
+    int64_t engine;              /* 0 = lumped records, 1 = full-state rows */
+    int64_t clades, clade_target, launches_per_pass;
+    int64_t inside_bytes_per_site, outside_bytes_per_site;   /* bytes the lumped passes must move per site */
 } pmm_info;
 int pmm_get_info(const pmm_handle *h, pmm_info *info);
 

@@ -31,7 +31,8 @@ class PMMError(RuntimeError):
 class PMMInfo(C.Structure):
     _fields_ = [(k, C.c_int64) for k in (
         "n_nodes", "n_leaves", "n_sites", "slots_per_node", "row_stride", "padded_slots_per_node", "n_chunks", "n_tiles", "tile_slots",
-        "inside_levels", "outside_levels", "device_bytes", "kernel_launches")]
+        "inside_levels", "outside_levels", "device_bytes", "kernel_launches", "engine", "clades", "clade_target",
+        "launches_per_pass", "inside_bytes_per_site", "outside_bytes_per_site")]
 
 
 _lib = None

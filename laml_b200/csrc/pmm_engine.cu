@@ -6,6 +6,7 @@
 #include "../../include/pmm_b200.h"
 #include "pmm_kernels.cuh"
 #include "pmm_nni.cuh"
+#include "pmm_lumped.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,19 @@ struct pmm_handle {
     NuState *d_nu_state = nullptr;
     double *d_nu_partial = nullptr;
     double *d_post0 = nullptr, *d_post1 = nullptr;
+    // ---- lumped-state engine (default): clade schedules and 40-byte records, see pmm_lumped.cuh
+    int engine = 0;                 // 0 = lumped (default), 1 = full-state rows (PMM_ENGINE=fullstate)
+    bool last_full = false;         // which engine ran the last pass (for pmm_last_timing)
+    bool full_ready = false;        // full-state buffers are allocated on first use (NNI batch, PMM_ENGINE=fullstate)
+    int clade_target = 0, n_clades = 0;
+    std::vector<int> lin_phase_ptr, lout_phase_ptr;     // launch -> first clade
+    int4 *d_lin_steps = nullptr, *d_lout_steps = nullptr, *d_lin_clades = nullptr, *d_lout_clades = nullptr;
+    int lKc = 0, lG = 0;            // sites per chunk, site groups (warps) per chunk
+    double4 *d_LX = nullptr, *d_LO = nullptr;
+    int2 *d_LXI = nullptr, *d_LOI = nullptr;
+    double *d_LinvL = nullptr, *d_Lroot_llh = nullptr, *d_LSpart = nullptr, *d_LRpart = nullptr, *d_qsum = nullptr, *d_prior = nullptr;
+    int *d_site_ptr = nullptr;
+    int64_t l_in_bytes_per_site = 0, l_out_bytes_per_site = 0;   // algorithmic bytes the lumped passes move per site
     size_t device_bytes = 0;
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -132,6 +146,10 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial);
     dfree(h->d_post0); dfree(h->d_post1);
+    dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
+    dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LXI); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
+    dfree(h->d_LSpart); dfree(h->d_LRpart);
+    h->full_ready = false;
     free_chunks(h);
 }
 
@@ -364,6 +382,228 @@ int launch_outside(pmm_handle *h, const KParams &P) {
     return 0;
 }
 
+
+// ======================================================== lumped-state engine: host side
+// Cut the forest into clades of ~m internal nodes (greedy, bottom-up: a node whose open subtree has
+// reached m internal nodes becomes a clade root; so does every tree root) and write, per clade, the
+// step lists the kernels in pmm_lumped.cuh walk.  `order` lists parents before children.
+int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const std::vector<int> &root_index) {
+    const int N = h->n_leaves, n = h->n_int + N;
+    const std::vector<int> &L = h->left, &R = h->right, &Pa = h->parent;
+    int m = env_int("PMM_CLADE", 0);
+    if (m <= 0) {
+        // enough CTAs for ~4 waves over the SMs, but chains no longer than 64 steps
+        const double ctas_per_node = (double)((h->K + LT - 1) / LT);
+        const double resident = 4.0 * h->n_sms * 4.0;
+        m = (int)((double)h->n_int * ctas_per_node / resident);
+        m = std::max(4, std::min(64, m));
+    }
+    h->clade_target = m;
+    std::vector<int> osz(n, 0), ph(n, 0), phase(n, -1);
+    std::vector<char> cut(n, 0);
+    int max_phase = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        const int u = order[i];
+        if (L[u] < 0) continue;
+        int sz = 1, p = 0;
+        for (int c : {L[u], R[u]}) {
+            if (c < N) continue;
+            if (cut[c]) p = std::max(p, phase[c] + 1);
+            else { sz += osz[c]; p = std::max(p, ph[c]); }
+        }
+        osz[u] = sz; ph[u] = p;
+        if (sz >= m || Pa[u] < 0) { cut[u] = 1; phase[u] = p; max_phase = std::max(max_phase, p); }
+    }
+    std::vector<std::vector<int>> by_phase(max_phase + 1);
+    for (int i = 0; i < n; i++) { const int u = order[i]; if (u >= N && cut[u]) by_phase[phase[u]].push_back(u); }
+    auto open_internal = [&](int c) { return c >= N && !cut[c]; };
+
+    std::vector<int4> in_steps, out_steps, in_clades, out_clades;
+    in_steps.reserve(h->n_int); out_steps.reserve(h->n_int);
+    h->lin_phase_ptr.assign(1, 0); h->lout_phase_ptr.assign(1, 0);
+    std::vector<int> clade_id(n, -1);
+    int64_t in_loads = 0, out_loads = 0, out_stores = 0;
+    int ncl = 0;
+    std::vector<std::pair<int, int>> stk;
+    // ---- inside: post-order; of two open internal children the bigger subtree goes first, the one
+    // visited last stays in registers (KIND_PREV), everything else is loaded
+    for (int p = 0; p <= max_phase; p++) {
+        for (int r : by_phase[p]) {
+            clade_id[r] = ncl++;
+            const int begin = (int)in_steps.size();
+            stk.clear(); stk.push_back({r, 0});
+            while (!stk.empty()) {
+                const int u = stk.back().first, stt = stk.back().second;
+                const int a = L[u], b = R[u];
+                int first = -1, second = -1;
+                const bool oa = open_internal(a), ob = open_internal(b);
+                if (oa && ob) { if (osz[a] >= osz[b]) { first = a; second = b; } else { first = b; second = a; } }
+                else if (oa) second = a;
+                else if (ob) second = b;
+                if (stt == 0) { stk.back().second = 1; if (first >= 0) stk.push_back({first, 0}); continue; }
+                if (stt == 1) { stk.back().second = 2; if (second >= 0) stk.push_back({second, 0}); continue; }
+                stk.pop_back();
+                auto kind = [&](int c) { return c < N ? KIND_LEAF : (c == second ? KIND_PREV : KIND_LOAD); };
+                const int kv = kind(a), kw = kind(b);
+                in_loads += (kv == KIND_LOAD) + (kw == KIND_LOAD);
+                in_steps.push_back(make_int4(u, a, b, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0)));
+            }
+            in_clades.push_back(make_int4(begin, (int)in_steps.size(), root_index[r], clade_id[r]));
+        }
+        h->lin_phase_ptr.push_back((int)in_clades.size());
+    }
+    // ---- outside: pre-order, top clades first; of two open internal children the smaller subtree
+    // goes first and its out-record stays in registers, the other one is stored and loaded later
+    std::vector<std::pair<int, int>> stk2;
+    for (int p = max_phase; p >= 0; p--) {
+        for (int r : by_phase[p]) {
+            const int begin = (int)out_steps.size();
+            stk2.clear(); stk2.push_back({r, Pa[r] < 0 ? 0 : KIND_LOAD});
+            while (!stk2.empty()) {
+                const int u = stk2.back().first, how = stk2.back().second;
+                stk2.pop_back();
+                const int a = L[u], b = R[u];
+                int first = -1, second = -1;
+                const bool oa = open_internal(a), ob = open_internal(b);
+                if (oa && ob) { if (osz[a] <= osz[b]) { first = a; second = b; } else { first = b; second = a; } }
+                else if (oa) first = a;
+                else if (ob) first = b;
+                int f = how | (a < N ? 4 : 0) | (b < N ? 8 : 0);
+                if (a >= N && a != first) { f |= 16; out_stores++; }
+                if (b >= N && b != first) { f |= 32; out_stores++; }
+                if (first == a) f |= 1 << 6; else if (first == b) f |= 2 << 6;
+                out_loads += (how == KIND_LOAD);
+                out_steps.push_back(make_int4(u, a, b, f));
+                if (second >= 0) stk2.push_back({second, KIND_LOAD});
+                if (first >= 0) stk2.push_back({first, KIND_PREV});
+            }
+            out_clades.push_back(make_int4(begin, (int)out_steps.size(), root_index[r], clade_id[r]));
+        }
+        h->lout_phase_ptr.push_back((int)out_clades.size());
+    }
+    h->n_clades = ncl;
+    if ((int)in_steps.size() != h->n_int || (int)out_steps.size() != h->n_int) return fail(h, "internal error: clade schedule does not cover the tree");
+    // algorithmic bytes per site: 40-byte records written once and read where not chained, 4-byte leaf codes,
+    // 40 bytes of expected counts per (branch, 32 sites)
+    h->l_in_bytes_per_site = 40 * (int64_t)h->n_int + 40 * in_loads + 4 * (int64_t)N + 16 * (int64_t)h->n_roots;
+    h->l_out_bytes_per_site = 40 * (int64_t)(h->n_int) /* inside records of internal children and roots */ + 4 * (int64_t)N +
+                              40 * (out_loads + out_stores) + 8 * (int64_t)h->n_roots + (40 * (int64_t)n) / 32;
+    // device copies (capacity n_int for every array, so that a new topology over the same counts reuses them)
+    const size_t cap = (size_t)std::max(h->n_int, 1);
+    if (!h->d_lin_steps &&
+        (dalloc(h, &h->d_lin_steps, cap) || dalloc(h, &h->d_lout_steps, cap) || dalloc(h, &h->d_lin_clades, cap) || dalloc(h, &h->d_lout_clades, cap)))
+        return 1;
+    CK(cudaMemcpy(h->d_lin_steps, in_steps.data(), sizeof(int4) * in_steps.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_lout_steps, out_steps.data(), sizeof(int4) * out_steps.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_lin_clades, in_clades.data(), sizeof(int4) * in_clades.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_lout_clades, out_clades.data(), sizeof(int4) * out_clades.size(), cudaMemcpyHostToDevice));
+    if (env_int("PMM_VERBOSE", 0))
+        fprintf(stderr, "[pmm] lumped schedule: clade target %d, %d clades, %d launches per pass, %lld inside loads, %lld outside loads, %lld outside stores\n",
+                m, ncl, max_phase + 1, (long long)in_loads, (long long)out_loads, (long long)out_stores);
+    return 0;
+}
+
+// records and partial sums of the lumped engine; sites are processed in chunks of lKc if they do not fit
+int alloc_lumped(pmm_handle *h) {
+    const int n = h->n_int + h->n_leaves, K = h->K;     // h->n is set only once pmm_set_tree has succeeded
+    size_t budget = h->budget;
+    if (budget == 0) {
+        size_t fr = 0, tot = 0;
+        cudaError_t e = cudaMemGetInfo(&fr, &tot);
+        if (e != cudaSuccess) return fail(h, "cudaMemGetInfo failed: %s", cudaGetErrorString(e));
+        budget = (size_t)(0.85 * (double)fr);
+    }
+    const double per_site = 80.0 * h->n_int + 16.0 * h->n_roots + (40.0 * n + 8.0 * h->n_int) / 32.0;
+    int Kc = K;
+    const int forced = env_int("PMM_CHUNKS", 0);
+    if (forced > 0) Kc = std::max(1, (K + forced - 1) / forced);
+    else if (per_site * K > (double)budget) Kc = std::min(K, std::max(32, (int)((double)budget / per_site) / 32 * 32));
+    h->lKc = Kc; h->lG = (Kc + 31) / 32;
+    const size_t rows = (size_t)h->n_int * Kc;
+    if (dalloc(h, &h->d_LX, rows) || dalloc(h, &h->d_LO, rows) || dalloc(h, &h->d_LXI, rows) || dalloc(h, &h->d_LOI, rows) ||
+        dalloc(h, &h->d_LinvL, (size_t)h->n_roots * Kc) || dalloc(h, &h->d_Lroot_llh, (size_t)h->n_roots * Kc) ||
+        dalloc(h, &h->d_LSpart, (size_t)h->lG * n * 5) || dalloc(h, &h->d_LRpart, (size_t)h->lG * std::max(h->n_int, 1)))
+        return 1;
+    return 0;
+}
+
+int run_lumped(pmm_handle *h, bool outside, bool with_post) {
+    const int n = h->n;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    pmm_branch_consts<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_d, h->d_params, n, h->d_bc);
+    h->launches++;
+    double *d_llh = h->d_stats + (size_t)5 * n + 1;
+    double *d_Rt = h->d_stats + (size_t)5 * n;
+    const int nchunks = (h->K + h->lKc - 1) / h->lKc;
+    float acc_in = 0, acc_out = 0;
+    for (int ci = 0; ci < nchunks; ci++) {
+        LParams P;
+        P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.code_stride = h->K;
+        P.n_leaves = h->n_leaves; P.n_nodes = n; P.n_clades = h->n_clades;
+        P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
+        P.params = h->d_params; P.bc = h->d_bc;
+        P.X = h->d_LX; P.XI = h->d_LXI; P.O = h->d_LO; P.OI = h->d_LOI;
+        P.invL = h->d_LinvL; P.root_site_llh = h->d_Lroot_llh; P.Spart = h->d_LSpart; P.Rpart = h->d_LRpart;
+        P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
+        P.K_total = h->K; P.store_all = env_int("PMM_STORE_ALL", 0);
+        const unsigned gy = (unsigned)((P.K + LT - 1) / LT);
+        const int G = (P.K + 31) / 32;
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        for (size_t p = 0; p + 1 < h->lin_phase_ptr.size(); p++) {
+            const int c0 = h->lin_phase_ptr[p], c1 = h->lin_phase_ptr[p + 1];
+            if (c1 <= c0) continue;
+            pmm_lumped_inside<<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lin_clades + c0, h->d_lin_steps);
+            h->launches++;
+        }
+        pmm_site_llh<<<(P.K + 255) / 256, 256, 0, h->stream>>>(h->d_Lroot_llh, h->n_roots, P.K, h->d_site_llh + P.site0);
+        pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_site_llh + P.site0, P.K, d_llh, ci > 0);
+        h->launches += 2;
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        if (outside) {
+            for (size_t p = 0; p + 1 < h->lout_phase_ptr.size(); p++) {
+                const int c0 = h->lout_phase_ptr[p], c1 = h->lout_phase_ptr[p + 1];
+                if (c1 <= c0) continue;
+                if (with_post) pmm_lumped_outside<true><<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lout_clades + c0, h->d_lout_steps);
+                else pmm_lumped_outside<false><<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lout_clades + c0, h->d_lout_steps);
+                h->launches++;
+            }
+            pmm_reduce_S<<<(5 * n + 255) / 256, 256, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0);
+            pmm_reduce_S<<<(h->n_clades + 255) / 256, 256, 0, h->stream>>>(h->d_LRpart, G, h->n_clades, h->d_Rnode, 0);
+            pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Rnode, h->n_clades, d_Rt, ci > 0);
+            h->launches += 3;
+        }
+        CK(cudaEventRecord(h->ev[3], h->stream));
+        if (nchunks > 1) {
+            CK(cudaEventSynchronize(h->ev[3]));
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, h->ev[1], h->ev[2]);
+            cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
+            acc_in += a; acc_out += b;
+        }
+    }
+    CK(cudaGetLastError());
+    h->t_inside = acc_in; h->t_outside = acc_out;
+    h->timing_valid = false;
+    return 0;
+}
+
+// full-state rows (pmm_kernels.cuh): allocated on first use -- the NNI batch scorer and PMM_ENGINE=fullstate
+int ensure_fullstate(pmm_handle *h) {
+    if (h->full_ready) return 0;
+    const int n = h->n;
+    if (plan_chunks(h)) return 1;
+    if (configure_kernels(h)) return 1;
+    const size_t rows = (size_t)h->n_int;
+    if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxKp) ||
+        dalloc(h, &h->d_dexp, rows * h->maxKp) || dalloc(h, &h->d_eX, rows * h->maxKp) || dalloc(h, &h->d_eO, rows * h->maxKp) ||
+        dalloc(h, &h->d_sqX, rows * h->maxKp) || dalloc(h, &h->d_rootInvL, (size_t)h->n_roots * h->maxKp) ||
+        dalloc(h, &h->d_root_site_llh, (size_t)h->n_roots * h->maxK) ||
+        dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
+        return 1;
+    h->full_ready = true;
+    return 0;
+}
+
 int check_ready(pmm_handle *h) {
     if (!h) return 1;
     if (h->n == 0) return fail(h, "pmm_set_tree has not been called");
@@ -372,7 +612,10 @@ int check_ready(pmm_handle *h) {
 }
 
 // inside (+ optionally outside/counts) over all chunks, parameters already on the device
-int run_passes(pmm_handle *h, bool outside, bool with_post) {
+int run_passes(pmm_handle *h, bool outside, bool with_post, bool force_full = false) {
+    if (h->engine == 0 && !force_full) { h->last_full = false; return run_lumped(h, outside, with_post); }
+    if (ensure_fullstate(h)) return 1;
+    h->last_full = true;
     const int n = h->n;
     CK(cudaEventRecord(h->ev[0], h->stream));
     pmm_branch_consts<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_d, h->d_params, n, h->d_bc);
@@ -417,7 +660,7 @@ int run_passes(pmm_handle *h, bool outside, bool with_post) {
 // =============================================================== C ABI
 extern "C" {
 
-int pmm_abi_version(void) { return 1; }
+int pmm_abi_version(void) { return 2; }
 
 const char *pmm_last_error(const pmm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -467,7 +710,27 @@ int pmm_create(int32_t n_leaves, int32_t n_sites, const int32_t *site_ptr, const
                 return bail(1);
             }
         }
-    if (dalloc(h, &h->d_codes, (size_t)n_leaves * n_sites) || dalloc(h, &h->d_params, 2)) return bail(1);
+    {
+        const char *eng = getenv("PMM_ENGINE");
+        h->engine = (eng && std::string(eng) == "fullstate") ? 1 : 0;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
+    }
+    std::vector<double> qsum((size_t)n_sites, 0.0);
+    for (int s = 0; s < n_sites; s++) {
+        double acc = 0.0;
+        for (int a = site_ptr[s]; a < site_ptr[s + 1]; a++) acc += prior[a];
+        qsum[s] = acc;
+    }
+    if (dalloc(h, &h->d_codes, (size_t)n_leaves * n_sites) || dalloc(h, &h->d_params, 2) || dalloc(h, &h->d_site_ptr, (size_t)n_sites + 1) ||
+        dalloc(h, &h->d_prior, (size_t)nnz) || dalloc(h, &h->d_qsum, (size_t)n_sites))
+        return bail(1);
+    if (cudaMemcpy(h->d_site_ptr, site_ptr, sizeof(int) * ((size_t)n_sites + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nnz > 0 && cudaMemcpy(h->d_prior, prior, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        cudaMemcpy(h->d_qsum, qsum.data(), sizeof(double) * (size_t)n_sites, cudaMemcpyHostToDevice) != cudaSuccess) {
+        h->err = "uploading the prior failed";
+        return bail(1);
+    }
     if (cudaMemcpy(h->d_codes, codes, sizeof(int) * (size_t)n_leaves * n_sites, cudaMemcpyHostToDevice) != cudaSuccess) {
         h->err = "uploading codes failed";
         return bail(1);
@@ -481,7 +744,7 @@ void pmm_destroy(pmm_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_tree_state(h);
-    dfree(h->d_codes); dfree(h->d_params);
+    dfree(h->d_codes); dfree(h->d_params); dfree(h->d_site_ptr); dfree(h->d_prior); dfree(h->d_qsum);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -520,11 +783,12 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     // a new topology over the same node / root counts (topology search: Topology_search.py:289-299 builds
     // a fresh solver per candidate) keeps every device buffer and the chunk plan: only the tree arrays and
     // the level schedules are replaced
-    const bool reuse = (h->n == n && h->n_roots == n_roots && h->d_X != nullptr);
+    const bool reuse = (h->n == n && h->n_roots == n_roots && h->d_LX != nullptr);
     (void)cudaGetLastError();      // a stale error of another library in this process is not ours
     if (!reuse) {
         free_tree_state(h);
-        h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16;   // what pmm_create holds
+        h->device_bytes = sizeof(int) * (size_t)h->n_leaves * h->K + 16 + sizeof(int) * ((size_t)h->K + 1) +
+                          sizeof(double) * (h->prior.size() + (size_t)h->K);   // what pmm_create holds
         h->n = 0;                  // "no tree" until this call has succeeded
     }
     // depth (root = 0) and height (leaf = 0) without recursion
@@ -592,21 +856,15 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     CK(cudaMemcpy(h->d_in_items, in_items.data(), sizeof(int4) * in_items.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_out_items, out_items.data(), sizeof(int4) * out_items.size(), cudaMemcpyHostToDevice));
 
+    if (build_lumped_schedule(h, order, root_index)) return 1;
     if (reuse) return 0;
-    // small per-node buffers first, then the chunk plan against what is left
+    // small per-node buffers first, then the records against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
         dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 4) || dalloc(h, &h->d_Rnode, h->n_int) ||
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
-    if (plan_chunks(h)) return 1;
-    if (configure_kernels(h)) return 1;
-    const size_t rows = (size_t)h->n_int;
-    if (dalloc(h, &h->d_X, rows * h->maxWp) || dalloc(h, &h->d_O, rows * h->maxWp) || dalloc(h, &h->d_iexp, rows * h->maxKp) ||
-        dalloc(h, &h->d_dexp, rows * h->maxKp) || dalloc(h, &h->d_eX, rows * h->maxKp) || dalloc(h, &h->d_eO, rows * h->maxKp) ||
-        dalloc(h, &h->d_sqX, rows * h->maxKp) || dalloc(h, &h->d_rootInvL, (size_t)n_roots * h->maxKp) ||
-        dalloc(h, &h->d_root_site_llh, (size_t)n_roots * h->maxK) ||
-        dalloc(h, &h->d_Spart, (size_t)h->max_tiles * n * 5) || dalloc(h, &h->d_Rpart, (size_t)h->max_tiles * h->n_int))
-        return 1;
+    if (alloc_lumped(h)) return 1;
+    if (h->engine == 1 && ensure_fullstate(h)) return 1;
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n = n;
@@ -768,6 +1026,7 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
                         int32_t *out_iters, int32_t *out_nodes) {
     if (n_cand <= 0) return 0;
     if (pmm_upload_params(h, d, nu, phi)) return 1;
+    if (ensure_fullstate(h)) return 1;       // the batch scorer works on cached full-state rows (pmm_nni.cuh)
     if (h->chunks.size() != 1) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk, have %zu)", h->chunks.size());
     const int N = h->n_leaves, n = h->n;
     std::vector<int> root_index(n, 0);
@@ -802,7 +1061,7 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         if (out_nodes) { int32_t *o = out_nodes + (size_t)5 * i; o[0] = v; o[1] = u; o[2] = ck; o[3] = co; o[4] = w; }
     }
     // caches of the current tree: one full E-step
-    if (run_passes(h, true, false)) return 1;
+    if (run_passes(h, true, false, true)) return 1;
     const Chunk &c0 = h->chunks[0];
     KParams P = make_params(h, c0, false);
     double llh_total = 0.0;
@@ -854,7 +1113,11 @@ int pmm_get_info(const pmm_handle *h, pmm_info *info) {
     info->slots_per_node = h->W; info->row_stride = h->maxWp;
     info->padded_slots_per_node = 0;
     for (auto &c : h->chunks) info->padded_slots_per_node += c.Wp;
-    info->n_chunks = (int64_t)h->chunks.size(); info->n_tiles = h->max_tiles; info->tile_slots = h->TS;
+    info->n_chunks = h->engine == 0 ? (int64_t)((h->K + std::max(h->lKc, 1) - 1) / std::max(h->lKc, 1)) : (int64_t)h->chunks.size();
+    info->n_tiles = h->max_tiles; info->tile_slots = h->TS;
+    info->engine = h->engine; info->clades = h->n_clades; info->clade_target = h->clade_target;
+    info->launches_per_pass = (int64_t)h->lin_phase_ptr.size() - 1;
+    info->inside_bytes_per_site = h->l_in_bytes_per_site; info->outside_bytes_per_site = h->l_out_bytes_per_site;
     info->inside_levels = (int64_t)h->in_ptr.size() - 1; info->outside_levels = (int64_t)h->out_ptr.size() - 1;
     info->device_bytes = (int64_t)h->device_bytes; info->kernel_launches = h->launches;
     return 0;
@@ -866,7 +1129,8 @@ int pmm_last_timing(const pmm_handle *hc, double *inside_ms, double *outside_ms,
     CK(cudaSetDevice(h->device));
     CK(cudaEventSynchronize(h->ev[3]));
     float a = h->t_inside, b = h->t_outside, tot = 0;
-    if (h->chunks.size() == 1) {
+    const bool one_chunk = h->last_full ? h->chunks.size() == 1 : h->lKc >= h->K;
+    if (one_chunk) {
         cudaEventElapsedTime(&a, h->ev[1], h->ev[2]);
         cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
     }

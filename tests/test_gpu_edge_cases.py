@@ -10,6 +10,13 @@ from laml_b200.synth import make_workload, random_priors, random_tree, simulate_
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["lumped", "fullstate"])
+def engine_mode(request, monkeypatch):
+    """both E-step engines (lumped-state records = default; full-state rows) face every edge case"""
+    monkeypatch.setenv("PMM_ENGINE", request.param)
+    return request.param
+
+
 def oracle_of(forest, codes, qptr, qval):
     from oracle.pmm_oracle import OracleProblem
     return OracleProblem(forest, np.arange(forest.n_leaves, dtype=np.int32), codes, qptr, qval)

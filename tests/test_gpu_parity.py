@@ -12,6 +12,16 @@ from helpers import (NPZ_CASES, env_override, json_case, load_json, load_npz_cas
 
 pytestmark = pytest.mark.gpu
 
+
+
+@pytest.fixture(autouse=True, params=["lumped", "fullstate"])
+def engine_mode(request, monkeypatch):
+    """every parity test runs on both E-step engines: the lumped-state records (default) and the
+    full-state rows (PMM_ENGINE=fullstate; also what the NNI batch scorer caches)"""
+    monkeypatch.setenv("PMM_ENGINE", request.param)
+    return request.param
+
+
 KAT = load_json("kat_likelihood.json")
 PROP = load_json("outside_cases.json")
 
@@ -66,7 +76,7 @@ def test_outside_cases(rec):
 
 
 @pytest.mark.parametrize("ts,group,chunks", [(64, 4, 1), (128, 8, 1), (256, 16, 2), (512, 32, 3), (2048, 8, 1)])
-def test_layout_variants(ts, group, chunks):
+def test_layout_variants(ts, group, chunks, engine_mode):
     """tile size, lane-group width and site chunking must not change results"""
     case, z = load_npz_case("ref_rand_ragged")
     with env_override(PMM_TILE_SLOTS=ts, PMM_GROUP=group, PMM_CHUNKS=chunks):
@@ -80,6 +90,22 @@ def test_layout_variants(ts, group, chunks):
         eng = make_engine(case)
         check_against_golden(case, z, eng)
         eng.close()
+
+
+@pytest.mark.parametrize("clade,chunks,store_all", [(1, 1, 0), (2, 1, 1), (3, 2, 0), (7, 1, 0), (16, 3, 1), (100000, 1, 0)])
+def test_lumped_schedule_variants(clade, chunks, store_all, engine_mode):
+    """clade size (1 = one launch per tree level ... whole tree in one clade), site chunking and
+    storing the register-chained out-records must not change the lumped engine's results"""
+    if engine_mode != "lumped":
+        pytest.skip("lumped engine only")
+    for name in ("ref_rand_ragged", "ref_rand_forest", "ref_rand_deep", "ref_test45_test1"):
+        case, z = load_npz_case(name)
+        with env_override(PMM_CLADE=clade, PMM_CHUNKS=chunks, PMM_STORE_ALL=store_all):
+            eng = make_engine(case)
+            info = eng.info()
+            assert info["engine"] == 0 and info["n_chunks"] == chunks and info["clade_target"] == clade
+            check_against_golden(case, z, eng)
+            eng.close()
 
 
 @pytest.mark.parametrize("cfg,seed", [("config2_1k_x_30", 1), ("config2_1k_x_30", 2)])
