@@ -261,39 +261,64 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (pmm_outside_level) -----------------------
+    # ---- roofline of the dominant kernel (the outside pass) ----------------------------
     peak, peak_src = hbm_peak()
     W_shard_max = info["slots_per_node"]
     n_roots = int((forest.parent < 0).sum())
     # 20 bytes per (child node, state slot) for outside+counts, 16 for inside
     out_bytes = 20.0 * W_shard_max * (n - n_roots)
     in_bytes = 16.0 * W_shard_max * n
-    # bytes this design actually has to move (leaf rows are never materialised): DESIGN.md
     n_int = n - N
-    Wrow = info["padded_slots_per_node"]     # slots per row incl. even-length padding, summed over site chunks
-    out_moved = 8.0 * Wrow * (n_int + 2 * (n_int - n_roots))      # read out[u]; read x[c], write out[c] for internal children
-    in_moved = 8.0 * Wrow * (n_int + (n_int - n_roots))           # write x[u]; read x[c] for internal children
-    out_launches = info["outside_levels"] * info["n_chunks"]     # at least; big levels take one launch per node class
-    # `achieved` counts the bytes this design must move: a true HBM utilisation.
-    # The SURVEY 8(d) per-unit figure (16 B inside / 20 B outside per node*slot, every vector stored) is
-    # reported next to it; it exceeds the moved bytes because leaf vectors are never materialised.
+    lumped = info["engine"] == 0
+    if lumped:
+        # lumped-state engine: 40-byte (node, site) records written once and read where
+        # they are not chained in registers, 4-byte leaf codes, 40 B of counts per (branch, 32 sites);
+        # the engine derives the exact per-site byte counts from its clade schedule
+        K_shard = hi - lo
+        out_moved = float(info["outside_bytes_per_site"]) * K_shard
+        in_moved = float(info["inside_bytes_per_site"]) * K_shard
+        out_launches = info["launches_per_pass"] * info["n_chunks"]
+        k_out, k_in = "pmm_lumped_outside", "pmm_lumped_inside"
+        note = ("rank 0's site shard; moved bytes = what the lumped-state engine must move (40-byte records per "
+                "(internal node, site), leaf codes, count partials); the SURVEY 8(d) figure charges 8 B per state slot "
+                "of every node and is shown beside it (SURVEY 8d: 'a compressed implementation ... must still report "
+                "against this figure'); traffic = ncu dram bytes per launch, profiles/")
+    else:
+        # full-state rows (PMM_ENGINE=fullstate): leaf rows are never materialised
+        Wrow = info["padded_slots_per_node"]     # slots per row incl. even-length padding, summed over site chunks
+        out_moved = 8.0 * Wrow * (n_int + 2 * (n_int - n_roots))      # read out[u]; read x[c], write out[c] for internal children
+        in_moved = 8.0 * Wrow * (n_int + (n_int - n_roots))           # write x[u]; read x[c] for internal children
+        out_launches = info["outside_levels"] * info["n_chunks"]     # at least; big levels take one launch per node class
+        k_out, k_in = "pmm_level<outside>", "pmm_level<inside>"
+        note = ("rank 0's site shard; moved bytes = internal-node rows only (leaf vectors are closed forms of "
+                "4-byte codes and are never stored); traffic: see profiles/ for the ncu dram__bytes of one launch")
+    # ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the dominant kernel, measured once per
+    # build on this workload (profiles/*_traffic.json, written by scripts/summarize_traffic.py)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s/n%d/%s" % (args.workload, world, "lumped" if lumped else "fullstate")
+        traffic = tj.get(key, {}).get(k_out)
+    except Exception:
+        pass
+    # `achieved` counts the bytes this design must move: a true HBM utilisation.  The SURVEY 8(d) per-unit
+    # figure (16 B inside / 20 B outside per node*slot, every vector stored) is reported next to it.
     ach = out_moved / (outside_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "pmm_level<outside>", "achieved": ach, "peak": peak, "unit": "GB/s",
-        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": k_out, "achieved": ach, "peak": peak, "unit": "GB/s",
+        "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_step_moved": out_moved, "launches_per_step": out_launches,
         "avg_launch_ms": outside_ms / max(out_launches, 1), "ms_per_step": outside_ms,
         "survey_figure": {"bytes_per_step": out_bytes, "achieved": out_bytes / (outside_ms * 1e-3) / 1e9,
                           "frac": out_bytes / (outside_ms * 1e-3) / 1e9 / peak},
-        "inside": {"kernel": "pmm_level<inside>", "achieved": in_moved / (inside_ms * 1e-3) / 1e9,
+        "inside": {"kernel": k_in, "achieved": in_moved / (inside_ms * 1e-3) / 1e9,
                    "frac": in_moved / (inside_ms * 1e-3) / 1e9 / peak, "ms_per_step": inside_ms,
                    "bytes_per_step_moved": in_moved,
                    "survey_figure": {"bytes_per_step": in_bytes, "achieved": in_bytes / (inside_ms * 1e-3) / 1e9,
                                      "frac": in_bytes / (inside_ms * 1e-3) / 1e9 / peak}},
         "estep": {"ms_per_step": estep_ms, "frac": (in_moved + out_moved) / (estep_ms * 1e-3) / 1e9 / peak,
                   "survey_figure_frac": (in_bytes + out_bytes) / (estep_ms * 1e-3) / 1e9 / peak},
-        "note": "rank 0's site shard; moved bytes = internal-node rows only (leaf vectors are closed forms of "
-                "4-byte codes and are never stored); traffic: see profiles/ for the ncu dram__bytes of one launch",
+        "note": note,
     }
 
     # ---- CPU baseline beside it (N=1 only) -----------------------------------------
@@ -319,8 +344,10 @@ def run_ours(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(config_dict(args.workload, spec, qptr, world),
-                       l2="state rows far exceed L2: %.1f GB per pass per GPU" % (8e-9 * info["row_stride"] * n_int),
-                       site_chunks=info["n_chunks"], tile_slots=info["tile_slots"]),
+                       engine="lumped-state records" if lumped else "full-state rows",
+                       l2=("per-node state far exceeds L2: %.1f GB per pass per GPU" %
+                           ((40e-9 * (hi - lo) if lumped else 8e-9 * info["row_stride"]) * n_int)),
+                       site_chunks=info["n_chunks"], clades=info["clades"], launches_per_pass=info["launches_per_pass"]),
         "em_iter_per_s": 1e3 / ms_step, "estep_ms": estep_ms, "inside_ms": inside_ms, "outside_ms": outside_ms,
         "estep_cell_site_per_s": N * Ktot / (estep_ms * 1e-3),
         "node_site_per_s": n * Ktot / (estep_ms * 1e-3),

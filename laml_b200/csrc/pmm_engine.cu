@@ -396,8 +396,9 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
         const double ctas_per_node = (double)((h->K + LT - 1) / LT);
         const double resident = 4.0 * h->n_sms * 4.0;
         m = (int)((double)h->n_int * ctas_per_node / resident);
-        m = std::max(4, std::min(64, m));
+        m = std::max(4, m);
     }
+    m = std::min(m, STEP_CAP / 2);     // a clade has at most 2m - 1 steps; the kernels stage them in shared memory
     h->clade_target = m;
     std::vector<int> osz(n, 0), ph(n, 0), phase(n, -1);
     std::vector<char> cut(n, 0);
@@ -443,10 +444,14 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
                 if (stt == 0) { stk.back().second = 1; if (first >= 0) stk.push_back({first, 0}); continue; }
                 if (stt == 1) { stk.back().second = 2; if (second >= 0) stk.push_back({second, 0}); continue; }
                 stk.pop_back();
+                // the recursion is symmetric in the children: list the chained one (if any) second
+                const int cv = (second == a) ? b : a, cw = (second == a) ? a : b;
                 auto kind = [&](int c) { return c < N ? KIND_LEAF : (c == second ? KIND_PREV : KIND_LOAD); };
-                const int kv = kind(a), kw = kind(b);
+                const int kv = kind(cv), kw = kind(cw);
                 in_loads += (kv == KIND_LOAD) + (kw == KIND_LOAD);
-                in_steps.push_back(make_int4(u, a, b, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0)));
+                // bits 5 / 6: the loaded record belongs to another clade, i.e. an earlier launch wrote it
+                const int far = ((kv == KIND_LOAD && cut[cv]) ? 32 : 0) | ((kw == KIND_LOAD && cut[cw]) ? 64 : 0);
+                in_steps.push_back(make_int4(u, cv, cw, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0) | far));
             }
             in_clades.push_back(make_int4(begin, (int)in_steps.size(), root_index[r], clade_id[r]));
         }
@@ -468,12 +473,14 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
                 if (oa && ob) { if (osz[a] <= osz[b]) { first = a; second = b; } else { first = b; second = a; } }
                 else if (oa) first = a;
                 else if (ob) first = b;
-                int f = how | (a < N ? 4 : 0) | (b < N ? 8 : 0);
-                if (a >= N && a != first) { f |= 16; out_stores++; }
-                if (b >= N && b != first) { f |= 32; out_stores++; }
-                if (first == a) f |= 1 << 6; else if (first == b) f |= 2 << 6;
+                // the child whose out-record stays in registers (if any) is listed first
+                const int cv = (first == b) ? b : a, cw = (first == b) ? a : b;
+                int f = how | (cv < N ? 4 : 0) | (cw < N ? 8 : 0);
+                if (cv >= N && cv != first) { f |= 16; out_stores++; }
+                if (cw >= N) { f |= 32; out_stores++; }
+                if (first >= 0) f |= 64;
                 out_loads += (how == KIND_LOAD);
-                out_steps.push_back(make_int4(u, a, b, f));
+                out_steps.push_back(make_int4(u, cv, cw, f));
                 if (second >= 0) stk2.push_back({second, KIND_LOAD});
                 if (first >= 0) stk2.push_back({first, KIND_PREV});
             }
@@ -590,7 +597,7 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
 // full-state rows (pmm_kernels.cuh): allocated on first use -- the NNI batch scorer and PMM_ENGINE=fullstate
 int ensure_fullstate(pmm_handle *h) {
     if (h->full_ready) return 0;
-    const int n = h->n;
+    const int n = h->n_int + h->n_leaves;      // h->n is set only once pmm_set_tree has succeeded
     if (plan_chunks(h)) return 1;
     if (configure_kernels(h)) return 1;
     const size_t rows = (size_t)h->n_int;

@@ -17,18 +17,21 @@
 // model tests/lumped_model.py restates these closed forms and is pinned to the reference's dumps.
 //
 // Execution: sites are independent given the tree, so ONE THREAD OWNS ONE SITE and walks a whole
-// CLADE (a connected piece of the tree with ~m internal nodes, cut out by the host) without any
+// CLADE (a connected piece of the tree with < 128 internal nodes, cut out by the host) without any
 // synchronisation: a CTA is (clade, 128 consecutive sites); its threads follow the clade's step
 // list -- post-order for the inside pass, pre-order for the outside pass -- so that
 //   * the record of the child visited last (inside) / the out-record of the child visited first
 //     (outside) stays in registers: no memory round trip on the dependency chain;
 //   * every other operand was written at least one step earlier (by this very thread, or by an
-//     earlier launch for children in other clades) and is PREFETCHED one step ahead;
+//     earlier launch for children in other clades) and is loaded one step ahead into a second
+//     register set (the loop is unrolled by two so that the sets swap roles without moves); leaf
+//     codes are loaded two steps ahead because the prior of a leaf's state is a dependent gather;
+//   * the step list and the branch constants of the clade sit in shared memory;
 //   * all global accesses are coalesced across the warp's 32 sites (32 B + 8 B per thread).
 // Clades that hang below other clades run in an earlier (inside) / later (outside) launch: a
-// 100k-cell tree needs ~4 launches per pass instead of one per tree level.
+// 100k-cell tree needs ~10 launches per pass instead of one per tree level.
 // Expected counts: the 10 per-thread values of a step (5 per child branch) are summed over the
-// warp's sites with a halving butterfly (16 shuffles) and written once per (warp, node) into
+// warp's sites through a transposed shared-memory tile and written once per (warp, node) into
 // Spart[site group][node][5]; pmm_reduce_S sums the site groups in a fixed order (bit-reproducible).
 #pragma once
 #include "pmm_kernels.cuh"
@@ -36,6 +39,17 @@
 namespace pmm {
 
 constexpr int LT = 128;                  // threads (= sites) per CTA
+constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (the host caps the clade size at 64)
+#ifndef PMM_LIN_MINB
+#define PMM_LIN_MINB 5
+#endif
+#ifndef PMM_LOUT_MINB
+#define PMM_LOUT_MINB 3
+#endif
+#ifndef PMM_PF_DIST
+#define PMM_PF_DIST 6                    // L2 prefetch distance in steps for operands of earlier launches (0 = off)
+#endif
+constexpr int PF_DIST = PMM_PF_DIST;
 
 struct LParams {
     int K;                   // sites of this chunk
@@ -59,78 +73,86 @@ struct LParams {
     int store_all;           // outside pass: also store the out-records that are chained in registers
 };
 
-// inside step flags:  bits 0-1 kind of child v, bits 2-3 kind of child w, bit 4 = u is a root
-// outside step flags: bits 0-1 where out[u] comes from (0 = u is a root, 1 = load, 2 = chained),
-//                     bit 2 / 3: v / w is a leaf, bit 4 / 5: store out[v] / out[w],
-//                     bits 6-7: 1 = out[v] is chained into the next step, 2 = out[w] is
 enum { KIND_LEAF = 0, KIND_LOAD = 1, KIND_PREV = 2 };
 
-struct Rec { double x0, xm, xz, qh; int h, cum; };
-struct ORec { double o0, om, oB, oD; int k, F; };
-struct Msg { double E0, Em, Eb, Eh, sq, xb; };
+// one prefetched operand: an inside / outside record, or (leaves) the prior of the leaf's state in r.w
+struct Opd { double4 r; int2 ri; };
 
-// what a step reads from memory for one child: a record (internal child) or a state code (leaf)
-struct Pre { double4 r; int2 ri; };
-
-// branch constants (a, b, c, g) of node v: uniform across the warp, read-only path
 __device__ __forceinline__ double4 ld_bc(const double *__restrict__ bc, int v) {
     const double2 lo = __ldg(reinterpret_cast<const double2 *>(bc) + 2 * (size_t)v);
     const double2 hi = __ldg(reinterpret_cast<const double2 *>(bc) + 2 * (size_t)v + 1);
     return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ Pre fetch_child(const LParams &P, int kind, int c, int s, int gs) {
-    Pre p;
-    p.r = make_double4(0.0, 0.0, 0.0, 0.0);
-    p.ri = make_int2(0, 0);
-    if (kind == KIND_LEAF) p.ri.x = __ldg(P.codes + (size_t)c * P.code_stride + gs);
-    else if (kind == KIND_LOAD) {
-        const size_t o = (size_t)(c - P.n_leaves) * P.K + s;
-        p.r = P.X[o];
-        p.ri = P.XI[o];
+// the clade's steps, the branch constants of every step's two children and the four leaf vectors
+// (EM_solver.py:103-116 in full-state form, indexed by min(code, 1) + 2:
+//   known silenced (-2) -> e_m   '?' (-1) -> (phi, 1, phi..)   0 -> (1-phi) e_0   a -> (1-phi) e_a)
+__device__ __forceinline__ void stage_clade(int4 *s_steps, double4 *s_bc, double4 *s_lut, const LParams &P,
+                                            const int4 *__restrict__ steps, int begin, int nsteps) {
+    for (int i = threadIdx.x; i < nsteps; i += LT) s_steps[i] = __ldg(steps + begin + i);
+    for (int i = threadIdx.x; i < 2 * nsteps; i += LT) {
+        const int4 d = __ldg(steps + begin + (i >> 1));
+        s_bc[i] = ld_bc(P.bc, (i & 1) ? d.z : d.y);
     }
-    return p;
+    if (threadIdx.x < 4) {
+        const double phi = __ldg(P.params + 1);
+        const int c = threadIdx.x;                  // (x0, xm, xz)
+        s_lut[c] = make_double4(c == 1 ? phi : (c == 2 ? 1.0 - phi : 0.0), c < 2 ? 1.0 : 0.0, c == 1 ? phi : (c == 3 ? 1.0 - phi : 0.0), 0.0);
+    }
+    __syncthreads();
 }
 
-// leaf record from its state code (EM_solver.py:103-116 in full-state form):
-//   '?' (-1) -> (phi, 1, phi..)   known silenced (-2) -> e_m   0 -> (1-phi) e_0   a -> (1-phi) e_a
-__device__ __forceinline__ Rec leaf_rec(int code, double phi, const double *__restrict__ prior_site) {
-    Rec r;
-    r.x0 = (code == 0) ? 1.0 - phi : ((code == -1) ? phi : 0.0);
-    r.xm = (code < 0) ? 1.0 : 0.0;
-    r.xz = (code == -1) ? phi : ((code > 0) ? 1.0 - phi : 0.0);
-    r.h = (code > 0) ? code - 1 : -1;
-    r.qh = (code > 0) ? __ldg(prior_site + (code - 1)) : 0.0;
-    r.cum = 0;
-    return r;
+// decoded child: record fields plus the message to the parent (SURVEY 3.5 "edge transfer"):
+//   E_0 = a x_0 + b sum(q x) + g x_m,  E_m = x_m,  E_alpha = c x_alpha + g x_m  (Eb off the hot slot, Eh on it;
+//   Eh == Eb when there is no hot state)
+struct Child {
+    double x0, xm, xz, qh, xb;
+    int h, cum;
+    double t0, t1, gm, E0, Eb, Eh;      // t0 = a x0, t1 = b sum(q x), gm = g xm
+};
+__device__ __forceinline__ void decode(Child &c, const Opd &p, const double4 bc, double qsum) {
+    c.x0 = p.r.x; c.xm = p.r.y; c.xz = p.r.z; c.qh = p.r.w; c.h = p.ri.x; c.cum = p.ri.y;
+    const bool hot = c.h >= 0;
+    c.xb = hot ? 0.0 : c.xz;
+    const double sq = c.xz * (hot ? c.qh : qsum);
+    c.gm = bc.w * c.xm;
+    c.t0 = bc.x * c.x0;
+    c.t1 = bc.y * sq;
+    c.E0 = c.t0 + c.t1 + c.gm;
+    c.Eb = fma(bc.z, c.xb, c.gm);
+    c.Eh = fma(bc.z, c.xz, c.gm);
 }
-
-__device__ __forceinline__ Rec child_rec(int kind, const Pre &p, const Rec &prev, double phi, const double *__restrict__ prior_site) {
-    if (kind == KIND_LEAF) return leaf_rec(p.ri.x, phi, prior_site);
-    if (kind == KIND_PREV) return prev;
-    Rec r;
-    r.x0 = p.r.x; r.xm = p.r.y; r.xz = p.r.z; r.qh = p.r.w; r.h = p.ri.x; r.cum = p.ri.y;
-    return r;
-}
-
-// child -> parent message (SURVEY 3.5 "edge transfer") in lumped form:
-//   E_0 = a x_0 + b sum(q x) + g x_m,  E_m = x_m,  E_alpha = c x_alpha + g x_m  (Eb off the hot slot, Eh on it)
-__device__ __forceinline__ Msg message(const Rec &r, const double4 c, double qsum) {
-    Msg m;
-    const bool hot = r.h >= 0;
-    m.xb = hot ? 0.0 : r.xz;
-    m.sq = r.xz * (hot ? r.qh : qsum);
-    const double gm = c.w * r.xm;
-    m.E0 = fma(c.x, r.x0, fma(c.y, m.sq, gm));
-    m.Em = r.xm;
-    m.Eb = fma(c.z, m.xb, gm);
-    m.Eh = fma(c.z, r.xz, gm);
-    return m;
+// a leaf's operand from its code: (x0, xm, xz) from the table; qh was gathered into p.r.w one step ahead
+__device__ __forceinline__ void leaf_operand(Opd &p, int code, const double4 *s_lut) {
+    const double4 t = s_lut[min(code, 1) + 2];
+    p.r.x = t.x; p.r.y = t.y; p.r.z = t.z;
+    p.ri.x = max(code, 0) - 1;
+    p.ri.y = 0;
 }
 
 // ---------------------------------------------------------------- inside pass
-__global__ void __launch_bounds__(LT) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+// step flags: bits 0-1 kind of child v (leaf / load), bits 2-3 kind of child w (leaf / load / chained:
+//             the host orders the children so that a chained child is w), bit 4 = u is a root,
+//             bit 5 / 6: the record of v / w was written by an earlier launch
+struct InSlot { Opd v, w; };
+
+__device__ __forceinline__ void inside_fetch(const LParams &P, const int4 d, int cv, int cw, InSlot &n, const double *__restrict__ prior_site,
+                                             int s, int N) {
+    const int kv = d.w & 3, kw = (d.w >> 2) & 3;
+    if (kv == KIND_LEAF) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
+    else { const size_t o = (size_t)(d.y - N) * P.K + s; n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
+    if (kw == KIND_LEAF) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
+    else if (kw == KIND_LOAD) { const size_t o = (size_t)(d.z - N) * P.K + s; n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+}
+
+__global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+    __shared__ int4 s_steps[STEP_CAP + 2];
+    __shared__ double4 s_bc[2 * STEP_CAP];
+    __shared__ double4 s_lut[4];
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z
+    const int nsteps = cl.y - cl.x;
+    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
     const int N = P.n_leaves;
     int s = blockIdx.y * LT + threadIdx.x;
     const bool valid = s < P.K;
@@ -138,134 +160,161 @@ __global__ void __launch_bounds__(LT) pmm_lumped_inside(LParams P, const int4 *_
     const int gs = P.site0 + s;
     const double *prior_site = P.prior + __ldg(P.site_ptr + gs);
     const double qsum = __ldg(P.qsum + gs);
-    const double phi = __ldg(P.params + 1);
+    const int *codes_s = P.codes + gs;
 
-    Rec prev;
-    prev.x0 = prev.xm = prev.xz = prev.qh = 0.0; prev.h = -1; prev.cum = 0;
-    int4 nst = __ldg(steps + cl.x);
-    Pre nv = fetch_child(P, nst.w & 3, nst.y, s, gs), nw = fetch_child(P, (nst.w >> 2) & 3, nst.z, s, gs);
-    for (int i = cl.x; i < cl.y; i++) {
-        const int4 st = nst;
-        const Pre pv = nv, pw = nw;
-        if (i + 1 < cl.y) {                              // operands of the next step: in flight during this one
-            nst = __ldg(steps + i + 1);
-            nv = fetch_child(P, nst.w & 3, nst.y, s, gs);
-            nw = fetch_child(P, (nst.w >> 2) & 3, nst.z, s, gs);
+    auto codes_of = [&](const int4 d, int &cv, int &cw) {
+        if ((d.w & 3) == KIND_LEAF) cv = __ldg(codes_s + (size_t)d.y * P.code_stride);
+        if (((d.w >> 2) & 3) == KIND_LEAF) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
+    };
+    Opd prev;                                            // the record computed by the previous step
+    prev.r = make_double4(0.0, 0.0, 0.0, 0.0); prev.ri = make_int2(-1, 0);
+    InSlot A, B;
+    A.v = A.w = B.v = B.w = prev;
+    int4 d0 = s_steps[0], d1 = (nsteps > 1) ? s_steps[1] : d0;
+    int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
+    codes_of(d0, c0v, c0w);
+    if (nsteps > 1) codes_of(d1, c1v, c1w);
+    inside_fetch(P, d0, c0v, c0w, A, prior_site, s, N);
+
+    auto step = [&](int i, InSlot &cur, InSlot &nxt) {
+        int4 d2 = d1;
+        int c2v = 0, c2w = 0;
+        if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
+        if (i + 1 < nsteps) inside_fetch(P, d1, c1v, c1w, nxt, prior_site, s, N);
+        if (PF_DIST > 0 && i + PF_DIST < nsteps) {
+            const int4 dp = s_steps[i + PF_DIST];
+            if ((dp.w & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
+            else if (dp.w & 32) { const size_t o = (size_t)(dp.y - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            if (((dp.w >> 2) & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
+            else if (dp.w & 64) { const size_t o = (size_t)(dp.z - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
         }
-        const int u = st.x, v = st.y, w = st.z;
-        const Rec rv = child_rec(st.w & 3, pv, prev, phi, prior_site);
-        const Rec rw = child_rec((st.w >> 2) & 3, pw, prev, phi, prior_site);
-        const Msg mv = message(rv, ld_bc(P.bc, v), qsum), mw = message(rw, ld_bc(P.bc, w), qsum);
-        // x_u = E^v .* E^w  (EM_solver.py:118-133)
-        const bool bv = rv.h >= 0, bw = rw.h >= 0;
-        const bool same = bv && bw && rv.h == rw.h;
-        double x0 = mv.E0 * mw.E0, xm = mv.Em * mw.Em;
-        const double xb = mv.Eb * mw.Eb;
-        double xz = bv ? mv.Eh * (same ? mw.Eh : mw.Eb) : (bw ? mv.Eb * mw.Eh : xb);
-        Rec ru;
-        ru.h = bv ? ((bw && !same) ? -1 : rv.h) : rw.h;      // two different hot states: all edited slots are 0
-        ru.qh = bv ? rv.qh : rw.qh;
+        const int kv = d0.w & 3, kw = (d0.w >> 2) & 3;
+        if (kv == KIND_LEAF) leaf_operand(cur.v, c0v, s_lut);
+        if (kw == KIND_LEAF) leaf_operand(cur.w, c0w, s_lut);
+        Child v, w;
+        decode(v, cur.v, s_bc[2 * i], qsum);
+        decode(w, (kw == KIND_PREV) ? prev : cur.w, s_bc[2 * i + 1], qsum);
+        // x_u = E^v .* E^w  (EM_solver.py:118-133); Eh == Eb for a child without a hot state, and two
+        // different hot states leave no edited slot alive (E^w_b = 0 then)
+        const bool bv = v.h >= 0, bw = w.h >= 0;
+        const bool clash = bv && bw && v.h != w.h;
+        const double x0 = v.E0 * w.E0, xm = v.xm * w.xm;
+        const double xz = v.Eh * (clash ? w.Eb : w.Eh);
         const int e = expo_of_hi(max(hi32(x0), max(hi32(xm), hi32(xz))));
         const double sc = pow2i(-e);
-        ru.x0 = x0 * sc; ru.xm = xm * sc; ru.xz = xz * sc;
-        ru.cum = rv.cum + rw.cum + e;
-        prev = ru;
+        prev.r.x = x0 * sc; prev.r.y = xm * sc; prev.r.z = xz * sc;
+        prev.r.w = bv ? v.qh : w.qh;
+        prev.ri.x = bv ? (clash ? -1 : v.h) : w.h;
+        prev.ri.y = v.cum + w.cum + e;
         if (valid) {
-            const size_t o = (size_t)(u - N) * P.K + s;
-            P.X[o] = make_double4(ru.x0, ru.xm, ru.xz, ru.qh);
-            P.XI[o] = make_int2(ru.h, ru.cum);
-            if (st.w & 16) {
+            const size_t o = (size_t)(d0.x - N) * P.K + s;
+            P.X[o] = prev.r;
+            P.XI[o] = prev.ri;
+            if (d0.w & 16) {
                 // root: site likelihood L = E[root]_0 (the root's own branch starts in state 0, EM_solver.py:140)
-                const Msg mr = message(ru, ld_bc(P.bc, u), qsum);
-                const double L = mr.E0;
+                Child r;
+                decode(r, prev, ld_bc(P.bc, d0.x), qsum);
+                const double L = r.E0;
                 P.invL[(size_t)cl.z * P.K + s] = (L > 0.0) ? 1.0 / L : 0.0;
-                P.root_site_llh[(size_t)cl.z * P.K + s] = (L > 0.0) ? log(L) + (double)ru.cum * 0.693147180559945309417232121458 : -INFINITY;
+                P.root_site_llh[(size_t)cl.z * P.K + s] = (L > 0.0) ? log(L) + (double)prev.ri.y * 0.693147180559945309417232121458 : -INFINITY;
             }
         }
-    }
+        d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
+    };
+    int i = 0;
+    for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
+    if (i < nsteps) step(i, A, B);
 }
 
 // ---------------------------------------------------------------- outside pass + expected counts
-// sum of 16 per-lane values over the warp with a halving butterfly: 8 + 4 + 2 + 1 + 1 shuffles;
-// afterwards lane L (L even) holds the warp total of value  8 b4 + 4 b3 + 2 b2 + b1  (bits of L).
-__device__ __forceinline__ double warp_sum16(double (&v)[16], int lane) {
-    const unsigned full = 0xffffffffu;
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double send = up ? v[j] : v[j + 8], keep = up ? v[j + 8] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double send = up ? v[j] : v[j + 4], keep = up ? v[j + 4] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const double send = up ? v[j] : v[j + 2], keep = up ? v[j + 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(full, send, 4);
-        }
-    }
-    {
-        const bool up = lane & 2;
-        const double send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(full, send, 2);
-    }
-    return v[0] + __shfl_xor_sync(full, v[0], 1);
-}
-
 // For child v of u with sibling w (EM_solver.py:143-300 in lumped full-state form):
 //   T^v = out[u] .* E^w;  out[v]_0 = a T_0, out[v]_a = b q_a T_0 + c T_a, out[v]_m = g (T_0 + sum_a T_a) + T_m
 //   S0 = T_0 a x_0 / L, S1 = T_0 b sum(q x) / L, S2 = T_0 g x_m / L, S3 = c sum_a T_a x_a / L, S4 = g x_m sum_a T_a / L.
-// Returns the unnormalised out-record of v; cnt[0..4] the five counts (already times fac).
-__device__ __forceinline__ ORec child_outside(const ORec &o, const Rec &rv, const Msg &mv, const Rec &rw, const Msg &mw,
-                                              const double4 cv, double qsum, double fac, double *__restrict__ cnt) {
-    const bool hotw = rw.h >= 0, hotv = rv.h >= 0, hotk = o.k >= 0;
-    const double T0 = o.o0 * mw.E0, Tm = o.om * mw.Em;
-    const double sqE = fma(mw.Eb, qsum, hotw ? (mw.Eh - mw.Eb) * rw.qh : 0.0);        // sum_a q_a E^w_a
-    const double Ewk = (hotk && o.k == rw.h) ? mw.Eh : mw.Eb;                          // E^w at slot k
-    const double dk = hotk ? o.oD * Ewk : 0.0;
-    const double sT = fma(o.oB, sqE, dk);                                              // sum_a T_a
-    ORec n;
-    n.o0 = cv.x * T0;
-    n.om = fma(cv.w, T0 + sT, Tm);
-    n.oB = fma(cv.y, T0, cv.z * o.oB * mw.Eb);
-    const double bq = o.oB * rw.qh;
-    n.oD = hotw ? cv.z * fma(bq + ((o.k == rw.h) ? o.oD : 0.0), mw.Eh, -bq * mw.Eb) : (hotk ? cv.z * o.oD * mw.Eb : 0.0);
-    n.k = hotw ? rw.h : o.k;
-    n.F = 0;
+// o = out-record of u (oD = 0 when k < 0); bcv = (a, b, c, g) of v.  Writes the unnormalised
+// out-record of v into n and the five counts (times fac) into cnt[0..4].
+__device__ __forceinline__ void child_outside(const Opd &o, const Child &v, const Child &w, const double4 bcv, double qsum, double fac,
+                                              Opd &n, double *__restrict__ cnt) {
+    const double o0 = o.r.x, om = o.r.y, oB = o.r.z, oD = o.r.w;
+    const int k = o.ri.x;
+    const bool hotw = w.h >= 0, eq_kw = k == w.h;
+    const double T0 = o0 * w.E0, Tm = om * w.xm;
+    const double sqE = fma(w.Eb, qsum, (w.Eh - w.Eb) * w.qh);            // sum_a q_a E^w_a
+    const double dk = oD * (eq_kw ? w.Eh : w.Eb);                          // oD E^w_k
+    const double sT = fma(oB, sqE, dk);                                    // sum_a T_a
+    n.r.x = bcv.x * T0;
+    n.r.y = fma(bcv.w, T0 + sT, Tm);
+    n.r.z = fma(bcv.y, T0, bcv.z * oB * w.Eb);
+    // hot slot of out[v]: w's hot state if it has one (then E^w vanishes elsewhere), else u's
+    n.r.w = bcv.z * w.Eh * (hotw ? fma(oB, w.qh, eq_kw ? oD : 0.0) : oD);
+    n.ri.x = hotw ? w.h : k;
     // counts of the branch above v
-    const double Ewhv = (hotv && rv.h == rw.h) ? mw.Eh : mw.Eb;                        // E^w at slot h_v
-    const double sqEx = fma(mv.xb, sqE, hotv ? (rv.xz - mv.xb) * rv.qh * Ewhv : 0.0);  // sum_a q_a E^w_a x^v_a
-    const double xvk = (hotk && o.k == rv.h) ? rv.xz : mv.xb;                           // x^v at slot k
-    const double sTx = fma(o.oB, sqEx, dk * xvk);                                      // sum_a T_a x^v_a
-    const double T0f = T0 * fac, gmf = cv.w * rv.xm * fac;
-    cnt[0] = T0f * cv.x * rv.x0;
-    cnt[1] = T0f * cv.y * mv.sq;
+    const double Ewhv = (v.h == w.h) ? w.Eh : w.Eb;                        // E^w at slot h_v
+    const double sqEx = fma(v.xb, sqE, (v.xz - v.xb) * v.qh * Ewhv);       // sum_a q_a E^w_a x^v_a
+    const double xvk = (k == v.h) ? v.xz : v.xb;                           // x^v at slot k
+    const double sTx = fma(oB, sqEx, dk * xvk);                            // sum_a T_a x^v_a
+    const double T0f = T0 * fac, gmf = v.gm * fac;
+    cnt[0] = T0f * v.t0;
+    cnt[1] = T0f * v.t1;
     cnt[2] = T0 * gmf;
-    cnt[3] = cv.z * sTx * fac;
+    cnt[3] = bcv.z * sTx * fac;
     cnt[4] = gmf * sT;
-    return n;
 }
 
-__device__ __forceinline__ void normalise_out(ORec &n, int F) {
-    const int e = expo_of_hi(max(max(hi32(n.o0), hi32(n.om)), max(hi32(n.oB), hi32(n.oD))));
+__device__ __forceinline__ void normalise_out(Opd &n, int F) {
+    const int e = expo_of_hi(max(max(hi32(n.r.x), hi32(n.r.y)), max(hi32(n.r.z), hi32(n.r.w))));
     const double sc = pow2i(-e);
-    n.o0 *= sc; n.om *= sc; n.oB *= sc; n.oD *= sc;
-    n.F = F + e;
+    n.r.x *= sc; n.r.y *= sc; n.r.z *= sc; n.r.w *= sc;
+    n.ri.y = F + e;
+}
+
+// Sum of 10 per-lane values over the warp through shared memory: lane l stores its values
+// transposed (row j = value j, 36 doubles per row: lanes 0-15, 2 pad, lanes 16-31, 2 pad --
+// conflict-free for both the 8-byte stores and the 16-byte loads); lanes 0..19 each add up half a
+// row and one shuffle joins the halves.  Returns the total of value (lane >> 1) on lanes < 20.
+constexpr int RED_ROW = 36;
+__device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__restrict__ red, int lane) {
+    __syncwarp();                                    // the previous step's readers are done
+    const int col = lane + ((lane >> 4) << 1);
+#pragma unroll
+    for (int j = 0; j < 10; j++) red[j * RED_ROW + col] = v[j];
+    __syncwarp();
+    double sum = 0.0;
+    if (lane < 20) {
+        const double2 *row = reinterpret_cast<const double2 *>(red + (lane >> 1) * RED_ROW + (lane & 1) * 18);
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) {
+            const double2 x = row[t], y = row[t + 1];
+            a += x.x; b += x.y; a += y.x; b += y.y;
+        }
+        sum = a + b;
+    }
+    return sum + __shfl_xor_sync(0xffffffffu, sum, 1);
+}
+
+// step flags: bits 0-1 where out[u] comes from (0 = u is a root, 1 = load, 2 = chained in registers),
+//             bit 2 / 3: v / w is a leaf, bit 4 / 5: store out[v] / out[w],
+//             bit 6: out[v] is chained into the next step (the host orders the children accordingly)
+struct OutSlot { Opd v, w, o; };
+
+__device__ __forceinline__ void outside_fetch(const LParams &P, const int4 d, int cv, int cw, OutSlot &n, const double *__restrict__ prior_site,
+                                              int s, int N) {
+    if (d.w & 4) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
+    else { const size_t o = (size_t)(d.y - N) * P.K + s; n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
+    if (d.w & 8) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
+    else { const size_t o = (size_t)(d.z - N) * P.K + s; n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+    if ((d.w & 3) == KIND_LOAD) { const size_t o = (size_t)(d.x - N) * P.K + s; n.o.r = P.O[o]; n.o.ri = P.OI[o]; }
 }
 
 template <bool POST>
-__global__ void __launch_bounds__(LT) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+__global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+    __shared__ int4 s_steps[STEP_CAP + 2];
+    __shared__ double4 s_bc[2 * STEP_CAP];
+    __shared__ double4 s_lut[4];
+    __shared__ __align__(16) double s_red[(LT / 32) * 10 * RED_ROW];
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z, clade id w
+    const int nsteps = cl.y - cl.x;
+    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
     const int N = P.n_leaves;
     const int s_raw = blockIdx.y * LT + threadIdx.x;
     const bool valid = s_raw < P.K;
@@ -274,111 +323,111 @@ __global__ void __launch_bounds__(LT) pmm_lumped_outside(LParams P, const int4 *
     const int lane = threadIdx.x & 31;
     const int grp = s_raw >> 5;                          // site group of this warp
     if (grp * 32 >= P.K) return;                         // whole warp beyond the last site
+    double *red = s_red + (threadIdx.x >> 5) * 10 * RED_ROW;
     const double *prior_site = P.prior + __ldg(P.site_ptr + gs);
     const double qsum = __ldg(P.qsum + gs);
-    const double phi = __ldg(P.params + 1);
+    const int *codes_s = P.codes + gs;
     const double invL = valid ? P.invL[(size_t)cl.z * P.K + s] : 0.0;
     double *Sg = P.Spart + (size_t)grp * P.n_nodes * 5;
-    // butterfly output: which of the 10 count values this lane ends up holding
-    const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
-    Rec dummy;
-    dummy.x0 = dummy.xm = dummy.xz = dummy.qh = 0.0; dummy.h = -1; dummy.cum = 0;
-    ORec chain;
-    chain.o0 = chain.om = chain.oB = chain.oD = 0.0; chain.k = -1; chain.F = 0;
+    auto codes_of = [&](const int4 d, int &cv, int &cw) {
+        if (d.w & 4) cv = __ldg(codes_s + (size_t)d.y * P.code_stride);
+        if (d.w & 8) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
+    };
+    Opd chain;                                           // out-record kept in registers for the next step
+    chain.r = make_double4(0.0, 0.0, 0.0, 0.0); chain.ri = make_int2(-1, 0);
+    OutSlot A, B;
+    A.v = A.w = A.o = B.v = B.w = B.o = chain;
     double rt = 0.0;
+    int4 d0 = s_steps[0], d1 = (nsteps > 1) ? s_steps[1] : d0;
+    int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
+    codes_of(d0, c0v, c0w);
+    if (nsteps > 1) codes_of(d1, c1v, c1w);
+    outside_fetch(P, d0, c0v, c0w, A, prior_site, s, N);
 
-    int4 nst = __ldg(steps + cl.x);
-    Pre nv = fetch_child(P, (nst.w & 4) ? KIND_LEAF : KIND_LOAD, nst.y, s, gs);
-    Pre nw = fetch_child(P, (nst.w & 8) ? KIND_LEAF : KIND_LOAD, nst.z, s, gs);
-    double4 no = make_double4(0.0, 0.0, 0.0, 0.0);
-    int2 noi = make_int2(-1, 0);
-    if ((nst.w & 3) == KIND_LOAD) { const size_t o = (size_t)(nst.x - N) * P.K + s; no = P.O[o]; noi = P.OI[o]; }
-    for (int i = cl.x; i < cl.y; i++) {
-        const int4 st = nst;
-        const Pre pv = nv, pw = nw;
-        const double4 po = no;
-        const int2 poi = noi;
-        if (i + 1 < cl.y) {
-            nst = __ldg(steps + i + 1);
-            nv = fetch_child(P, (nst.w & 4) ? KIND_LEAF : KIND_LOAD, nst.y, s, gs);
-            nw = fetch_child(P, (nst.w & 8) ? KIND_LEAF : KIND_LOAD, nst.z, s, gs);
-            if ((nst.w & 3) == KIND_LOAD) { const size_t o = (size_t)(nst.x - N) * P.K + s; no = P.O[o]; noi = P.OI[o]; }
+    auto step = [&](int i, OutSlot &cur, OutSlot &nxt) {
+        int4 d2 = d1;
+        int c2v = 0, c2w = 0;
+        if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
+        if (i + 1 < nsteps) outside_fetch(P, d1, c1v, c1w, nxt, prior_site, s, N);
+        if (PF_DIST > 0 && i + PF_DIST < nsteps) {
+            const int4 dp = s_steps[i + PF_DIST];
+            if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
+            else { const size_t o = (size_t)(dp.y - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
+            else { const size_t o = (size_t)(dp.z - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
         }
-        const int u = st.x, v = st.y, w = st.z, f = st.w;
+        const int u = d0.x, f = d0.w;
         const bool vleaf = f & 4, wleaf = f & 8;
-        const double4 cv = ld_bc(P.bc, v), cw = ld_bc(P.bc, w);
-        const Rec rv = child_rec(vleaf ? KIND_LEAF : KIND_LOAD, pv, dummy, phi, prior_site);
-        const Rec rw = child_rec(wleaf ? KIND_LEAF : KIND_LOAD, pw, dummy, phi, prior_site);
-        const Msg mv = message(rv, cv, qsum), mw = message(rw, cw, qsum);
-        ORec o;
+        const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
+        if (vleaf) leaf_operand(cur.v, c0v, s_lut);
+        if (wleaf) leaf_operand(cur.w, c0w, s_lut);
+        Child v, w;
+        decode(v, cur.v, bcv, qsum);
+        decode(w, cur.w, bcw, qsum);
         const int how = f & 3;
-        if (how == KIND_PREV) o = chain;
-        else if (how == KIND_LOAD) { o.o0 = po.x; o.om = po.y; o.oB = po.z; o.oD = po.w; o.k = poi.x; o.F = poi.y; }
-        else {
+        if (how == 0) {
             // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
             const size_t ou = (size_t)(u - N) * P.K + s;
-            const double4 xr = P.X[ou];
-            const int2 xri = P.XI[ou];
+            Opd pr;
+            pr.r = P.X[ou]; pr.ri = P.XI[ou];
             const double4 cr = ld_bc(P.bc, u);
-            Rec ru;
-            ru.x0 = xr.x; ru.xm = xr.y; ru.xz = xr.z; ru.qh = xr.w; ru.h = xri.x; ru.cum = xri.y;
-            const Msg mr = message(ru, cr, qsum);
-            o.o0 = cr.x; o.om = cr.w; o.oB = cr.y; o.oD = 0.0; o.k = -1; o.F = -ru.cum;
-            double r16[16];
+            Child r;
+            decode(r, pr, cr, qsum);
+            chain.r = make_double4(cr.x, cr.w, cr.y, 0.0); chain.ri = make_int2(-1, -r.cum);
+            const double t0 = r.t0 * invL, t2 = r.gm * invL;
+            double r10[10];
 #pragma unroll
-            for (int q = 0; q < 16; q++) r16[q] = 0.0;
-            const double t0 = cr.x * ru.x0 * invL, t2 = cr.w * ru.xm * invL;
-            r16[0] = t0; r16[1] = cr.y * mr.sq * invL; r16[2] = t2;
-            const double tot = warp_sum16(r16, lane);
-            if (!(lane & 1) && vidx < 5) Sg[(size_t)u * 5 + vidx] = tot;
+            for (int q = 0; q < 10; q++) r10[q] = 0.0;
+            r10[0] = t0; r10[1] = r.t1 * invL; r10[2] = t2;
+            const double tot = warp_sum10(r10, red, lane);
+            if (lane < 10 && !(lane & 1)) Sg[(size_t)u * 5 + (lane >> 1)] = tot;
             if (POST && valid) {
                 const size_t gp = (size_t)u * P.K_total + P.site0 + s;
                 P.post0[gp] = (t0 > 0.0) ? log(t0) : -INFINITY;
                 P.post1[gp] = (t2 > 0.0) ? log(t2) : -INFINITY;
             }
         }
+        if (how == KIND_LOAD) chain = cur.o;
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
-        const int delta = max(-1000, min(1000, o.F + rv.cum + rw.cum));
-        const double fac = invL * pow2i(delta);
-        double c16[16];
-#pragma unroll
-        for (int q = 10; q < 16; q++) c16[q] = 0.0;
-        ORec ov = child_outside(o, rv, mv, rw, mw, cv, qsum, fac, c16);
-        ORec ow = child_outside(o, rw, mw, rv, mv, cw, qsum, fac, c16 + 5);
+        const int F = chain.ri.y;
+        const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
+        double c10[10];
+        Opd ov, ow;
+        child_outside(chain, v, w, bcv, qsum, fac, ov, c10);
+        child_outside(chain, w, v, bcw, qsum, fac, ow, c10 + 5);
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
-        if (vleaf && valid && pv.ri.x == -1) rt += 1.0 - ov.om * rv.xm * fac;
-        if (wleaf && valid && pw.ri.x == -1) rt += 1.0 - ow.om * rw.xm * fac;
+        if (vleaf && valid && c0v == -1) rt += 1.0 - ov.r.y * fac;
+        if (wleaf && valid && c0w == -1) rt += 1.0 - ow.r.y * fac;
         if (POST && valid) {
             // post0 = log P(node in state 0 | D), post1 likewise for the silenced state (EM_solver.py:276-277)
-            const size_t gv = (size_t)v * P.K_total + P.site0 + s, gw = (size_t)w * P.K_total + P.site0 + s;
-            const double p0v = ov.o0 * rv.x0 * fac, p1v = ov.om * rv.xm * fac;
-            const double p0w = ow.o0 * rw.x0 * fac, p1w = ow.om * rw.xm * fac;
+            const size_t gv = (size_t)d0.y * P.K_total + P.site0 + s, gw = (size_t)d0.z * P.K_total + P.site0 + s;
+            const double p0v = ov.r.x * v.x0 * fac, p1v = ov.r.y * v.xm * fac;
+            const double p0w = ow.r.x * w.x0 * fac, p1w = ow.r.y * w.xm * fac;
             P.post0[gv] = (p0v > 0.0) ? log(p0v) : -INFINITY; P.post1[gv] = (p1v > 0.0) ? log(p1v) : -INFINITY;
             P.post0[gw] = (p0w > 0.0) ? log(p0w) : -INFINITY; P.post1[gw] = (p1w > 0.0) ? log(p1w) : -INFINITY;
         }
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
-        if (!vleaf) normalise_out(ov, o.F + rw.cum);
-        if (!wleaf) normalise_out(ow, o.F + rv.cum);
-        if (valid) {
-            if (!vleaf && ((f & 16) || P.store_all)) {
-                const size_t oo = (size_t)(v - N) * P.K + s;
-                P.O[oo] = make_double4(ov.o0, ov.om, ov.oB, ov.oD); P.OI[oo] = make_int2(ov.k, ov.F);
-            }
-            if (!wleaf && ((f & 32) || P.store_all)) {
-                const size_t oo = (size_t)(w - N) * P.K + s;
-                P.O[oo] = make_double4(ow.o0, ow.om, ow.oB, ow.oD); P.OI[oo] = make_int2(ow.k, ow.F);
-            }
+        if (!wleaf) {
+            normalise_out(ow, F + v.cum);
+            if (valid && ((f & 32) || P.store_all)) { const size_t oo = (size_t)(d0.z - N) * P.K + s; P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
         }
-        const int keep = (f >> 6) & 3;
-        if (keep == 1) chain = ov; else if (keep == 2) chain = ow;
+        if (!vleaf) {
+            normalise_out(ov, F + w.cum);
+            if (valid && ((f & 16) || P.store_all)) { const size_t oo = (size_t)(d0.y - N) * P.K + s; P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
+            chain = ov;
+        }
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
-        const double tot = warp_sum16(c16, lane);
-        if (!(lane & 1) && vidx < 10) {
-            const int node = (vidx < 5) ? v : w;
-            Sg[(size_t)node * 5 + (vidx < 5 ? vidx : vidx - 5)] = tot;
+        const double tot = warp_sum10(c10, red, lane);
+        if (lane < 20 && !(lane & 1)) {
+            const int j = lane >> 1;
+            Sg[(size_t)((j < 5) ? d0.y : d0.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
         }
-    }
+        d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
+    };
+    int i = 0;
+    for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
+    if (i < nsteps) step(i, A, B);
     // R~ of this (warp, clade)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);

@@ -28,7 +28,7 @@ def test_library_exports_all_symbols():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.pmm_abi_version() == 1
+    assert lib.pmm_abi_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -103,7 +103,7 @@ def test_lumped_schedule_variants(clade, chunks, store_all, engine_mode):
         with env_override(PMM_CLADE=clade, PMM_CHUNKS=chunks, PMM_STORE_ALL=store_all):
             eng = make_engine(case)
             info = eng.info()
-            assert info["engine"] == 0 and info["n_chunks"] == chunks and info["clade_target"] == clade
+            assert info["engine"] == 0 and info["n_chunks"] == chunks and info["clade_target"] == min(clade, 64)
             check_against_golden(case, z, eng)
             eng.close()
 
