@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -384,107 +385,145 @@ int launch_outside(pmm_handle *h, const KParams &P) {
 
 
 // ======================================================== lumped-state engine: host side
-// Cut the forest into clades of ~m internal nodes (greedy, bottom-up: a node whose open subtree has
-// reached m internal nodes becomes a clade root; so does every tree root) and write, per clade, the
-// step lists the kernels in pmm_lumped.cuh walk.  `order` lists parents before children.
+// Partition the forest into TIERS and write, per clade (= one CTA's work), the step lists the kernels
+// in pmm_lumped.cuh walk.  Tier 0 holds every maximal subtree with fewer than M0 internal nodes: all of
+// them are independent, so one launch covers ~97 % of the tree; what is left (the nodes with >= M0
+// internal descendants, ~2 n / M0 of them) is a small "top tree" that is peeled the same way with a
+// small threshold, because its launches are latency-bound chains.  The subtrees of a tier are packed
+// (best fit, decreasing) into clades of at most C steps.  `order` lists parents before children.
 int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const std::vector<int> &root_index) {
     const int N = h->n_leaves, n = h->n_int + N;
     const std::vector<int> &L = h->left, &R = h->right, &Pa = h->parent;
-    int m = env_int("PMM_CLADE", 0);
-    if (m <= 0) {
-        // enough CTAs for ~4 waves over the SMs, but chains no longer than 64 steps
-        const double ctas_per_node = (double)((h->K + LT - 1) / LT);
-        const double resident = 4.0 * h->n_sms * 4.0;
-        m = (int)((double)h->n_int * ctas_per_node / resident);
-        m = std::max(4, m);
+    int C0 = env_int("PMM_CLADE", 0);
+    if (C0 <= 0) {
+        // enough CTAs for ~8 waves over the SMs, chains of 16..120 steps
+        const double site_blocks = (double)((h->K + LT - 1) / LT);
+        const double want_clades = 8.0 * h->n_sms * 4.0 / site_blocks;
+        C0 = (int)((double)h->n_int / std::max(want_clades, 1.0));
+        C0 = std::max(16, std::min(120, C0));
     }
-    m = std::min(m, STEP_CAP / 2);     // a clade has at most 2m - 1 steps; the kernels stage them in shared memory
-    h->clade_target = m;
-    std::vector<int> osz(n, 0), ph(n, 0), phase(n, -1);
-    std::vector<char> cut(n, 0);
-    int max_phase = 0;
-    for (int i = n - 1; i >= 0; i--) {
-        const int u = order[i];
-        if (L[u] < 0) continue;
-        int sz = 1, p = 0;
-        for (int c : {L[u], R[u]}) {
-            if (c < N) continue;
-            if (cut[c]) p = std::max(p, phase[c] + 1);
-            else { sz += osz[c]; p = std::max(p, ph[c]); }
+    C0 = std::max(1, std::min(C0, STEP_CAP - 1));      // the kernels stage a clade's steps in shared memory
+    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", 16), STEP_CAP - 1));
+    h->clade_target = C0;
+    // ---- tiers
+    std::vector<int> tier(n, -1), tsz(n, 0), sz(n, 0);
+    int remaining = h->n_int, n_tiers = 0;
+    while (remaining > 0) {
+        const int M = (n_tiers == 0 ? C0 : Ctop) + 1;
+        for (int i = n - 1; i >= 0; i--) {
+            const int u = order[i];
+            if (u < N || tier[u] >= 0) { sz[u] = 0; continue; }
+            sz[u] = 1 + sz[L[u]] + sz[R[u]];
         }
-        osz[u] = sz; ph[u] = p;
-        if (sz >= m || Pa[u] < 0) { cut[u] = 1; phase[u] = p; max_phase = std::max(max_phase, p); }
+        for (int u = N; u < n; u++)
+            if (tier[u] < 0 && sz[u] < M) { tier[u] = n_tiers; tsz[u] = sz[u]; remaining--; }
+        for (int u = N; u < n; u++) if (tier[u] == n_tiers) sz[u] = 0;
+        n_tiers++;
     }
-    std::vector<std::vector<int>> by_phase(max_phase + 1);
-    for (int i = 0; i < n; i++) { const int u = order[i]; if (u >= N && cut[u]) by_phase[phase[u]].push_back(u); }
-    auto open_internal = [&](int c) { return c >= N && !cut[c]; };
+    auto open_internal = [&](int u, int c) { return c >= N && tier[c] == tier[u]; };
+
+    // ---- clades: subtree roots of each tier packed into bins of <= C steps, one tree of the forest per bin
+    struct Bin { std::vector<int> roots; int root_index; };
+    std::vector<std::vector<Bin>> bins(n_tiers);
+    {
+        std::vector<std::vector<int>> roots_of(n_tiers);
+        for (int i = 0; i < n; i++) {
+            const int u = order[i];
+            if (u >= N && (Pa[u] < 0 || tier[Pa[u]] != tier[u])) roots_of[tier[u]].push_back(u);
+        }
+        for (int t = 0; t < n_tiers; t++) {
+            const int C = (t == 0) ? C0 : Ctop;
+            std::vector<int> &rs = roots_of[t];
+            std::stable_sort(rs.begin(), rs.end(), [&](int a, int b) {
+                return root_index[a] != root_index[b] ? root_index[a] < root_index[b] : tsz[a] > tsz[b]; });
+            std::multimap<int, int> open_bins;          // remaining capacity -> bin (of the current tree)
+            int cur_tree = -1;
+            for (int r : rs) {
+                if (root_index[r] != cur_tree) { open_bins.clear(); cur_tree = root_index[r]; }
+                auto it = open_bins.lower_bound(tsz[r]);
+                int b;
+                if (it == open_bins.end()) { b = (int)bins[t].size(); bins[t].push_back(Bin{{}, cur_tree}); it = open_bins.emplace(C, b); }
+                b = it->second;
+                const int rem = it->first - tsz[r];
+                open_bins.erase(it);
+                if (rem > 0) open_bins.emplace(rem, b);
+                bins[t][b].roots.push_back(r);
+            }
+        }
+    }
 
     std::vector<int4> in_steps, out_steps, in_clades, out_clades;
     in_steps.reserve(h->n_int); out_steps.reserve(h->n_int);
     h->lin_phase_ptr.assign(1, 0); h->lout_phase_ptr.assign(1, 0);
-    std::vector<int> clade_id(n, -1);
     int64_t in_loads = 0, out_loads = 0, out_stores = 0;
     int ncl = 0;
+    std::vector<std::vector<int>> bin_id(n_tiers);
     std::vector<std::pair<int, int>> stk;
     // ---- inside: post-order; of two open internal children the bigger subtree goes first, the one
     // visited last stays in registers (KIND_PREV), everything else is loaded
-    for (int p = 0; p <= max_phase; p++) {
-        for (int r : by_phase[p]) {
-            clade_id[r] = ncl++;
+    for (int t = 0; t < n_tiers; t++) {
+        for (const Bin &bin : bins[t]) {
+            bin_id[t].push_back(ncl);
             const int begin = (int)in_steps.size();
-            stk.clear(); stk.push_back({r, 0});
-            while (!stk.empty()) {
-                const int u = stk.back().first, stt = stk.back().second;
-                const int a = L[u], b = R[u];
-                int first = -1, second = -1;
-                const bool oa = open_internal(a), ob = open_internal(b);
-                if (oa && ob) { if (osz[a] >= osz[b]) { first = a; second = b; } else { first = b; second = a; } }
-                else if (oa) second = a;
-                else if (ob) second = b;
-                if (stt == 0) { stk.back().second = 1; if (first >= 0) stk.push_back({first, 0}); continue; }
-                if (stt == 1) { stk.back().second = 2; if (second >= 0) stk.push_back({second, 0}); continue; }
-                stk.pop_back();
-                // the recursion is symmetric in the children: list the chained one (if any) second
-                const int cv = (second == a) ? b : a, cw = (second == a) ? a : b;
-                auto kind = [&](int c) { return c < N ? KIND_LEAF : (c == second ? KIND_PREV : KIND_LOAD); };
-                const int kv = kind(cv), kw = kind(cw);
-                in_loads += (kv == KIND_LOAD) + (kw == KIND_LOAD);
-                // bits 5 / 6: the loaded record belongs to another clade, i.e. an earlier launch wrote it
-                const int far = ((kv == KIND_LOAD && cut[cv]) ? 32 : 0) | ((kw == KIND_LOAD && cut[cw]) ? 64 : 0);
-                in_steps.push_back(make_int4(u, cv, cw, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0) | far));
+            for (int r : bin.roots) {
+                stk.clear(); stk.push_back({r, 0});
+                while (!stk.empty()) {
+                    const int u = stk.back().first, stt = stk.back().second;
+                    const int a = L[u], b = R[u];
+                    int first = -1, second = -1;
+                    const bool oa = open_internal(u, a), ob = open_internal(u, b);
+                    if (oa && ob) { if (tsz[a] >= tsz[b]) { first = a; second = b; } else { first = b; second = a; } }
+                    else if (oa) second = a;
+                    else if (ob) second = b;
+                    if (stt == 0) { stk.back().second = 1; if (first >= 0) stk.push_back({first, 0}); continue; }
+                    if (stt == 1) { stk.back().second = 2; if (second >= 0) stk.push_back({second, 0}); continue; }
+                    stk.pop_back();
+                    // the recursion is symmetric in the children: list the chained one (if any) second
+                    const int cv = (second == a) ? b : a, cw = (second == a) ? a : b;
+                    auto kind = [&](int c) { return c < N ? KIND_LEAF : (c == second ? KIND_PREV : KIND_LOAD); };
+                    const int kv = kind(cv), kw = kind(cw);
+                    in_loads += (kv == KIND_LOAD) + (kw == KIND_LOAD);
+                    // bits 5 / 6: the loaded record belongs to a lower tier, i.e. an earlier launch wrote it
+                    const int far = ((kv == KIND_LOAD && tier[cv] != t) ? 32 : 0) | ((kw == KIND_LOAD && tier[cw] != t) ? 64 : 0);
+                    in_steps.push_back(make_int4(u, cv, cw, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0) | far));
+                }
             }
-            in_clades.push_back(make_int4(begin, (int)in_steps.size(), root_index[r], clade_id[r]));
+            in_clades.push_back(make_int4(begin, (int)in_steps.size(), bin.root_index, ncl));
+            ncl++;
         }
         h->lin_phase_ptr.push_back((int)in_clades.size());
     }
-    // ---- outside: pre-order, top clades first; of two open internal children the smaller subtree
+    // ---- outside: pre-order, top tiers first; of two open internal children the smaller subtree
     // goes first and its out-record stays in registers, the other one is stored and loaded later
     std::vector<std::pair<int, int>> stk2;
-    for (int p = max_phase; p >= 0; p--) {
-        for (int r : by_phase[p]) {
+    for (int t = n_tiers - 1; t >= 0; t--) {
+        for (size_t bi = 0; bi < bins[t].size(); bi++) {
+            const Bin &bin = bins[t][bi];
             const int begin = (int)out_steps.size();
-            stk2.clear(); stk2.push_back({r, Pa[r] < 0 ? 0 : KIND_LOAD});
-            while (!stk2.empty()) {
-                const int u = stk2.back().first, how = stk2.back().second;
-                stk2.pop_back();
-                const int a = L[u], b = R[u];
-                int first = -1, second = -1;
-                const bool oa = open_internal(a), ob = open_internal(b);
-                if (oa && ob) { if (osz[a] <= osz[b]) { first = a; second = b; } else { first = b; second = a; } }
-                else if (oa) first = a;
-                else if (ob) first = b;
-                // the child whose out-record stays in registers (if any) is listed first
-                const int cv = (first == b) ? b : a, cw = (first == b) ? a : b;
-                int f = how | (cv < N ? 4 : 0) | (cw < N ? 8 : 0);
-                if (cv >= N && cv != first) { f |= 16; out_stores++; }
-                if (cw >= N) { f |= 32; out_stores++; }
-                if (first >= 0) f |= 64;
-                out_loads += (how == KIND_LOAD);
-                out_steps.push_back(make_int4(u, cv, cw, f));
-                if (second >= 0) stk2.push_back({second, KIND_LOAD});
-                if (first >= 0) stk2.push_back({first, KIND_PREV});
+            for (int r : bin.roots) {
+                stk2.clear(); stk2.push_back({r, Pa[r] < 0 ? 0 : KIND_LOAD});
+                while (!stk2.empty()) {
+                    const int u = stk2.back().first, how = stk2.back().second;
+                    stk2.pop_back();
+                    const int a = L[u], b = R[u];
+                    int first = -1, second = -1;
+                    const bool oa = open_internal(u, a), ob = open_internal(u, b);
+                    if (oa && ob) { if (tsz[a] <= tsz[b]) { first = a; second = b; } else { first = b; second = a; } }
+                    else if (oa) first = a;
+                    else if (ob) first = b;
+                    // the child whose out-record stays in registers (if any) is listed first
+                    const int cv = (first == b) ? b : a, cw = (first == b) ? a : b;
+                    int f = how | (cv < N ? 4 : 0) | (cw < N ? 8 : 0);
+                    if (cv >= N && cv != first) { f |= 16; out_stores++; }
+                    if (cw >= N) { f |= 32; out_stores++; }
+                    if (first >= 0) f |= 64;
+                    out_loads += (how == KIND_LOAD);
+                    out_steps.push_back(make_int4(u, cv, cw, f));
+                    if (second >= 0) stk2.push_back({second, KIND_LOAD});
+                    if (first >= 0) stk2.push_back({first, KIND_PREV});
+                }
             }
-            out_clades.push_back(make_int4(begin, (int)out_steps.size(), root_index[r], clade_id[r]));
+            out_clades.push_back(make_int4(begin, (int)out_steps.size(), bin.root_index, bin_id[t][bi]));
         }
         h->lout_phase_ptr.push_back((int)out_clades.size());
     }
@@ -504,9 +543,11 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     CK(cudaMemcpy(h->d_lout_steps, out_steps.data(), sizeof(int4) * out_steps.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_lin_clades, in_clades.data(), sizeof(int4) * in_clades.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_lout_clades, out_clades.data(), sizeof(int4) * out_clades.size(), cudaMemcpyHostToDevice));
-    if (env_int("PMM_VERBOSE", 0))
-        fprintf(stderr, "[pmm] lumped schedule: clade target %d, %d clades, %d launches per pass, %lld inside loads, %lld outside loads, %lld outside stores\n",
-                m, ncl, max_phase + 1, (long long)in_loads, (long long)out_loads, (long long)out_stores);
+    if (env_int("PMM_VERBOSE", 0)) {
+        fprintf(stderr, "[pmm] lumped schedule: clade capacity %d (top %d), %d clades in %d tiers:", C0, Ctop, ncl, n_tiers);
+        for (int t = 0; t < n_tiers; t++) fprintf(stderr, " %zu", bins[t].size());
+        fprintf(stderr, "; %lld inside loads, %lld outside loads, %lld outside stores\n", (long long)in_loads, (long long)out_loads, (long long)out_stores);
+    }
     return 0;
 }
 
