@@ -74,6 +74,7 @@ struct pmm_handle {
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
     NuState *d_nu_state = nullptr;
+    unsigned *d_nu_bar = nullptr;
     double *d_nu_partial = nullptr;
     double *d_post0 = nullptr, *d_post1 = nullptr;
     // ---- lumped-state engine (default): clade schedules and 40-byte records, see pmm_lumped.cuh
@@ -145,7 +146,7 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp); dfree(h->d_eX); dfree(h->d_eO); dfree(h->d_sqX);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
-    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial);
+    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
     dfree(h->d_post0); dfree(h->d_post1);
     dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
     dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LXI); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
@@ -908,7 +909,7 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     if (reuse) return 0;
     // small per-node buffers first, then the records against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
-        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 4) || dalloc(h, &h->d_Rnode, h->n_int) ||
+        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 8) || dalloc(h, &h->d_nu_bar, 1) || dalloc(h, &h->d_Rnode, h->n_int) ||
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
     if (alloc_lumped(h)) return 1;
@@ -1011,13 +1012,26 @@ int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_
                                                                dmin, dmax, eps_s, eps_nu);
     h->launches += 1;
     if (optimize_nu) {
-        // fixed launch count: the state stops changing once `done` is set (kernels return at once)
-        const int iters = env_int("PMM_NU_ITERS", 24);
-        for (int it = 0; it <= iters; it++) {
-            pmm_nu_eval<<<NU_BLOCKS, 256, 0, h->stream>>>(h->d_free, n, h->d_Snorm, h->d_d, h->d_nu_state, it == 0, h->d_nu_partial);
-            pmm_nu_step<<<1, NU_BLOCKS, 0, h->stream>>>(h->d_nu_partial, h->d_nu_state, it == 0, h->d_params);
+        const bool multi = env_int("PMM_NU_MULTI_LAUNCH", 0) != 0;
+        const int iters = env_int("PMM_NU_ITERS", multi ? 24 : 60);
+        if (multi) {
+            // two launches per Newton iteration, fixed launch count: the state stops changing once `done` is set
+            for (int it = 0; it <= iters; it++) {
+                pmm_nu_eval<<<NU_BLOCKS, 256, 0, h->stream>>>(h->d_free, n, h->d_Snorm, h->d_d, h->d_nu_state, it == 0, h->d_nu_partial);
+                pmm_nu_step<<<1, NU_BLOCKS, 0, h->stream>>>(h->d_nu_partial, h->d_nu_state, it == 0, h->d_params);
+            }
+            h->launches += 2 * (iters + 1);
+        } else {
+            // one cooperative launch: a grid barrier per Newton iteration (all CTAs co-resident: <= one per SM)
+            int G = std::min(h->n_sms, NU_BLOCKS);
+            G = std::max(1, std::min(G, (n + 255) / 256));
+            CK(cudaMemsetAsync(h->d_nu_bar, 0, sizeof(unsigned), h->stream));
+            const unsigned char *fm = h->d_free; int nn = n; const double *sn = h->d_Snorm, *dd = h->d_d;
+            double *part = h->d_nu_partial; unsigned *bar = h->d_nu_bar; NuState *st = h->d_nu_state; double *prm = h->d_params; int mi = iters;
+            void *args[] = {&fm, &nn, &sn, &dd, &part, &bar, &st, &prm, &mi};
+            CK(cudaLaunchCooperativeKernel((void *)pmm_nu_solve, dim3((unsigned)G), dim3(256), args, 0, h->stream));
+            h->launches += 1;
         }
-        h->launches += 2 * (iters + 1);
     }
     if (optimize_phi) {
         pmm_phi_step<<<1, 1, 0, h->stream>>>(h->d_stats, n, h->d_params, R, (double)K_total * (double)n_cells);

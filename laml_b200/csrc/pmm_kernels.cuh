@@ -756,12 +756,26 @@ __global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsig
     if (dobj_dd(lo, nu, use_nu, s[0], s[1], s24, s[3]) <= 0.0) res = lo;
     else if (dobj_dd(hi, nu, use_nu, s[0], s[1], s24, s[3]) >= 0.0) res = hi;
     else {
-        for (int it = 0; it < 200; it++) {
-            double mid = 0.5 * (lo + hi);
-            if (mid <= lo || mid >= hi) break;
-            if (dobj_dd(mid, nu, use_nu, s[0], s[1], s24, s[3]) > 0.0) lo = mid; else hi = mid;
+        // f' is convex and strictly decreasing: Newton from the left of the root increases monotonically
+        // towards it; the bracket is kept and bisection is the fallback (rounding near the root)
+        const double lin = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
+        double x = fmin(fmax(log1p(s[1] / lin), lo), hi);        // root of the program without the nu terms
+        if (dobj_dd(x, nu, use_nu, s[0], s[1], s24, s[3]) < 0.0) { hi = x; x = lo; }
+        for (int it = 0; it < 100; it++) {
+            const double em = expm1(x), r = 1.0 / em;
+            double g = -lin + s[1] * r, gp = -s[1] * r * r * (em + 1.0);
+            if (use_nu) {
+                const double en = expm1(nu * x), rn = nu / en;
+                g += s24 * rn;
+                gp -= s24 * rn * rn * (en + 1.0);
+            }
+            if (g > 0.0) lo = x; else if (g < 0.0) hi = x; else break;
+            double xn = x - g / gp;
+            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+            if (xn <= lo || xn >= hi || fabs(xn - x) <= 2e-16 * x) { x = xn; break; }
+            x = xn;
         }
-        res = 0.5 * (lo + hi);
+        res = fmin(fmax(x, dmin), dmax);
     }
     d[v] = res;
 }
@@ -842,6 +856,86 @@ __global__ void __launch_bounds__(NU_BLOCKS) pmm_nu_step(const double *__restric
     }
     *st = s;
     params[0] = s.x;
+}
+
+// The same Newton iteration in ONE cooperative launch: every CTA evaluates its branches, a grid
+// barrier (monotonic counter) publishes the partial sums, and every CTA combines them in the same
+// fixed order and takes the same step -- one barrier per iteration instead of two launches.
+// partial: [2][gridDim.x][4] (double-buffered across iterations); bar: zeroed before the launch.
+__global__ void __launch_bounds__(256) pmm_nu_solve(const unsigned char *__restrict__ free_mask, int n, const double *__restrict__ Snorm,
+                                                     const double *__restrict__ d, double *__restrict__ partial, unsigned *bar,
+                                                     NuState *__restrict__ st_out, double *__restrict__ params, int max_iter) {
+    __shared__ double sh[4][256];
+    const int tid = threadIdx.x, G = gridDim.x;
+    NuState s;
+    s.x = 1.0; s.lo = 0.0; s.hi = 1.0; s.lin = 0.0; s.wsum = 0.0; s.done = 0; s.iters = 0;
+    for (int it = 0; it <= max_iter; it++) {
+        const bool first = it == 0;
+        const double x = s.x;
+        double f = 0.0, fp = 0.0, lin = 0.0, ws = 0.0;
+        for (int v = blockIdx.x * 256 + tid; v < n; v += G * 256)
+            if (free_mask[v]) {
+                const double dv = d[v], w = Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
+                const double em = expm1(x * dv);
+                const double r = dv / em;
+                f += w * r;
+                fp -= w * r * r * (em + 1.0);
+                if (first) { lin += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * dv; ws += w; }
+            }
+        sh[0][tid] = f; sh[1][tid] = fp; sh[2][tid] = lin; sh[3][tid] = ws;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
+            }
+            __syncthreads();
+        }
+        double *pb = partial + (size_t)(it & 1) * G * 4;
+        if (tid < 4) pb[blockIdx.x * 4 + tid] = sh[tid][0];
+        // ---- grid barrier
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const unsigned target = (unsigned)(it + 1) * (unsigned)G;
+            while (*((volatile unsigned *)bar) < target) {}
+            __threadfence();
+        }
+        __syncthreads();
+        // ---- every CTA: fixed-order sum of the G partials (G <= 256), same step everywhere
+#pragma unroll
+        for (int k = 0; k < 4; k++) sh[k][tid] = (tid < G) ? __ldcg(pb + tid * 4 + k) : 0.0;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
+            }
+            __syncthreads();
+        }
+        const double F = sh[0][0], FP = sh[1][0];
+        if (first) {
+            s.lin = sh[2][0]; s.wsum = sh[3][0];
+            if (F - s.lin >= 0.0 || !(s.lin > 0.0)) { s.x = 1.0; s.done = 1; }          // upper bound active (EM_solver.py:402)
+            else { s.lo = 0.0; s.hi = 1.0; s.x = fmin(0.5, s.wsum / s.lin); }             // 1/expm1(t) < 1/t  =>  root < wsum/lin
+        } else {
+            const double g = F - s.lin, xo = s.x;
+            if (g > 0.0) s.lo = xo; else s.hi = xo;
+            s.iters++;
+            if (g == 0.0) s.done = 1;
+            else {
+                double xn = xo - g / FP;
+                if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
+                if (fabs(xn - xo) <= 4e-16 * xo) s.done = 1;
+                if (xn < 1e-300) { xn = 0.0; s.done = 1; }
+                s.x = xn;
+            }
+        }
+        __syncthreads();
+        if (s.done) break;          // identical on every CTA: all leave together
+    }
+    if (blockIdx.x == 0 && tid == 0) { *st_out = s; params[0] = s.x; }
 }
 
 __global__ void pmm_phi_step(const double *__restrict__ stats, int n, double *__restrict__ params, double R, double cells_times_sites) {

@@ -17,14 +17,21 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 
-def partition_sites(qptr: np.ndarray, world_size: int) -> List[Tuple[int, int]]:
-    """Contiguous site ranges with (nearly) equal numbers of state slots
-    ``sum(A_s + 2)`` -- equal bytes streamed per GPU, not equal site counts."""
+def partition_sites(qptr: np.ndarray, world_size: int, balance: str = "sites") -> List[Tuple[int, int]]:
+    """Contiguous site ranges of (nearly) equal cost.  ``balance="sites"``: equal site counts -- the
+    lumped-state engine's work and bytes are per (node, site), independent of the alphabet;
+    ``balance="slots"``: equal numbers of state slots ``sum(A_s + 2)`` -- equal bytes streamed per GPU
+    by the full-state row engine (``PMM_ENGINE=fullstate``)."""
     K = len(qptr) - 1
     if K < world_size:
         raise ValueError("cannot shard %d sites over %d ranks" % (K, world_size))
-    slots = np.diff(np.asarray(qptr, np.int64)) + 2
-    cum = np.concatenate([[0], np.cumsum(slots)])
+    if balance == "sites":
+        cost = np.ones(K, np.int64)
+    elif balance == "slots":
+        cost = np.diff(np.asarray(qptr, np.int64)) + 2
+    else:
+        raise ValueError("balance must be 'sites' or 'slots'")
+    cum = np.concatenate([[0], np.cumsum(cost)])
     bounds = [0]
     for r in range(1, world_size):
         s = int(np.argmin(np.abs(cum - cum[-1] * r / world_size)))

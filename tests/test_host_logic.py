@@ -56,11 +56,16 @@ def test_encode_sites():
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_partition_sites_balanced(world):
     qptr, _ = random_priors(400, 2, 100, seed=3)
-    parts = partition_sites(qptr, world)
-    assert parts[0][0] == 0 and parts[-1][1] == 400
-    assert all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and all(hi > lo for lo, hi in parts)
-    slots = [int(qptr[hi] - qptr[lo] + 2 * (hi - lo)) for lo, hi in parts]
-    assert max(slots) - min(slots) <= 2 * 102
+    for balance in ("sites", "slots"):
+        parts = partition_sites(qptr, world, balance=balance)
+        assert parts[0][0] == 0 and parts[-1][1] == 400
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and all(hi > lo for lo, hi in parts)
+        if balance == "slots":          # equal bytes for the full-state row engine
+            slots = [int(qptr[hi] - qptr[lo] + 2 * (hi - lo)) for lo, hi in parts]
+            assert max(slots) - min(slots) <= 2 * 102
+        else:                           # equal (node, site) records for the lumped engine
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
 
 
 def test_synthetic_shard_consistency():
