@@ -158,6 +158,9 @@ def config_dict(name, spec, qptr, gpus):
 
 
 def run_ours(args, rank, local_rank, world):
+    # keep stdout for the ONE JSON line: anything a library prints there (e.g. "NCCL version ...") goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from laml_b200.capi import Engine
@@ -211,24 +214,36 @@ def run_ours(args, rank, local_rank, world):
         sampler.start()
     launches0 = eng.info()["kernel_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase = np.zeros(3)
     with torch.cuda.stream(sh.stream):
         ev0.record()
         for _ in range(args.steps):
-            step_device()
-            tm = eng.last_timing()          # CUDA events on the launching stream (syncs this step)
-            phase += (tm["inside_ms"], tm["outside_ms"], tm["total_ms"])
+            step_device()                   # enqueued back to back: no host synchronisation inside the timed region
         ev1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = eng.info()["kernel_launches"] - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda:%d" % local_rank)
-    ph = torch.tensor(phase / args.steps, dtype=torch.float64, device="cuda:%d" % local_rank)
+    # phase breakdown (untimed extra steps; CUDA events on the engine's stream, one sync per step)
+    phase = np.zeros(5)
+    nb = max(3, min(10, args.steps))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for _ in range(nb):
+        with torch.cuda.stream(sh.stream):
+            eng.estep_dev()
+            evs[0].record()
+            sh._allreduce()
+            evs[1].record()
+            eng.mstep_dev(R, N)
+            evs[2].record()
+        evs[2].synchronize()
+        tm = eng.last_timing()
+        phase += (tm["inside_ms"], tm["outside_ms"], tm["total_ms"], evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]))
+    ph = torch.tensor(phase / nb, dtype=torch.float64, device="cuda:%d" % local_rank)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.steps
-    inside_ms, outside_ms, estep_ms = [float(x) for x in ph.tolist()]
+    inside_ms, outside_ms, estep_ms, allreduce_ms, mstep_ms = [float(x) for x in ph.tolist()]
 
     # ---- end to end through the host-buffer API ("e2e") ----------------------------
     d_pin = torch.from_numpy(d.copy()).pin_memory().numpy()
@@ -349,6 +364,7 @@ def run_ours(args, rank, local_rank, world):
                            ((40e-9 * (hi - lo) if lumped else 8e-9 * info["row_stride"]) * n_int)),
                        site_chunks=info["n_chunks"], clades=info["clades"], launches_per_pass=info["launches_per_pass"]),
         "em_iter_per_s": 1e3 / ms_step, "estep_ms": estep_ms, "inside_ms": inside_ms, "outside_ms": outside_ms,
+        "allreduce_ms": allreduce_ms, "mstep_ms": mstep_ms,
         "estep_cell_site_per_s": N * Ktot / (estep_ms * 1e-3),
         "node_site_per_s": n * Ktot / (estep_ms * 1e-3),
         "e2e": {"value": N * Ktot / e2e_s, "unit": "cell*site/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -356,7 +372,8 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "device_bytes": info["device_bytes"],
     }
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -364,7 +381,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PMM_BENCH_WORKLOAD", "config4_100k_x_2k"))

@@ -737,12 +737,20 @@ __device__ __forceinline__ double dobj_dd(double d, double nu, bool use_nu, doub
     return g;
 }
 
-__global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask, int n,
-                                   int K_total, double *__restrict__ params, double *__restrict__ d,
-                                   double *__restrict__ Snorm, double dmin, double dmax, double eps_s, double eps_nu) {
+__global__ void __launch_bounds__(128) pmm_mstep_branches(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask, int n,
+                                                          int K_total, double *__restrict__ params, double *__restrict__ d,
+                                                          double *__restrict__ Snorm, double dmin, double dmax, double eps_s, double eps_nu) {
+    // 1/expm1 at the two bounds is the same for every branch: once per CTA
+    __shared__ double s_end[4];
+    const double nu = params[0];
+    const bool use_nu = nu > eps_nu;
+    if (threadIdx.x < 4) {
+        const double t = (threadIdx.x & 1) ? dmax : dmin;
+        s_end[threadIdx.x] = (threadIdx.x < 2) ? 1.0 / expm1(t) : (use_nu ? nu / expm1(nu * t) : 0.0);
+    }
+    __syncthreads();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n || !free_mask[v]) return;
-    const double nu = params[0];
     double s[5], tot = 0.0;
 #pragma unroll
     for (int k = 0; k < 5; k++) { s[k] = fmax(stats[(size_t)v * 5 + k], eps_s); }
@@ -750,17 +758,19 @@ __global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsig
     for (int k = 0; k < 5; k++) tot += s[k];
 #pragma unroll
     for (int k = 0; k < 5; k++) { s[k] = s[k] / tot * (double)K_total; Snorm[(size_t)v * 5 + k] = s[k]; }
-    const bool use_nu = nu > eps_nu;
     const double s24 = s[2] + s[4];
+    const double lin = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
     double lo = dmin, hi = dmax, res;
-    if (dobj_dd(lo, nu, use_nu, s[0], s[1], s24, s[3]) <= 0.0) res = lo;
-    else if (dobj_dd(hi, nu, use_nu, s[0], s[1], s24, s[3]) >= 0.0) res = hi;
+    if (-lin + s[1] * s_end[0] + s24 * s_end[2] <= 0.0) res = lo;            // f'(dmin) <= 0
+    else if (-lin + s[1] * s_end[1] + s24 * s_end[3] >= 0.0) res = hi;       // f'(dmax) >= 0
     else {
-        // f' is convex and strictly decreasing: Newton from the left of the root increases monotonically
-        // towards it; the bracket is kept and bisection is the fallback (rounding near the root)
-        const double lin = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
-        double x = fmin(fmax(log1p(s[1] / lin), lo), hi);        // root of the program without the nu terms
-        if (dobj_dd(x, nu, use_nu, s[0], s[1], s24, s[3]) < 0.0) { hi = x; x = lo; }
+        // f' is convex and strictly decreasing, so Newton from the left of the root increases monotonically
+        // towards it.  Start from the current length (EM moves it little) or, if that is a bound, from the
+        // root of the lower bound 1/expm1(t) >= 1/t - 1/2, which lies left of the true root.  The bracket
+        // is kept and bisection is the fallback.
+        const double w24 = use_nu ? s24 : 0.0;
+        double x = d[v];
+        if (!(x > lo && x < hi)) x = fmin(fmax((s[1] + w24) / (lin + 0.5 * s[1] + 0.5 * nu * w24), lo), hi);
         for (int it = 0; it < 100; it++) {
             const double em = expm1(x), r = 1.0 / em;
             double g = -lin + s[1] * r, gp = -s[1] * r * r * (em + 1.0);
@@ -772,7 +782,7 @@ __global__ void pmm_mstep_branches(const double *__restrict__ stats, const unsig
             if (g > 0.0) lo = x; else if (g < 0.0) hi = x; else break;
             double xn = x - g / gp;
             if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-            if (xn <= lo || xn >= hi || fabs(xn - x) <= 2e-16 * x) { x = xn; break; }
+            if (xn <= lo || xn >= hi || fabs(xn - x) <= 1e-15 * x) { x = xn; break; }
             x = xn;
         }
         res = fmin(fmax(x, dmin), dmax);
@@ -869,6 +879,7 @@ __global__ void __launch_bounds__(256) pmm_nu_solve(const unsigned char *__restr
     const int tid = threadIdx.x, G = gridDim.x;
     NuState s;
     s.x = 1.0; s.lo = 0.0; s.hi = 1.0; s.lin = 0.0; s.wsum = 0.0; s.done = 0; s.iters = 0;
+    const double nu_cur = params[0];         // read by every CTA before the first barrier; written after the last one
     for (int it = 0; it <= max_iter; it++) {
         const bool first = it == 0;
         const double x = s.x;
@@ -918,7 +929,11 @@ __global__ void __launch_bounds__(256) pmm_nu_solve(const unsigned char *__restr
         if (first) {
             s.lin = sh[2][0]; s.wsum = sh[3][0];
             if (F - s.lin >= 0.0 || !(s.lin > 0.0)) { s.x = 1.0; s.done = 1; }          // upper bound active (EM_solver.py:402)
-            else { s.lo = 0.0; s.hi = 1.0; s.x = fmin(0.5, s.wsum / s.lin); }             // 1/expm1(t) < 1/t  =>  root < wsum/lin
+            else {
+                // start from the current nu (EM moves it little); else 1/expm1(t) < 1/t  =>  root < wsum/lin
+                s.lo = 0.0; s.hi = 1.0;
+                s.x = (nu_cur > 0.0 && nu_cur < 1.0) ? nu_cur : fmin(0.5, s.wsum / s.lin);
+            }
         } else {
             const double g = F - s.lin, xo = s.x;
             if (g > 0.0) s.lo = xo; else s.hi = xo;
