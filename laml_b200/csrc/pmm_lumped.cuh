@@ -38,7 +38,10 @@
 
 namespace pmm {
 
-constexpr int LT = 128;                  // threads (= sites) per CTA
+#ifndef PMM_LT
+#define PMM_LT 128
+#endif
+constexpr int LT = PMM_LT;               // threads (= sites) per CTA
 constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (the host caps the clade size at 64)
 #ifndef PMM_LIN_MINB
 #define PMM_LIN_MINB 5
@@ -272,11 +275,12 @@ __device__ __forceinline__ void normalise_out(Opd &n, int F) {
 // conflict-free for both the 8-byte stores and the 16-byte loads); lanes 0..19 each add up half a
 // row and one shuffle joins the halves.  Returns the total of value (lane >> 1) on lanes < 20.
 constexpr int RED_ROW = 36;
-__device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__restrict__ red, int lane) {
-    __syncwarp();                                    // the previous step's readers are done
+__device__ __forceinline__ void red_put5(const double *__restrict__ v, double *__restrict__ red, int lane, int first) {
     const int col = lane + ((lane >> 4) << 1);
 #pragma unroll
-    for (int j = 0; j < 10; j++) red[j * RED_ROW + col] = v[j];
+    for (int j = 0; j < 5; j++) red[(first + j) * RED_ROW + col] = v[j];
+}
+__device__ __forceinline__ double red_finish(const double *__restrict__ red, int lane) {
     __syncwarp();
     double sum = 0.0;
     if (lane < 20) {
@@ -289,7 +293,14 @@ __device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__re
         }
         sum = a + b;
     }
-    return sum + __shfl_xor_sync(0xffffffffu, sum, 1);
+    const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
+    __syncwarp();                                    // readers done before the next step's writers
+    return tot;
+}
+__device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__restrict__ red, int lane) {
+    red_put5(v, red, lane, 0);
+    red_put5(v + 5, red, lane, 5);
+    return red_finish(red, lane);
 }
 
 // step flags: bits 0-1 where out[u] comes from (0 = u is a root, 1 = load, 2 = chained in registers),
@@ -392,10 +403,12 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
         const int F = chain.ri.y;
         const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
-        double c10[10];
+        double c5[5];
         Opd ov, ow;
-        child_outside(chain, v, w, bcv, qsum, fac, ov, c10);
-        child_outside(chain, w, v, bcw, qsum, fac, ow, c10 + 5);
+        child_outside(chain, w, v, bcw, qsum, fac, ow, c5);
+        red_put5(c5, red, lane, 5);                      // counts leave the registers at once
+        child_outside(chain, v, w, bcv, qsum, fac, ov, c5);
+        red_put5(c5, red, lane, 0);
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
         if (vleaf && valid && c0v == -1) rt += 1.0 - ov.r.y * fac;
         if (wleaf && valid && c0w == -1) rt += 1.0 - ow.r.y * fac;
@@ -418,7 +431,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             chain = ov;
         }
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
-        const double tot = warp_sum10(c10, red, lane);
+        const double tot = red_finish(red, lane);
         if (lane < 20 && !(lane & 1)) {
             const int j = lane >> 1;
             Sg[(size_t)((j < 5) ? d0.y : d0.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
