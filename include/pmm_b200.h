@@ -151,6 +151,14 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
                         int32_t max_iter, double *out_nllh, double *out_d5, int32_t *out_iters,
                         int32_t *out_nodes);
 
+/*
+ * Runtime options.  "slices" (1..4, default 2 or PMM_SLICES): the sites of a handle are processed as this many
+ * slices on separate CUDA streams so that the latency-bound top-of-the-tree launches of one slice overlap the
+ * big launch of another; with 1 the passes run back to back on the handle's stream and pmm_last_timing can
+ * split the E-step into its inside and outside pass.
+ */
+int pmm_set_option(pmm_handle *h, const char *name, int64_t value);
+
 /* ---- introspection for benchmarks ------------------------------------------------- */
 typedef struct {
     int64_t n_nodes, n_leaves, n_sites;
@@ -168,7 +176,8 @@ typedef struct {
 } pmm_info;
 int pmm_get_info(const pmm_handle *h, pmm_info *info);
 
-/* Timing of the last pmm_estep / pmm_inside on the handle's stream (CUDA events), ms. */
+/* Timing of the last pmm_estep / pmm_inside on the handle's stream (CUDA events), ms.  With site slices
+ * (pmm_set_option "slices" > 1) the two passes interleave: inside_ms then covers both and outside_ms is 0. */
 int pmm_last_timing(const pmm_handle *h, double *inside_ms, double *outside_ms, double *total_ms);
 
 #ifdef __cplusplus

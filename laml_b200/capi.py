@@ -20,7 +20,7 @@ SYMBOLS = [
     "pmm_abi_version", "pmm_last_error", "pmm_create", "pmm_destroy", "pmm_set_stream", "pmm_set_tree",
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
-    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch",
+    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library():
     L.pmm_mstep_dev.argtypes = [vp, f64, i32, vp, i32, i32, f64, f64, f64, f64]
     L.pmm_score_nni_batch.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
     L.pmm_sync.argtypes = [vp]
+    L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
     _lib = L
@@ -130,6 +131,10 @@ class Engine:
         parent, left, right = _i32(parent), _i32(left), _i32(right)
         self._ck(self._L.pmm_set_tree(self._h, parent.shape[0], parent.ctypes.data, left.ctypes.data, right.ctypes.data))
         self.n_nodes = int(parent.shape[0])
+
+    def set_option(self, name: str, value: int):
+        """runtime options of the handle (``include/pmm_b200.h``: "slices")"""
+        self._ck(self._L.pmm_set_option(self._h, name.encode(), int(value)))
 
     def set_total_sites(self, k: int):
         self._ck(self._L.pmm_set_total_sites(self._h, int(k)))

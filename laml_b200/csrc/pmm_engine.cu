@@ -79,12 +79,19 @@ struct pmm_handle {
     double *d_post0 = nullptr, *d_post1 = nullptr;
     // ---- lumped-state engine (default): clade schedules and 40-byte records, see pmm_lumped.cuh
     int engine = 0;                 // 0 = lumped (default), 1 = full-state rows (PMM_ENGINE=fullstate)
+    bool last_sliced = false;       // the last lumped pass ran site slices on several streams (no inside/outside split)
     bool last_full = false;         // which engine ran the last pass (for pmm_last_timing)
     bool full_ready = false;        // full-state buffers are allocated on first use (NNI batch, PMM_ENGINE=fullstate)
     int clade_target = 0, n_clades = 0;
     std::vector<int> lin_phase_ptr, lout_phase_ptr;     // launch -> first clade
     int4 *d_lin_steps = nullptr, *d_lout_steps = nullptr, *d_lin_clades = nullptr, *d_lout_clades = nullptr;
     int lKc = 0, lG = 0;            // sites per chunk, site groups (warps) per chunk
+    // site slices: the sites of a chunk are split into `slices` ranges whose launches go to separate streams,
+    // so that one slice's latency-bound top-tier launches overlap another slice's big tier-0 launch
+    int slices = 2;
+    int stagger = 0;
+    cudaStream_t aux[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per slice: normal, high priority
+    cudaEvent_t ev_fork = nullptr, ev_s[4][3] = {};
     double4 *d_LX = nullptr, *d_LO = nullptr;
     int2 *d_LXI = nullptr, *d_LOI = nullptr;
     double *d_LinvL = nullptr, *d_Lroot_llh = nullptr, *d_LSpart = nullptr, *d_LRpart = nullptr, *d_qsum = nullptr, *d_prior = nullptr;
@@ -554,6 +561,15 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
 
 // records and partial sums of the lumped engine; sites are processed in chunks of lKc if they do not fit
 int alloc_lumped(pmm_handle *h) {
+    if (!h->ev_fork) {
+        int lo_pri = 0, hi_pri = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        for (int j = 0; j < 8; j++) CK(cudaStreamCreateWithPriority(&h->aux[j], cudaStreamNonBlocking, (j & 1) ? hi_pri : lo_pri));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (auto &row : h->ev_s) for (auto &e : row) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->slices = std::max(1, std::min(4, env_int("PMM_SLICES", 2)));
+        h->stagger = env_int("PMM_STAGGER", 0);
+    }
     const int n = h->n_int + h->n_leaves, K = h->K;     // h->n is set only once pmm_set_tree has succeeded
     size_t budget = h->budget;
     if (budget == 0) {
@@ -597,25 +613,58 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
         P.K_total = h->K; P.store_all = env_int("PMM_STORE_ALL", 0);
         const unsigned gy = (unsigned)((P.K + LT - 1) / LT);
         const int G = (P.K + 31) / 32;
+        P.sblk0 = 0;
         CK(cudaEventRecord(h->ev[1], h->stream));
-        for (size_t p = 0; p + 1 < h->lin_phase_ptr.size(); p++) {
+        auto launch_in = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq) {
             const int c0 = h->lin_phase_ptr[p], c1 = h->lin_phase_ptr[p + 1];
-            if (c1 <= c0) continue;
-            pmm_lumped_inside<<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lin_clades + c0, h->d_lin_steps);
+            if (c1 <= c0) return;
+            pmm_lumped_inside<<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lin_clades + c0, h->d_lin_steps);
             h->launches++;
+        };
+        auto launch_out = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq) {
+            const int c0 = h->lout_phase_ptr[p], c1 = h->lout_phase_ptr[p + 1];
+            if (c1 <= c0) return;
+            if (with_post) pmm_lumped_outside<true><<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lout_clades + c0, h->d_lout_steps);
+            else pmm_lumped_outside<false><<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lout_clades + c0, h->d_lout_steps);
+            h->launches++;
+        };
+        const size_t n_in = h->lin_phase_ptr.size() - 1, n_out = h->lout_phase_ptr.size() - 1;
+        const int nslice = std::max(1, std::min({h->slices, (int)gy, 4}));
+        h->last_sliced = nslice > 1;
+        if (nslice == 1) {
+            for (size_t p = 0; p < n_in; p++) launch_in(h->stream, p, P, gy);
+            CK(cudaEventRecord(h->ev[2], h->stream));
+            if (outside) for (size_t p = 0; p < n_out; p++) launch_out(h->stream, p, P, gy);
+        } else {
+            // per slice: tier 0 (inside) on a normal-priority stream, every top-tier launch of both passes on a
+            // high-priority stream, tier 0 (outside) on the normal stream again
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            for (int j = 0; j < nslice; j++) {
+                cudaStream_t sn = h->aux[2 * j], sh = h->aux[2 * j + 1];
+                LParams Q = P;
+                Q.sblk0 = (int)((uint64_t)gy * j / nslice);
+                const unsigned gyq = (unsigned)((uint64_t)gy * (j + 1) / nslice) - (unsigned)Q.sblk0;
+                CK(cudaStreamWaitEvent(sn, h->ev_fork, 0));
+                // stagger: a slice's big launch starts when the previous slice's has finished, i.e. while that
+                // slice walks its latency-bound top tiers
+                if (j > 0 && h->stagger) CK(cudaStreamWaitEvent(sn, h->ev_s[j - 1][0], 0));
+                launch_in(sn, 0, Q, gyq);
+                CK(cudaEventRecord(h->ev_s[j][0], sn));
+                CK(cudaStreamWaitEvent(sh, h->ev_s[j][0], 0));
+                for (size_t p = 1; p < n_in; p++) launch_in(sh, p, Q, gyq);
+                if (outside) for (size_t p = 0; p + 1 < n_out; p++) launch_out(sh, p, Q, gyq);
+                CK(cudaEventRecord(h->ev_s[j][1], sh));
+                CK(cudaStreamWaitEvent(sn, h->ev_s[j][1], 0));
+                if (outside) launch_out(sn, n_out - 1, Q, gyq);
+                CK(cudaEventRecord(h->ev_s[j][2], sn));
+            }
+            for (int j = 0; j < nslice; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_s[j][2], 0));
+            CK(cudaEventRecord(h->ev[2], h->stream));
         }
         pmm_site_llh<<<(P.K + 255) / 256, 256, 0, h->stream>>>(h->d_Lroot_llh, h->n_roots, P.K, h->d_site_llh + P.site0);
         pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_site_llh + P.site0, P.K, d_llh, ci > 0);
         h->launches += 2;
-        CK(cudaEventRecord(h->ev[2], h->stream));
         if (outside) {
-            for (size_t p = 0; p + 1 < h->lout_phase_ptr.size(); p++) {
-                const int c0 = h->lout_phase_ptr[p], c1 = h->lout_phase_ptr[p + 1];
-                if (c1 <= c0) continue;
-                if (with_post) pmm_lumped_outside<true><<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lout_clades + c0, h->d_lout_steps);
-                else pmm_lumped_outside<false><<<dim3((unsigned)(c1 - c0), gy), LT, 0, h->stream>>>(P, h->d_lout_clades + c0, h->d_lout_steps);
-                h->launches++;
-            }
             pmm_reduce_S<<<(5 * n + 255) / 256, 256, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0);
             pmm_reduce_S<<<(h->n_clades + 255) / 256, 256, 0, h->stream>>>(h->d_LRpart, G, h->n_clades, h->d_Rnode, 0);
             pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Rnode, h->n_clades, d_Rt, ci > 0);
@@ -795,6 +844,9 @@ void pmm_destroy(pmm_handle *h) {
     free_tree_state(h);
     dfree(h->d_codes); dfree(h->d_params); dfree(h->d_site_ptr); dfree(h->d_prior); dfree(h->d_qsum);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &st : h->aux) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto &row : h->ev_s) for (auto &e : row) if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -918,6 +970,13 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     CK(cudaStreamSynchronize(h->stream));
     h->n = n;
     return 0;
+}
+
+int pmm_set_option(pmm_handle *h, const char *name, int64_t value) {
+    if (!h || !name) return 1;
+    const std::string k(name);
+    if (k == "slices") { h->slices = (int)std::max<int64_t>(1, std::min<int64_t>(4, value)); return 0; }
+    return fail(h, "pmm_set_option: unknown option '%s'", name);
 }
 
 int pmm_set_total_sites(pmm_handle *h, int32_t n_sites_total) {
@@ -1196,6 +1255,7 @@ int pmm_last_timing(const pmm_handle *hc, double *inside_ms, double *outside_ms,
         cudaEventElapsedTime(&a, h->ev[1], h->ev[2]);
         cudaEventElapsedTime(&b, h->ev[2], h->ev[3]);
     }
+    if (!h->last_full && h->last_sliced) b = 0.0f;      // site slices interleave the passes: `a` covers both
     cudaEventElapsedTime(&tot, h->ev[0], h->ev[3]);
     if (inside_ms) *inside_ms = a;
     if (outside_ms) *outside_ms = b;

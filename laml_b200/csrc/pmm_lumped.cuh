@@ -74,6 +74,7 @@ struct LParams {
     double *post0, *post1;   // optional [n][K_total] log posteriors (annotation path), or null
     int K_total;
     int store_all;           // outside pass: also store the out-records that are chained in registers
+    int sblk0;               // first site block (of LT sites) this launch covers: site slices run on separate streams
 };
 
 enum { KIND_LEAF = 0, KIND_LOAD = 1, KIND_PREV = 2 };
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
     const int N = P.n_leaves;
-    int s = blockIdx.y * LT + threadIdx.x;
+    int s = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
     const bool valid = s < P.K;
     s = min(s, P.K - 1);
     const int gs = P.site0 + s;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
     const int N = P.n_leaves;
-    const int s_raw = blockIdx.y * LT + threadIdx.x;
+    const int s_raw = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
     const bool valid = s_raw < P.K;
     const int s = min(s_raw, P.K - 1);
     const int gs = P.site0 + s;

@@ -27,6 +27,6 @@ for _ in range(10):
     t = eng.last_timing()
     acc += (t["inside_ms"], t["outside_ms"], t["total_ms"], ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]))
 acc /= 10
-print("K=%d clades %d launches/pass %d: inside %.3f outside %.3f estep(kernel events) %.3f estep(stream) %.3f mstep %.3f ms" % (
-    K, eng.info()["clades"], eng.info()["launches_per_pass"], *acc))
+print("slices=%s K=%d clades %d launches/pass %d: inside %.3f outside %.3f estep(kernel events) %.3f estep(stream) %.3f mstep %.3f ms" % (
+    os.environ.get("PMM_SLICES", "2"), K, eng.info()["clades"], eng.info()["launches_per_pass"], *acc))
 eng.close()
