@@ -133,6 +133,31 @@ def test_synthetic_vs_oracle(cfg, seed):
     eng.close()
 
 
+def test_site_slices_are_bit_identical(engine_mode):
+    """site slices on auxiliary streams (pmm_set_option "slices") only reorder launches: same bits"""
+    if engine_mode != "lumped":
+        pytest.skip("lumped engine only")
+    from laml_b200.capi import Engine, PMMError
+    from laml_b200.synth import make_workload
+    w = make_workload(400, 700, 2, 30, 0.2, 0.2, seed=71)          # 700 sites = 6 site blocks of 128
+    eng = Engine(400, w.qptr, w.qval, w.codes)
+    eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    ref = None
+    for slices in (1, 2, 3, 4):
+        eng.set_option("slices", slices)
+        out = eng.estep(w.d, w.nu, w.phi, want_site_llh=True)
+        tm = eng.last_timing()
+        assert (tm["outside_ms"] > 0) == (slices == 1)              # the split exists only without slices
+        if ref is None:
+            ref = out
+        else:
+            assert out["llh"] == ref["llh"] and (out["S"] == ref["S"]).all() and out["Rtilde"] == ref["Rtilde"]
+            assert (out["site_llh"] == ref["site_llh"]).all()
+    with pytest.raises(PMMError):
+        eng.set_option("no_such_option", 1)
+    eng.close()
+
+
 def test_mstep_and_em_vs_oracle():
     case, z = load_npz_case("ref_test4_zero")
     orc = case.oracle()
