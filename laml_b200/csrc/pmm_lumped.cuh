@@ -111,18 +111,18 @@ __device__ __forceinline__ void stage_clade(int4 *s_steps, double4 *s_bc, double
 //   E_0 = a x_0 + b sum(q x) + g x_m,  E_m = x_m,  E_alpha = c x_alpha + g x_m  (Eb off the hot slot, Eh on it;
 //   Eh == Eb when there is no hot state)
 struct Child {
-    double x0, xm, xz, qh, xb;
+    double x0, xm, xz, qh, xb, sq;      // sq = sum_a q_a x_a
     int h, cum;
-    double t0, t1, gm, E0, Eb, Eh;      // t0 = a x0, t1 = b sum(q x), gm = g xm
+    double t0, t1, gm, E0, Eb, Eh;      // t0 = a x0, t1 = b sq, gm = g xm
 };
 __device__ __forceinline__ void decode(Child &c, const Opd &p, const double4 bc, double qsum) {
     c.x0 = p.r.x; c.xm = p.r.y; c.xz = p.r.z; c.qh = p.r.w; c.h = p.ri.x; c.cum = p.ri.y;
     const bool hot = c.h >= 0;
     c.xb = hot ? 0.0 : c.xz;
-    const double sq = c.xz * (hot ? c.qh : qsum);
+    c.sq = c.xz * (hot ? c.qh : qsum);
     c.gm = bc.w * c.xm;
     c.t0 = bc.x * c.x0;
-    c.t1 = bc.y * sq;
+    c.t1 = bc.y * c.sq;
     c.E0 = c.t0 + c.t1 + c.gm;
     c.Eb = fma(bc.z, c.xb, c.gm);
     c.Eh = fma(bc.z, c.xz, c.gm);
@@ -234,34 +234,41 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
 // For child v of u with sibling w (EM_solver.py:143-300 in lumped full-state form):
 //   T^v = out[u] .* E^w;  out[v]_0 = a T_0, out[v]_a = b q_a T_0 + c T_a, out[v]_m = g (T_0 + sum_a T_a) + T_m
 //   S0 = T_0 a x_0 / L, S1 = T_0 b sum(q x) / L, S2 = T_0 g x_m / L, S3 = c sum_a T_a x_a / L, S4 = g x_m sum_a T_a / L.
-// o = out-record of u (oD = 0 when k < 0); bcv = (a, b, c, g) of v.  Writes the unnormalised
-// out-record of v into n and the five counts (times fac) into cnt[0..4].
-__device__ __forceinline__ void child_outside(const Opd &o, const Child &v, const Child &w, const double4 bcv, double qsum, double fac,
-                                              Opd &n, double *__restrict__ cnt) {
-    const double o0 = o.r.x, om = o.r.y, oB = o.r.z, oD = o.r.w;
-    const int k = o.ri.x;
-    const bool hotw = w.h >= 0, eq_kw = k == w.h;
-    const double T0 = o0 * w.E0, Tm = om * w.xm;
-    const double sqE = fma(w.Eb, qsum, (w.Eh - w.Eb) * w.qh);            // sum_a q_a E^w_a
-    const double dk = oD * (eq_kw ? w.Eh : w.Eb);                          // oD E^w_k
-    const double sT = fma(oB, sqE, dk);                                    // sum_a T_a
-    n.r.x = bcv.x * T0;
-    n.r.y = fma(bcv.w, T0 + sT, Tm);
-    n.r.z = fma(bcv.y, T0, bcv.z * oB * w.Eb);
-    // hot slot of out[v]: w's hot state if it has one (then E^w vanishes elsewhere), else u's
-    n.r.w = bcv.z * w.Eh * (hotw ? fma(oB, w.qh, eq_kw ? oD : 0.0) : oD);
-    n.ri.x = hotw ? w.h : k;
-    // counts of the branch above v
-    const double Ewhv = (v.h == w.h) ? w.Eh : w.Eb;                        // E^w at slot h_v
-    const double sqEx = fma(v.xb, sqE, (v.xz - v.xb) * v.qh * Ewhv);       // sum_a q_a E^w_a x^v_a
-    const double xvk = (k == v.h) ? v.xz : v.xb;                           // x^v at slot k
-    const double sTx = fma(oB, sqEx, dk * xvk);                            // sum_a T_a x^v_a
-    const double T0f = T0 * fac, gmf = v.gm * fac;
+// T has the same lumped shape as an out-record: T_a = tB q_a + [a == tk] tD  (if w has a hot state E^w vanishes
+// off it, so tB = 0 and the hot slot is w's; otherwise E^w is flat and u's hot slot, if any, survives).
+struct TRec { double T0, Tm, tB, tD; int tk; };
+__device__ __forceinline__ TRec make_T(const Opd &o, const Child &w) {
+    TRec t;
+    const double oB = o.r.z, oD = o.r.w;
+    const bool hotw = w.h >= 0;
+    t.T0 = o.r.x * w.E0;
+    t.Tm = o.r.y * w.xm;
+    t.tB = oB * w.Eb;
+    t.tD = w.Eh * (hotw ? fma(oB, w.qh, (o.ri.x == w.h) ? oD : 0.0) : oD);
+    t.tk = hotw ? w.h : o.ri.x;
+    return t;
+}
+// out-record of v (unnormalised) and the five counts of the branch above v (times fac) from T^v
+__device__ __forceinline__ void finish_T(const TRec &t, const Child &v, const double4 bcv, double qsum, double fac,
+                                         Opd &n, double *__restrict__ cnt) {
+    const double sT = fma(t.tB, qsum, t.tD);                               // sum_a T_a   (tD = 0 without a hot slot)
+    n.r.x = bcv.x * t.T0;
+    n.r.y = fma(bcv.w, t.T0 + sT, t.Tm);
+    n.r.z = fma(bcv.y, t.T0, bcv.z * t.tB);
+    n.r.w = bcv.z * t.tD;
+    n.ri.x = t.tk;
+    const double xvk = (t.tk == v.h) ? v.xz : v.xb;                        // x^v at slot tk
+    const double sTx = fma(t.tB, v.sq, t.tD * xvk);                        // sum_a T_a x^v_a
+    const double T0f = t.T0 * fac, gmf = v.gm * fac;
     cnt[0] = T0f * v.t0;
     cnt[1] = T0f * v.t1;
-    cnt[2] = T0 * gmf;
+    cnt[2] = t.T0 * gmf;
     cnt[3] = bcv.z * sTx * fac;
     cnt[4] = gmf * sT;
+}
+__device__ __forceinline__ void child_outside(const Opd &o, const Child &v, const Child &w, const double4 bcv, double qsum, double fac,
+                                              Opd &n, double *__restrict__ cnt) {
+    finish_T(make_T(o, w), v, bcv, qsum, fac, n, cnt);
 }
 
 __device__ __forceinline__ void normalise_out(Opd &n, int F) {
