@@ -7,6 +7,7 @@
 #include "pmm_kernels.cuh"
 #include "pmm_nni.cuh"
 #include "pmm_lumped.cuh"
+#include "pmm_nni_lumped.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -79,6 +80,7 @@ struct pmm_handle {
     double *d_post0 = nullptr, *d_post1 = nullptr;
     // ---- lumped-state engine (default): clade schedules and 40-byte records, see pmm_lumped.cuh
     int engine = 0;                 // 0 = lumped (default), 1 = full-state rows (PMM_ENGINE=fullstate)
+    bool force_store_all = false;   // the NNI batch scorer needs every out-record of the cached E-step
     bool last_sliced = false;       // the last lumped pass ran site slices on several streams (no inside/outside split)
     bool last_full = false;         // which engine ran the last pass (for pmm_last_timing)
     bool full_ready = false;        // full-state buffers are allocated on first use (NNI batch, PMM_ENGINE=fullstate)
@@ -592,6 +594,20 @@ int alloc_lumped(pmm_handle *h) {
     return 0;
 }
 
+LParams make_lparams(pmm_handle *h, int ci, bool with_post) {
+    LParams P;
+    P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.code_stride = h->K;
+    P.n_leaves = h->n_leaves; P.n_nodes = h->n; P.n_clades = h->n_clades;
+    P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
+    P.params = h->d_params; P.bc = h->d_bc;
+    P.X = h->d_LX; P.XI = h->d_LXI; P.O = h->d_LO; P.OI = h->d_LOI;
+    P.invL = h->d_LinvL; P.root_site_llh = h->d_Lroot_llh; P.Spart = h->d_LSpart; P.Rpart = h->d_LRpart;
+    P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
+    P.K_total = h->K; P.store_all = (env_int("PMM_STORE_ALL", 0) || h->force_store_all) ? 1 : 0;
+    P.sblk0 = 0;
+    return P;
+}
+
 int run_lumped(pmm_handle *h, bool outside, bool with_post) {
     const int n = h->n;
     CK(cudaEventRecord(h->ev[0], h->stream));
@@ -602,15 +618,7 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
     const int nchunks = (h->K + h->lKc - 1) / h->lKc;
     float acc_in = 0, acc_out = 0;
     for (int ci = 0; ci < nchunks; ci++) {
-        LParams P;
-        P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.code_stride = h->K;
-        P.n_leaves = h->n_leaves; P.n_nodes = n; P.n_clades = h->n_clades;
-        P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
-        P.params = h->d_params; P.bc = h->d_bc;
-        P.X = h->d_LX; P.XI = h->d_LXI; P.O = h->d_LO; P.OI = h->d_LOI;
-        P.invL = h->d_LinvL; P.root_site_llh = h->d_Lroot_llh; P.Spart = h->d_LSpart; P.Rpart = h->d_LRpart;
-        P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
-        P.K_total = h->K; P.store_all = env_int("PMM_STORE_ALL", 0);
+        LParams P = make_lparams(h, ci, with_post);
         const unsigned gy = (unsigned)((P.K + LT - 1) / LT);
         const int G = (P.K + 31) / 32;
         P.sblk0 = 0;
@@ -1147,8 +1155,10 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
                         int32_t *out_iters, int32_t *out_nodes) {
     if (n_cand <= 0) return 0;
     if (pmm_upload_params(h, d, nu, phi)) return 1;
-    if (ensure_fullstate(h)) return 1;       // the batch scorer works on cached full-state rows (pmm_nni.cuh)
-    if (h->chunks.size() != 1) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk, have %zu)", h->chunks.size());
+    const bool lumped_nni = h->engine == 0 && !env_int("PMM_NNI_ROWS", 0);
+    if (lumped_nni && h->lKc < h->K) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk)");
+    if (!lumped_nni && ensure_fullstate(h)) return 1;       // PMM_NNI_ROWS=1 / PMM_ENGINE=fullstate: cached full-state rows (pmm_nni.cuh)
+    if (!lumped_nni && h->chunks.size() != 1) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk, have %zu)", h->chunks.size());
     const int N = h->n_leaves, n = h->n;
     std::vector<int> root_index(n, 0);
     {   // root index per node (host copy of the tree)
@@ -1181,7 +1191,44 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         st[i] = z;
         if (out_nodes) { int32_t *o = out_nodes + (size_t)5 * i; o[0] = v; o[1] = u; o[2] = ck; o[3] = co; o[4] = w; }
     }
-    // caches of the current tree: one full E-step
+    if (lumped_nni) {
+        // ---- lumped records: one E-step that stores every out-record, then ONE launch, one CTA per candidate
+        h->force_store_all = true;
+        const int rc = run_passes(h, true, false);
+        h->force_store_all = false;
+        if (rc) return 1;
+        double llh_total = 0.0;
+        CK(cudaMemcpyAsync(&llh_total, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        NniCand *d_c = nullptr; NniState *d_s = nullptr; double *d_rsum = nullptr;
+        auto cleanup = [&]() { dfree(d_c); dfree(d_s); dfree(d_rsum); };
+        const size_t keep = h->device_bytes;
+        if (dalloc(h, &d_c, n_cand) || dalloc(h, &d_s, n_cand) || dalloc(h, &d_rsum, h->n_roots)) { cleanup(); h->device_bytes = keep; return 1; }
+        h->device_bytes = keep;     // scratch of this call only
+        cudaError_t e = cudaMemcpyAsync(d_c, cands.data(), sizeof(NniCand) * n_cand, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, st.data(), sizeof(NniState) * n_cand, cudaMemcpyHostToDevice, h->stream);
+        for (int r = 0; r < h->n_roots && e == cudaSuccess; r++)
+            pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Lroot_llh + (size_t)r * h->K, h->K, d_rsum + r, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);          // llh_total is on the host now
+        if (e == cudaSuccess) {
+            const LParams P = make_lparams(h, 0, false);
+            const int K_total = h->K_total > 0 ? h->K_total : h->K;
+            pmm_nni_lumped<<<(unsigned)n_cand, NNIL_THREADS, 0, h->stream>>>(P, d_c, d_s, d_rsum, llh_total, K_total, dmin, dmax, 1e-6, 1e-5,
+                                                                            conv_eps, max_iter);
+            h->launches += 1 + h->n_roots;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_s, sizeof(NniState) * n_cand, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cleanup();
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(h, "pmm_score_nni_batch: %s", cudaGetErrorString(e)); }
+        for (int i = 0; i < n_cand; i++) {
+            if (out_nllh) out_nllh[i] = -st[i].llh_cur;
+            if (out_iters) out_iters[i] = st[i].iters;
+            if (out_d5) for (int b = 0; b < 5; b++) out_d5[(size_t)5 * i + b] = st[i].d[b];
+        }
+        return 0;
+    }
+    // ---- full-state rows: caches of the current tree: one full E-step
     if (run_passes(h, true, false, true)) return 1;
     const Chunk &c0 = h->chunks[0];
     KParams P = make_params(h, c0, false);

@@ -737,17 +737,51 @@ __device__ __forceinline__ double dobj_dd(double d, double nu, bool use_nu, doub
     return g;
 }
 
+// 1 / expm1 at the two bounds (the same for every branch): e[0] = 1/expm1(dmin), e[1] = 1/expm1(dmax),
+// e[2] = nu/expm1(nu dmin), e[3] = nu/expm1(nu dmax) (0 when nu is switched off)
+__device__ __forceinline__ double mstep_end_const(int i, double nu, bool use_nu, double dmin, double dmax) {
+    const double t = (i & 1) ? dmax : dmin;
+    return (i < 2) ? 1.0 / expm1(t) : (use_nu ? nu / expm1(nu * t) : 0.0);
+}
+// argmax over [dmin, dmax] of the per-branch program EM_solver.py:351-357 for normalised statistics s[0..4].
+// f' is convex and strictly decreasing, so Newton from the left of the root increases monotonically towards
+// it.  Start from the current length (EM moves it little) or, if that is a bound, from the root of the lower
+// bound 1/expm1(t) >= 1/t - 1/2, which lies left of the true root.  The bracket is kept and bisection is
+// the fallback; the two bound tests need no transcendental.
+__device__ __forceinline__ double mstep_branch_length(const double *s, double nu, bool use_nu, double dmin, double dmax, double d_cur,
+                                                      const double *__restrict__ e) {
+    const double s24 = s[2] + s[4];
+    const double lin = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
+    double lo = dmin, hi = dmax;
+    if (-lin + s[1] * e[0] + s24 * e[2] <= 0.0) return lo;            // f'(dmin) <= 0
+    if (-lin + s[1] * e[1] + s24 * e[3] >= 0.0) return hi;            // f'(dmax) >= 0
+    const double w24 = use_nu ? s24 : 0.0;
+    double x = d_cur;
+    if (!(x > lo && x < hi)) x = fmin(fmax((s[1] + w24) / (lin + 0.5 * s[1] + 0.5 * nu * w24), lo), hi);
+    for (int it = 0; it < 100; it++) {
+        const double em = expm1(x), r = 1.0 / em;
+        double g = -lin + s[1] * r, gp = -s[1] * r * r * (em + 1.0);
+        if (use_nu) {
+            const double en = expm1(nu * x), rn = nu / en;
+            g += s24 * rn;
+            gp -= s24 * rn * rn * (en + 1.0);
+        }
+        if (g > 0.0) lo = x; else if (g < 0.0) hi = x; else break;
+        double xn = x - g / gp;
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+        if (xn <= lo || xn >= hi || fabs(xn - x) <= 1e-15 * x) { x = xn; break; }
+        x = xn;
+    }
+    return fmin(fmax(x, dmin), dmax);
+}
+
 __global__ void __launch_bounds__(128) pmm_mstep_branches(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask, int n,
                                                           int K_total, double *__restrict__ params, double *__restrict__ d,
                                                           double *__restrict__ Snorm, double dmin, double dmax, double eps_s, double eps_nu) {
-    // 1/expm1 at the two bounds is the same for every branch: once per CTA
     __shared__ double s_end[4];
     const double nu = params[0];
     const bool use_nu = nu > eps_nu;
-    if (threadIdx.x < 4) {
-        const double t = (threadIdx.x & 1) ? dmax : dmin;
-        s_end[threadIdx.x] = (threadIdx.x < 2) ? 1.0 / expm1(t) : (use_nu ? nu / expm1(nu * t) : 0.0);
-    }
+    if (threadIdx.x < 4) s_end[threadIdx.x] = mstep_end_const(threadIdx.x, nu, use_nu, dmin, dmax);
     __syncthreads();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n || !free_mask[v]) return;
@@ -758,36 +792,7 @@ __global__ void __launch_bounds__(128) pmm_mstep_branches(const double *__restri
     for (int k = 0; k < 5; k++) tot += s[k];
 #pragma unroll
     for (int k = 0; k < 5; k++) { s[k] = s[k] / tot * (double)K_total; Snorm[(size_t)v * 5 + k] = s[k]; }
-    const double s24 = s[2] + s[4];
-    const double lin = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
-    double lo = dmin, hi = dmax, res;
-    if (-lin + s[1] * s_end[0] + s24 * s_end[2] <= 0.0) res = lo;            // f'(dmin) <= 0
-    else if (-lin + s[1] * s_end[1] + s24 * s_end[3] >= 0.0) res = hi;       // f'(dmax) >= 0
-    else {
-        // f' is convex and strictly decreasing, so Newton from the left of the root increases monotonically
-        // towards it.  Start from the current length (EM moves it little) or, if that is a bound, from the
-        // root of the lower bound 1/expm1(t) >= 1/t - 1/2, which lies left of the true root.  The bracket
-        // is kept and bisection is the fallback.
-        const double w24 = use_nu ? s24 : 0.0;
-        double x = d[v];
-        if (!(x > lo && x < hi)) x = fmin(fmax((s[1] + w24) / (lin + 0.5 * s[1] + 0.5 * nu * w24), lo), hi);
-        for (int it = 0; it < 100; it++) {
-            const double em = expm1(x), r = 1.0 / em;
-            double g = -lin + s[1] * r, gp = -s[1] * r * r * (em + 1.0);
-            if (use_nu) {
-                const double en = expm1(nu * x), rn = nu / en;
-                g += s24 * rn;
-                gp -= s24 * rn * rn * (en + 1.0);
-            }
-            if (g > 0.0) lo = x; else if (g < 0.0) hi = x; else break;
-            double xn = x - g / gp;
-            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-            if (xn <= lo || xn >= hi || fabs(xn - x) <= 1e-15 * x) { x = xn; break; }
-            x = xn;
-        }
-        res = fmin(fmax(x, dmin), dmax);
-    }
-    d[v] = res;
+    d[v] = mstep_branch_length(s, nu, use_nu, dmin, dmax, d[v], s_end);
 }
 
 // ---- the 1-D problem in nu (EM_solver.py:394-407) and phi (:318-326)

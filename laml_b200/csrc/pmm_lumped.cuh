@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             Child r;
             decode(r, pr, cr, qsum);
             chain.r = make_double4(cr.x, cr.w, cr.y, 0.0); chain.ri = make_int2(-1, -r.cum);
+            if (P.store_all && valid) { P.O[ou] = chain.r; P.OI[ou] = chain.ri; }      // the NNI scorer reads out[root] too
             const double t0 = r.t0 * invL, t2 = r.gm * invL;
             double r10[10];
 #pragma unroll

@@ -11,6 +11,13 @@ from laml_b200.synth import make_workload
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["records", "rows"])
+def nni_cache(request, monkeypatch):
+    """the batch scorer on the lumped records (default) and on cached full-state rows (PMM_NNI_ROWS=1)"""
+    monkeypatch.setenv("PMM_NNI_ROWS", "1" if request.param == "rows" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("seed,n,K,amax,nu,phi", [(71, 40, 14, 12, 0.15, 0.1), (72, 25, 9, 40, 0.0, 0.2), (73, 60, 20, 6, 0.3, 0.0)])
 def test_batch_matches_full_tree_em(seed, n, K, amax, nu, phi):
     w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
