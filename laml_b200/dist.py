@@ -74,6 +74,7 @@ class ShardedEngine:
             ptr, n = engine.stats_ptr()
             stats_tensor = torch.as_tensor(_DeviceArray(ptr, n), device="cuda:%d" % engine.device)
         self.stats = stats_tensor
+        self._host_stats = None
         self.n_nodes = engine.n_nodes
 
     def _on_stream(self):
@@ -102,8 +103,16 @@ class ShardedEngine:
         download ``S``, ``Rtilde``, ``llh``."""
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
-        with self._on_stream():
+        if self.stream is None:                       # CPU stand-in (gloo tests)
             st = np.array(self.stats.cpu().numpy(), copy=True)
+        else:
+            import torch
+            if self._host_stats is None:              # pinned staging buffer, reused: the returned S is a view of it
+                self._host_stats = torch.empty(self.stats.shape, dtype=self.stats.dtype).pin_memory()
+            with self._on_stream():
+                self._host_stats.copy_(self.stats, non_blocking=True)
+            self.stream.synchronize()
+            st = self._host_stats.numpy()
         n5 = 5 * self.n_nodes
         return {"S": st[:n5].reshape(self.n_nodes, 5), "Rtilde": float(st[n5]), "llh": float(st[n5 + 1])}
 
