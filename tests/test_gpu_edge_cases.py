@@ -138,6 +138,18 @@ def test_forest_of_two_trees():
     compare(forest, codes, qptr, qval, d, 0.2, 0.2)
 
 
+def test_smallest_problems():
+    """two leaves under one root, a single site; and a three-leaf tree with one site of one state"""
+    for n_leaves in (2, 3):
+        f = random_tree(n_leaves, seed=91)
+        d = lognormal_branch_lengths(f, seed=92)
+        qptr = np.array([0, 1], np.int32)
+        qval = np.array([1.0])
+        for codes in ([1, 0, -1], [-1, -1, -1], [1, 1, 1], [0, -2, 1]):
+            c = np.array(codes[:n_leaves], np.int32).reshape(n_leaves, 1)
+            compare(f, c, qptr, qval, d, 0.2, 0.1)
+
+
 def test_usage_errors_are_loud():
     with pytest.raises(PMMError):
         Engine(4, np.array([0, 2], np.int32), np.array([0.5, 0.5]), np.array([[3], [0], [0], [0]], np.int32))   # state 3 of 2

@@ -158,6 +158,33 @@ def test_site_slices_are_bit_identical(engine_mode):
     eng.close()
 
 
+def test_engines_agree_at_config3_size(monkeypatch):
+    """BASELINE config 3 (10k cells x 500 sites, alphabets up to 100 states) is beyond what the oracle finishes in
+    seconds: the two independent GPU engines (lumped records vs full-state rows) must agree there, and the
+    size-independent properties of the counts must hold"""
+    from laml_b200.capi import Engine
+    from laml_b200.synth import CONFIGS, make_workload
+    w = make_workload(seed=3, **CONFIGS["config3_10k_x_500"])
+    N, K = w.forest.n_leaves, w.codes.shape[1]
+    out = {}
+    for mode in ("lumped", "fullstate"):
+        monkeypatch.setenv("PMM_ENGINE", mode)
+        eng = Engine(N, w.qptr, w.qval, w.codes)
+        eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+        out[mode] = eng.estep(w.d, w.nu, w.phi, want_site_llh=True)
+        eng.close()
+    a, b = out["lumped"], out["fullstate"]
+    assert abs(a["llh"] - b["llh"]) <= 1e-12 * abs(b["llh"])
+    np.testing.assert_allclose(a["site_llh"], b["site_llh"], rtol=1e-12)
+    np.testing.assert_allclose(a["S"], b["S"], rtol=1e-8, atol=1e-10 * K)
+    assert abs(a["Rtilde"] - b["Rtilde"]) <= 1e-10 * b["Rtilde"]
+    # the five counts and the silenced-stays-silenced mass partition each site: 0 <= sum_k S_k <= K per branch
+    assert (a["S"] >= -1e-9).all() and (a["S"].sum(axis=1) <= K * (1 + 1e-9)).all()
+    # a leaf observed in an unsilenced state cannot have a silenced parent edge: its S2 + S4 vanish on those sites
+    obs = (w.codes >= 0).sum(axis=1)
+    assert (a["S"][:N, 2] + a["S"][:N, 4] <= (K - obs) + 1e-6).all()
+
+
 def test_mstep_and_em_vs_oracle():
     case, z = load_npz_case("ref_test4_zero")
     orc = case.oracle()
