@@ -585,6 +585,8 @@ int alloc_lumped(pmm_handle *h) {
     const int forced = env_int("PMM_CHUNKS", 0);
     if (forced > 0) Kc = std::max(1, (K + forced - 1) / forced);
     else if (per_site * K > (double)budget) Kc = std::min(K, std::max(32, (int)((double)budget / per_site) / 32 * 32));
+    // the kernels index records with 32 bits
+    Kc = (int)std::min<int64_t>(Kc, std::max<int64_t>(1, ((int64_t)1 << 31) / std::max(h->n_int, 1) - 1));
     h->lKc = Kc; h->lG = (Kc + 31) / 32;
     const size_t rows = (size_t)h->n_int * Kc;
     if (dalloc(h, &h->d_LX, rows) || dalloc(h, &h->d_LO, rows) || dalloc(h, &h->d_LXI, rows) || dalloc(h, &h->d_LOI, rows) ||

@@ -79,6 +79,12 @@ struct LParams {
 
 enum { KIND_LEAF = 0, KIND_LOAD = 1, KIND_PREV = 2 };
 
+// index of (internal node, site) in the record arrays.  32 bits: a chunk never holds 2^31 records (they would
+// need 172 GB; the host caps the chunk accordingly), and 32-bit indices halve the address arithmetic
+__device__ __forceinline__ unsigned rec_index(const LParams &P, int node, int s) {
+    return (unsigned)(node - P.n_leaves) * (unsigned)P.K + (unsigned)s;
+}
+
 // one prefetched operand: an inside / outside record, or (leaves) the prior of the leaf's state in r.w
 struct Opd { double4 r; int2 ri; };
 
@@ -145,9 +151,9 @@ __device__ __forceinline__ void inside_fetch(const LParams &P, const int4 d, int
                                              int s, int N) {
     const int kv = d.w & 3, kw = (d.w >> 2) & 3;
     if (kv == KIND_LEAF) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
-    else { const size_t o = (size_t)(d.y - N) * P.K + s; n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
+    else { const unsigned o = rec_index(P, d.y, s); n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
     if (kw == KIND_LEAF) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
-    else if (kw == KIND_LOAD) { const size_t o = (size_t)(d.z - N) * P.K + s; n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+    else if (kw == KIND_LOAD) { const unsigned o = rec_index(P, d.z, s); n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
 }
 
 __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
@@ -188,9 +194,9 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         if (PF_DIST > 0 && i + PF_DIST < nsteps) {
             const int4 dp = s_steps[i + PF_DIST];
             if ((dp.w & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else if (dp.w & 32) { const size_t o = (size_t)(dp.y - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
             if (((dp.w >> 2) & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else if (dp.w & 64) { const size_t o = (size_t)(dp.z - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
         }
         const int kv = d0.w & 3, kw = (d0.w >> 2) & 3;
         if (kv == KIND_LEAF) leaf_operand(cur.v, c0v, s_lut);
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         prev.ri.x = bv ? (clash ? -1 : v.h) : w.h;
         prev.ri.y = v.cum + w.cum + e;
         if (valid) {
-            const size_t o = (size_t)(d0.x - N) * P.K + s;
+            const unsigned o = rec_index(P, d0.x, s);
             P.X[o] = prev.r;
             P.XI[o] = prev.ri;
             if (d0.w & 16) {
@@ -319,10 +325,10 @@ struct OutSlot { Opd v, w, o; };
 __device__ __forceinline__ void outside_fetch(const LParams &P, const int4 d, int cv, int cw, OutSlot &n, const double *__restrict__ prior_site,
                                               int s, int N) {
     if (d.w & 4) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
-    else { const size_t o = (size_t)(d.y - N) * P.K + s; n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
+    else { const unsigned o = rec_index(P, d.y, s); n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
     if (d.w & 8) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
-    else { const size_t o = (size_t)(d.z - N) * P.K + s; n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
-    if ((d.w & 3) == KIND_LOAD) { const size_t o = (size_t)(d.x - N) * P.K + s; n.o.r = P.O[o]; n.o.ri = P.OI[o]; }
+    else { const unsigned o = rec_index(P, d.z, s); n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+    if ((d.w & 3) == KIND_LOAD) { const unsigned o = rec_index(P, d.x, s); n.o.r = P.O[o]; n.o.ri = P.OI[o]; }
 }
 
 template <bool POST>
@@ -372,9 +378,9 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         if (PF_DIST > 0 && i + PF_DIST < nsteps) {
             const int4 dp = s_steps[i + PF_DIST];
             if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else { const size_t o = (size_t)(dp.y - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
             if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else { const size_t o = (size_t)(dp.z - N) * P.K + s; prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
         }
         const int u = d0.x, f = d0.w;
         const bool vleaf = f & 4, wleaf = f & 8;
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         const int how = f & 3;
         if (how == 0) {
             // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
-            const size_t ou = (size_t)(u - N) * P.K + s;
+            const unsigned ou = rec_index(P, u, s);
             Opd pr;
             pr.r = P.X[ou]; pr.ri = P.XI[ou];
             const double4 cr = ld_bc(P.bc, u);
@@ -432,11 +438,11 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
         if (!wleaf) {
             normalise_out(ow, F + v.cum);
-            if (valid && ((f & 32) || P.store_all)) { const size_t oo = (size_t)(d0.z - N) * P.K + s; P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
+            if (valid && ((f & 32) || P.store_all)) { const unsigned oo = rec_index(P, d0.z, s); P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
         }
         if (!vleaf) {
             normalise_out(ov, F + w.cum);
-            if (valid && ((f & 16) || P.store_all)) { const size_t oo = (size_t)(d0.y - N) * P.K + s; P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
+            if (valid && ((f & 16) || P.store_all)) { const unsigned oo = rec_index(P, d0.y, s); P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
             chain = ov;
         }
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
     // a subtree root as an operand: its inside record, or the leaf table + the prior of the leaf's state
     auto operand = [&](int node, int s, int gs, const double *prior_site) {
         Opd p;
-        if (node >= N) { const size_t o = (size_t)(node - N) * P.K + s; p.r = P.X[o]; p.ri = P.XI[o]; }
+        if (node >= N) { const unsigned o = rec_index(P, node, s); p.r = P.X[o]; p.ri = P.XI[o]; }
         else {
             const int code = __ldg(P.codes + (size_t)node * P.code_stride + gs);
             p.r.w = (code > 0) ? __ldg(prior_site + (code - 1)) : 0.0;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
             T.T0 = 1.0; T.Tm = 0.0; T.tB = 0.0; T.tD = 0.0; T.tk = -1;
             double invL = 1.0;
             if (cd.g >= 0) {
-                const size_t og = (size_t)(cd.g - N) * P.K + s;
+                const unsigned og = rec_index(P, cd.g, s);
                 Opd o;
                 o.r = P.O[og]; o.ri = P.OI[og];
                 const Opd oS = operand(cd.s, s, gs, prior_site);
