@@ -94,8 +94,9 @@ struct pmm_handle {
     int stagger = 0;
     cudaStream_t aux[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per slice: normal, high priority
     cudaEvent_t ev_fork = nullptr, ev_s[4][3] = {};
-    double4 *d_LX = nullptr, *d_LO = nullptr;
-    int2 *d_LXI = nullptr, *d_LOI = nullptr;
+    double2 *d_LX = nullptr;        // packed 32-byte inside records (two double2 each)
+    double4 *d_LO = nullptr;
+    int2 *d_LOI = nullptr;
     double *d_LinvL = nullptr, *d_Lroot_llh = nullptr, *d_LSpart = nullptr, *d_LRpart = nullptr, *d_qsum = nullptr, *d_prior = nullptr;
     int *d_site_ptr = nullptr;
     int64_t l_in_bytes_per_site = 0, l_out_bytes_per_site = 0;   // algorithmic bytes the lumped passes move per site
@@ -158,7 +159,7 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
     dfree(h->d_post0); dfree(h->d_post1);
     dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
-    dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LXI); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
+    dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
     dfree(h->d_LSpart); dfree(h->d_LRpart);
     h->full_ready = false;
     free_chunks(h);
@@ -539,10 +540,10 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     }
     h->n_clades = ncl;
     if ((int)in_steps.size() != h->n_int || (int)out_steps.size() != h->n_int) return fail(h, "internal error: clade schedule does not cover the tree");
-    // algorithmic bytes per site: 40-byte records written once and read where not chained, 4-byte leaf codes,
+    // algorithmic bytes per site: 32-byte inside / 40-byte outside records written once and read where not chained, 4-byte leaf codes,
     // 40 bytes of expected counts per (branch, 32 sites)
-    h->l_in_bytes_per_site = 40 * (int64_t)h->n_int + 40 * in_loads + 4 * (int64_t)N + 16 * (int64_t)h->n_roots;
-    h->l_out_bytes_per_site = 40 * (int64_t)(h->n_int) /* inside records of internal children and roots */ + 4 * (int64_t)N +
+    h->l_in_bytes_per_site = 32 * (int64_t)h->n_int + 32 * in_loads + 4 * (int64_t)N + 16 * (int64_t)h->n_roots;
+    h->l_out_bytes_per_site = 32 * (int64_t)(h->n_int) /* inside records of internal children and roots */ + 4 * (int64_t)N +
                               40 * (out_loads + out_stores) + 8 * (int64_t)h->n_roots + (40 * (int64_t)n) / 32;
     // device copies (capacity n_int for every array, so that a new topology over the same counts reuses them)
     const size_t cap = (size_t)std::max(h->n_int, 1);
@@ -580,7 +581,7 @@ int alloc_lumped(pmm_handle *h) {
         if (e != cudaSuccess) return fail(h, "cudaMemGetInfo failed: %s", cudaGetErrorString(e));
         budget = (size_t)(0.85 * (double)fr);
     }
-    const double per_site = 80.0 * h->n_int + 16.0 * h->n_roots + (40.0 * n + 8.0 * h->n_int) / 32.0;
+    const double per_site = 72.0 * h->n_int + 16.0 * h->n_roots + (40.0 * n + 8.0 * h->n_int) / 32.0;
     int Kc = K;
     const int forced = env_int("PMM_CHUNKS", 0);
     if (forced > 0) Kc = std::max(1, (K + forced - 1) / forced);
@@ -589,7 +590,7 @@ int alloc_lumped(pmm_handle *h) {
     Kc = (int)std::min<int64_t>(Kc, std::max<int64_t>(1, ((int64_t)1 << 31) / std::max(h->n_int, 1) - 1));
     h->lKc = Kc; h->lG = (Kc + 31) / 32;
     const size_t rows = (size_t)h->n_int * Kc;
-    if (dalloc(h, &h->d_LX, rows) || dalloc(h, &h->d_LO, rows) || dalloc(h, &h->d_LXI, rows) || dalloc(h, &h->d_LOI, rows) ||
+    if (dalloc(h, &h->d_LX, 2 * rows) || dalloc(h, &h->d_LO, rows) || dalloc(h, &h->d_LOI, rows) ||
         dalloc(h, &h->d_LinvL, (size_t)h->n_roots * Kc) || dalloc(h, &h->d_Lroot_llh, (size_t)h->n_roots * Kc) ||
         dalloc(h, &h->d_LSpart, (size_t)h->lG * n * 5) || dalloc(h, &h->d_LRpart, (size_t)h->lG * std::max(h->n_int, 1)))
         return 1;
@@ -602,7 +603,7 @@ LParams make_lparams(pmm_handle *h, int ci, bool with_post) {
     P.n_leaves = h->n_leaves; P.n_nodes = h->n; P.n_clades = h->n_clades;
     P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
     P.params = h->d_params; P.bc = h->d_bc;
-    P.X = h->d_LX; P.XI = h->d_LXI; P.O = h->d_LO; P.OI = h->d_LOI;
+    P.X = h->d_LX; P.O = h->d_LO; P.OI = h->d_LOI;
     P.invL = h->d_LinvL; P.root_site_llh = h->d_Lroot_llh; P.Spart = h->d_LSpart; P.Rpart = h->d_LRpart;
     P.post0 = with_post ? h->d_post0 : nullptr; P.post1 = with_post ? h->d_post1 : nullptr;
     P.K_total = h->K; P.store_all = (env_int("PMM_STORE_ALL", 0) || h->force_store_all) ? 1 : 0;

@@ -65,7 +65,8 @@ struct LParams {
     const double *qsum;      // [K_handle] sum_alpha q_alpha
     const double *params;    // [0] = nu, [1] = phi
     const double *bc;        // [n][4] = a, b, c, g per branch (pmm_branch_consts)
-    double4 *X; int2 *XI;    // [n_int][K] inside records (x0, xm, xz, qh), (h, cum)
+    double2 *X;              // [n_int][K][2] inside records, 32 bytes: (x0, xz), (t, h | cum) -- t = q_h with a hot state
+                             // (then x_m = 0 exactly), x_m without one
     double4 *O; int2 *OI;    // [n_int][K] outside records (o0, om, oB, oD), (k, F)
     double *invL;            // [n_roots][K] 1 / (normalised site likelihood)
     double *root_site_llh;   // [n_roots][K]
@@ -87,6 +88,19 @@ __device__ __forceinline__ unsigned rec_index(const LParams &P, int node, int s)
 
 // one prefetched operand: an inside / outside record, or (leaves) the prior of the leaf's state in r.w
 struct Opd { double4 r; int2 ri; };
+
+// An INSIDE operand is kept in the packed form of the 32-byte record: r = (x0, xz, t, h | cum) -- a record with a
+// hot state has x_m = 0 exactly and one without has no q_h, so the two share the slot t; h and cum ride in the
+// last 8 bytes.  Nothing is unpacked at load time (that would wait for the load): `decode` does it at the use.
+__device__ __forceinline__ void ld_xrec(Opd &p, const double2 *__restrict__ X, unsigned o) {
+    const double2 a = X[2 * (size_t)o], b = X[2 * (size_t)o + 1];
+    p.r = make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_xrec(double2 *__restrict__ X, unsigned o, const Opd &p) {
+    X[2 * (size_t)o] = make_double2(p.r.x, p.r.y);
+    X[2 * (size_t)o + 1] = make_double2(p.r.z, p.r.w);
+}
+__device__ __forceinline__ double pack_hc(int h, int cum) { return __hiloint2double(cum, h); }
 
 __device__ __forceinline__ double4 ld_bc(const double *__restrict__ bc, int v) {
     const double2 lo = __ldg(reinterpret_cast<const double2 *>(bc) + 2 * (size_t)v);
@@ -122,8 +136,10 @@ struct Child {
     double t0, t1, gm, E0, Eb, Eh;      // t0 = a x0, t1 = b sq, gm = g xm
 };
 __device__ __forceinline__ void decode(Child &c, const Opd &p, const double4 bc, double qsum) {
-    c.x0 = p.r.x; c.xm = p.r.y; c.xz = p.r.z; c.qh = p.r.w; c.h = p.ri.x; c.cum = p.ri.y;
+    c.x0 = p.r.x; c.xz = p.r.y; c.qh = p.r.z;                 // qh is meaningful only with a hot state
+    c.h = __double2loint(p.r.w); c.cum = __double2hiint(p.r.w);
     const bool hot = c.h >= 0;
+    c.xm = hot ? 0.0 : p.r.z;
     c.xb = hot ? 0.0 : c.xz;
     c.sq = c.xz * (hot ? c.qh : qsum);
     c.gm = bc.w * c.xm;
@@ -133,12 +149,12 @@ __device__ __forceinline__ void decode(Child &c, const Opd &p, const double4 bc,
     c.Eb = fma(bc.z, c.xb, c.gm);
     c.Eh = fma(bc.z, c.xz, c.gm);
 }
-// a leaf's operand from its code: (x0, xm, xz) from the table; qh was gathered into p.r.w one step ahead
+// a leaf's operand from its code: (x0, xm, xz) from the table; q of its state was gathered into p.r.z one step ahead
 __device__ __forceinline__ void leaf_operand(Opd &p, int code, const double4 *s_lut) {
     const double4 t = s_lut[min(code, 1) + 2];
-    p.r.x = t.x; p.r.y = t.y; p.r.z = t.z;
-    p.ri.x = max(code, 0) - 1;
-    p.ri.y = 0;
+    p.r.x = t.x; p.r.y = t.z;
+    p.r.z = (code > 0) ? p.r.z : t.y;
+    p.r.w = pack_hc(max(code, 0) - 1, 0);
 }
 
 // ---------------------------------------------------------------- inside pass
@@ -150,10 +166,10 @@ struct InSlot { Opd v, w; };
 __device__ __forceinline__ void inside_fetch(const LParams &P, const int4 d, int cv, int cw, InSlot &n, const double *__restrict__ prior_site,
                                              int s, int N) {
     const int kv = d.w & 3, kw = (d.w >> 2) & 3;
-    if (kv == KIND_LEAF) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
-    else { const unsigned o = rec_index(P, d.y, s); n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
-    if (kw == KIND_LEAF) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
-    else if (kw == KIND_LOAD) { const unsigned o = rec_index(P, d.z, s); n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+    if (kv == KIND_LEAF) n.v.r.z = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
+    else { const unsigned o = rec_index(P, d.y, s); ld_xrec(n.v, P.X, o); }
+    if (kw == KIND_LEAF) n.w.r.z = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
+    else if (kw == KIND_LOAD) { const unsigned o = rec_index(P, d.z, s); ld_xrec(n.w, P.X, o); }
 }
 
 __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         if (((d.w >> 2) & 3) == KIND_LEAF) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
     };
     Opd prev;                                            // the record computed by the previous step
-    prev.r = make_double4(0.0, 0.0, 0.0, 0.0); prev.ri = make_int2(-1, 0);
+    prev.r = make_double4(0.0, 0.0, 0.0, pack_hc(-1, 0)); prev.ri = make_int2(-1, 0);
     InSlot A, B;
     A.v = A.w = B.v = B.w = prev;
     int4 d0 = s_steps[0], d1 = (nsteps > 1) ? s_steps[1] : d0;
@@ -194,9 +210,9 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         if (PF_DIST > 0 && i + PF_DIST < nsteps) {
             const int4 dp = s_steps[i + PF_DIST];
             if ((dp.w & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + 2 * (size_t)o); }
             if (((dp.w >> 2) & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int kv = d0.w & 3, kw = (d0.w >> 2) & 3;
         if (kv == KIND_LEAF) leaf_operand(cur.v, c0v, s_lut);
@@ -212,21 +228,20 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         const double xz = v.Eh * (clash ? w.Eb : w.Eh);
         const int e = expo_of_hi(max(hi32(x0), max(hi32(xm), hi32(xz))));
         const double sc = pow2i(-e);
-        prev.r.x = x0 * sc; prev.r.y = xm * sc; prev.r.z = xz * sc;
-        prev.r.w = bv ? v.qh : w.qh;
-        prev.ri.x = bv ? (clash ? -1 : v.h) : w.h;
-        prev.ri.y = v.cum + w.cum + e;
+        const int hu = bv ? (clash ? -1 : v.h) : w.h;
+        prev.r.x = x0 * sc; prev.r.y = xz * sc;
+        prev.r.z = (hu >= 0) ? (bv ? v.qh : w.qh) : xm * sc;
+        prev.r.w = pack_hc(hu, v.cum + w.cum + e);
         if (valid) {
             const unsigned o = rec_index(P, d0.x, s);
-            P.X[o] = prev.r;
-            P.XI[o] = prev.ri;
+            st_xrec(P.X, o, prev);
             if (d0.w & 16) {
                 // root: site likelihood L = E[root]_0 (the root's own branch starts in state 0, EM_solver.py:140)
                 Child r;
                 decode(r, prev, ld_bc(P.bc, d0.x), qsum);
                 const double L = r.E0;
                 P.invL[(size_t)cl.z * P.K + s] = (L > 0.0) ? 1.0 / L : 0.0;
-                P.root_site_llh[(size_t)cl.z * P.K + s] = (L > 0.0) ? log(L) + (double)prev.ri.y * 0.693147180559945309417232121458 : -INFINITY;
+                P.root_site_llh[(size_t)cl.z * P.K + s] = (L > 0.0) ? log(L) + (double)r.cum * 0.693147180559945309417232121458 : -INFINITY;
             }
         }
         d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
@@ -324,10 +339,10 @@ struct OutSlot { Opd v, w, o; };
 
 __device__ __forceinline__ void outside_fetch(const LParams &P, const int4 d, int cv, int cw, OutSlot &n, const double *__restrict__ prior_site,
                                               int s, int N) {
-    if (d.w & 4) n.v.r.w = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
-    else { const unsigned o = rec_index(P, d.y, s); n.v.r = P.X[o]; n.v.ri = P.XI[o]; }
-    if (d.w & 8) n.w.r.w = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
-    else { const unsigned o = rec_index(P, d.z, s); n.w.r = P.X[o]; n.w.ri = P.XI[o]; }
+    if (d.w & 4) n.v.r.z = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
+    else { const unsigned o = rec_index(P, d.y, s); ld_xrec(n.v, P.X, o); }
+    if (d.w & 8) n.w.r.z = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
+    else { const unsigned o = rec_index(P, d.z, s); ld_xrec(n.w, P.X, o); }
     if ((d.w & 3) == KIND_LOAD) { const unsigned o = rec_index(P, d.x, s); n.o.r = P.O[o]; n.o.ri = P.OI[o]; }
 }
 
@@ -378,9 +393,9 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         if (PF_DIST > 0 && i + PF_DIST < nsteps) {
             const int4 dp = s_steps[i + PF_DIST];
             if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + 2 * (size_t)o); }
             if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + o); prefetch_l2(P.XI + o); }
+            else { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int u = d0.x, f = d0.w;
         const bool vleaf = f & 4, wleaf = f & 8;
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
             const unsigned ou = rec_index(P, u, s);
             Opd pr;
-            pr.r = P.X[ou]; pr.ri = P.XI[ou];
+            ld_xrec(pr, P.X, ou);
             const double4 cr = ld_bc(P.bc, u);
             Child r;
             decode(r, pr, cr, qsum);

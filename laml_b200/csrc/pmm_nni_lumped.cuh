@@ -24,12 +24,12 @@ __device__ __forceinline__ Opd merge_children(const Child &v, const Child &w) {
     Opd r;
     const bool bv = v.h >= 0, bw = w.h >= 0;
     const bool clash = bv && bw && v.h != w.h;
+    const int hu = bv ? (clash ? -1 : v.h) : w.h;
     r.r.x = v.E0 * w.E0;
-    r.r.y = v.xm * w.xm;
-    r.r.z = v.Eh * (clash ? w.Eb : w.Eh);
-    r.r.w = bv ? v.qh : w.qh;
-    r.ri.x = bv ? (clash ? -1 : v.h) : w.h;
-    r.ri.y = 0;
+    r.r.y = v.Eh * (clash ? w.Eb : w.Eh);
+    r.r.z = (hu >= 0) ? (bv ? v.qh : w.qh) : v.xm * w.xm;
+    r.r.w = pack_hc(hu, 0);
+    r.ri = make_int2(0, 0);
     return r;
 }
 
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
     // a subtree root as an operand: its inside record, or the leaf table + the prior of the leaf's state
     auto operand = [&](int node, int s, int gs, const double *prior_site) {
         Opd p;
-        if (node >= N) { const unsigned o = rec_index(P, node, s); p.r = P.X[o]; p.ri = P.XI[o]; }
+        if (node >= N) { const unsigned o = rec_index(P, node, s); ld_xrec(p, P.X, o); }
         else {
             const int code = __ldg(P.codes + (size_t)node * P.code_stride + gs);
-            p.r.w = (code > 0) ? __ldg(prior_site + (code - 1)) : 0.0;
+            p.r.z = (code > 0) ? __ldg(prior_site + (code - 1)) : 0.0;
             leaf_operand(p, code, s_lut);
         }
         return p;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
             const double *prior_site = P.prior + __ldg(P.site_ptr + gs);
             const double qsum = __ldg(P.qsum + gs);
             const Opd oA = operand(cd.A, s, gs, prior_site), oB = operand(cd.B, s, gs, prior_site), oC = operand(cd.C, s, gs, prior_site);
-            int shift = oA.ri.y + oB.ri.y + oC.ri.y;             // exponent of L' relative to the records' scales
+            int shift = __double2hiint(oA.r.w) + __double2hiint(oB.r.w) + __double2hiint(oC.r.w);   // exponent of L' relative to the records' scales
             // T^v = out[g] .* E^s, or e_0 when v is a root
             TRec T;
             T.T0 = 1.0; T.Tm = 0.0; T.tB = 0.0; T.tD = 0.0; T.tk = -1;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
                 Child cs;
                 decode(cs, oS, bcs, qsum);
                 T = make_T(o, cs);
-                shift += o.ri.y + oS.ri.y;                       // F_g + cum_s
+                shift += o.ri.y + __double2hiint(oS.r.w);        // F_g + cum_s
                 invL = P.invL[(size_t)cd.root * P.K + s];
             }
             Child a, b, c, u, v;
