@@ -768,8 +768,11 @@ __device__ __forceinline__ double mstep_branch_length(const double *s, double nu
         }
         if (g > 0.0) lo = x; else if (g < 0.0) hi = x; else break;
         double xn = x - g / gp;
+        // converged: test the Newton step itself first -- a monotone approach from the left never moves `hi`, and
+        // a step that rounds to x must end the iteration, not send it to the middle of a stale bracket
+        if (fabs(xn - x) <= 1e-15 * x) { x = fmin(fmax(xn, lo), hi); break; }
         if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        if (xn <= lo || xn >= hi || fabs(xn - x) <= 1e-15 * x) { x = xn; break; }
+        if (xn <= lo || xn >= hi) { x = xn; break; }
         x = xn;
     }
     return fmin(fmax(x, dmin), dmax);
@@ -863,8 +866,8 @@ __global__ void __launch_bounds__(NU_BLOCKS) pmm_nu_step(const double *__restric
         if (g == 0.0) s.done = 1;
         else {
             double xn = x - g / fp;
-            if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
-            if (fabs(xn - x) <= 4e-16 * x) s.done = 1;
+            if (fabs(xn - x) <= 4e-16 * x) { s.done = 1; xn = fmin(fmax(xn, s.lo), s.hi); }
+            else if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
             if (xn < 1e-300) { xn = 0.0; s.done = 1; }
             s.x = xn;
         }
@@ -946,8 +949,8 @@ __global__ void __launch_bounds__(256) pmm_nu_solve(const unsigned char *__restr
             if (g == 0.0) s.done = 1;
             else {
                 double xn = xo - g / FP;
-                if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
-                if (fabs(xn - xo) <= 4e-16 * xo) s.done = 1;
+                if (fabs(xn - xo) <= 4e-16 * xo) { s.done = 1; xn = fmin(fmax(xn, s.lo), s.hi); }     // the step itself first (see mstep_branch_length)
+                else if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
                 if (xn < 1e-300) { xn = 0.0; s.done = 1; }
                 s.x = xn;
             }
