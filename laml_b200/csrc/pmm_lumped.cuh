@@ -44,7 +44,7 @@ namespace pmm {
 constexpr int LT = PMM_LT;               // threads (= sites) per CTA
 constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (the host caps the clade size at 64)
 #ifndef PMM_LIN_MINB
-#define PMM_LIN_MINB 5
+#define PMM_LIN_MINB 6
 #endif
 #ifndef PMM_LOUT_MINB
 #define PMM_LOUT_MINB 3
@@ -53,6 +53,10 @@ constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (t
 #define PMM_PF_DIST 6                    // L2 prefetch distance in steps for operands of earlier launches (0 = off)
 #endif
 constexpr int PF_DIST = PMM_PF_DIST;
+#ifndef PMM_PF_DIST_OUT
+#define PMM_PF_DIST_OUT 3
+#endif
+constexpr int PF_DIST_OUT = PMM_PF_DIST_OUT;
 
 struct LParams {
     int K;                   // sites of this chunk
@@ -390,8 +394,8 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         int c2v = 0, c2w = 0;
         if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
         if (i + 1 < nsteps) outside_fetch(P, d1, c1v, c1w, nxt, prior_site, s, N);
-        if (PF_DIST > 0 && i + PF_DIST < nsteps) {
-            const int4 dp = s_steps[i + PF_DIST];
+        if (PF_DIST_OUT > 0 && i + PF_DIST_OUT < nsteps) {
+            const int4 dp = s_steps[i + PF_DIST_OUT];
             if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
             else { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + 2 * (size_t)o); }
             if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
