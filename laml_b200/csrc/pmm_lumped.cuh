@@ -35,6 +35,7 @@
 // Spart[site group][node][5]; pmm_reduce_S sums the site groups in a fixed order (bit-reproducible).
 #pragma once
 #include "pmm_kernels.cuh"
+#include <type_traits>
 
 namespace pmm {
 
@@ -53,6 +54,9 @@ constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (t
 #define PMM_PF_DIST 6                    // L2 prefetch distance in steps for operands of earlier launches (0 = off)
 #endif
 constexpr int PF_DIST = PMM_PF_DIST;
+#ifndef PMM_LOUT_SHAPES
+#define PMM_LOUT_SHAPES 1                // 1: one specialised step body per (v leaf?, w leaf?) shape
+#endif
 #ifndef PMM_PF_DIST_OUT
 #define PMM_PF_DIST_OUT 3
 #endif
@@ -126,7 +130,8 @@ __device__ __forceinline__ void stage_clade(int4 *s_steps, double4 *s_bc, double
     if (threadIdx.x < 4) {
         const double phi = __ldg(P.params + 1);
         const int c = threadIdx.x;                  // (x0, xm, xz)
-        s_lut[c] = make_double4(c == 1 ? phi : (c == 2 ? 1.0 - phi : 0.0), c < 2 ? 1.0 : 0.0, c == 1 ? phi : (c == 3 ? 1.0 - phi : 0.0), 0.0);
+        s_lut[c] = make_double4(c == 1 ? phi : (c == 2 ? 1.0 - phi : 0.0), c < 2 ? 1.0 : 0.0, c == 1 ? phi : (c == 3 ? 1.0 - phi : 0.0),
+                                c == 1 ? phi : 0.0);        // (x0, xm, xz, xb)
     }
     __syncthreads();
 }
@@ -146,6 +151,19 @@ __device__ __forceinline__ void decode(Child &c, const Opd &p, const double4 bc,
     c.xm = hot ? 0.0 : p.r.z;
     c.xb = hot ? 0.0 : c.xz;
     c.sq = c.xz * (hot ? c.qh : qsum);
+    c.gm = bc.w * c.xm;
+    c.t0 = bc.x * c.x0;
+    c.t1 = bc.y * c.sq;
+    c.E0 = c.t0 + c.t1 + c.gm;
+    c.Eb = fma(bc.z, c.xb, c.gm);
+    c.Eh = fma(bc.z, c.xz, c.gm);
+}
+// a leaf decoded straight from its code (no packing round trip): (x0, xm, xz, xb) from the table, qh = the gathered prior
+__device__ __forceinline__ void decode_leaf(Child &c, int code, double qh, const double4 bc, double qsum, const double4 *s_lut) {
+    const double4 t = s_lut[min(code, 1) + 2];
+    c.x0 = t.x; c.xm = t.y; c.xz = t.z; c.xb = t.w; c.qh = qh;
+    c.h = max(code, 0) - 1; c.cum = 0;
+    c.sq = c.xz * ((code > 0) ? qh : qsum);
     c.gm = bc.w * c.xm;
     c.t0 = bc.x * c.x0;
     c.t1 = bc.y * c.sq;
@@ -274,14 +292,17 @@ __device__ __forceinline__ TRec make_T(const Opd &o, const Child &w) {
     return t;
 }
 // out-record of v (unnormalised) and the five counts of the branch above v (times fac) from T^v
+template <bool REC = true>                                               // REC = false: v is a leaf, only out[v]_0 and out[v]_m are formed
 __device__ __forceinline__ void finish_T(const TRec &t, const Child &v, const double4 bcv, double qsum, double fac,
                                          Opd &n, double *__restrict__ cnt) {
     const double sT = fma(t.tB, qsum, t.tD);                               // sum_a T_a   (tD = 0 without a hot slot)
     n.r.x = bcv.x * t.T0;
     n.r.y = fma(bcv.w, t.T0 + sT, t.Tm);
-    n.r.z = fma(bcv.y, t.T0, bcv.z * t.tB);
-    n.r.w = bcv.z * t.tD;
-    n.ri.x = t.tk;
+    if (REC) {
+        n.r.z = fma(bcv.y, t.T0, bcv.z * t.tB);
+        n.r.w = bcv.z * t.tD;
+        n.ri.x = t.tk;
+    }
     const double xvk = (t.tk == v.h) ? v.xz : v.xb;                        // x^v at slot tk
     const double sTx = fma(t.tB, v.sq, t.tD * xvk);                        // sum_a T_a x^v_a
     const double T0f = t.T0 * fac, gmf = v.gm * fac;
@@ -291,9 +312,10 @@ __device__ __forceinline__ void finish_T(const TRec &t, const Child &v, const do
     cnt[3] = bcv.z * sTx * fac;
     cnt[4] = gmf * sT;
 }
+template <bool REC = true>
 __device__ __forceinline__ void child_outside(const Opd &o, const Child &v, const Child &w, const double4 bcv, double qsum, double fac,
                                               Opd &n, double *__restrict__ cnt) {
-    finish_T(make_T(o, w), v, bcv, qsum, fac, n, cnt);
+    finish_T<REC>(make_T(o, w), v, bcv, qsum, fac, n, cnt);
 }
 
 __device__ __forceinline__ void normalise_out(Opd &n, int F) {
@@ -402,13 +424,18 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             else { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int u = d0.x, f = d0.w;
-        const bool vleaf = f & 4, wleaf = f & 8;
         const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
-        if (vleaf) leaf_operand(cur.v, c0v, s_lut);
-        if (wleaf) leaf_operand(cur.w, c0w, s_lut);
+#if PMM_LOUT_SHAPES
+        // one straight-line body per step shape (which children are leaves): big basic blocks for the scheduler,
+        // and everything a leaf does not need (out-record, normalisation, store) is compiled out
+        auto core = [&](auto VL, auto WL) {
+        constexpr bool vleaf = decltype(VL)::value, wleaf = decltype(WL)::value;
+#else
+        const bool vleaf = f & 4, wleaf = f & 8;
+#endif
         Child v, w;
-        decode(v, cur.v, bcv, qsum);
-        decode(w, cur.w, bcw, qsum);
+        if (vleaf) decode_leaf(v, c0v, cur.v.r.z, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
+        if (wleaf) decode_leaf(w, c0w, cur.w.r.z, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
         const int how = f & 3;
         if (how == 0) {
             // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
@@ -439,10 +466,17 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
         double c5[5];
         Opd ov, ow;
+#if PMM_LOUT_SHAPES
+        child_outside<!wleaf>(chain, w, v, bcw, qsum, fac, ow, c5);
+        red_put5(c5, red, lane, 5);                      // counts leave the registers at once
+        child_outside<!vleaf>(chain, v, w, bcv, qsum, fac, ov, c5);
+        red_put5(c5, red, lane, 0);
+#else
         child_outside(chain, w, v, bcw, qsum, fac, ow, c5);
         red_put5(c5, red, lane, 5);                      // counts leave the registers at once
         child_outside(chain, v, w, bcv, qsum, fac, ov, c5);
         red_put5(c5, red, lane, 0);
+#endif
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
         if (vleaf && valid && c0v == -1) rt += 1.0 - ov.r.y * fac;
         if (wleaf && valid && c0w == -1) rt += 1.0 - ow.r.y * fac;
@@ -470,6 +504,15 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             const int j = lane >> 1;
             Sg[(size_t)((j < 5) ? d0.y : d0.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
         }
+#if PMM_LOUT_SHAPES
+        };
+        switch ((f >> 2) & 3) {
+            case 0: core(std::false_type{}, std::false_type{}); break;
+            case 1: core(std::true_type{}, std::false_type{}); break;
+            case 2: core(std::false_type{}, std::true_type{}); break;
+            default: core(std::true_type{}, std::true_type{}); break;
+        }
+#endif
         d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
     };
     int i = 0;

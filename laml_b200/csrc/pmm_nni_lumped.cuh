@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const 
     if (tid < 4) {
         s_end[tid] = mstep_end_const(tid, nu, use_nu, dmin, dmax);
         const int c = tid;
-        s_lut[c] = make_double4(c == 1 ? phi : (c == 2 ? 1.0 - phi : 0.0), c < 2 ? 1.0 : 0.0, c == 1 ? phi : (c == 3 ? 1.0 - phi : 0.0), 0.0);
+        s_lut[c] = make_double4(c == 1 ? phi : (c == 2 ? 1.0 - phi : 0.0), c < 2 ? 1.0 : 0.0, c == 1 ? phi : (c == 3 ? 1.0 - phi : 0.0),
+                                c == 1 ? phi : 0.0);
     }
     if (tid == 0) s_done = 0;
     const double4 bcs = (cd.g >= 0) ? ld_bc(P.bc, cd.s) : make_double4(0.0, 0.0, 0.0, 0.0);
