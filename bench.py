@@ -318,6 +318,8 @@ def run_ours(args, rank, local_rank, world):
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = "%s/n%d/%s" % (args.workload, world, "lumped" if lumped else "fullstate")
         traffic = tj.get(key, {}).get(k_out)
+        if traffic is not None:             # profiled launches cover 1/slices of the sites; `achieved` is per whole-tier launch
+            traffic *= tj[key].get("_slices", 1)
     except Exception:
         pass
     # `achieved` counts the bytes this design must move: a true HBM utilisation.  The SURVEY 8(d) per-unit

@@ -2,7 +2,8 @@
 """Per-kernel DRAM traffic and time from an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
 dram__bytes_write.sum --csv` launch list; optionally records the per-launch averages in profiles/traffic.json.
 
-    python scripts/summarize_traffic.py launches.csv [key]      # key e.g. config4_100k_x_2k/n1/lumped
+    python scripts/summarize_traffic.py launches.csv [key [slices]]      # key e.g. config4_100k_x_2k/n1/lumped;
+                                                                         # slices = PMM_SLICES of the profiled run (default 2)
 """
 import collections, csv, json, os, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
@@ -29,5 +30,6 @@ if len(sys.argv) > 2:
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     tj = json.load(open(path)) if os.path.exists(path) else {}
     tj[sys.argv[2]] = {re.match(r'\w+', k).group(0): (rd + wr) / c for k, (c, t, rd, wr) in agg.items() if k.startswith("pmm_l")}
+    tj[sys.argv[2]]["_slices"] = int(sys.argv[3]) if len(sys.argv) > 3 else 2      # a sliced launch covers 1/slices of the sites
     tj[sys.argv[2]]["_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of %s)" % os.path.basename(sys.argv[1])
     json.dump(tj, open(path, "w"), indent=1, sort_keys=True)
