@@ -9,12 +9,13 @@
 // hang below a silenced or differently edited ancestor; a second, different hot state below the
 // same node zeroes every edited slot).  The outside vector is
 //       out_alpha = oB q_alpha + [alpha == k] oD .
-// So a (node, site) is the 40-byte record (x0, xm, xz, qh | h, cum) -- xz is xb when there is no hot
-// state and the hot value when there is one, qh = q_h, cum the accumulated power-of-two exponent --
-// and (o0, om, oB, oD | k, F) for the outside pass.  Every sum over the alphabet has a closed form
-// in qsum = sum_alpha q_alpha and q_h: SURVEY.md section 8's "exact lumping" (states no leaf of the
-// subtree shows are indistinguishable) applied per (node, site) instead of per site.  The numpy
-// model tests/lumped_model.py restates these closed forms and is pinned to the reference's dumps.
+// So a (node, site) is the record (x0, xm, xz, qh | h, cum) -- xz is xb when there is no hot state and the hot
+// value when there is one, qh = q_h, cum the accumulated power-of-two exponent; 32 bytes, because x_m (zero
+// with a hot state) and q_h (absent without one) share a slot -- and the 40-byte record (o0, om, oB, oD | k, F)
+// for the outside pass.  Every sum over the alphabet has a closed form in qsum = sum_alpha q_alpha and q_h:
+// SURVEY.md section 8's "exact lumping" (states no leaf of the subtree shows are indistinguishable) applied
+// per (node, site) instead of per site.  The numpy model tests/lumped_model.py restates these closed forms
+// and is pinned to the reference's dumps.
 //
 // Execution: sites are independent given the tree, so ONE THREAD OWNS ONE SITE and walks a whole
 // CLADE (a connected piece of the tree with < 128 internal nodes, cut out by the host) without any
@@ -27,9 +28,11 @@
 //     register set (the loop is unrolled by two so that the sets swap roles without moves); leaf
 //     codes are loaded two steps ahead because the prior of a leaf's state is a dependent gather;
 //   * the step list and the branch constants of the clade sit in shared memory;
-//   * all global accesses are coalesced across the warp's 32 sites (32 B + 8 B per thread).
-// Clades that hang below other clades run in an earlier (inside) / later (outside) launch: a
-// 100k-cell tree needs ~10 launches per pass instead of one per tree level.
+//   * all global accesses are coalesced across the warp's 32 sites (32 B, or 32 B + 8 B, per thread);
+//   * the outside step exists in one straight-line variant per shape (which children are leaves).
+// The host cuts the forest into tiers (pmm_engine.cu: build_lumped_schedule): tier 0 = every maximal
+// subtree below a size threshold (one launch, ~97 % of the nodes), then the small top tree peeled the
+// same way: a 100k-cell tree needs 5 launches per pass instead of one per tree level.
 // Expected counts: the 10 per-thread values of a step (5 per child branch) are summed over the
 // warp's sites through a transposed shared-memory tile and written once per (warp, node) into
 // Spart[site group][node][5]; pmm_reduce_S sums the site groups in a fixed order (bit-reproducible).
@@ -237,11 +240,10 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
             else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int kv = d0.w & 3, kw = (d0.w >> 2) & 3;
-        if (kv == KIND_LEAF) leaf_operand(cur.v, c0v, s_lut);
-        if (kw == KIND_LEAF) leaf_operand(cur.w, c0w, s_lut);
         Child v, w;
-        decode(v, cur.v, s_bc[2 * i], qsum);
-        decode(w, (kw == KIND_PREV) ? prev : cur.w, s_bc[2 * i + 1], qsum);
+        if (kv == KIND_LEAF) decode_leaf(v, c0v, cur.v.r.z, s_bc[2 * i], qsum, s_lut); else decode(v, cur.v, s_bc[2 * i], qsum);
+        if (kw == KIND_LEAF) decode_leaf(w, c0w, cur.w.r.z, s_bc[2 * i + 1], qsum, s_lut);
+        else decode(w, (kw == KIND_PREV) ? prev : cur.w, s_bc[2 * i + 1], qsum);
         // x_u = E^v .* E^w  (EM_solver.py:118-133); Eh == Eb for a child without a hot state, and two
         // different hot states leave no edited slot alive (E^w_b = 0 then)
         const bool bv = v.h >= 0, bw = w.h >= 0;
