@@ -1,9 +1,12 @@
-// pmm_kernels.cuh -- sm_100a kernels of the PMM likelihood / E-step engine.
+// pmm_kernels.cuh -- sm_100a kernels of the PMM engine shared by both E-step engines (branch constants,
+// fixed-order reductions, the M-step) and the full-state ROW engine (`pmm_level`, `pmm_root_llh`:
+// PMM_ENGINE=fullstate and the PMM_NNI_ROWS cache).  The default E-step kernels are in pmm_lumped.cuh.
 //
 // Model and formulas: SURVEY.md section 3.5 (full-state restatement of
 // laml_libs/EM_solver.py:91-300; verified against the reference in
 // tests/test_fullstate_model.py).  Design notes: DESIGN.md.
 //
+// ---- row engine ----
 // Data layout (per site chunk): every INTERNAL node owns one row of `Wp` fp64
 // slots in X (inside vectors) and one in O (outside vectors).  A site s occupies
 // `len_s = roundup2(A_s + 2)` consecutive slots starting at the even offset
@@ -34,8 +37,8 @@
 // PERSISTENT over the level's nodes p, p+P, ... for tile t.  Warp NCW is the
 // producer: it stages the next nodes' child rows (TMA) and their per-site
 // metadata into an S-stage shared-memory ring, signalling `full` mbarriers;
-// NCW consumer warps (lane groups of G=8, one site per group, double2 per
-// lane => 128 contiguous bytes per group and iteration) compute and write their
+// NCW consumer warps (lane groups of G=4, one site per group, double2 per
+// lane => 64 contiguous bytes per group and iteration) compute and write their
 // results straight to global memory with 16-byte stores, then arrive on the
 // stage's `done` mbarrier.  The tile's prior q and site table stay resident in
 // shared memory for the whole launch.
