@@ -92,6 +92,7 @@ struct pmm_handle {
     // so that one slice's latency-bound top-tier launches overlap another slice's big tier-0 launch
     int slices = 2;
     int stagger = 0;
+    int pdl = 1;                    // programmatic dependent launch between consecutive lumped launches of a stream (PMM_PDL)
     cudaStream_t aux[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per slice: normal, high priority
     cudaEvent_t ev_fork = nullptr, ev_s[4][3] = {};
     double2 *d_LX = nullptr;        // packed 32-byte inside records (two double2 each)
@@ -572,6 +573,7 @@ int alloc_lumped(pmm_handle *h) {
         for (auto &row : h->ev_s) for (auto &e : row) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->slices = std::max(1, std::min(4, env_int("PMM_SLICES", 2)));
         h->stagger = env_int("PMM_STAGGER", 0);
+        h->pdl = env_int("PMM_PDL", 1);
     }
     const int n = h->n_int + h->n_leaves, K = h->K;     // h->n is set only once pmm_set_tree has succeeded
     size_t budget = h->budget;
@@ -626,26 +628,37 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
         const int G = (P.K + 31) / 32;
         P.sblk0 = 0;
         CK(cudaEventRecord(h->ev[1], h->stream));
-        auto launch_in = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq) {
-            const int c0 = h->lin_phase_ptr[p], c1 = h->lin_phase_ptr[p + 1];
-            if (c1 <= c0) return;
-            pmm_lumped_inside<<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lin_clades + c0, h->d_lin_steps);
+        // pdl: programmatic dependent launch -- the kernel may start while its predecessor in the stream drains
+        // (it stages its clade, then waits for the predecessor's records); only between two lumped launches
+        const bool use_pdl = h->pdl != 0;
+        auto launch_k = [&](auto kern, cudaStream_t st, dim3 grid, bool pdl, LParams Q, const int4 *cl, const int4 *steps) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = (pdl && use_pdl) ? 1 : 0;
+            cudaLaunchKernelEx(&cfg, kern, Q, cl, steps);
             h->launches++;
         };
-        auto launch_out = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq) {
+        auto launch_in = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq, bool pdl) {
+            const int c0 = h->lin_phase_ptr[p], c1 = h->lin_phase_ptr[p + 1];
+            if (c1 <= c0) return;
+            launch_k(pmm_lumped_inside, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lin_clades + c0), (const int4 *)h->d_lin_steps);
+        };
+        auto launch_out = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq, bool pdl) {
             const int c0 = h->lout_phase_ptr[p], c1 = h->lout_phase_ptr[p + 1];
             if (c1 <= c0) return;
-            if (with_post) pmm_lumped_outside<true><<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lout_clades + c0, h->d_lout_steps);
-            else pmm_lumped_outside<false><<<dim3((unsigned)(c1 - c0), gyq), LT, 0, st>>>(Q, h->d_lout_clades + c0, h->d_lout_steps);
-            h->launches++;
+            if (with_post) launch_k(pmm_lumped_outside<true>, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lout_clades + c0), (const int4 *)h->d_lout_steps);
+            else launch_k(pmm_lumped_outside<false>, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lout_clades + c0), (const int4 *)h->d_lout_steps);
         };
         const size_t n_in = h->lin_phase_ptr.size() - 1, n_out = h->lout_phase_ptr.size() - 1;
         const int nslice = std::max(1, std::min({h->slices, (int)gy, 4}));
         h->last_sliced = nslice > 1;
         if (nslice == 1) {
-            for (size_t p = 0; p < n_in; p++) launch_in(h->stream, p, P, gy);
+            for (size_t p = 0; p < n_in; p++) launch_in(h->stream, p, P, gy, p > 0);      // the first follows pmm_branch_consts
             CK(cudaEventRecord(h->ev[2], h->stream));
-            if (outside) for (size_t p = 0; p < n_out; p++) launch_out(h->stream, p, P, gy);
+            if (outside) for (size_t p = 0; p < n_out; p++) launch_out(h->stream, p, P, gy, p > 0);   // the first follows the timing event
         } else {
             // per slice: tier 0 (inside) on a normal-priority stream, every top-tier launch of both passes on a
             // high-priority stream, tier 0 (outside) on the normal stream again
@@ -659,14 +672,14 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
                 // stagger: a slice's big launch starts when the previous slice's has finished, i.e. while that
                 // slice walks its latency-bound top tiers
                 if (j > 0 && h->stagger) CK(cudaStreamWaitEvent(sn, h->ev_s[j - 1][0], 0));
-                launch_in(sn, 0, Q, gyq);
+                launch_in(sn, 0, Q, gyq, false);
                 CK(cudaEventRecord(h->ev_s[j][0], sn));
                 CK(cudaStreamWaitEvent(sh, h->ev_s[j][0], 0));
-                for (size_t p = 1; p < n_in; p++) launch_in(sh, p, Q, gyq);
-                if (outside) for (size_t p = 0; p + 1 < n_out; p++) launch_out(sh, p, Q, gyq);
+                for (size_t p = 1; p < n_in; p++) launch_in(sh, p, Q, gyq, p > 1);
+                if (outside) for (size_t p = 0; p + 1 < n_out; p++) launch_out(sh, p, Q, gyq, n_in > 1 || p > 0);
                 CK(cudaEventRecord(h->ev_s[j][1], sh));
                 CK(cudaStreamWaitEvent(sn, h->ev_s[j][1], 0));
-                if (outside) launch_out(sn, n_out - 1, Q, gyq);
+                if (outside) launch_out(sn, n_out - 1, Q, gyq, false);
                 CK(cudaEventRecord(h->ev_s[j][2], sn));
             }
             for (int j = 0; j < nslice; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_s[j][2], 0));

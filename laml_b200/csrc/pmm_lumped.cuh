@@ -119,6 +119,10 @@ __device__ __forceinline__ double4 ld_bc(const double *__restrict__ bc, int v) {
     return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// programmatic dependent launch: the next launch of the stream may start (and stage its clade) while this grid
+// drains; it must not touch records before grid_dependency_wait() (no-ops without the launch attribute)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // the clade's steps, the branch constants of every step's two children and the four leaf vectors
 // (EM_solver.py:103-116 in full-state form, indexed by min(code, 1) + 2:
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
+    grid_dependency_wait();
     const int N = P.n_leaves;
     int s = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
     const bool valid = s < P.K;
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     int i = 0;
     for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
     if (i < nsteps) step(i, A, B);
+    grid_launch_dependents();
 }
 
 // ---------------------------------------------------------------- outside pass + expected counts
@@ -383,6 +389,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z, clade id w
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
+    grid_dependency_wait();
     const int N = P.n_leaves;
     const int s_raw = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
     const bool valid = s_raw < P.K;
@@ -520,6 +527,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     int i = 0;
     for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
     if (i < nsteps) step(i, A, B);
+    grid_launch_dependents();
     // R~ of this (warp, clade)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);

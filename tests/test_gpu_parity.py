@@ -96,13 +96,13 @@ def test_layout_variants(ts, group, chunks, engine_mode):
                                                       (100000, 100000, 1, 0)])
 def test_lumped_schedule_variants(clade, top, chunks, store_all, engine_mode):
     """clade capacity of the bottom tier and of the top tiers (1 = one launch per tree level ... 127 steps
-    per CTA), site chunking and storing the register-chained out-records must not change the lumped
-    engine's results"""
+    per CTA), site chunking, storing the register-chained out-records and programmatic dependent launch
+    on / off must not change the lumped engine's results"""
     if engine_mode != "lumped":
         pytest.skip("lumped engine only")
     for name in ("ref_rand_ragged", "ref_rand_forest", "ref_rand_deep", "ref_test45_test1"):
         case, z = load_npz_case(name)
-        with env_override(PMM_CLADE=clade, PMM_CLADE_TOP=top, PMM_CHUNKS=chunks, PMM_STORE_ALL=store_all):
+        with env_override(PMM_CLADE=clade, PMM_CLADE_TOP=top, PMM_CHUNKS=chunks, PMM_STORE_ALL=store_all, PMM_PDL=store_all):
             eng = make_engine(case)
             info = eng.info()
             assert info["engine"] == 0 and info["n_chunks"] == chunks and info["clade_target"] == min(clade, 127)
