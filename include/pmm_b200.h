@@ -159,6 +159,18 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
  */
 int pmm_set_option(pmm_handle *h, const char *name, int64_t value);
 
+/*
+ * Test hook, pure host code (works without a GPU): the clade schedule the lumped-state engine derives for a
+ * forest -- what pmm_set_tree computes, with the clade capacities given explicitly (1..127).  Outputs (caller
+ * allocated; n_int = n_nodes - n_leaves): in_steps / out_steps [n_int][4] = (u, v, w, flags) in walking order
+ * (flags: laml_b200/csrc/pmm_lumped.cuh), in_clades / out_clades [n_clades][4] = (first step, end step, tree
+ * index, clade id), *_phase_ptr [n_phases + 1] = first clade of every launch.
+ */
+int pmm_debug_lumped_schedule(int32_t n_leaves, int32_t n_nodes, const int32_t *parent, const int32_t *left,
+                              const int32_t *right, int32_t clade_cap, int32_t clade_cap_top, int32_t *in_steps,
+                              int32_t *out_steps, int32_t *in_clades, int32_t *out_clades, int32_t *in_phase_ptr,
+                              int32_t *out_phase_ptr, int32_t *n_clades, int32_t *n_phases);
+
 /* ---- introspection for benchmarks ------------------------------------------------- */
 typedef struct {
     int64_t n_nodes, n_leaves, n_sites;

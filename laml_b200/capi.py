@@ -20,7 +20,7 @@ SYMBOLS = [
     "pmm_abi_version", "pmm_last_error", "pmm_create", "pmm_destroy", "pmm_set_stream", "pmm_set_tree",
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
-    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option",
+    "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
 ]
 
 
@@ -82,10 +82,33 @@ def load_library():
     L.pmm_score_nni_batch.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
     L.pmm_sync.argtypes = [vp]
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
     _lib = L
     return L
+
+
+def lumped_schedule(n_leaves, parent, left, right, clade_cap=16, clade_cap_top=16):
+    """The clade schedule of the lumped-state engine for a forest (``pmm_debug_lumped_schedule``; pure host code,
+    no GPU needed).  Returns a dict of int32 arrays: ``in_steps`` / ``out_steps`` ``(n_int, 4)`` = (u, v, w, flags),
+    ``in_clades`` / ``out_clades`` ``(n_clades, 4)`` = (first step, end step, tree index, clade id) and the
+    ``*_phase_ptr`` arrays (first clade of every launch)."""
+    L = load_library()
+    parent, left, right = _i32(parent), _i32(left), _i32(right)
+    n = int(parent.shape[0]); n_int = n - int(n_leaves)
+    ins, outs = np.zeros((n_int, 4), np.int32), np.zeros((n_int, 4), np.int32)
+    inc, outc = np.zeros((n_int, 4), np.int32), np.zeros((n_int, 4), np.int32)
+    ipp, opp = np.zeros(n_int + 2, np.int32), np.zeros(n_int + 2, np.int32)
+    ncl, nph = C.c_int32(), C.c_int32()
+    rc = L.pmm_debug_lumped_schedule(int(n_leaves), n, parent.ctypes.data, left.ctypes.data, right.ctypes.data, int(clade_cap),
+                                     int(clade_cap_top), ins.ctypes.data, outs.ctypes.data, inc.ctypes.data, outc.ctypes.data,
+                                     ipp.ctypes.data, opp.ctypes.data, C.byref(ncl), C.byref(nph))
+    if rc:
+        raise PMMError("pmm_debug_lumped_schedule: invalid tree arrays")
+    k, p = ncl.value, nph.value
+    return {"in_steps": ins, "out_steps": outs, "in_clades": inc[:k], "out_clades": outc[:k],
+            "in_phase_ptr": ipp[:p + 1], "out_phase_ptr": opp[:p + 1], "n_clades": k, "n_phases": p}
 
 
 class Engine:

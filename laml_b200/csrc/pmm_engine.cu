@@ -403,23 +403,21 @@ int launch_outside(pmm_handle *h, const KParams &P) {
 // internal descendants, ~2 n / M0 of them) is a small "top tree" that is peeled the same way with a
 // small threshold, because its launches are latency-bound chains.  The subtrees of a tier are packed
 // (best fit, decreasing) into clades of at most C steps.  `order` lists parents before children.
-int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const std::vector<int> &root_index) {
-    const int N = h->n_leaves, n = h->n_int + N;
-    const std::vector<int> &L = h->left, &R = h->right, &Pa = h->parent;
-    int C0 = env_int("PMM_CLADE", 0);
-    if (C0 <= 0) {
-        // enough CTAs for ~8 waves over the SMs, chains of 16..120 steps
-        const double site_blocks = (double)((h->K + LT - 1) / LT);
-        const double want_clades = 8.0 * h->n_sms * 4.0 / site_blocks;
-        C0 = (int)((double)h->n_int / std::max(want_clades, 1.0));
-        C0 = std::max(16, std::min(120, C0));
-    }
-    C0 = std::max(1, std::min(C0, STEP_CAP - 1));      // the kernels stage a clade's steps in shared memory
-    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", 16), STEP_CAP - 1));
-    h->clade_target = C0;
+struct LumpedSchedule {
+    std::vector<int4> in_steps, out_steps, in_clades, out_clades;
+    std::vector<int> in_phase_ptr, out_phase_ptr;       // launch -> first clade
+    std::vector<size_t> tier_clades;
+    int n_clades = 0, n_tiers = 0;
+    int64_t in_loads = 0, out_loads = 0, out_stores = 0;
+};
+
+// pure host function (no CUDA): also reachable through pmm_debug_lumped_schedule for the CPU tests
+void make_lumped_schedule(int N, int n, const int *L, const int *R, const int *Pa, const std::vector<int> &order,
+                          const std::vector<int> &root_index, int C0, int Ctop, LumpedSchedule &S) {
+    const int n_int = n - N;
     // ---- tiers
     std::vector<int> tier(n, -1), tsz(n, 0), sz(n, 0);
-    int remaining = h->n_int, n_tiers = 0;
+    int remaining = n_int, n_tiers = 0;
     while (remaining > 0) {
         const int M = (n_tiers == 0 ? C0 : Ctop) + 1;
         for (int i = n - 1; i >= 0; i--) {
@@ -464,10 +462,12 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
         }
     }
 
-    std::vector<int4> in_steps, out_steps, in_clades, out_clades;
-    in_steps.reserve(h->n_int); out_steps.reserve(h->n_int);
-    h->lin_phase_ptr.assign(1, 0); h->lout_phase_ptr.assign(1, 0);
-    int64_t in_loads = 0, out_loads = 0, out_stores = 0;
+    std::vector<int4> &in_steps = S.in_steps, &out_steps = S.out_steps, &in_clades = S.in_clades, &out_clades = S.out_clades;
+    in_steps.clear(); out_steps.clear(); in_clades.clear(); out_clades.clear();
+    in_steps.reserve(n_int); out_steps.reserve(n_int);
+    S.in_phase_ptr.assign(1, 0); S.out_phase_ptr.assign(1, 0);
+    int64_t &in_loads = S.in_loads, &out_loads = S.out_loads, &out_stores = S.out_stores;
+    in_loads = out_loads = out_stores = 0;
     int ncl = 0;
     std::vector<std::vector<int>> bin_id(n_tiers);
     std::vector<std::pair<int, int>> stk;
@@ -503,7 +503,7 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
             in_clades.push_back(make_int4(begin, (int)in_steps.size(), bin.root_index, ncl));
             ncl++;
         }
-        h->lin_phase_ptr.push_back((int)in_clades.size());
+        S.in_phase_ptr.push_back((int)in_clades.size());
     }
     // ---- outside: pre-order, top tiers first; of two open internal children the smaller subtree
     // goes first and its out-record stays in registers, the other one is stored and loaded later
@@ -537,8 +537,32 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
             }
             out_clades.push_back(make_int4(begin, (int)out_steps.size(), bin.root_index, bin_id[t][bi]));
         }
-        h->lout_phase_ptr.push_back((int)out_clades.size());
+        S.out_phase_ptr.push_back((int)out_clades.size());
     }
+    S.n_clades = ncl; S.n_tiers = n_tiers;
+    S.tier_clades.clear();
+    for (int t = 0; t < n_tiers; t++) S.tier_clades.push_back(bins[t].size());
+}
+
+int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const std::vector<int> &root_index) {
+    const int N = h->n_leaves, n = h->n_int + N;
+    int C0 = env_int("PMM_CLADE", 0);
+    if (C0 <= 0) {
+        // enough CTAs for ~8 waves over the SMs, chains of 16..120 steps
+        const double site_blocks = (double)((h->K + LT - 1) / LT);
+        const double want_clades = 8.0 * h->n_sms * 4.0 / site_blocks;
+        C0 = (int)((double)h->n_int / std::max(want_clades, 1.0));
+        C0 = std::max(16, std::min(120, C0));
+    }
+    C0 = std::max(1, std::min(C0, STEP_CAP - 1));      // the kernels stage a clade's steps in shared memory
+    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", 16), STEP_CAP - 1));
+    h->clade_target = C0;
+    LumpedSchedule S;
+    make_lumped_schedule(N, n, h->left.data(), h->right.data(), h->parent.data(), order, root_index, C0, Ctop, S);
+    const std::vector<int4> &in_steps = S.in_steps, &out_steps = S.out_steps, &in_clades = S.in_clades, &out_clades = S.out_clades;
+    h->lin_phase_ptr = S.in_phase_ptr; h->lout_phase_ptr = S.out_phase_ptr;
+    const int64_t in_loads = S.in_loads, out_loads = S.out_loads, out_stores = S.out_stores;
+    const int ncl = S.n_clades, n_tiers = S.n_tiers;
     h->n_clades = ncl;
     if ((int)in_steps.size() != h->n_int || (int)out_steps.size() != h->n_int) return fail(h, "internal error: clade schedule does not cover the tree");
     // algorithmic bytes per site: 32-byte inside / 40-byte outside records written once and read where not chained, 4-byte leaf codes,
@@ -557,7 +581,7 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     CK(cudaMemcpy(h->d_lout_clades, out_clades.data(), sizeof(int4) * out_clades.size(), cudaMemcpyHostToDevice));
     if (env_int("PMM_VERBOSE", 0)) {
         fprintf(stderr, "[pmm] lumped schedule: clade capacity %d (top %d), %d clades in %d tiers:", C0, Ctop, ncl, n_tiers);
-        for (int t = 0; t < n_tiers; t++) fprintf(stderr, " %zu", bins[t].size());
+        for (int t = 0; t < n_tiers; t++) fprintf(stderr, " %zu", S.tier_clades[t]);
         fprintf(stderr, "; %lld inside loads, %lld outside loads, %lld outside stores\n", (long long)in_loads, (long long)out_loads, (long long)out_stores);
     }
     return 0;
@@ -993,6 +1017,33 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n = n;
+    return 0;
+}
+
+int pmm_debug_lumped_schedule(int32_t n_leaves, int32_t n_nodes, const int32_t *parent, const int32_t *left, const int32_t *right,
+                              int32_t clade_cap, int32_t clade_cap_top, int32_t *in_steps, int32_t *out_steps, int32_t *in_clades,
+                              int32_t *out_clades, int32_t *in_phase_ptr, int32_t *out_phase_ptr, int32_t *n_clades, int32_t *n_phases) {
+    const int N = n_leaves, n = n_nodes;
+    if (N < 2 || n <= N || n > 2 * N - 1 || !parent || !left || !right) return 1;
+    std::vector<int> order, root_index(n, 0);
+    order.reserve(n);
+    int nr = 0;
+    for (int v = 0; v < n; v++) if (parent[v] < 0) { root_index[v] = nr++; order.push_back(v); }
+    for (size_t i = 0; i < order.size(); i++) {
+        const int v = order[i];
+        if (left[v] >= 0) for (int c : {left[v], right[v]}) { if (c < 0 || c >= n) return 1; root_index[c] = root_index[v]; order.push_back(c); }
+        if ((int)order.size() > n) return 1;
+    }
+    if ((int)order.size() != n) return 1;
+    LumpedSchedule S;
+    make_lumped_schedule(N, n, left, right, parent, order, root_index, std::max(1, std::min((int)clade_cap, STEP_CAP - 1)),
+                         std::max(1, std::min((int)clade_cap_top, STEP_CAP - 1)), S);
+    auto put = [](const std::vector<int4> &v, int32_t *o) { if (o) memcpy(o, v.data(), sizeof(int4) * v.size()); };
+    put(S.in_steps, in_steps); put(S.out_steps, out_steps); put(S.in_clades, in_clades); put(S.out_clades, out_clades);
+    if (in_phase_ptr) memcpy(in_phase_ptr, S.in_phase_ptr.data(), sizeof(int) * S.in_phase_ptr.size());
+    if (out_phase_ptr) memcpy(out_phase_ptr, S.out_phase_ptr.data(), sizeof(int) * S.out_phase_ptr.size());
+    if (n_clades) *n_clades = S.n_clades;
+    if (n_phases) *n_phases = S.n_tiers;
     return 0;
 }
 
