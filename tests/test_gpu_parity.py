@@ -185,6 +185,42 @@ def test_engines_agree_at_config3_size(monkeypatch):
     assert (a["S"][:N, 2] + a["S"][:N, 4] <= (K - obs) + 1e-6).all()
 
 
+def test_full_size_properties_config4():
+    """BASELINE config 4 (100k cells x 2k sites) on the default engine: properties that need no oracle.
+    Additivity over sites (two site shards sum to the whole -- what the multi-GPU all-reduce relies on), counts
+    partition every site, llh = sum of site log-likelihoods, and likelihood-only pass == E-step's likelihood."""
+    import torch
+    from laml_b200.capi import Engine
+    from laml_b200.synth import CONFIGS, make_workload
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~35 GB of device memory")
+    w = make_workload(seed=1, device="cuda", **CONFIGS["config4_100k_x_2k"])
+    N, K = w.forest.n_leaves, w.codes.shape[1]
+
+    def run(lo, hi):
+        qp = (w.qptr[lo:hi + 1] - w.qptr[lo]).astype(np.int32)
+        qv = w.qval[w.qptr[lo]:w.qptr[hi]].copy()
+        eng = Engine(N, qp, qv, np.ascontiguousarray(w.codes[:, lo:hi]))
+        eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+        out = eng.estep(w.d, w.nu, w.phi, want_site_llh=True)
+        llh_only = eng.inside(w.d, w.nu, w.phi)
+        eng.close()
+        assert llh_only == out["llh"]
+        return out
+
+    whole = run(0, K)
+    a, b = run(0, 1000), run(1000, K)
+    assert np.isfinite(whole["llh"]) and abs(whole["llh"] - whole["site_llh"].sum()) <= 1e-9 * abs(whole["llh"])
+    assert abs((a["llh"] + b["llh"]) - whole["llh"]) <= 1e-12 * abs(whole["llh"])
+    assert (np.concatenate([a["site_llh"], b["site_llh"]]) == whole["site_llh"]).all()       # per-site results are shard-independent
+    np.testing.assert_allclose(a["S"] + b["S"], whole["S"], rtol=1e-10, atol=1e-9)
+    assert abs((a["Rtilde"] + b["Rtilde"]) - whole["Rtilde"]) <= 1e-10 * whole["Rtilde"]
+    S = whole["S"]
+    assert (S >= -1e-9).all() and (S.sum(axis=1) <= K * (1 + 1e-9)).all()
+    obs = (w.codes >= 0).sum(axis=1)
+    assert (S[:N, 2] + S[:N, 4] <= (K - obs) + 1e-6).all()       # an observed leaf is not silenced on its own branch
+
+
 def test_mstep_and_em_vs_oracle():
     case, z = load_npz_case("ref_test4_zero")
     orc = case.oracle()
