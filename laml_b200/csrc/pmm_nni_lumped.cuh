@@ -33,7 +33,7 @@ __device__ __forceinline__ Opd merge_children(const Child &v, const Child &w) {
     return r;
 }
 
-__global__ void __launch_bounds__(NNIL_THREADS) pmm_nni_lumped(LParams P, const NniCand *__restrict__ cands, NniState *__restrict__ state,
+__global__ void __launch_bounds__(NNIL_THREADS, 3) pmm_nni_lumped(LParams P, const NniCand *__restrict__ cands, NniState *__restrict__ state,
                                                                 const double *__restrict__ root_llh_sum, double llh_total, int K_total,
                                                                 double dmin, double dmax, double eps_s, double eps_nu, double conv_eps,
                                                                 int max_iter) {
