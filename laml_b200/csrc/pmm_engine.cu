@@ -613,9 +613,9 @@ int alloc_lumped(pmm_handle *h) {
     if (forced > 0) Kc = std::max(1, (K + forced - 1) / forced);
     else if (per_site * K > (double)budget) Kc = std::min(K, std::max(32, (int)((double)budget / per_site) / 32 * 32));
     // the kernels index records with 32 bits
-    Kc = (int)std::min<int64_t>(Kc, std::max<int64_t>(1, ((int64_t)1 << 31) / std::max(h->n_int, 1) - 1));
+    Kc = (int)std::min<int64_t>(Kc, std::max<int64_t>(1, ((int64_t)1 << 31) / std::max(h->n_int, 1) - 32));
     h->lKc = Kc; h->lG = (Kc + 31) / 32;
-    const size_t rows = (size_t)h->n_int * Kc;
+    const size_t rows = (size_t)h->n_int * (size_t)((Kc + 31) & ~31);      // record rows are padded to whole warps
     if (dalloc(h, &h->d_LX, 2 * rows) || dalloc(h, &h->d_LO, rows) || dalloc(h, &h->d_LOI, rows) ||
         dalloc(h, &h->d_LinvL, (size_t)h->n_roots * Kc) || dalloc(h, &h->d_Lroot_llh, (size_t)h->n_roots * Kc) ||
         dalloc(h, &h->d_LSpart, (size_t)h->lG * n * 5) || dalloc(h, &h->d_LRpart, (size_t)h->lG * std::max(h->n_int, 1)))
@@ -625,7 +625,7 @@ int alloc_lumped(pmm_handle *h) {
 
 LParams make_lparams(pmm_handle *h, int ci, bool with_post) {
     LParams P;
-    P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.code_stride = h->K;
+    P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.Kp = (h->lKc + 31) & ~31; P.code_stride = h->K;
     P.n_leaves = h->n_leaves; P.n_nodes = h->n; P.n_clades = h->n_clades;
     P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
     P.params = h->d_params; P.bc = h->d_bc;

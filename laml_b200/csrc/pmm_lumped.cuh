@@ -48,7 +48,7 @@ namespace pmm {
 constexpr int LT = PMM_LT;               // threads (= sites) per CTA
 constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (the host caps the clade size at 64)
 #ifndef PMM_LIN_MINB
-#define PMM_LIN_MINB 6
+#define PMM_LIN_MINB 5
 #endif
 #ifndef PMM_LOUT_MINB
 #define PMM_LOUT_MINB 3
@@ -67,6 +67,8 @@ constexpr int PF_DIST_OUT = PMM_PF_DIST_OUT;
 
 struct LParams {
     int K;                   // sites of this chunk
+    int Kp;                  // K rounded up to a multiple of 32: row stride of the record arrays, so that the idle
+                             // lanes of the last warp own (and privately read / write) padding records
     int site0;               // first site of the chunk in the handle's site space
     int code_stride;         // row stride of `codes` (all sites of the handle)
     int n_leaves, n_nodes, n_clades;
@@ -94,7 +96,7 @@ enum { KIND_LEAF = 0, KIND_LOAD = 1, KIND_PREV = 2 };
 // index of (internal node, site) in the record arrays.  32 bits: a chunk never holds 2^31 records (they would
 // need 172 GB; the host caps the chunk accordingly), and 32-bit indices halve the address arithmetic
 __device__ __forceinline__ unsigned rec_index(const LParams &P, int node, int s) {
-    return (unsigned)(node - P.n_leaves) * (unsigned)P.K + (unsigned)s;
+    return (unsigned)(node - P.n_leaves) * (unsigned)P.Kp + (unsigned)s;
 }
 
 // one prefetched operand: an inside / outside record, or (leaves) the prior of the leaf's state in r.w
@@ -210,9 +212,10 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
     grid_dependency_wait();
     const int N = P.n_leaves;
-    int s = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
-    const bool valid = s < P.K;
-    s = min(s, P.K - 1);
+    const int sr = (blockIdx.y + P.sblk0) * LT + threadIdx.x;     // record column (idle lanes own padding columns)
+    if ((sr & ~31) >= P.K) return;                                   // whole warp beyond the last site
+    const bool valid = sr < P.K;
+    const int s = min(sr, P.K - 1);                                   // inputs of an idle lane: those of the last site
     const int gs = P.site0 + s;
     const double *prior_site = P.prior + __ldg(P.site_ptr + gs);
     const double qsum = __ldg(P.qsum + gs);
@@ -230,19 +233,19 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(d0, c0v, c0w);
     if (nsteps > 1) codes_of(d1, c1v, c1w);
-    inside_fetch(P, d0, c0v, c0w, A, prior_site, s, N);
+    inside_fetch(P, d0, c0v, c0w, A, prior_site, sr, N);
 
     auto step = [&](int i, InSlot &cur, InSlot &nxt) {
         int4 d2 = d1;
         int c2v = 0, c2w = 0;
         if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
-        if (i + 1 < nsteps) inside_fetch(P, d1, c1v, c1w, nxt, prior_site, s, N);
+        if (i + 1 < nsteps) inside_fetch(P, d1, c1v, c1w, nxt, prior_site, sr, N);
         if (PF_DIST > 0 && i + PF_DIST < nsteps) {
             const int4 dp = s_steps[i + PF_DIST];
             if ((dp.w & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + 2 * (size_t)o); }
+            else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, sr); prefetch_l2(P.X + 2 * (size_t)o); }
             if (((dp.w >> 2) & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
+            else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, sr); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int kv = d0.w & 3, kw = (d0.w >> 2) & 3;
         Child v, w;
@@ -261,9 +264,8 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         prev.r.x = x0 * sc; prev.r.y = xz * sc;
         prev.r.z = (hu >= 0) ? (bv ? v.qh : w.qh) : xm * sc;
         prev.r.w = pack_hc(hu, v.cum + w.cum + e);
+        st_xrec(P.X, rec_index(P, d0.x, sr), prev);               // idle lanes write their own padding column
         if (valid) {
-            const unsigned o = rec_index(P, d0.x, s);
-            st_xrec(P.X, o, prev);
             if (d0.w & 16) {
                 // root: site likelihood L = E[root]_0 (the root's own branch starts in state 0, EM_solver.py:140)
                 Child r;
@@ -418,19 +420,19 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(d0, c0v, c0w);
     if (nsteps > 1) codes_of(d1, c1v, c1w);
-    outside_fetch(P, d0, c0v, c0w, A, prior_site, s, N);
+    outside_fetch(P, d0, c0v, c0w, A, prior_site, s_raw, N);
 
     auto step = [&](int i, OutSlot &cur, OutSlot &nxt) {
         int4 d2 = d1;
         int c2v = 0, c2w = 0;
         if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
-        if (i + 1 < nsteps) outside_fetch(P, d1, c1v, c1w, nxt, prior_site, s, N);
+        if (i + 1 < nsteps) outside_fetch(P, d1, c1v, c1w, nxt, prior_site, s_raw, N);
         if (PF_DIST_OUT > 0 && i + PF_DIST_OUT < nsteps) {
             const int4 dp = s_steps[i + PF_DIST_OUT];
             if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.y, s); prefetch_l2(P.X + 2 * (size_t)o); }
+            else { const unsigned o = rec_index(P, dp.y, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
             if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.z, s); prefetch_l2(P.X + 2 * (size_t)o); }
+            else { const unsigned o = rec_index(P, dp.z, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
         }
         const int u = d0.x, f = d0.w;
         const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
@@ -448,14 +450,14 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         const int how = f & 3;
         if (how == 0) {
             // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
-            const unsigned ou = rec_index(P, u, s);
+            const unsigned ou = rec_index(P, u, s_raw);
             Opd pr;
             ld_xrec(pr, P.X, ou);
             const double4 cr = ld_bc(P.bc, u);
             Child r;
             decode(r, pr, cr, qsum);
             chain.r = make_double4(cr.x, cr.w, cr.y, 0.0); chain.ri = make_int2(-1, -r.cum);
-            if (P.store_all && valid) { P.O[ou] = chain.r; P.OI[ou] = chain.ri; }      // the NNI scorer reads out[root] too
+            if (P.store_all) { P.O[ou] = chain.r; P.OI[ou] = chain.ri; }      // the NNI scorer reads out[root] too
             const double t0 = r.t0 * invL, t2 = r.gm * invL;
             double r10[10];
 #pragma unroll
@@ -500,11 +502,11 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
         if (!wleaf) {
             normalise_out(ow, F + v.cum);
-            if (valid && ((f & 32) || P.store_all)) { const unsigned oo = rec_index(P, d0.z, s); P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
+            if ((f & 32) || P.store_all) { const unsigned oo = rec_index(P, d0.z, s_raw); P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
         }
         if (!vleaf) {
             normalise_out(ov, F + w.cum);
-            if (valid && ((f & 16) || P.store_all)) { const unsigned oo = rec_index(P, d0.y, s); P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
+            if ((f & 16) || P.store_all) { const unsigned oo = rec_index(P, d0.y, s_raw); P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
             chain = ov;
         }
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
