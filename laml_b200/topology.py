@@ -1,0 +1,328 @@
+"""NNI topology search on the batched scorer: the tree-level side of
+``pmm_score_nni_batch``.
+
+The reference's ``Topology_search`` (``laml_libs/Topology_search.py``) tries candidates one at a time:
+for a branch ``u`` it re-wires the tree objects, serialises them to newick, constructs a NEW solver from
+the strings (re-parsing the trees, re-normalising the prior, re-encoding the character matrix), finds the
+LCAs of every fixed branch to pin its length, runs a local EM with five free branches, and accepts or
+reverts (``apply_nni``, ``:242-322``).  Here the solver object and its GPU handle live for the whole
+search; one call scores EVERY candidate around the current tree (:func:`score_neighbourhood`, 2(N-2)
+local EMs in one launch), the acceptance policy -- the reference's own: random branch order, the two
+moves of a branch in random order, simulated-annealing acceptance (``:67-80,221-240``) -- is replayed on
+the host over the returned scores, and an accepted move is a pointer swap on the tree objects plus a
+``pmm_set_tree`` on the live handle (:func:`apply_move`).
+
+What is deliberately NOT reproduced: the reference's random-number stream (every ``score_tree`` call
+re-seeds the global generator, ``ML_solver.py:273-276,EM_solver.py:516``, so its trajectory depends on
+how many candidates were scored) and the stale branch lengths it keeps on ``treeList_obj`` after an
+accepted move (``Topology_search.py:289``: "possibility 1 ..."); here the accepted lengths are the
+current lengths.  Scores of individual candidates are identical to the reference's call
+``solver(newick of the re-wired tree).score_tree(strategy with fixed_brlen / fixed_nu / fixed_phi)``
+(``tests/test_topology_host.py``, ``tests/test_zz_gpu_topology.py``).
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from dataclasses import dataclass
+from math import exp
+from random import random, shuffle
+from typing import List, Optional
+
+import numpy as np
+
+from .nni import nni_candidates
+from .solver import DEFAULT_STRATEGY, GPU_EM_solver
+
+chkpt_freq = 10                                   # laml_libs/core_constants.py
+
+
+@dataclass
+class Neighbourhood:
+    """Scores of the NNI candidates around a solver's current forest.  Candidate ``i`` swaps child
+    ``cand_k[i]`` (index into ``u.children``) of node ``cand_u[i]`` with ``u``'s sibling; ``score[i]`` is the
+    log-likelihood after the local EM, ``d5[i]`` the optimised lengths of ``nodes[i]`` = (v, u, moved child,
+    other child, former sibling); ``d0`` the lengths every other branch was held at."""
+    cand_u: np.ndarray
+    cand_k: np.ndarray
+    score: np.ndarray
+    d5: np.ndarray
+    nodes: np.ndarray
+    iters: np.ndarray
+    d0: np.ndarray
+
+    def index(self):
+        return {(int(u), int(k)): i for i, (u, k) in enumerate(zip(self.cand_u, self.cand_k))}
+
+
+def start_lengths(solver: GPU_EM_solver) -> np.ndarray:
+    """The point the reference's candidate EM starts from: every length raised to ``2 dmin``
+    (``ini_brlens``, ``ML_solver.py:195-203``, applied to fixed and free branches alike by ``x2brlen``)."""
+    solver._ensure()
+    return np.maximum(solver._d(), 2 * solver.dmin)
+
+
+def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False) -> Neighbourhood:
+    """One batched call for all candidates ``Topology_search.single_nni`` could try on ``solver``'s trees
+    (``:221-231``: every internal non-root node; with ``only_marked`` those carrying ``node.mark``), each
+    scored as ``apply_nni`` does with ``local_brlen_opt`` (``:253-300``): nu, phi and all lengths fixed
+    except the five around the move."""
+    forest = solver._ensure()
+    if any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
+        raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
+                         "a solver-inserted branch is never optimised and cannot take part in a move")
+    cu, ck = nni_candidates(forest.parent, forest.left, forest.n_leaves)
+    if only_marked:
+        keep = np.array([bool(getattr(forest.nodes[u], "mark", False)) for u in cu], bool)
+        cu, ck = cu[keep], ck[keep]
+    d0 = start_lengths(solver)
+    if len(cu) == 0:
+        z = np.zeros(0)
+        return Neighbourhood(cu, ck, z, np.zeros((0, 5)), np.zeros((0, 5), np.int32), np.zeros(0, np.int32), d0)
+    res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax)
+    return Neighbourhood(cu, ck, -res["nllh"], res["d5"], res["nodes"], res["iters"], d0)
+
+
+def apply_move(solver: GPU_EM_solver, nb: Neighbourhood, i: int) -> None:
+    """Make candidate ``i`` the solver's current tree: the pointer swap of ``apply_nni`` (``:281-287``) on
+    the solver's own node objects, the five optimised lengths, and a re-bind -- ``pmm_set_tree`` on the live
+    handle, the character matrix stays on the device."""
+    forest = solver._forest
+    u = forest.nodes[int(nb.cand_u[i])]
+    v = u.parent
+    w = next(c for c in v.children if c is not u)
+    child = u.children[int(nb.cand_k[i])]
+    for nd, length in zip(forest.nodes, nb.d0):
+        nd.edge_length = float(length)
+    for node_id, length in zip(nb.nodes[i], nb.d5[i]):
+        forest.nodes[int(node_id)].edge_length = float(length)
+    u.remove_child(child); v.add_child(child)
+    v.remove_child(w); u.add_child(w)
+    solver._forest = None
+    solver._stats = None
+    solver._ensure()
+
+
+class GPU_Topology_search:
+    """``Topology_search`` (``laml_libs/Topology_search.py:10-216``) with the same constructor, ``search``
+    signature and return value ``(best_trees, best_score, best_params)``, on one persistent solver."""
+
+    def __init__(self, treeTopoList, solver=GPU_EM_solver, data={}, prior={}, params={}, T_cooldown=20, alpha_cooldown=0.9,
+                 device: int = 0):
+        self.treeTopoList = list(treeTopoList)
+        self.solver = solver
+        self.data, self.prior, self.params = data, prior, dict(params)
+        self.device = device
+        self.T_cooldown, self.alpha_cooldown = T_cooldown, alpha_cooldown
+        self.b = 1 / (1 - 1 / self.alpha_cooldown ** self.T_cooldown)          # :29-30
+        self.a = -self.b / self.alpha_cooldown ** self.T_cooldown
+        self._solver: Optional[GPU_EM_solver] = None
+        self.has_polytomy = False
+        self.trees_scored = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def get_solver(self) -> GPU_EM_solver:
+        if self.device:
+            return self.solver(self.treeTopoList, self.data, self.prior, self.params, device=self.device)
+        return self.solver(self.treeTopoList, self.data, self.prior, self.params)
+
+    def _open(self, resolve_polytomies: bool, eps_len: float = 1e-3) -> GPU_EM_solver:
+        """the search's solver for ``self.treeTopoList``; polytomies are resolved and the inserted nodes marked
+        BEFORE the solver sees the trees (``__mark_polytomies__``, ``:51-66``), so that they are ordinary,
+        optimisable branches of length ``eps_len`` and the only ones ``only_marked`` moves"""
+        from .tree import read_tree_newick
+        trees = []
+        self.has_polytomy = False
+        for topo in self.treeTopoList:
+            t = read_tree_newick(topo)
+            t.suppress_unifurcations()
+            trees.append(t)
+        for t in trees:
+            for nd in t.traverse_preorder():
+                nd.mark = False
+                if len(nd.children) > 2:
+                    self.has_polytomy = True
+            if resolve_polytomies:
+                t.resolve_polytomies()
+                for nd in t.traverse_preorder():
+                    if not hasattr(nd, 'mark'):
+                        nd.mark = True
+                        nd.edge_length = eps_len
+        if self._solver is not None:
+            self._solver.close()
+        self.treeTopoList = [t.newick() for t in trees]
+        s = self.get_solver()
+        if not isinstance(s, GPU_EM_solver):
+            raise TypeError("GPU_Topology_search drives GPU_EM_solver (batched scoring needs its engine handle)")
+        # carry the marks over to the solver's own node objects (same newick, same traversal order)
+        for t_mine, t_solver in zip(trees, s.trees):
+            mine, theirs = list(t_mine.traverse_preorder()), list(t_solver.traverse_preorder())
+            for a, b in zip(mine, theirs if len(mine) == len(theirs) else []):
+                b.mark = a.mark
+        self._solver = s
+        return s
+
+    def close(self):
+        if self._solver is not None:
+            self._solver.close()
+            self._solver = None
+
+    def _sync_from_solver(self):
+        self.treeTopoList = self._solver.get_tree_newick()
+        self.params = self._solver.get_params()
+
+    def __accept_proposal__(self, curr_score, new_score, t):                   # :67-80
+        if new_score > curr_score:
+            return True
+        T = max(1e-12, self.a * self.alpha_cooldown ** t + self.b)
+        p = min(exp((new_score - curr_score - 1e-12) / T), 1)
+        return random() < p
+
+    def _score_all(self, strategy) -> float:
+        """all numerical parameters on the current topology (``__search_one__`` ``:176-181``, ``search``
+        ``:152-158``); ``optimize`` re-reads its best trees, so marks are re-attached by traversal order"""
+        s = self._solver
+        marks = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+        st = deepcopy(strategy)
+        st['fixed_brlen'] = None
+        st['nodes_to_recompute'] = None
+        score, status = s.score_tree(strategy=st)
+        for t, ms in zip(s.trees, marks):
+            nodes = list(t.traverse_preorder())
+            if len(nodes) == len(ms):                         # nothing was collapsed
+                for nd, m in zip(nodes, ms):
+                    nd.mark = m
+        self.trees_scored += 1
+        return score
+
+    # ------------------------------------------------------------------ the search
+    def single_nni(self, curr_score, nni_iter, strategy, only_marked=False, verbose=False):
+        """``single_nni`` + ``apply_nni`` (``:221-322``): returns ``(score, n_attempts, took)``."""
+        s = self._solver
+        forest = s._ensure()
+        branches = [i for i, nd in enumerate(forest.nodes)
+                    if nd.children and nd.parent is not None and (not only_marked or getattr(nd, "mark", False))]
+        shuffle(branches)
+        if strategy.get('local_brlen_opt', True):
+            nb = score_neighbourhood(s, only_marked=only_marked)
+            self.trees_scored += len(nb.score)
+            where = nb.index()
+            n_attempts = 0
+            while branches:
+                u = branches.pop()
+                moves = [0, 1]
+                shuffle(moves)
+                n_attempts += 2
+                for k in moves:
+                    i = where[(u, k)]
+                    new_score = float(nb.score[i])
+                    if self.__accept_proposal__(curr_score, new_score, nni_iter):
+                        apply_move(s, nb, i)
+                        self._sync_from_solver()
+                        return new_score, n_attempts, True
+            return curr_score, n_attempts, False
+        # every parameter re-optimised per candidate (local_brlen_opt = False, :249-251 + :297-300): one full EM
+        # per candidate on the live handle; a rejected candidate is undone by re-reading the trees it started
+        # from (same newick => same node ids after flattening)
+        before, params0 = s.get_tree_newick(), (s.params.nu, s.params.phi)
+        marks = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+        n_attempts = 0
+        while branches:
+            u_id = branches.pop()
+            moves = [0, 1]
+            shuffle(moves)
+            n_attempts += 2
+            for k in moves:
+                forest = s._ensure()
+                u = forest.nodes[u_id]
+                v = u.parent
+                w = next(c for c in v.children if c is not u)
+                child = u.children[k]
+                u.remove_child(child); v.add_child(child)
+                v.remove_child(w); u.add_child(w)
+                s._forest = None
+                new_score = self._score_all(strategy)
+                if new_score is not None and self.__accept_proposal__(curr_score, new_score, nni_iter):
+                    self._sync_from_solver()
+                    return new_score, n_attempts, True
+                self._restore(before, params0, marks)
+        return curr_score, n_attempts, False
+
+    def _restore(self, newicks, params, marks):
+        from .tree import read_tree_newick
+        s = self._solver
+        s.trees = [read_tree_newick(t) for t in newicks]
+        for j, t in enumerate(s.trees):
+            nodes = list(t.traverse_preorder())
+            ms = marks[j] if marks is not None and len(marks[j]) == len(nodes) else [False] * len(nodes)
+            for nd, m in zip(nodes, ms):
+                nd.mark, nd.mark_fixed, nd.polytomy_mark = m, False, False
+        s.params.nu, s.params.phi = params
+        s._forest = None
+        s._stats = None
+
+    def __search_one__(self, strategy, maxiter=100, verbose=False, only_marked=False, checkpoint_file=None):   # :174-219
+        curr_score = self._score_all(strategy)
+        if verbose:
+            print("Initial score: " + str(curr_score), flush=True)
+        self._sync_from_solver()
+        best_score, best_trees, best_params = curr_score, self.treeTopoList, self.params
+        for nni_iter in range(maxiter):
+            if verbose:
+                print("NNI Iter:", nni_iter, flush=True)
+            new_score, n_attempts, success = self.single_nni(curr_score, nni_iter, strategy, only_marked=only_marked)
+            if verbose:
+                print(f"Number of trees checked: {n_attempts}", flush=True)
+            if not success:
+                break
+            curr_score = new_score
+            if curr_score > best_score:
+                best_score, best_trees, best_params = curr_score, self.treeTopoList, self.params
+            if verbose:
+                print("Current score: " + str(curr_score), flush=True)
+            if nni_iter % chkpt_freq == 0 and checkpoint_file is not None:
+                with open(checkpoint_file, "a") as fout:
+                    fout.write(f"NNI Iteration: {nni_iter}\n")
+                    fout.write(f"Current newick tree: {best_trees}\n")
+                    fout.write(f"Current negative-llh: {best_score}\n")
+                    fout.write(f"Current dropout rate: {best_params['phi']}\n")
+                    fout.write(f"Current silencing rate: {best_params['nu']}\n")
+        if verbose:
+            print("Best score for this search: " + str(best_score), flush=True)
+        return best_trees, best_score, best_params
+
+    def search(self, resolve_polytomies=True, maxiter=100, verbose=False, nreps=1, strategy=DEFAULT_STRATEGY,
+               checkpoint_file=None):                                                                       # :108-172
+        original_topos, original_params = self.treeTopoList, self.params
+        best_trees, best_score, best_params = None, -float("inf"), None
+        try:
+            for i in range(nreps):
+                if verbose:
+                    print("Performing nni-search " + str(i + 1), flush=True)
+                self.treeTopoList, self.params = original_topos, original_params
+                self._open(resolve_polytomies)
+                if strategy.get('resolve_search_only'):
+                    if self.has_polytomy:
+                        trees, score, params = self.__search_one__(strategy, maxiter=maxiter, verbose=verbose,
+                                                                   only_marked=True, checkpoint_file=checkpoint_file)
+                    else:
+                        score = self._score_all(strategy)
+                        self._sync_from_solver()
+                        trees, params = self.treeTopoList, self.params
+                else:
+                    trees, score, params = self.__search_one__(strategy, maxiter=maxiter, verbose=verbose,
+                                                               only_marked=False, checkpoint_file=checkpoint_file)
+                # the final optimisation of all parameters on the chosen topology (:146-160)
+                self.treeTopoList, self.params = trees, params
+                self._restore(trees, (params['nu'], params['phi']), None)      # same handle: only the tree changes
+                st = deepcopy(strategy)
+                st['final_optimization'] = True
+                score = self._score_all(st)
+                self._sync_from_solver()
+                if verbose:
+                    print("Optimal score for this search: " + str(score), flush=True)
+                if score > best_score:
+                    best_score, best_trees, best_params = score, self.treeTopoList, self.params
+        finally:
+            self.close()
+        self.treeTopoList, self.params = best_trees, best_params
+        return best_trees, best_score, best_params

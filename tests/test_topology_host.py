@@ -1,0 +1,148 @@
+"""NNI search on the batched scorer on CPU, with the engine swapped for the
+oracle-backed stand-in (tests/oracle_engine.py -- test infrastructure only; its ``score_nni_batch`` is a
+full-tree EM per candidate, i.e. the definition the GPU scorer is tested against in tests/test_gpu_nni.py).
+What is checked here is the HOST side: candidate enumeration, the call the reference's ``apply_nni`` makes
+(new solver from the re-wired newick + ``score_tree`` with ``fixed_brlen`` anchors, ``Topology_search.py:
+253-300``) giving the same score as the batch entry, an accepted move on the live handle, and the
+reference's own search tests (laml_unit_tests/unit_tests_TopoSearch.py) against their brute-force optima."""
+from copy import deepcopy
+
+import numpy as np
+import pytest
+
+import laml_b200.solver as solver_mod
+from helpers import load_npz_case
+from laml_b200.solver import DEFAULT_STRATEGY, GPU_EM_solver
+from laml_b200.topology import GPU_Topology_search, apply_move, score_neighbourhood, start_lengths
+from oracle_engine import OracleEngine
+from topo_reference_call import score_candidate_like_the_reference
+
+
+@pytest.fixture(autouse=True)
+def oracle_engine(monkeypatch):
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    OracleEngine.instances = 0
+
+
+def _solver(case):
+    return GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': case.phi, 'nu': case.nu})
+
+
+@pytest.mark.parametrize("name", ["ref_rand_small", "ref_rand_forest"])
+def test_batch_scores_equal_the_reference_call(name):
+    case, z = load_npz_case(name)
+    s = _solver(case)
+    nb = score_neighbourhood(s)
+    n_int = sum(1 for t in s.trees for nd in t.traverse_preorder() if nd.children and nd.parent is not None)
+    assert len(nb.score) == 2 * n_int
+    for i in range(len(nb.score)):
+        ref_score, status = score_candidate_like_the_reference(s, int(nb.cand_u[i]), int(nb.cand_k[i]), case)
+        assert status == "optimal"
+        assert abs(ref_score - nb.score[i]) <= 1e-9 * abs(ref_score), (i, ref_score, nb.score[i])
+
+
+def test_accepted_move_lives_on_the_same_handle():
+    case, z = load_npz_case("ref_rand_small")
+    s = _solver(case)
+    nb = score_neighbourhood(s)
+    i = int(np.argmax(nb.score))
+    eng = s._engine
+    apply_move(s, nb, i)
+    assert s._engine is eng and OracleEngine.instances == 1
+    assert abs(-s.negative_llh() - nb.score[i]) <= 1e-9 * abs(nb.score[i])
+    fresh = GPU_EM_solver(s.get_tree_newick(), {'charMtrx': case.msa}, {'Q': case.Q}, s.get_params())
+    assert abs(fresh.negative_llh() - s.negative_llh()) <= 1e-9 * abs(s.negative_llh())
+    # the five optimised lengths are on the tree, every other branch sits at the clamped start
+    d_now = s._d()
+    lab_now = {id(nd): j for j, nd in enumerate(s._forest.nodes)}
+    assert np.isfinite(d_now).all() and (d_now >= s.dmin - 1e-15).all()
+
+
+def test_only_marked_restricts_the_candidates():
+    case, z = load_npz_case("ref_rand_small")
+    s = _solver(case)
+    f = s._ensure()
+    internal = [nd for nd in f.nodes if nd.children and nd.parent is not None]
+    internal[1].mark = True
+    nb = score_neighbourhood(s, only_marked=True)
+    assert len(nb.score) == 2 and all(f.nodes[u] is internal[1] for u in nb.cand_u)
+    full = score_neighbourhood(s)
+    idx = full.index()
+    for j in range(2):
+        assert nb.score[j] == full.score[idx[(int(nb.cand_u[j]), int(nb.cand_k[j]))]]
+
+
+Q5 = [{0: 0, 1: 1.0}] * 5
+MSA_A = {'a': [1, 1, 0, 0, 0], 'b': [1, 1, 1, 0, 0], 'c': [0, 0, 0, 1, 0], 'd': [0, 0, 0, 1, 0]}
+MSA_B = {'a': [0, 1, 1, 1, 1], 'b': [1, 0, 0, 0, 0], 'c': [1, 0, 0, 0, 0], 'd': [0, 1, 1, 1, 1]}
+
+
+def _all_topologies(leaves):
+    """every rooted binary topology on the leaves, by inserting one leaf at a time on every branch
+    (what unit_tests_TopoSearch.py:11-49 enumerates)"""
+    def insert(tree, leaf):
+        # tree: nested tuples / str; returns all trees with `leaf` attached above every node
+        out = [(tree, leaf)]
+        if isinstance(tree, tuple):
+            l, r = tree
+            out += [(t, r) for t in insert(l, leaf)] + [(l, t) for t in insert(r, leaf)]
+        return out
+    trees = [leaves[0]]
+    for leaf in leaves[1:]:
+        trees = [t for base in trees for t in insert(base, leaf)]
+    def nwk(t):
+        return t if isinstance(t, str) else "(" + nwk(t[0]) + "," + nwk(t[1]) + ")"
+    return [nwk(t) + ";" for t in trees]
+
+
+def _brute_force(msa, Q):
+    best = float("inf")
+    for T in _all_topologies(sorted(msa)):
+        s = GPU_EM_solver([T], {'charMtrx': msa}, {'Q': Q})
+        nllh, _ = s.optimize(initials=1, verbose=-1, ultra_constr=False)
+        best = min(best, nllh)
+    return best
+
+
+def test_topology_enumeration():
+    assert len(_all_topologies(list("abcd"))) == 15 and len(set(_all_topologies(list("abcde")))) == 105
+
+
+@pytest.mark.parametrize("no,msa,T0,resolve_only,nllh_bf", [
+    (1, MSA_A, '((a,c),(b,d));', False, None),                    # unit_tests_TopoSearch.py:66-80   live brute force
+    (3, MSA_A, '(a,b,c,d);', False, None),                        # :101-115  polytomy start
+    (4, MSA_A, '((a,b),c,d);', True, None),                       # :118-134  only resolve polytomies
+    (5, MSA_A, '((a,c),(b,d));', True, 11.809140958825493),       # :137-153  nothing to resolve: the optimum of T0 itself
+    (6, MSA_B, '((a,b),(c,d));', False, None),                    # :156-172
+    (7, MSA_B, '((a,b),c,d);', True, 10.083048489886435),         # :175-191  the reference's stored constants
+    (8, MSA_B, '((c,d),a,b);', True, 10.08306053772235),          # :194-210
+])
+def test_reference_search_tests(no, msa, T0, resolve_only, nllh_bf):
+    """the reference asserts its NNI result against a brute-force optimum to 4 places"""
+    from random import seed
+    seed(a=1000 + no)
+    Q = [dict(q) for q in Q5]
+    if nllh_bf is None:
+        nllh_bf = _brute_force(msa, Q)
+    ts = GPU_Topology_search([T0], GPU_EM_solver, data={'charMtrx': msa}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['resolve_search_only'] = resolve_only
+    best_trees, max_score, best_params = ts.search(maxiter=200, verbose=False, strategy=st, nreps=1)
+    assert abs(nllh_bf + max_score) < 5e-5, (no, -max_score, nllh_bf, best_trees)          # places=4
+    assert set(best_params) == {'phi', 'nu'}
+
+
+def test_search_uses_one_handle_and_improves():
+    from random import seed
+    seed(a=77)
+    case, z = load_npz_case("ref_rand_small")
+    # scramble the topology: the generating tree should score better than a random re-wiring
+    s0 = _solver(case)
+    start = -s0.negative_llh()
+    ts = GPU_Topology_search(case.newicks, GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
+                             params={'phi': case.phi, 'nu': case.nu})
+    OracleEngine.instances = 0
+    best_trees, best_score, best_params = ts.search(maxiter=5, nreps=1)
+    assert OracleEngine.instances == 1                     # one engine for the whole search
+    assert best_score >= start - 1e-9
+    assert ts.trees_scored >= 14
