@@ -190,3 +190,27 @@ CONFIGS = {
     "config4_100k_x_2k": dict(n_leaves=100000, n_sites=2000, a_lo=2, a_hi=100, nu=0.3, phi=0.3),
     "config5_5k_x_300": dict(n_leaves=5000, n_sites=300, a_lo=2, a_hi=30, nu=0.1, phi=0.1),
 }
+
+
+def reference_inputs(w: Workload):
+    """A synthetic workload in the form the reference's solver constructor takes (``ML_solver.py:19-26``):
+    ``(newick strings, {cell: [states]}, [ {state: prior} per site ])`` -- leaf ``i`` is cell ``"c<i>"``,
+    state ids are the 1-based ranks, ``'?'`` for missing entries, -1 for known-silenced ones."""
+    f = w.forest
+    text = [None] * f.n_nodes
+    for v in f.order:                                   # children first
+        v = int(v)
+        length = ":%r" % float(w.d[v])
+        if f.left[v] < 0:
+            text[v] = "c%d%s" % (v, length)
+        else:
+            l, r = int(f.left[v]), int(f.right[v])
+            text[v] = "(" + text[l] + "," + text[r] + ")" + length
+            text[l] = text[r] = None
+    newicks = [text[int(r)] + ";" for r in f.roots]
+    K = w.codes.shape[1]
+    msa = {}
+    for i in range(f.n_leaves):
+        msa["c%d" % i] = ['?' if x == -1 else (-1 if x == -2 else x) for x in w.codes[i].tolist()]
+    Q = [{a + 1: float(w.qval[w.qptr[s] + a]) for a in range(int(w.qptr[s + 1] - w.qptr[s]))} for s in range(K)]
+    return newicks, msa, Q

@@ -30,7 +30,8 @@ from typing import List, Optional
 
 import numpy as np
 
-from .nni import nni_candidates
+from .flatten import forest_from_parent
+from .nni import apply_nni, nni_candidates
 from .solver import DEFAULT_STRATEGY, GPU_EM_solver
 
 chkpt_freq = 10                                   # laml_libs/core_constants.py
@@ -41,7 +42,8 @@ class Neighbourhood:
     """Scores of the NNI candidates around a solver's current forest.  Candidate ``i`` swaps child
     ``cand_k[i]`` (index into ``u.children``) of node ``cand_u[i]`` with ``u``'s sibling; ``score[i]`` is the
     log-likelihood after the local EM, ``d5[i]`` the optimised lengths of ``nodes[i]`` = (v, u, moved child,
-    other child, former sibling); ``d0`` the lengths every other branch was held at."""
+    other child, former sibling); ``d0`` the lengths every other branch was held at (``d_raw`` raised to
+    ``2 dmin``)."""
     cand_u: np.ndarray
     cand_k: np.ndarray
     score: np.ndarray
@@ -49,6 +51,7 @@ class Neighbourhood:
     nodes: np.ndarray
     iters: np.ndarray
     d0: np.ndarray
+    d_raw: np.ndarray
 
     def index(self):
         return {(int(u), int(k)): i for i, (u, k) in enumerate(zip(self.cand_u, self.cand_k))}
@@ -61,11 +64,15 @@ def start_lengths(solver: GPU_EM_solver) -> np.ndarray:
     return np.maximum(solver._d(), 2 * solver.dmin)
 
 
-def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False) -> Neighbourhood:
+def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp: bool = True) -> Neighbourhood:
     """One batched call for all candidates ``Topology_search.single_nni`` could try on ``solver``'s trees
     (``:221-231``: every internal non-root node; with ``only_marked`` those carrying ``node.mark``), each
     scored as ``apply_nni`` does with ``local_brlen_opt`` (``:253-300``): nu, phi and all lengths fixed
-    except the five around the move."""
+    except the five around the move.
+
+    ``clamp=True`` reproduces the reference's scores exactly: its candidate solver raises EVERY length --
+    the fixed ones too -- to ``2 dmin`` before the local EM (:func:`start_lengths`).  With ``clamp=False`` the
+    other branches stay where they are (see :class:`GPU_Topology_search`)."""
     forest = solver._ensure()
     if any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
         raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
@@ -74,40 +81,59 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False) -> Nei
     if only_marked:
         keep = np.array([bool(getattr(forest.nodes[u], "mark", False)) for u in cu], bool)
         cu, ck = cu[keep], ck[keep]
-    d0 = start_lengths(solver)
+    d_raw = solver._d()
+    d0 = np.maximum(d_raw, 2 * solver.dmin) if clamp else d_raw.copy()
     if len(cu) == 0:
         z = np.zeros(0)
-        return Neighbourhood(cu, ck, z, np.zeros((0, 5)), np.zeros((0, 5), np.int32), np.zeros(0, np.int32), d0)
+        return Neighbourhood(cu, ck, z, np.zeros((0, 5)), np.zeros((0, 5), np.int32), np.zeros(0, np.int32), d0, d_raw)
     res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax)
-    return Neighbourhood(cu, ck, -res["nllh"], res["d5"], res["nodes"], res["iters"], d0)
+    return Neighbourhood(cu, ck, -res["nllh"], res["d5"], res["nodes"], res["iters"], d0, d_raw)
 
 
 def apply_move(solver: GPU_EM_solver, nb: Neighbourhood, i: int) -> None:
-    """Make candidate ``i`` the solver's current tree: the pointer swap of ``apply_nni`` (``:281-287``) on
-    the solver's own node objects, the five optimised lengths, and a re-bind -- ``pmm_set_tree`` on the live
-    handle, the character matrix stays on the device."""
+    """Make candidate ``i`` the solver's current tree: the swap of ``apply_nni`` (``:281-287``) on the
+    solver's own node objects and, in step, on the flat arrays -- node ids do not change under an NNI, so
+    nothing is re-flattened -- the five optimised lengths, and ``pmm_set_tree`` on the live handle (the
+    character matrix stays on the device)."""
     forest = solver._forest
-    u = forest.nodes[int(nb.cand_u[i])]
+    u_id, k = int(nb.cand_u[i]), int(nb.cand_k[i])
+    u = forest.nodes[u_id]
     v = u.parent
     w = next(c for c in v.children if c is not u)
-    child = u.children[int(nb.cand_k[i])]
-    for nd, length in zip(forest.nodes, nb.d0):
-        nd.edge_length = float(length)
+    child = u.children[k]
+    for j in np.nonzero(nb.d0 != nb.d_raw)[0]:                    # the clamp of start_lengths, where it bit
+        forest.nodes[int(j)].edge_length = float(nb.d0[j])
     for node_id, length in zip(nb.nodes[i], nb.d5[i]):
         forest.nodes[int(node_id)].edge_length = float(length)
-    u.remove_child(child); v.add_child(child)
-    v.remove_child(w); u.add_child(w)
-    solver._forest = None
+    # slot swap: w takes the moved child's place under u, the child takes w's place under v -- the same
+    # convention as nni.apply_nni, so children[0] / children[1] stay the arrays' left / right
+    u.children[k], v.children[v.children.index(w)] = w, child
+    w.parent, child.parent = u, v
+    parent, left, right = apply_nni(forest.parent, forest.left, forest.right, u_id, k)
+    new = forest_from_parent(parent, left, right)
+    new.nodes, new.leaf_labels = forest.nodes, forest.leaf_labels
+    solver._engine.set_tree(parent, left, right)
+    solver._forest = new
     solver._stats = None
-    solver._ensure()
 
 
 class GPU_Topology_search:
     """``Topology_search`` (``laml_libs/Topology_search.py:10-216``) with the same constructor, ``search``
-    signature and return value ``(best_trees, best_score, best_params)``, on one persistent solver."""
+    signature and return value ``(best_trees, best_score, best_params)``, on one persistent solver.
+
+    ``clamp_start`` (default False) is the one place the search departs from the reference on purpose.  The
+    reference compares a candidate scored with ALL branches raised to ``2 dmin = 0.01`` (``ini_brlens`` through
+    ``x2brlen``, ``ML_solver.py:195-203``, ``EM_solver.py:45-51``) against a current score obtained with
+    branches as short as ``dmin = 0.005``.  Every candidate therefore carries the same penalty -- the likelihood
+    lost by lengthening all short branches -- which is small on a 100-cell tree and larger than any NNI gain at
+    5 000 cells: measured on BASELINE config 5 from a tree 100 NNI moves away from the generating one, not one of
+    9 996 candidates was accepted (``profiles/r1_nni_search_config5.json``).  With ``clamp_start=False`` candidates
+    keep the current lengths outside the five free branches, so scores are comparable with the current score;
+    ``clamp_start=True`` gives the reference's literal behaviour."""
 
     def __init__(self, treeTopoList, solver=GPU_EM_solver, data={}, prior={}, params={}, T_cooldown=20, alpha_cooldown=0.9,
-                 device: int = 0):
+                 device: int = 0, clamp_start: bool = False):
+        self.clamp_start = clamp_start
         self.treeTopoList = list(treeTopoList)
         self.solver = solver
         self.data, self.prior, self.params = data, prior, dict(params)
@@ -195,7 +221,7 @@ class GPU_Topology_search:
         return score
 
     # ------------------------------------------------------------------ the search
-    def single_nni(self, curr_score, nni_iter, strategy, only_marked=False, verbose=False):
+    def single_nni(self, curr_score, nni_iter, strategy, only_marked=False, verbose=False, sync=True):
         """``single_nni`` + ``apply_nni`` (``:221-322``): returns ``(score, n_attempts, took)``."""
         s = self._solver
         forest = s._ensure()
@@ -203,7 +229,7 @@ class GPU_Topology_search:
                     if nd.children and nd.parent is not None and (not only_marked or getattr(nd, "mark", False))]
         shuffle(branches)
         if strategy.get('local_brlen_opt', True):
-            nb = score_neighbourhood(s, only_marked=only_marked)
+            nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start)
             self.trees_scored += len(nb.score)
             where = nb.index()
             n_attempts = 0
@@ -217,7 +243,8 @@ class GPU_Topology_search:
                     new_score = float(nb.score[i])
                     if self.__accept_proposal__(curr_score, new_score, nni_iter):
                         apply_move(s, nb, i)
-                        self._sync_from_solver()
+                        if sync:                      # ``sync=False``: the caller tracks snapshots (__search_one__)
+                            self._sync_from_solver()
                         return new_score, n_attempts, True
             return curr_score, n_attempts, False
         # every parameter re-optimised per candidate (local_brlen_opt = False, :249-251 + :297-300): one full EM
@@ -260,26 +287,59 @@ class GPU_Topology_search:
         s._forest = None
         s._stats = None
 
+    # -- snapshots: during a local-move search the trees are only arrays + lengths (node ids are stable under NNI);
+    #    newick strings are produced when somebody needs them (checkpoints, the end), not per accepted move
+    def _snapshot(self):
+        s = self._solver
+        f = s._ensure()
+        return (f.parent.copy(), f.left.copy(), f.right.copy(), s._d(), (s.params.nu, s.params.phi))
+
+    def _load(self, snap):
+        s = self._solver
+        parent, left, right, d, (nu, phi) = snap
+        nodes = s._forest.nodes
+        for i, nd in enumerate(nodes):
+            nd.edge_length = float(d[i])
+            if left[i] >= 0:
+                nd.children = [nodes[left[i]], nodes[right[i]]]
+            nd.parent = nodes[parent[i]] if parent[i] >= 0 else None
+        new = forest_from_parent(parent, left, right)
+        new.nodes, new.leaf_labels = nodes, s._forest.leaf_labels
+        s._engine.set_tree(parent, left, right)
+        s._forest, s._stats = new, None
+        s.params.nu, s.params.phi = nu, phi
+
+    def _materialise(self, snap):
+        """(newick strings, params) of a snapshot; the solver is left where it was"""
+        here = self._snapshot()
+        self._load(snap)
+        out = (self._solver.get_tree_newick(), self._solver.get_params())
+        self._load(here)
+        return out
+
     def __search_one__(self, strategy, maxiter=100, verbose=False, only_marked=False, checkpoint_file=None):   # :174-219
         curr_score = self._score_all(strategy)
         if verbose:
             print("Initial score: " + str(curr_score), flush=True)
         self._sync_from_solver()
-        best_score, best_trees, best_params = curr_score, self.treeTopoList, self.params
+        lazy = bool(strategy.get('local_brlen_opt', True))      # the full-optimisation path replaces the node objects
+        best_score, best = curr_score, (self._snapshot() if lazy else (self.treeTopoList, self.params))
         for nni_iter in range(maxiter):
             if verbose:
                 print("NNI Iter:", nni_iter, flush=True)
-            new_score, n_attempts, success = self.single_nni(curr_score, nni_iter, strategy, only_marked=only_marked)
+            new_score, n_attempts, success = self.single_nni(curr_score, nni_iter, strategy, only_marked=only_marked,
+                                                             sync=not lazy)
             if verbose:
                 print(f"Number of trees checked: {n_attempts}", flush=True)
             if not success:
                 break
             curr_score = new_score
             if curr_score > best_score:
-                best_score, best_trees, best_params = curr_score, self.treeTopoList, self.params
+                best_score, best = curr_score, (self._snapshot() if lazy else (self.treeTopoList, self.params))
             if verbose:
                 print("Current score: " + str(curr_score), flush=True)
             if nni_iter % chkpt_freq == 0 and checkpoint_file is not None:
+                best_trees, best_params = self._materialise(best) if lazy else best
                 with open(checkpoint_file, "a") as fout:
                     fout.write(f"NNI Iteration: {nni_iter}\n")
                     fout.write(f"Current newick tree: {best_trees}\n")
@@ -288,6 +348,7 @@ class GPU_Topology_search:
                     fout.write(f"Current silencing rate: {best_params['nu']}\n")
         if verbose:
             print("Best score for this search: " + str(best_score), flush=True)
+        best_trees, best_params = self._materialise(best) if lazy else best
         return best_trees, best_score, best_params
 
     def search(self, resolve_polytomies=True, maxiter=100, verbose=False, nreps=1, strategy=DEFAULT_STRATEGY,

@@ -146,3 +146,84 @@ def test_search_uses_one_handle_and_improves():
     assert OracleEngine.instances == 1                     # one engine for the whole search
     assert best_score >= start - 1e-9
     assert ts.trees_scored >= 14
+
+
+def test_best_snapshot_materialises_to_the_best_score(tmp_path):
+    """__search_one__ tracks the best tree as arrays; the newick it finally returns must evaluate to the best
+    score, also when annealing accepted worse moves afterwards, and checkpoints hold the same thing"""
+    from random import seed
+    seed(a=5)
+    case, z = load_npz_case("ref_rand_ragged")
+    ts = GPU_Topology_search(case.newicks, GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
+                             params={'phi': case.phi, 'nu': case.nu}, T_cooldown=2000, alpha_cooldown=0.999)   # hot: accepts worse moves
+    ts._open(True)
+    ck = tmp_path / "ckpt.txt"
+    trees, score, params = ts.__search_one__(deepcopy(DEFAULT_STRATEGY), maxiter=12, checkpoint_file=str(ck))
+    current = -ts._solver.negative_llh()
+    fresh = GPU_EM_solver(trees, {'charMtrx': case.msa}, {'Q': case.Q}, params)
+    assert abs(-fresh.negative_llh() - score) <= 1e-9 * abs(score)
+    assert score >= current - 1e-9                                     # best is at least the place the walk ended
+    text = ck.read_text()
+    assert text.count("NNI Iteration:") == 2 and "Current newick tree: ['" in text
+    # the solver still sits on the walk's last tree, node objects and arrays in step
+    f = ts._solver._forest
+    for i, nd in enumerate(f.nodes):
+        if nd.children:
+            assert f.nodes[f.left[i]] is nd.children[0] and f.nodes[f.right[i]] is nd.children[1]
+            assert nd.children[0].parent is nd and nd.children[1].parent is nd
+    ts.close()
+
+
+def test_clamp_modes():
+    """clamp=True is the reference's candidate (every length raised to 2 dmin); clamp=False keeps the other
+    branches where they are.  Either way a local EM cannot end below the re-wired tree's likelihood at its
+    starting lengths; and after a full EM the clamp alone costs likelihood, which is why the search compares
+    un-clamped candidates (GPU_Topology_search docstring)."""
+    from laml_b200.nni import apply_nni
+    case, z = load_npz_case("ref_rand_ragged")
+    s = _solver(case)
+    s.optimize(initials=1, random_seeds=3, verbose=-1)                 # branches with no support end at dmin
+    f = s._ensure()
+    d_raw = s._d()
+    assert (d_raw < 2 * s.dmin).sum() >= 3
+    at_raw = -s.negative_llh()
+    d0 = start_lengths(s)
+    at_clamped = s._engine.inside(d0, s.params.nu, s.params.phi)
+    assert at_clamped < at_raw - 1e-3                                  # the uniform penalty every clamped candidate carries
+    probe = OracleEngine(f.n_leaves, s._enc.qptr, s._enc.qval, s._enc.codes[s._leaf_row_bound])
+    for clamp, start in ((True, d0), (False, d_raw)):
+        nb = score_neighbourhood(s, clamp=clamp)
+        assert (nb.d0 == start).all()
+        for i in range(0, len(nb.score), 7):
+            p, l, r = apply_nni(f.parent, f.left, f.right, int(nb.cand_u[i]), int(nb.cand_k[i]))
+            probe.set_tree(p, l, r)
+            assert nb.score[i] >= probe.inside(start, s.params.nu, s.params.phi) - 1e-9
+    # un-clamped candidates are comparable with the current score: the best one is not far below it, whereas
+    # every clamped one sits below by at least most of the penalty
+    assert score_neighbourhood(s, clamp=False).score.max() > score_neighbourhood(s, clamp=True).score.max()
+
+
+def test_search_from_a_perturbed_tree_climbs():
+    from random import seed
+    from laml_b200.flatten import forest_from_parent
+    from laml_b200.nni import apply_nni
+    from laml_b200.synth import Workload, make_workload, reference_inputs
+    w = make_workload(24, 40, 2, 8, 0.1, 0.1, seed=12)
+    rng = np.random.default_rng(1)
+    p, l, r = w.forest.parent, w.forest.left, w.forest.right
+    for _ in range(12):
+        u = int(rng.integers(w.forest.n_leaves, w.forest.n_nodes))
+        if p[u] >= 0:
+            p, l, r = apply_nni(p, l, r, u, int(rng.integers(2)))
+    newicks, msa, Q = reference_inputs(Workload(forest_from_parent(p, l, r), w.d, w.qptr, w.qval, w.codes, w.nu, w.phi))
+    true_newicks, _, _ = reference_inputs(w)
+    t = GPU_EM_solver(true_newicks, {'charMtrx': msa}, {'Q': Q}, {'phi': 0.1, 'nu': 0.1})
+    true_score = -t.optimize(initials=1, random_seeds=2, verbose=-1)[0]
+    seed(a=3)
+    ts = GPU_Topology_search(newicks, GPU_EM_solver, data={'charMtrx': msa}, prior={'Q': Q}, params={'phi': 0.1, 'nu': 0.1})
+    ts._open(True)
+    start = ts._score_all(deepcopy(DEFAULT_STRATEGY))
+    trees, best, params = ts.__search_one__(deepcopy(DEFAULT_STRATEGY), maxiter=25)
+    ts.close()
+    assert start < true_score - 5                      # the perturbation hurt
+    assert best > start + 0.5 * (true_score - start)   # and the search won most of it back
