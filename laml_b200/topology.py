@@ -64,7 +64,8 @@ def start_lengths(solver: GPU_EM_solver) -> np.ndarray:
     return np.maximum(solver._d(), 2 * solver.dmin)
 
 
-def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp: bool = True) -> Neighbourhood:
+def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp: bool = True, shard: bool = False,
+                        group=None, device=None) -> Neighbourhood:
     """One batched call for all candidates ``Topology_search.single_nni`` could try on ``solver``'s trees
     (``:221-231``: every internal non-root node; with ``only_marked`` those carrying ``node.mark``), each
     scored as ``apply_nni`` does with ``local_brlen_opt`` (``:253-300``): nu, phi and all lengths fixed
@@ -72,7 +73,11 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
 
     ``clamp=True`` reproduces the reference's scores exactly: its candidate solver raises EVERY length --
     the fixed ones too -- to ``2 dmin`` before the local EM (:func:`start_lengths`).  With ``clamp=False`` the
-    other branches stay where they are (see :class:`GPU_Topology_search`)."""
+    other branches stay where they are (see :class:`GPU_Topology_search`).
+
+    ``shard=True`` under ``torch.distributed``: candidate trees are independent units, so every rank -- each
+    holding all sites -- scores the candidates ``rank::world`` and one ``all_gather`` gives every rank the full
+    result (``dist.score_nni_sharded``, BASELINE config 5 on 8 GPUs)."""
     forest = solver._ensure()
     if any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
         raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
@@ -86,7 +91,12 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
     if len(cu) == 0:
         z = np.zeros(0)
         return Neighbourhood(cu, ck, z, np.zeros((0, 5)), np.zeros((0, 5), np.int32), np.zeros(0, np.int32), d0, d_raw)
-    res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax)
+    if shard:
+        from .dist import score_nni_sharded
+        res = score_nni_sharded(solver._engine, cu, ck, d0, solver.params.nu, solver.params.phi, group=group, device=device,
+                                dmin=solver.dmin, dmax=solver.dmax)
+    else:
+        res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax)
     return Neighbourhood(cu, ck, -res["nllh"], res["d5"], res["nodes"], res["iters"], d0, d_raw)
 
 
@@ -132,8 +142,12 @@ class GPU_Topology_search:
     ``clamp_start=True`` gives the reference's literal behaviour."""
 
     def __init__(self, treeTopoList, solver=GPU_EM_solver, data={}, prior={}, params={}, T_cooldown=20, alpha_cooldown=0.9,
-                 device: int = 0, clamp_start: bool = False):
+                 device: int = 0, clamp_start: bool = False, shard_candidates: bool = False, group=None, gather_device=None):
+        # shard_candidates: one process per GPU (torchrun), every rank runs this same search with the same
+        # ``random`` seed -- the policy is replayed identically everywhere -- and scores 1/world of each
+        # neighbourhood (``dist.score_nni_sharded``)
         self.clamp_start = clamp_start
+        self.shard_candidates, self.group, self.gather_device = shard_candidates, group, gather_device
         self.treeTopoList = list(treeTopoList)
         self.solver = solver
         self.data, self.prior, self.params = data, prior, dict(params)
@@ -229,7 +243,8 @@ class GPU_Topology_search:
                     if nd.children and nd.parent is not None and (not only_marked or getattr(nd, "mark", False))]
         shuffle(branches)
         if strategy.get('local_brlen_opt', True):
-            nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start)
+            nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start, shard=self.shard_candidates,
+                                     group=self.group, device=self.gather_device)
             self.trees_scored += len(nb.score)
             where = nb.index()
             n_attempts = 0

@@ -135,3 +135,37 @@ def test_nni_candidate_sharding():
         nllh, d5, iters, nodes = ret[r]
         np.testing.assert_array_equal(nllh, want["nllh"]); np.testing.assert_array_equal(d5, want["d5"])
         np.testing.assert_array_equal(iters, want["iters"]); np.testing.assert_array_equal(nodes, want["nodes"])
+
+
+def _search_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from random import seed
+    import laml_b200.solver as solver_mod
+    from helpers import load_npz_case
+    from laml_b200.topology import GPU_Topology_search
+    from oracle_engine import OracleEngine
+    solver_mod.Engine = OracleEngine                 # test stand-in for the GPU engine (tests/oracle_engine.py)
+    case, z = load_npz_case("ref_rand_small")
+    seed(a=21)                                       # the same policy stream on every rank
+    ts = GPU_Topology_search(case.newicks, solver_mod.GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
+                             params={'phi': case.phi, 'nu': case.nu}, shard_candidates=world > 1, gather_device="cpu")
+    trees, score, params = ts.search(maxiter=4, nreps=1)
+    ret[rank] = (trees, score, params, ts.trees_scored)
+    dist.destroy_process_group()
+
+
+def test_candidate_sharded_search_matches_single_process():
+    """GPU_Topology_search with shard_candidates: two ranks, same seed, each scoring half of every neighbourhood,
+    end on the same trees and score as one process scoring everything"""
+    mgr = mp.Manager()
+    ret2, ret1 = mgr.dict(), mgr.dict()
+    port = 29700 + os.getpid() % 90
+    mp.spawn(_search_worker, args=(2, port, ret2), nprocs=2, join=True)
+    mp.spawn(_search_worker, args=(1, port + 100, ret1), nprocs=1, join=True)
+    assert ret2[0][0] == ret2[1][0] == ret1[0][0]
+    assert ret2[0][1] == ret2[1][1] == ret1[0][1]
+    assert ret2[0][2] == ret1[0][2] and ret2[0][3] == ret1[0][3]
