@@ -156,8 +156,14 @@ class GPU_Topology_search:
         self.b = 1 / (1 - 1 / self.alpha_cooldown ** self.T_cooldown)          # :29-30
         self.a = -self.b / self.alpha_cooldown ** self.T_cooldown
         self._solver: Optional[GPU_EM_solver] = None
-        self.has_polytomy = False
         self.trees_scored = 0
+        from .tree import read_tree_newick
+        self.has_polytomy = False                                              # :18-24 (read by runner.py:301)
+        for topo in self.treeTopoList:
+            t = read_tree_newick(topo)
+            t.suppress_unifurcations()
+            if any(len(nd.children) > 2 for nd in t.traverse_preorder()):
+                self.has_polytomy = True
 
     # ------------------------------------------------------------------ plumbing
     def get_solver(self) -> GPU_EM_solver:
@@ -242,7 +248,7 @@ class GPU_Topology_search:
         branches = [i for i, nd in enumerate(forest.nodes)
                     if nd.children and nd.parent is not None and (not only_marked or getattr(nd, "mark", False))]
         shuffle(branches)
-        if strategy.get('local_brlen_opt', True):
+        if self._batched(strategy):
             nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start, shard=self.shard_candidates,
                                      group=self.group, device=self.gather_device)
             self.trees_scored += len(nb.score)
@@ -262,11 +268,14 @@ class GPU_Topology_search:
                             self._sync_from_solver()
                         return new_score, n_attempts, True
             return curr_score, n_attempts, False
-        # every parameter re-optimised per candidate (local_brlen_opt = False, :249-251 + :297-300): one full EM
-        # per candidate on the live handle; a rejected candidate is undone by re-reading the trees it started
-        # from (same newick => same node ids after flattening)
+        # One candidate at a time -- the reference's own call sequence (:246-306) on the live solver and handle --
+        # for what the batch kernel does not cover: the ultrametric equalities (its local EM is unconstrained) and
+        # local_brlen_opt = False (every parameter re-optimised per candidate).  ``score_tree`` replaces the
+        # solver's node objects; a rejected candidate is undone by re-reading the trees it started from (same
+        # newick => same node ids after flattening).
         before, params0 = s.get_tree_newick(), (s.params.nu, s.params.phi)
         marks = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+        local = bool(strategy.get('local_brlen_opt', True))
         n_attempts = 0
         while branches:
             u_id = branches.pop()
@@ -279,15 +288,52 @@ class GPU_Topology_search:
                 v = u.parent
                 w = next(c for c in v.children if c is not u)
                 child = u.children[k]
+                st = deepcopy(strategy)
+                st['fixed_brlen'] = None
+                st['nodes_to_recompute'] = None
+                if local:                                                   # :253-277
+                    st['fixed_nu'], st['fixed_phi'] = s.params.nu, s.params.phi
+                    free = {id(x) for x in (u.children + v.children + [v])}
+                    fixed_brlen = []
+                    for tree in s.trees:
+                        fb = {}
+                        for nd in tree.traverse_postorder():
+                            nd.anchors = (nd.label, nd.label) if not nd.children else \
+                                (nd.children[0].anchors[0], nd.children[-1].anchors[0])
+                            if id(nd) not in free:
+                                fb[nd.anchors] = nd.edge_length
+                        fixed_brlen.append(fb)
+                    st['fixed_brlen'] = fixed_brlen
                 u.remove_child(child); v.add_child(child)
                 v.remove_child(w); u.add_child(w)
                 s._forest = None
-                new_score = self._score_all(strategy)
+                marks_moved = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+                new_score, status = s.score_tree(strategy=st)
+                self.trees_scored += 1
+                if local and status != "optimal":                           # :301-306: retry with everything free
+                    self._restore(before, params0, marks)
+                    forest = s._ensure()
+                    u = forest.nodes[u_id]; v = u.parent
+                    w = next(c for c in v.children if c is not u); child = u.children[k]
+                    u.remove_child(child); v.add_child(child)
+                    v.remove_child(w); u.add_child(w)
+                    s._forest = None
+                    st['fixed_brlen'] = None
+                    new_score, status = s.score_tree(strategy=st)
+                    self.trees_scored += 1
                 if new_score is not None and self.__accept_proposal__(curr_score, new_score, nni_iter):
+                    for t, ms in zip(s.trees, marks_moved):                 # score_tree re-read the moved trees: marks by position
+                        nodes = list(t.traverse_preorder())
+                        for nd, m in zip(nodes, ms if len(ms) == len(nodes) else [False] * len(nodes)):
+                            nd.mark = m
                     self._sync_from_solver()
                     return new_score, n_attempts, True
                 self._restore(before, params0, marks)
         return curr_score, n_attempts, False
+
+    @staticmethod
+    def _batched(strategy) -> bool:
+        return bool(strategy.get('local_brlen_opt', True)) and not strategy.get('ultra_constr', False)
 
     def _restore(self, newicks, params, marks):
         from .tree import read_tree_newick
@@ -337,7 +383,7 @@ class GPU_Topology_search:
         if verbose:
             print("Initial score: " + str(curr_score), flush=True)
         self._sync_from_solver()
-        lazy = bool(strategy.get('local_brlen_opt', True))      # the full-optimisation path replaces the node objects
+        lazy = self._batched(strategy)      # the one-at-a-time path replaces the node objects: no array snapshots
         best_score, best = curr_score, (self._snapshot() if lazy else (self.treeTopoList, self.params))
         for nni_iter in range(maxiter):
             if verbose:

@@ -227,3 +227,43 @@ def test_search_from_a_perturbed_tree_climbs():
     ts.close()
     assert start < true_score - 5                      # the perturbation hurt
     assert best > start + 0.5 * (true_score - start)   # and the search won most of it back
+
+
+def test_ultrametric_search_goes_candidate_by_candidate():
+    """strategy['ultra_constr'] = True (the runner's default): the batch kernel's local EM is unconstrained, so
+    candidates are scored one at a time by the reference's own call on the live solver; trees stay ultrametric"""
+    from random import seed
+    from laml_b200.tree import read_tree_newick
+    seed(a=9)
+    Q = [dict(q) for q in Q5]
+    ts = GPU_Topology_search(['((a,c),(b,d));'], GPU_EM_solver, data={'charMtrx': MSA_A}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    OracleEngine.instances = 0
+    trees, score, params = ts.search(maxiter=4, nreps=1, strategy=st)
+    assert OracleEngine.instances == 1 and np.isfinite(score) and ts.trees_scored >= 4
+    t = read_tree_newick(trees[0])
+    dist = {}
+    for nd in t.traverse_preorder():
+        dist[nd] = (dist[nd.parent] if nd.parent is not None else 0.0) + (nd.edge_length or 0.0)
+    tips = np.array([dist[nd] for nd in t.traverse_leaves()])
+    assert np.ptp(tips) < 1e-5 * tips.mean() + 1e-3
+    fresh = GPU_EM_solver(trees, {'charMtrx': MSA_A}, {'Q': Q}, params)
+    assert abs(-fresh.negative_llh() - score) <= 1e-6 * abs(score)
+    # the ultrametric optimum cannot beat the unconstrained brute-force optimum, and the start topology
+    # ((a,c),(b,d)) is worse than what the search ends on
+    assert -score >= _brute_force(MSA_A, Q) - 1e-6
+    s0 = GPU_EM_solver(['((a,c),(b,d));'], {'charMtrx': MSA_A}, {'Q': Q}, {'phi': 0, 'nu': 0})
+    assert score >= -s0.optimize(initials=1, random_seeds=4, verbose=-1, ultra_constr=True)[0] - 1e-6
+
+
+def test_full_reoptimisation_per_candidate():
+    """local_brlen_opt = False: every parameter re-optimised per candidate on the live handle"""
+    from random import seed
+    seed(a=10)
+    ts = GPU_Topology_search(['((a,c),(b,d));'], GPU_EM_solver, data={'charMtrx': MSA_A}, prior={'Q': [dict(q) for q in Q5]},
+                             params={'phi': 0, 'nu': 0})
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['local_brlen_opt'] = False
+    trees, score, params = ts.search(maxiter=20, nreps=1, strategy=st)
+    assert abs(_brute_force(MSA_A, [dict(q) for q in Q5]) + score) < 5e-5
