@@ -1,0 +1,31 @@
+"""The reference's shipped case tests (``case_tests/old/test{1,2,3,6}``) through the real engine, both
+engines: statistics against the reference's EM_solver dump at the stored point, and the number the reference's
+own run printed (tests/test_case_test_goldens.py has the same checks for the oracle and the numpy models)."""
+import numpy as np
+import pytest
+
+from helpers import env_override, load_json, load_npz_case, make_engine
+from test_case_test_goldens import _em_binarised_to_polytomy
+
+pytestmark = pytest.mark.gpu
+CASES = load_json("case_tests.json")
+
+
+@pytest.mark.parametrize("engine", ["lumped", "fullstate"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_case_test_known_answers(name, engine):
+    rec = CASES[name]
+    case, z = load_npz_case(rec["fixture"])
+    with env_override(PMM_ENGINE=engine):
+        eng = make_engine(case)
+    out = eng.estep(case.d, case.nu, case.phi)
+    ids = case.ids(z["labels"], z["tree_of"])
+    K = case.enc.n_sites
+    assert abs(-out["llh"] - rec["em_solver_nllh"]) <= 1e-9 * rec["em_solver_nllh"]
+    np.testing.assert_allclose(out["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * K)
+    assert abs(out["Rtilde"] - float(z["Rtilde"])) <= 1e-8 * max(1.0, float(z["Rtilde"]))
+    ml = -eng.inside(_em_binarised_to_polytomy(case), case.nu, case.phi)
+    assert abs(ml - rec["ml_solver_nllh"]) <= 1e-9 * rec["ml_solver_nllh"]
+    stored = rec["stored_nllh"]
+    assert min(abs(ml - stored), abs(-out["llh"] - stored)) <= (1e-9 if name == "test6" else 1e-8) * stored
+    eng.close()
