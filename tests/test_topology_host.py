@@ -95,11 +95,11 @@ def _all_topologies(leaves):
     return [nwk(t) + ";" for t in trees]
 
 
-def _brute_force(msa, Q):
+def _brute_force(msa, Q, ultra_constr=False):
     best = float("inf")
     for T in _all_topologies(sorted(msa)):
         s = GPU_EM_solver([T], {'charMtrx': msa}, {'Q': Q})
-        nllh, _ = s.optimize(initials=1, verbose=-1, ultra_constr=False)
+        nllh, _ = s.optimize(initials=1, verbose=-1, ultra_constr=ultra_constr)
         best = min(best, nllh)
     return best
 
@@ -130,6 +130,23 @@ def test_reference_search_tests(no, msa, T0, resolve_only, nllh_bf):
     best_trees, max_score, best_params = ts.search(maxiter=200, verbose=False, strategy=st, nreps=1)
     assert abs(nllh_bf + max_score) < 5e-5, (no, -max_score, nllh_bf, best_trees)          # places=4
     assert set(best_params) == {'phi', 'nu'}
+
+
+@pytest.mark.parametrize("no,T0", [(9, '((a,b),(c,d));'), (10, '(a,b,c,d);')])
+def test_reference_search_tests_ultrametric(no, T0):
+    """unit_tests_TopoSearch.py:213-250 (tests 9 and 10): ultra_constr search against the ultrametric brute force"""
+    from random import seed
+    seed(a=1000 + no)
+    Q = [dict(q) for q in Q5]
+    nllh_bf = _brute_force(MSA_B, Q, ultra_constr=True)
+    # the reference's own pre-computed brute-force value (unit_tests_TopoSearch.py:237, MOSEK M-step) -- an
+    # independent pin of laml_b200/ultrametric.py, to the 4 places the reference's tests use
+    assert abs(nllh_bf - 7.0063474330891236) < 5e-5
+    ts = GPU_Topology_search([T0], GPU_EM_solver, data={'charMtrx': MSA_B}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    best_trees, max_score, best_params = ts.search(maxiter=200, verbose=False, strategy=st, nreps=1)
+    assert abs(nllh_bf + max_score) < 5e-5, (no, -max_score, nllh_bf, best_trees)
 
 
 def test_search_uses_one_handle_and_improves():
