@@ -84,3 +84,16 @@ def test_usage_errors():
     h = g.copy(); h.remove_node(case.forest.n_nodes - 1)
     with pytest.raises(ValueError):
         opt.optimize(h, case.d, 0.1, 0.1, np.ones(case.forest.n_nodes, bool))
+
+
+def test_reference_fastEM_test_1():
+    """laml_unit_tests/unit_tests_fastEMSolver.py:15-44 at the EMOptimizer level: test4's data from the start
+    fastEM_solver uses (nu = phi = 0.5, fastEM_solver.py:232-233) reaches nllh 1007.009158767873 with
+    phi = nu = 0 -- the reference accepts |diff| < 10 for its float32 gradient M-step; here 1e-4 relative as
+    for EM_solver (unit_tests_EMSolver.py:556-566)"""
+    case, z = load_npz_case("ref_test4_zero")
+    pri, cm, g = arrays_of(case)
+    opt = fe.EMOptimizer(pri, cm)
+    out = opt.optimize(g, np.maximum(case.d, 0.01), 0.5, 0.5, np.ones(case.forest.n_nodes, bool))
+    assert abs(out["nllh"] - 1007.009158767873) < 1e-4 * 1007.009158767873
+    assert abs(out["phi"]) < 1e-4 and abs(out["nu"]) < 1e-4

@@ -28,3 +28,14 @@ def test_optimize_matches_oracle_em():
     out = opt.optimize(g, d0, 0.2, 0.15, mask, fixed_nu=True, fixed_phi=True)
     assert out["nu"] == 0.2 and out["phi"] == 0.15 and (out["branch_lengths"][~mask] == d0[~mask]).all()
     opt.close()
+
+
+def test_reference_fastEM_test_1():
+    """unit_tests_fastEMSolver.py:15-44 at the EMOptimizer level (see tests/test_fast_em_host.py)"""
+    case, z = load_npz_case("ref_test4_zero")
+    pri, cm, g = arrays_of(case)
+    opt = EMOptimizer(pri, cm)
+    out = opt.optimize(g, np.maximum(case.d, 0.01), 0.5, 0.5, np.ones(case.forest.n_nodes, bool))
+    assert abs(out["nllh"] - 1007.009158767873) < 1e-4 * 1007.009158767873
+    assert abs(out["phi"]) < 1e-4 and abs(out["nu"]) < 1e-4
+    opt.close()
