@@ -258,32 +258,38 @@ class GPU_EM_solver:
         from the GPU's statistics and nu / phi are then solved on the GPU."""
         if self._stats is None:
             raise RuntimeError("Mstep needs a preceding Estep")
-        S, Rt = self._stats["S"], self._stats["Rtilde"]
         fm = self._free_mask(local_brlen_opt)
-        d = self._d()
-        n_cells = len(self.charMtrx)
-        if ultra_constr_cache is None:
-            d_new, nu_new, phi_new = self._engine.mstep(S, Rt, self._R, n_cells, d, self.params.nu, self.params.phi, fm,
-                                                        optimize_nu, optimize_phi, self.dmin, self.dmax, eps_s, eps_nu)
-            status_d = "optimal"
-        else:
-            d_new, status_d = self._host_brlen(S, fm, d, self.params.nu, eps_nu, eps_s, ultra_constr_cache)
-            if status_d == "infeasible":
-                return False, "d_infeasible"                      # EM_solver.py:425-426
-            # nu with d fixed at d_new (EM_solver.py:427-433) and phi in closed form (:318-326): scalar
-            # problems on O(n) statistics, solved here because d_new only exists on the host
-            nu_new = _nu_given_d(S, fm, d_new, self.numsites, eps_s) if optimize_nu else self.params.nu
-            phi_new = self.params.phi
-            if optimize_phi:
-                phi_new = Rt / (self._R + Rt)
-                if abs(phi_new) < 1 / (self.numsites * n_cells):
-                    phi_new = 0
+        d_new, nu_new, phi_new, status_d = self._mstep_arrays(self._stats["S"], self._stats["Rtilde"], fm, self._d(),
+                                                              self.params.nu, self.params.phi, optimize_phi, optimize_nu,
+                                                              eps_nu, eps_s, ultra_constr_cache)
+        if status_d == "infeasible":
+            return False, "d_infeasible"                          # EM_solver.py:425-426
         self.params.phi, self.params.nu = phi_new, nu_new
         for i, nd in enumerate(self._forest.nodes):
             if fm[i]:
                 nd.edge_length = float(d_new[i])
         success = status_d == "optimal"
         return success, ("optimal" if success else "failed_d")
+
+    def _mstep_arrays(self, S, Rt, fm, d, nu, phi, optimize_phi, optimize_nu, eps_nu, eps_s, cache):
+        """one M-step on arrays: ``(d_new, nu_new, phi_new, status_d)``; ``cache`` = the ultrametric problem or None"""
+        n_cells = len(self.charMtrx)
+        if cache is None:
+            d_new, nu_new, phi_new = self._engine.mstep(S, Rt, self._R, n_cells, d, nu, phi, fm,
+                                                        optimize_nu, optimize_phi, self.dmin, self.dmax, eps_s, eps_nu)
+            return d_new, nu_new, phi_new, "optimal"
+        d_new, status_d = self._host_brlen(S, fm, d, nu, eps_nu, eps_s, cache)
+        if status_d == "infeasible":
+            return d, nu, phi, status_d
+        # nu with d fixed at d_new (EM_solver.py:427-433) and phi in closed form (:318-326): scalar
+        # problems on O(n) statistics, solved here because d_new only exists on the host
+        nu_new = _nu_given_d(S, fm, d_new, self.numsites, eps_s) if optimize_nu else nu
+        phi_new = phi
+        if optimize_phi:
+            phi_new = Rt / (self._R + Rt)
+            if abs(phi_new) < 1 / (self.numsites * n_cells):
+                phi_new = 0
+        return d_new, nu_new, phi_new, status_d
 
     def _host_brlen(self, S, fm, d, nu, eps_nu, eps_s, cache):
         """argmax of EM_solver.py:351-357 subject to the box and the ultrametric equalities, from the
@@ -333,20 +339,29 @@ class GPU_EM_solver:
             if verbose >= 0 and res["iters"] > maxIter:
                 print("Warning: exceeded maximum number of EM iterations (" + str(maxIter) + " iters)!")
             return res["nllh"], res["iters"], res["status"]
-        pre_llh = self.lineage_llh()
+        # the ultrametric loop keeps lengths and parameters in arrays (no per-node Python work per iteration);
+        # node objects and self.params are written once at the end -- same sequence of engine calls as
+        # Estep / Mstep / lineage_llh (EM_solver.py:495-507)
+        eng = self._engine
+        d, fm = self._d(), self._free_mask(True)
+        nu, phi = self.params.nu, self.params.phi
+        pre_llh = eng.inside(d, nu, phi)
         if verbose >= 0:
-            print("Initial phi: " + str(self.params.phi) + ". Initial nu: " + str(self.params.nu) + ". Initial nllh: " + str(-pre_llh))
+            print("Initial phi: " + str(phi) + ". Initial nu: " + str(nu) + ". Initial nllh: " + str(-pre_llh))
         cache = self._ultrametric_problem(local_brlen_opt=True)
         em_iter, converged, status, curr_llh = 1, False, "optimal", pre_llh
+        infeasible = False
         while em_iter <= maxIter:
-            self.Estep()
-            ok, status = self.Mstep(optimize_phi=optimize_phi, optimize_nu=optimize_nu, verbose=verbose,
-                                    local_brlen_opt=True, ultra_constr_cache=cache)
-            if not ok and status == "d_infeasible":
-                if verbose >= 0:
-                    print("Warning: EM failed to optimize parameters in one Mstep due to infeasible constraints")
-                return -pre_llh, em_iter, status
-            curr_llh = self.lineage_llh()
+            est = eng.estep(d, nu, phi)
+            self._stats = est
+            d_new, nu, phi, status_d = self._mstep_arrays(est["S"], est["Rtilde"], fm, d, nu, phi, optimize_phi, optimize_nu,
+                                                          1e-5, 1e-6, cache)
+            if status_d == "infeasible":
+                infeasible = True
+                break
+            status = "optimal" if status_d == "optimal" else "failed_d"
+            d = np.where(fm.astype(bool), d_new, d)
+            curr_llh = eng.inside(d, nu, phi)
             if verbose > 0:
                 print("Finished EM iter: " + str(em_iter) + ". Current nllh: " + str(-curr_llh))
             if abs((curr_llh - pre_llh) / pre_llh) < conv_eps:
@@ -354,6 +369,13 @@ class GPU_EM_solver:
                 break
             pre_llh = curr_llh
             em_iter += 1
+        self.params.nu, self.params.phi = nu, phi
+        for nd, length in zip(self._forest.nodes, d.tolist()):
+            nd.edge_length = length
+        if infeasible:
+            if verbose >= 0:
+                print("Warning: EM failed to optimize parameters in one Mstep due to infeasible constraints")
+            return -pre_llh, em_iter, "d_infeasible"
         if not converged and verbose >= 0:
             print("Warning: exceeded maximum number of EM iterations (" + str(maxIter) + " iters)!")
         return -curr_llh, em_iter, status
