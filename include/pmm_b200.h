@@ -160,6 +160,23 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
 int pmm_set_option(pmm_handle *h, const char *name, int64_t value);
 
 /*
+ * Ultrametric-constrained branch-length M-step, pure host code (works without a GPU): replaces the cvxpy -> MOSEK
+ * program of EM_solver.Mstep under ultra_constr (EM_solver.py:349-366) and the dense equality rows M d = b of
+ * EM_solver.ultrametric_constr (EM_solver.py:53-89; O(N B) Python lists) by a log-barrier Newton method on node
+ * heights whose linear systems have the tree's sparsity (laml_b200/csrc/pmm_ultrametric.cpp; O(n) per Newton
+ * step).  parent[n]: -1 for roots (all trees of a forest end at the same height, EM_solver.py:80-83).
+ * kind[n]: 0 = free branch in [lo, hi], 1 = fixed at fixed_len (mark_fixed), 2 = counts as 0 (polytomy mark,
+ * EM_solver.py:60-79).  S[n*5]: the clamped and rescaled statistics of EM_solver.py:343-346 (rows of non-free
+ * branches are ignored).  H0[n+1] or NULL: heights returned by the previous EM iteration -- the barrier path then
+ * starts from them (pulled warm_theta of the way to an interior point) at weight warm_mu instead of 1.
+ * Outputs: d_out[n] branch lengths, H_out[n+1] heights (H_out[n] = the common height), newton_iters.
+ * Returns 0 = optimal, 1 = infeasible (the reference's "d_infeasible"), 2 = failed ("failed_d"), -1 = bad arguments.
+ */
+int pmm_ultrametric_solve(int32_t n, const int32_t *parent, const int8_t *kind, const double *fixed_len, double lo,
+                          double hi, const double *S, double nu, double eps_nu, const double *H0, double mu_final,
+                          double warm_theta, double warm_mu, double *d_out, double *H_out, int32_t *newton_iters);
+
+/*
  * Test hook, pure host code (works without a GPU): the clade schedule the lumped-state engine derives for a
  * forest -- what pmm_set_tree computes, with the clade capacities given explicitly (1..127).  Outputs (caller
  * allocated; n_int = n_nodes - n_leaves): in_steps / out_steps [n_int][4] = (u, v, w, flags) in walking order

@@ -21,6 +21,7 @@ SYMBOLS = [
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
+    "pmm_ultrametric_solve",
 ]
 
 
@@ -83,10 +84,35 @@ def load_library():
     L.pmm_sync.argtypes = [vp]
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
+    L.pmm_ultrametric_solve.argtypes = [i32, vp, vp, vp, f64, f64, vp, f64, f64, vp, f64, f64, f64, vp, vp, P(i32)]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
     _lib = L
     return L
+
+
+def ultrametric_solve(parent, kind, fixed_len, lo, hi, S, nu, eps_nu=1e-5, H0=None, mu_final=1e-11, warm_theta=1e-6,
+                      warm_mu=1e-9):
+    """``pmm_ultrametric_solve`` (host code of the library; no GPU needed): ``(d, H, status, newton_iters)`` with
+    status 0 optimal / 1 infeasible / 2 failed."""
+    L = load_library()
+    parent = _i32(parent)
+    n = int(parent.shape[0])
+    kind = np.ascontiguousarray(kind, np.int8)
+    fixed_len = _f64(fixed_len)
+    S = _f64(S)
+    if kind.shape[0] != n or fixed_len.shape[0] != n or S.shape != (n, 5):
+        raise PMMError("pmm_ultrametric_solve: kind, fixed_len must have n entries and S must be (n, 5)")
+    h0 = _f64(H0) if H0 is not None else None
+    if h0 is not None and h0.shape[0] != n + 1:
+        raise PMMError("pmm_ultrametric_solve: H0 must have n + 1 entries")
+    d = np.empty(n); H = np.empty(n + 1); it = C.c_int32()
+    rc = L.pmm_ultrametric_solve(n, parent.ctypes.data, kind.ctypes.data, fixed_len.ctypes.data, float(lo), float(hi),
+                                 S.ctypes.data, float(nu), float(eps_nu), h0.ctypes.data if h0 is not None else None,
+                                 float(mu_final), float(warm_theta), float(warm_mu), d.ctypes.data, H.ctypes.data, C.byref(it))
+    if rc < 0:
+        raise PMMError("pmm_ultrametric_solve: invalid arguments (parent must describe a forest)")
+    return d, H, int(rc), int(it.value)
 
 
 def lumped_schedule(n_leaves, parent, left, right, clade_cap=16, clade_cap_top=16):

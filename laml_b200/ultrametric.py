@@ -18,6 +18,10 @@ the tree's own sparsity: one children-to-parents sweep eliminates every node (th
 an edge is the "series" combination ``w b / (w + b)`` of its curvature with the child's), one
 parents-to-children sweep back-substitutes.  The objective is strictly concave in ``d`` so the
 optimum is unique: it is the one MOSEK returns.
+
+The product path is the C++ routine behind ``pmm_ultrametric_solve`` (:func:`solve`); this module keeps the
+topology-dependent set-up (:class:`UltrametricProblem`) and the numpy statement of the algorithm
+(:func:`solve_numpy`) it is checked against.
 """
 from __future__ import annotations
 
@@ -105,6 +109,24 @@ def _f_derivs(x, k, S1, S24, nu, use_nu):
 
 def solve(problem: UltrametricProblem, S, nu, eps_nu=1e-5, H0=None, mu_final=1e-11, verbose=False, warm_theta=1e-6,
           warm_mu=1e-9):
+    """argmax of EM_solver.py:351-357 under the ultrametric equalities and the box: the library's host routine
+    ``pmm_ultrametric_solve`` (``laml_b200/csrc/pmm_ultrametric.cpp``, declared in ``include/pmm_b200.h``).
+    ``S`` : (n,5) clamped / rescaled statistics of the branches (rows of non-free branches are ignored).
+    Returns ``(d, H, info)`` with ``d`` the lengths of all branches (fixed / zero ones as given), or
+    ``(None, None, {"status": "infeasible"})``.  :func:`solve_numpy` is the same algorithm in numpy -- the model
+    the C++ is tested against (tests/test_ultrametric_host.py)."""
+    from .capi import ultrametric_solve
+    P = problem
+    parent = np.where(P.par[: P.n] == P.n, -1, P.par[: P.n]).astype(np.int32)
+    d, H, rc, iters = ultrametric_solve(parent, P.kind, P.fixed_len, P.lo, P.hi, S, nu, eps_nu=eps_nu, H0=H0,
+                                        mu_final=mu_final, warm_theta=warm_theta, warm_mu=warm_mu)
+    if rc == 1:
+        return None, None, {"status": "infeasible"}
+    return d, H, {"status": "optimal" if rc == 0 else "failed_d", "newton_iters": iters}
+
+
+def solve_numpy(problem: UltrametricProblem, S, nu, eps_nu=1e-5, H0=None, mu_final=1e-11, verbose=False, warm_theta=1e-6,
+                warm_mu=1e-9):
     """argmax of EM_solver.py:351-357 under the ultrametric equalities and the box.
     ``S`` : (n,5) clamped / rescaled statistics of the branches (rows of non-free branches are ignored).
     Returns ``(d, H, info)`` with ``d`` the lengths of all branches (fixed / zero ones as given).

@@ -81,3 +81,53 @@ def test_infeasible_fixed_branches_are_reported():
     prob = s._ultrametric_problem()
     d, H, info = um.solve(prob, S, 0.1)
     assert d is None and info["status"] == "infeasible"
+
+
+@pytest.mark.parametrize("name", ["ref_rand_small", "ref_rand_ragged", "ref_rand_forest", "ref_rand_deep", "ref_example1_start"])
+def test_native_solver_matches_the_numpy_model(name):
+    """pmm_ultrametric_solve (C++, laml_b200/csrc/pmm_ultrametric.cpp) against the numpy statement of the same
+    algorithm: cold start, warm start from the previous heights with perturbed statistics, nu below eps_nu,
+    fixed and polytomy-marked (zero) branches"""
+    s, S = _setup(name)
+    rng = np.random.default_rng(5)
+    nodes = s._forest.nodes
+    internal = [nd for nd in nodes if nd.children and nd.parent is not None]
+    for variant in ("plain", "fixed", "zero"):
+        for nd in nodes:
+            nd.mark_fixed, nd.polytomy_mark = False, False
+        if variant == "fixed":
+            # fix a few internal branches at their current lengths (what fixed_brlen does, ML_solver.py:296-305)
+            for nd in internal[::4]:
+                nd.mark_fixed = True
+                nd.edge_length = float(max(nd.edge_length, 0.02))
+        if variant == "zero" and internal:
+            internal[len(internal) // 2].polytomy_mark = True
+        prob = s._ultrametric_problem()
+        for nu in (0.1, 0.0):
+            d0, H0, i0 = um.solve_numpy(prob, S, nu)
+            d1, H1, i1 = um.solve(prob, S, nu)
+            if d0 is None:
+                assert d1 is None and i1["status"] == "infeasible" == i0["status"]
+                continue
+            assert i0["status"] == i1["status"] == "optimal"
+            # both stop inside the same solver tolerance (barrier weight 1e-11, Newton decrement test): ~1e-8
+            np.testing.assert_allclose(d1, d0, rtol=0, atol=5e-8)
+            np.testing.assert_allclose(H1, H0, rtol=0, atol=5e-8)
+            S2 = S * rng.uniform(0.9, 1.1, S.shape)
+            dw0, Hw0, iw0 = um.solve_numpy(prob, S2, nu, H0=H0)
+            dw1, Hw1, iw1 = um.solve(prob, S2, nu, H0=H1)
+            np.testing.assert_allclose(dw1, dw0, rtol=0, atol=5e-8)
+            dc, _, ic = um.solve(prob, S2, nu)                       # cold start: same optimum, more steps
+            np.testing.assert_allclose(dw1, dc, rtol=0, atol=5e-8)
+            assert iw1["newton_iters"] < ic["newton_iters"]
+
+
+def test_native_solver_usage_errors():
+    from laml_b200.capi import PMMError, ultrametric_solve
+    parent = np.array([2, 2, -1], np.int32)
+    with pytest.raises(PMMError):
+        ultrametric_solve(parent, np.zeros(3, np.int8), np.zeros(3), 0.005, 10.0, np.ones((2, 5)), 0.1)
+    with pytest.raises(PMMError):
+        ultrametric_solve(np.array([1, 0, -1], np.int32), np.zeros(3, np.int8), np.zeros(3), 0.005, 10.0, np.ones((3, 5)), 0.1)   # a cycle
+    d, H, rc, it = ultrametric_solve(parent, np.zeros(3, np.int8), np.zeros(3), 0.005, 10.0, np.ones((3, 5)), 0.1)
+    assert rc == 0 and abs(d[0] - d[1]) < 1e-12 and H[0] == H[1] == 0.0
