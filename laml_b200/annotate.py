@@ -96,7 +96,7 @@ def write_annotations(solver, Q, out_annotate) -> None:
     annotate).  ``Q`` is the prior as the caller holds it (list of dicts; the runner passes its raw, possibly
     un-normalised one, ``runner.py:433``).  The solver's trees are left as they were."""
     from .tree import Node
-    forest = solver._ensure()
+    forest = solver._ensure().derived()
     enc = solver._enc
     K = enc.n_sites
     d = solver._d()

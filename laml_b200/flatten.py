@@ -47,6 +47,13 @@ class FlatForest:
         return np.array([float(nd.edge_length) if nd.edge_length is not None else np.nan
                          for nd in self.nodes], dtype=np.float64)
 
+    def derived(self) -> "FlatForest":
+        """this forest with ``order`` / ``depth`` / ``height`` present (see ``forest_from_parent(derive=False)``)"""
+        if self.order is None:
+            full = forest_from_parent(self.parent, self.left, self.right)
+            self.order, self.depth, self.height = full.order, full.depth, full.height
+        return self
+
 
 def flatten_trees(trees: Sequence, leaf_key=None) -> FlatForest:
     """Flatten tree objects (anything with ``traverse_postorder`` and nodes
@@ -103,9 +110,11 @@ def depth_and_height(parent, left, right, order):
     return depth, height
 
 
-def forest_from_parent(parent: np.ndarray, left: np.ndarray, right: np.ndarray) -> FlatForest:
+def forest_from_parent(parent: np.ndarray, left: np.ndarray, right: np.ndarray, derive: bool = True) -> FlatForest:
     """Build a :class:`FlatForest` straight from arrays (synthetic workloads):
-    leaves must already be ids ``0..n_leaves-1``."""
+    leaves must already be ids ``0..n_leaves-1``.  ``derive=False`` leaves ``order`` / ``depth`` / ``height``
+    unset (None) for callers that only need the topology -- an NNI move on a live solver, where deriving them
+    would cost as much as scoring the move; :meth:`FlatForest.derived` fills them in on demand."""
     parent = np.ascontiguousarray(parent, np.int32)
     left = np.ascontiguousarray(left, np.int32)
     right = np.ascontiguousarray(right, np.int32)
@@ -114,6 +123,8 @@ def forest_from_parent(parent: np.ndarray, left: np.ndarray, right: np.ndarray) 
     n_leaves = int(is_leaf.sum())
     if not is_leaf[:n_leaves].all():
         raise ValueError("leaves must come first")
+    if not derive:
+        return FlatForest(parent, left, right, None, None, None, n_leaves)
     # iterative postorder via depth: sort by decreasing depth is children-before-parents
     depth = np.zeros(n, np.int32)
     roots = np.nonzero(parent < 0)[0]

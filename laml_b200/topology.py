@@ -25,7 +25,7 @@ from __future__ import annotations
 from copy import deepcopy
 from dataclasses import dataclass
 from math import exp
-from random import random, shuffle
+from random import getrandbits, random, shuffle
 from typing import List, Optional
 
 import numpy as np
@@ -56,6 +56,12 @@ class Neighbourhood:
     def index(self):
         return {(int(u), int(k)): i for i, (u, k) in enumerate(zip(self.cand_u, self.cand_k))}
 
+    def first_of(self, n_nodes: int) -> np.ndarray:
+        """``pos[u]`` = index of candidate ``(u, 0)`` (``(u, 1)`` follows it), -1 for nodes without candidates"""
+        pos = np.full(n_nodes, -1, np.int64)
+        pos[self.cand_u[::2]] = np.arange(0, len(self.cand_u), 2)
+        return pos
+
 
 def start_lengths(solver: GPU_EM_solver) -> np.ndarray:
     """The point the reference's candidate EM starts from: every length raised to ``2 dmin``
@@ -79,7 +85,7 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
     holding all sites -- scores the candidates ``rank::world`` and one ``all_gather`` gives every rank the full
     result (``dist.score_nni_sharded``, BASELINE config 5 on 8 GPUs)."""
     forest = solver._ensure()
-    if any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
+    if solver.num_polytomy_mark and any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
         raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
                          "a solver-inserted branch is never optimised and cannot take part in a move")
     cu, ck = nni_candidates(forest.parent, forest.left, forest.n_leaves)
@@ -120,7 +126,7 @@ def apply_move(solver: GPU_EM_solver, nb: Neighbourhood, i: int) -> None:
     u.children[k], v.children[v.children.index(w)] = w, child
     w.parent, child.parent = u, v
     parent, left, right = apply_nni(forest.parent, forest.left, forest.right, u_id, k)
-    new = forest_from_parent(parent, left, right)
+    new = forest_from_parent(parent, left, right, derive=False)      # traversal orders on demand (FlatForest.derived)
     new.nodes, new.leaf_labels = forest.nodes, forest.leaf_labels
     solver._engine.set_tree(parent, left, right)
     solver._forest = new
@@ -245,14 +251,18 @@ class GPU_Topology_search:
         """``single_nni`` + ``apply_nni`` (``:221-322``): returns ``(score, n_attempts, took)``."""
         s = self._solver
         forest = s._ensure()
-        branches = [i for i, nd in enumerate(forest.nodes)
-                    if nd.children and nd.parent is not None and (not only_marked or getattr(nd, "mark", False))]
-        shuffle(branches)
+        branches = np.nonzero((forest.left >= 0) & (forest.parent >= 0))[0]
+        if only_marked:
+            branches = np.array([i for i in branches if getattr(forest.nodes[i], "mark", False)], np.int64)
+        # the reference shuffles the branch list with ``random.shuffle`` (:231); a permutation drawn from a numpy
+        # generator seeded by ``random`` is the same policy (and stays reproducible under ``random.seed``) without
+        # a Python-level pass over 10^4 branches per iteration
+        branches = np.random.default_rng(getrandbits(63)).permutation(branches).tolist()
         if self._batched(strategy):
             nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start, shard=self.shard_candidates,
                                      group=self.group, device=self.gather_device)
             self.trees_scored += len(nb.score)
-            where = nb.index()
+            first = nb.first_of(forest.n_nodes)
             n_attempts = 0
             while branches:
                 u = branches.pop()
@@ -260,7 +270,7 @@ class GPU_Topology_search:
                 shuffle(moves)
                 n_attempts += 2
                 for k in moves:
-                    i = where[(u, k)]
+                    i = int(first[u]) + k
                     new_score = float(nb.score[i])
                     if self.__accept_proposal__(curr_score, new_score, nni_iter):
                         apply_move(s, nb, i)
@@ -364,7 +374,7 @@ class GPU_Topology_search:
             if left[i] >= 0:
                 nd.children = [nodes[left[i]], nodes[right[i]]]
             nd.parent = nodes[parent[i]] if parent[i] >= 0 else None
-        new = forest_from_parent(parent, left, right)
+        new = forest_from_parent(parent, left, right, derive=False)
         new.nodes, new.leaf_labels = nodes, s._forest.leaf_labels
         s._engine.set_tree(parent, left, right)
         s._forest, s._stats = new, None
