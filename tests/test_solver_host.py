@@ -164,3 +164,49 @@ def test_example1_ultrametric_em_reaches_published_optimum():
     assert abs(nllh - ref["nllh"]) < 1e-3
     assert abs(s.params.phi - ref["phi"]) < 3e-4 and abs(s.params.nu - ref["nu"]) < 1e-3
     assert np.ptp(_tip_depths(s.trees[0])) < 1e-6
+
+
+def test_optimize_argument_errors_return_none():
+    """ML_solver.py:262-281: too few seeds / a wrong seed type are reported by returning None, not by raising"""
+    case, z = load_npz_case("ref_rand_small")
+    s = _solver(case)
+    assert s.optimize(initials=3, random_seeds=[1, 2], verbose=-1) is None
+    assert s.optimize(initials=1, random_seeds="7", verbose=-1) is None
+    out = s.optimize(initials=2, random_seeds=[1, 2, 3], verbose=-1)           # surplus seeds are ignored
+    assert out is not None and out[1] == "optimal"
+
+
+def test_uninformative_sites_are_dropped_to_match_the_prior(capsys):
+    """ML_solver.py:47-67: when Q has fewer entries than the matrix has columns and exactly that many columns
+    are uninformative (only 0 / -1 / '?'), those columns are dropped"""
+    msa = {"a": [1, 0, 2], "b": [1, '?', 0], "c": [0, 0, 2]}
+    Q = [{1: 1.0}, {2: 0.5, 3: 0.5}]
+    s = GPU_EM_solver(["((a:0.2,b:0.3):0.1,c:0.4):0.1;"], {'charMtrx': msa}, {'Q': Q}, {'phi': 0.1, 'nu': 0.1})
+    assert s.numsites == 2 and s.charMtrx["a"] == [1, 2]
+    assert "uninformative" in capsys.readouterr().out
+    full = GPU_EM_solver(["((a:0.2,b:0.3):0.1,c:0.4):0.1;"], {'charMtrx': {k: [v[0], v[2]] for k, v in msa.items()}},
+                         {'Q': Q}, {'phi': 0.1, 'nu': 0.1})
+    assert s.negative_llh() == full.negative_llh()
+
+
+def test_missing_cell_and_unknown_state_raise():
+    with pytest.raises(KeyError):
+        GPU_EM_solver(["(a:1,b:1):1;"], {'charMtrx': {"a": [1]}}, {'Q': [{1: 1.0}]}, {'phi': 0, 'nu': 0}).negative_llh()
+    with pytest.raises(KeyError):
+        GPU_EM_solver(["(a:1,b:1):1;"], {'charMtrx': {"a": [1], "b": [5]}}, {'Q': [{1: 1.0}]}, {'phi': 0, 'nu': 0})
+
+
+def test_estep_leaves_statistics_and_posteriors_on_the_nodes():
+    """runner.py:391-435 reads node.S1.. and node.post0/post1 after Estep()"""
+    case, z = load_npz_case("ref_rand_small")
+    s = _solver(case)
+    out = s.Estep(posteriors=True)
+    ids = {str(nd.label): nd for nd in s._forest.nodes}
+    lab = [str(x) for x in z["labels"]]
+    for k in range(5):
+        got = np.array([getattr(ids[l], "S%d" % k) for l in lab])
+        np.testing.assert_allclose(got, z["Ssum"][k], rtol=1e-10, atol=1e-12)
+    p0 = np.array([ids[l].post0 for l in lab])
+    from helpers import assert_close_loginf
+    assert_close_loginf(p0, z["post0"], 1e-10, 1e-12, "post0")
+    assert abs(out["llh"] + float(z["nllh"])) <= 1e-12 * float(z["nllh"])
