@@ -516,6 +516,10 @@ def _nu_given_d(S, fm, d, numsites, eps_s):
     def grad(x):
         return float((w * dd / np.expm1(x * dd)).sum()) - lin
 
+    def grad2(x):
+        em = np.expm1(x * dd)
+        return -float((w * dd * dd * (em + 1.0) / (em * em)).sum())
+
     if grad(1.0) >= 0:
         return 1.0
     lo, hi = 0.5, 1.0
@@ -523,12 +527,21 @@ def _nu_given_d(S, fm, d, numsites, eps_s):
         hi, lo = lo, lo * 0.5
         if lo < 1e-300:
             return 0.0
-    for _ in range(200):
-        mid = 0.5 * (lo + hi)
-        if mid <= lo or mid >= hi:
-            break
-        if grad(mid) > 0:
-            lo = mid
+    # grad is decreasing and convex on (0, 1]: Newton from the left end of the bracket rises monotonically to
+    # the root; the bracket is kept only as a safeguard
+    x = lo
+    for _ in range(100):
+        g = grad(x)
+        if g > 0:
+            lo = x
         else:
-            hi = mid
-    return 0.5 * (lo + hi)
+            hi = x
+        step = -g / grad2(x)
+        nx = x + step
+        if not (lo < nx < hi):
+            nx = 0.5 * (lo + hi)
+        if abs(nx - x) <= 4e-16 * x:
+            x = nx
+            break
+        x = nx
+    return x
