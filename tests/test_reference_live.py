@@ -1,0 +1,116 @@
+"""Live cross-checks against the reference itself, imported verbatim from /root/reference (tests/golden/ref_loader.py).
+They run wherever the reference tree is present -- this container -- and skip themselves elsewhere (the GPU box has
+no /root/reference).  CPU only; the engine is the oracle-backed stand-in (tests/oracle_engine.py).
+
+* fresh random problems (not among the committed fixtures): reference EM_solver vs the oracle and vs the numpy
+  models of both engines' arithmetic;
+* the reference's OWN ``Topology_search`` class driving ``GPU_EM_solver`` as its solver plug-in -- the drop-in
+  INTEGRATION.md describes -- on the reference's own search tests;
+* ``GPU_Topology_search`` against that run: same optimum."""
+import os
+import sys
+from copy import deepcopy
+from random import seed
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import ref_loader  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+import laml_b200.solver as solver_mod  # noqa: E402
+from helpers import Case  # noqa: E402
+from laml_b200.solver import DEFAULT_STRATEGY, GPU_EM_solver  # noqa: E402
+from laml_b200.topology import GPU_Topology_search  # noqa: E402
+from oracle_engine import OracleEngine  # noqa: E402
+from test_topology_host import MSA_A, MSA_B, Q5, _brute_force  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def oracle_engine(monkeypatch):
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("sd", [101, 102, 103, 104])
+def test_fresh_random_problems(R, sd):
+    import make_golden as G
+    kw = dict(seed=sd, n_leaves=10 + 7 * (sd % 5), K=6 + sd % 7, max_A=4 + sd % 9, phi=0.05 * (sd % 4), nu=0.1 * (sd % 3),
+              n_trees=1 + (sd % 2))
+    trees, msa, Q = G.random_case(**kw)
+    ref = G.run_reference(trees, msa, Q, kw["phi"], kw["nu"])
+    case = Case(ref["newick_out"], msa, Q, kw["phi"], kw["nu"])
+    ids = case.ids(ref["labels"], ref["tree_of"])
+    out = case.oracle().estep(case.d, case.nu, case.phi, dump=True)
+    assert abs(-out["llh"] - ref["nllh"]) <= 1e-12 * abs(ref["nllh"])
+    for k in range(5):
+        np.testing.assert_allclose(out["S%d" % k][ids], ref["S%d" % k], rtol=1e-10, atol=1e-12)
+    from fullstate_model import estep as full_estep
+    from lumped_model import estep as lumped_estep
+    Ssum = np.stack([ref["S%d" % k].sum(axis=1) for k in range(5)])
+    for model in (lumped_estep, full_estep):
+        m = model(case.forest, case.leaf_row, case.enc.codes, case.enc.qptr, case.enc.qval, case.d, case.nu, case.phi)
+        assert abs(-m["llh"] - ref["nllh"]) <= 1e-10 * abs(ref["nllh"])
+        np.testing.assert_allclose(m["S"][ids].T, Ssum, rtol=1e-8, atol=1e-10 * case.enc.n_sites)
+    # and through the solver class
+    s = GPU_EM_solver(trees, {'charMtrx': msa}, {'Q': Q}, {'phi': kw["phi"], 'nu': kw["nu"]})
+    assert abs(s.negative_llh() - ref["nllh"]) <= 1e-12 * abs(ref["nllh"])
+
+
+@pytest.mark.parametrize("no,msa,T0,resolve_only,stored", [
+    (1, MSA_A, '((a,c),(b,d));', False, None), (3, MSA_A, '(a,b,c,d);', False, None), (4, MSA_A, '((a,b),c,d);', True, None),
+    (6, MSA_B, '((a,b),(c,d));', False, None),
+    (8, MSA_B, '((c,d),a,b);', True, 10.08306053772235)])       # only the polytomy may move: the reference's stored value
+def test_reference_topology_search_drives_the_solver_class(R, no, msa, T0, resolve_only, stored):
+    """laml_libs/Topology_search.py, unmodified, with solver=GPU_EM_solver (unit_tests_TopoSearch.py tests 1, 3, 4,
+    6, 8): every protocol call it makes -- constructor from newick strings, score_tree(strategy) with fixed_brlen
+    anchors / fixed_nu / fixed_phi, get_tree_newick, get_params, solver_name -- is served by the class"""
+    from laml_libs.Topology_search import Topology_search
+    Q = [dict(q) for q in Q5]
+    nllh_bf = stored if stored is not None else _brute_force(msa, Q)
+    seed(a=2000 + no)
+    ts = Topology_search([T0], GPU_EM_solver, data={'charMtrx': msa}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['resolve_search_only'] = resolve_only
+    best_tree, max_score, best_params = ts.search(maxiter=200, verbose=False, strategy=st, nreps=1)
+    assert abs(nllh_bf + max_score) < 5e-5, (no, -max_score, nllh_bf)                    # the reference's places=4
+    # the batched search class ends on the same optimum
+    seed(a=2000 + no)
+    mine = GPU_Topology_search([T0], GPU_EM_solver, data={'charMtrx': msa}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    _, my_score, my_params = mine.search(maxiter=200, verbose=False, strategy=st, nreps=1)
+    assert abs(my_score - max_score) < 5e-5
+    assert set(my_params) == set(best_params) == {'phi', 'nu'}
+
+
+def test_reference_apply_nni_scores_equal_the_batch(R):
+    """the reference's apply_nni (its own code: anchors, LCAs, new solver, score_tree) on every branch of a small
+    tree, with an acceptance rule that rejects everything so that all candidates get scored; the scores it sees are
+    the batch scorer's (clamp=True)"""
+    from laml_libs.Topology_search import Topology_search
+    from helpers import load_npz_case
+    from laml_b200.topology import score_neighbourhood
+    case, z = load_npz_case("ref_rand_small")
+    params = {'phi': case.phi, 'nu': case.nu}
+    seen = []
+
+    class Recording(Topology_search):
+        def _Topology_search__accept_proposal__(self, curr, new, t):      # not name-mangled in the reference, kept for safety
+            seen.append(new); return False
+
+        def __accept_proposal__(self, curr, new, t):
+            seen.append(new); return False
+
+    ts = Recording(case.newicks, GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q}, params=params)
+    seed(a=5)
+    score, n_attempts, took = ts.single_nni(-1e18, 0, deepcopy(DEFAULT_STRATEGY))
+    assert not took and n_attempts == len(seen) == 14
+    s = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, params)
+    nb = score_neighbourhood(s, clamp=True)
+    np.testing.assert_allclose(np.sort(seen), np.sort(nb.score), rtol=1e-9)
