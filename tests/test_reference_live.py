@@ -114,3 +114,22 @@ def test_reference_apply_nni_scores_equal_the_batch(R):
     s = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, params)
     nb = score_neighbourhood(s, clamp=True)
     np.testing.assert_allclose(np.sort(seen), np.sort(nb.score), rtol=1e-9)
+
+
+@pytest.mark.parametrize("sd", [201, 202, 203])
+def test_annotation_writer_on_fresh_problems(R, sd, tmp_path):
+    """the reference's own annotation block (runner.py:367-435, executed from the reference tree) against
+    laml_b200.annotate on problems that are not among the committed files: byte-identical"""
+    import make_golden as G
+    from make_annotation_golden import reference_writer, strip_internal_labels
+    from laml_b200.annotate import annotate
+    kw = dict(seed=sd, n_leaves=8 + 5 * (sd % 4), K=5 + sd % 6, max_A=3 + sd % 8, phi=0.1 + 0.05 * (sd % 3), nu=0.15 * (sd % 3),
+              n_trees=1 + (sd % 2))
+    trees, msa, Q = G.random_case(**kw)
+    if sd % 2:
+        trees = [strip_internal_labels(t) for t in trees]
+    params = {"phi": kw["phi"], "nu": kw["nu"]}
+    ref_out, my_out = tmp_path / "ref.txt", tmp_path / "mine.txt"
+    reference_writer(R)(list(trees), msa, Q, params, str(ref_out))
+    annotate(list(trees), msa, Q, params, str(my_out))
+    assert my_out.read_text() == ref_out.read_text()
