@@ -46,3 +46,15 @@ def load():
     from laml_libs.ML_solver import ML_solver
     from laml_libs import sequence_lib
     return types.SimpleNamespace(EM_solver=EM_solver, ML_solver=ML_solver, sequence_lib=sequence_lib, root=REF)
+
+
+def enable_cvxpy_shim():
+    """Give the ``cvxpy`` module object the reference imported (an empty stub, see :func:`load`) the few names
+    ``EM_solver.Mstep`` uses, backed by scipy (tests/golden/cvxpy_shim.py).  Works whether or not the reference
+    has been imported already: ``EM_solver``'s ``cp`` is this same module object."""
+    load()
+    import cvxpy_shim
+    mod = sys.modules["cvxpy"]
+    for name in cvxpy_shim.API:
+        setattr(mod, name, getattr(cvxpy_shim, name))
+    return mod

@@ -133,3 +133,108 @@ def test_annotation_writer_on_fresh_problems(R, sd, tmp_path):
     reference_writer(R)(list(trees), msa, Q, params, str(ref_out))
     annotate(list(trees), msa, Q, params, str(my_out))
     assert my_out.read_text() == ref_out.read_text()
+
+
+# ---- the reference's own M-step / EM code, verbatim, with only the numerical solver behind cvxpy substituted -----------------
+@pytest.fixture()
+def R_with_solver(R):
+    ref_loader.enable_cvxpy_shim()           # tests/golden/cvxpy_shim.py: the cvxpy calls of EM_solver.py:349-407 on scipy
+    return R
+
+
+def _ref_solver(R, case, phi, nu):
+    s = R.EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': phi, 'nu': nu})
+    for tree in s.trees:
+        for nd in tree.traverse_postorder():
+            nd.mark_fixed = False             # what optimize() does before every start (ML_solver.py:296-299)
+    return s
+
+
+@pytest.mark.parametrize("name,phi,nu", [("ref_rand_small", 0.17, 0.23), ("ref_rand_ragged", 0.17, 0.23), ("ref_rand_forest", 0.12, 0.4),
+                                         ("ref_rand_nu0", 0.2, 0.0)])
+def test_reference_mstep_unconstrained(R_with_solver, name, phi, nu):
+    """EM_solver.Estep + EM_solver.Mstep of the reference against the M-step the engine is tested against
+    (oracle: per-branch bisection; the GPU kernels: per-branch Newton) from the same statistics"""
+    from helpers import load_npz_case
+    case, z = load_npz_case(name)
+    s = _ref_solver(R_with_solver, case, phi, nu)
+    s.az_partition(); s.Estep()
+    ok, status = s.Mstep(verbose=-1)
+    assert ok and status == "optimal"
+    orc = case.oracle()
+    est = orc.estep(case.d, nu, phi)
+    d1, nu1, phi1, _ = orc.mstep(est["S"], est["Rtilde"], case.d, nu)
+    # statistics as Mstep prepares them (EM_solver.py:341-346), the objective (:351-357) and its curvature
+    Sn = np.maximum(est["S"].T, 1e-6)
+    Sn = Sn / Sn.sum(axis=1, keepdims=True) * case.enc.n_sites
+    use_nu = nu > 1e-5
+
+    def objective(d):
+        f = -(nu + 1) * Sn[:, 0] * d - nu * (Sn[:, 1] + Sn[:, 3]) * d + Sn[:, 1] * np.log(-np.expm1(-d))
+        return f + ((Sn[:, 2] + Sn[:, 4]) * np.log(-np.expm1(-nu * d)) if use_nu else 0.0)
+
+    by_key = {(str(nd.label), ti): i for i, (nd, ti) in enumerate(_with_tree_index(case))}
+    d_ref = np.empty_like(d1)
+    for ti, tree in enumerate(s.trees):
+        for nd in tree.traverse_postorder():
+            d_ref[by_key[(str(nd.label), ti)]] = nd.edge_length
+    f_mine, f_ref = objective(d1), objective(d_ref)
+    assert f_mine.sum() >= f_ref.sum() - 1e-9 * abs(f_ref.sum())           # at least as optimal as the reference's solve
+    assert (f_mine >= f_ref - 1e-9).all()                                  # ... branch by branch (the program is separable)
+    em = np.expm1(d1)
+    curv = Sn[:, 1] * (em + 1) / em ** 2 + (nu * nu * (Sn[:, 2] + Sn[:, 4]) * (np.expm1(nu * d1) + 1) / np.expm1(nu * d1) ** 2 if use_nu else 0.0)
+    sharp = curv > 1e-2                                                    # where the optimum is well determined
+    assert sharp.sum() >= len(d1) // 3
+    np.testing.assert_allclose(d1[sharp], d_ref[sharp], rtol=2e-6, atol=2e-6)
+    assert abs(s.params.nu - nu1) < 2e-6 and abs(s.params.phi - phi1) < 1e-12
+
+
+def _with_tree_index(case):
+    where = {}
+    for ti, t in enumerate(case.trees):
+        for nd in t.traverse_postorder():
+            where[id(nd)] = ti
+    return [(nd, where[id(nd)]) for nd in case.forest.nodes]
+
+
+@pytest.mark.parametrize("name", ["ref_rand_small", "ref_rand_forest"])
+def test_reference_mstep_ultrametric(R_with_solver, name):
+    """the reference's ultrametric program -- its own dense rows ``M d = b`` (EM_solver.py:53-89) in its own Mstep --
+    against pmm_ultrametric_solve on the same statistics"""
+    from helpers import load_npz_case
+    from laml_b200 import ultrametric as um
+    case, z = load_npz_case(name)
+    phi, nu = 0.1, 0.2
+    s = _ref_solver(R_with_solver, case, phi, nu)
+    s.az_partition(); s.Estep()
+    cache = s.ultrametric_constr(local_brlen_opt=True)
+    ok, status = s.Mstep(verbose=-1, ultra_constr_cache=cache)
+    assert ok and status == "optimal"
+    est = case.oracle().estep(case.d, nu, phi)
+    S = np.maximum(est["S"].T, 1e-6)
+    S = S / S.sum(axis=1, keepdims=True) * case.enc.n_sites
+    n = case.forest.n_nodes
+    prob = um.UltrametricProblem(case.forest.parent, np.zeros(n, np.int8), np.zeros(n), 0.005, 10.0)
+    d, H, info = um.solve(prob, S, nu)
+    assert info["status"] == "optimal"
+    mine = {(str(nd.label), ti): d[i] for i, (nd, ti) in enumerate(_with_tree_index(case))}
+    worst = max(abs(mine[(str(nd.label), ti)] - nd.edge_length) for ti, tree in enumerate(s.trees) for nd in tree.traverse_postorder())
+    assert worst < 5e-6, worst
+
+
+@pytest.mark.parametrize("name,ultra,sd", [("ref_rand_small", False, 31), ("ref_rand_small", True, 32), ("ref_rand_nu0", False, 33)])
+def test_reference_optimize_end_to_end(R_with_solver, name, ultra, sd):
+    """EM_solver.optimize of the reference (initial point from the seed, EM loop, convergence test, multi-start
+    bookkeeping, newick write-back) against GPU_EM_solver.optimize with the same seed: same optimum"""
+    from helpers import load_npz_case
+    case, z = load_npz_case(name)
+    ref = R_with_solver.EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': 0.1, 'nu': 0.1})
+    r_nllh, r_status = ref.optimize(initials=1, random_seeds=sd, verbose=-1, ultra_constr=ultra)
+    mine = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': 0.1, 'nu': 0.1})
+    m_nllh, m_status = mine.optimize(initials=1, random_seeds=sd, verbose=-1, ultra_constr=ultra)
+    assert r_status == m_status == "optimal"
+    assert abs(r_nllh - m_nllh) <= 1e-6 * abs(r_nllh), (r_nllh, m_nllh)
+    assert abs(ref.params.phi - mine.params.phi) < 1e-5 and abs(ref.params.nu - mine.params.nu) < 1e-4
+    # the trees that come back evaluate to the same likelihood under the reference's own likelihood code
+    back = R_with_solver.EM_solver(mine.get_tree_newick(), {'charMtrx': case.msa}, {'Q': case.Q}, mine.get_params())
+    assert abs(back.negative_llh() - m_nllh) <= 1e-9 * abs(m_nllh)
