@@ -304,9 +304,13 @@ def read_tree_newick(newick) -> Tree:
         with open(os.path.expanduser(text)) as fh:
             text = fh.read().strip()
     tree = Tree()
+    # treeswift keeps the rooting comment of the input: a string without ``[&R]`` is written back without it
+    # (the reference's published trees, examples/out_example1/example1_trees.nwk, and the string slicing in
+    # laml_unit_tests/unit_tests_TopoSearch.py:47 rely on that)
+    tree.is_rooted = False
     if text.startswith("[&"):
         close = text.index("]")
-        tree.is_rooted = text[2:close].strip().upper() != "U"
+        tree.is_rooted = text[2:close].strip().upper() == "R"
         text = text[close + 1:].strip()
     node = tree.root
     i = 0

@@ -238,3 +238,48 @@ def test_reference_optimize_end_to_end(R_with_solver, name, ultra, sd):
     # the trees that come back evaluate to the same likelihood under the reference's own likelihood code
     back = R_with_solver.EM_solver(mine.get_tree_newick(), {'charMtrx': case.msa}, {'Q': case.Q}, mine.get_params())
     assert abs(back.negative_llh() - m_nllh) <= 1e-9 * abs(m_nllh)
+
+
+def _run_reference_unittests(R, module_name, names=None):
+    """load a unittest file of the reference, rebind its ``EM_solver`` to the drop-in class, run it"""
+    import importlib
+    import types
+    import unittest
+    if "laml_unit_tests" not in sys.modules:
+        pkg = types.ModuleType("laml_unit_tests")
+        pkg.__path__ = [os.path.join(R.root, "laml_unit_tests")]
+        sys.modules["laml_unit_tests"] = pkg
+    mod = importlib.import_module("laml_unit_tests." + module_name)
+    original = mod.EM_solver
+    mod.EM_solver = GPU_EM_solver
+    cls = next(c for c in vars(mod).values() if isinstance(c, type) and issubclass(c, unittest.TestCase))
+    suite = (unittest.defaultTestLoader.loadTestsFromTestCase(cls) if names is None
+             else unittest.TestSuite([cls(n) for n in names]))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(R.root, "laml_unit_tests"))                 # the reference's tests open 'test_data/...' relatively
+    try:
+        with open(os.devnull, "w") as sink:
+            res = unittest.TextTestRunner(stream=sink, verbosity=0).run(suite)
+    finally:
+        os.chdir(cwd)
+        mod.EM_solver = original
+    return res
+
+
+def test_reference_unittest_file_toposearch(R_with_solver):
+    """laml_unit_tests/unit_tests_TopoSearch.py, all 10 tests, unmodified, with ``EM_solver`` bound to GPU_EM_solver:
+    the reference's own Topology_search drives the class and the reference's own assertions judge the result
+    (brute force through the reference's ML_solver, ultrametric tests 9-10 included)"""
+    seed(a=4)
+    res = _run_reference_unittests(R_with_solver, "unit_tests_TopoSearch")
+    assert res.testsRun == 10 and not res.failures and not res.errors, (res.failures + res.errors)[:1]
+
+
+def test_reference_unittest_file_emsolver(R_with_solver):
+    """laml_unit_tests/unit_tests_EMSolver.py: the tests that use the solver PROTOCOL (1-20, 46: likelihood known
+    answers; 47: optimize; 48: score_tree) against GPU_EM_solver.  Tests 21-45 call EM_solver internals
+    (Estep_in_llh / Estep_out_llh and per-node log arrays of the compressed representation); their inputs are
+    covered through the dumps in tests/test_oracle_golden.py and tests/test_gpu_parity.py"""
+    names = ["test_%d" % i for i in list(range(1, 21)) + [46, 47, 48]]
+    res = _run_reference_unittests(R_with_solver, "unit_tests_EMSolver", names)
+    assert res.testsRun == 23 and not res.failures and not res.errors, (res.failures + res.errors)[:1]
