@@ -240,8 +240,8 @@ def test_reference_optimize_end_to_end(R_with_solver, name, ultra, sd):
     assert abs(back.negative_llh() - m_nllh) <= 1e-9 * abs(m_nllh)
 
 
-def _run_reference_unittests(R, module_name, names=None):
-    """load a unittest file of the reference, rebind its ``EM_solver`` to the drop-in class, run it"""
+def _run_reference_unittests(R, module_name, names=None, rebind="EM_solver"):
+    """load a unittest file of the reference, rebind its ``EM_solver`` (or ``rebind``) to the drop-in class, run it"""
     import importlib
     import types
     import unittest
@@ -250,8 +250,8 @@ def _run_reference_unittests(R, module_name, names=None):
         pkg.__path__ = [os.path.join(R.root, "laml_unit_tests")]
         sys.modules["laml_unit_tests"] = pkg
     mod = importlib.import_module("laml_unit_tests." + module_name)
-    original = mod.EM_solver
-    mod.EM_solver = GPU_EM_solver
+    original = getattr(mod, rebind)
+    setattr(mod, rebind, GPU_EM_solver)
     cls = next(c for c in vars(mod).values() if isinstance(c, type) and issubclass(c, unittest.TestCase))
     suite = (unittest.defaultTestLoader.loadTestsFromTestCase(cls) if names is None
              else unittest.TestSuite([cls(n) for n in names]))
@@ -262,7 +262,7 @@ def _run_reference_unittests(R, module_name, names=None):
             res = unittest.TextTestRunner(stream=sink, verbosity=0).run(suite)
     finally:
         os.chdir(cwd)
-        mod.EM_solver = original
+        setattr(mod, rebind, original)
     return res
 
 
@@ -283,3 +283,10 @@ def test_reference_unittest_file_emsolver(R_with_solver):
     names = ["test_%d" % i for i in list(range(1, 21)) + [46, 47, 48]]
     res = _run_reference_unittests(R_with_solver, "unit_tests_EMSolver", names)
     assert res.testsRun == 23 and not res.failures and not res.errors, (res.failures + res.errors)[:1]
+
+
+def test_reference_unittest_file_mlsolver(R_with_solver):
+    """laml_unit_tests/unit_tests_MLSolver.py (21 likelihood known answers written for ML_solver) with ``ML_solver``
+    bound to GPU_EM_solver: on binary trees the two reference solvers define the same likelihood"""
+    res = _run_reference_unittests(R_with_solver, "unit_tests_MLSolver", rebind="ML_solver")
+    assert res.testsRun == 21 and not res.failures and not res.errors, (res.failures + res.errors)[:1]
