@@ -290,3 +290,30 @@ def test_reference_unittest_file_mlsolver(R_with_solver):
     bound to GPU_EM_solver: on binary trees the two reference solvers define the same likelihood"""
     res = _run_reference_unittests(R_with_solver, "unit_tests_MLSolver", rebind="ML_solver")
     assert res.testsRun == 21 and not res.failures and not res.errors, (res.failures + res.errors)[:1]
+
+
+def test_find_lcas_matches_the_reference(R):
+    """laml_libs/lca_lib.find_LCAs (Euler tour + segment tree) against solver.find_LCAs on random trees and anchors"""
+    from laml_libs.lca_lib import find_LCAs as ref_find
+    from laml_b200.solver import find_LCAs
+    from laml_b200.synth import make_workload, reference_inputs
+    from laml_b200.tree import read_tree_newick
+    rng = np.random.default_rng(3)
+    for sd in range(4):
+        w = make_workload(int(rng.integers(5, 60)), 2, 1, 3, 0.1, 0.1, seed=60 + sd, caterpillar_bias=0.4 * (sd % 2))
+        newicks, _, _ = reference_inputs(w)
+        t1, t2 = read_tree_newick(newicks[0]), read_tree_newick(newicks[0])
+        leaves = [nd.label for nd in t1.traverse_leaves()]
+        queries = [tuple(rng.choice(leaves, size=2)) for _ in range(40)] + [(l, l) for l in leaves[:5]]
+        a = ref_find(t1, queries)
+        b = find_LCAs(t2, queries)
+        def leafset(nd):
+            out, stack = set(), [nd]
+            while stack:
+                x = stack.pop()
+                if x.children:
+                    stack.extend(x.children)
+                else:
+                    out.add(x.label)
+            return frozenset(out)
+        assert [leafset(x) for x in a] == [leafset(x) for x in b]
