@@ -280,6 +280,7 @@ class Tree:
     def extract_tree_without(self, labels, suppress_unifurcations=True) -> "Tree":
         drop = set(labels)
         out = read_tree_newick(self.newick())
+        out.is_rooted = True          # treeswift builds the result in a fresh Tree(), whose default is rooted
         for leaf in list(out.traverse_leaves()):
             if leaf.label in drop:
                 n = leaf

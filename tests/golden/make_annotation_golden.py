@@ -29,7 +29,6 @@ CASES = {
     "zeroprior": ("ref_rand_zeroprior", True),
     "nu0": ("ref_rand_nu0", True),
     "test4_interior": ("ref_test4_interior", False),
-    "example1_optimum": ("ref_example1_optimum", False),
 }
 POLYTOMY = {
     "trees": ["((a:0.3,b:0.2,c:0.4,d:0.1):0.2,(e:0.1,f:0.3):0.1,g:0.5):0.05;"],

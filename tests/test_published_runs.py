@@ -1,0 +1,75 @@
+"""The reference's PUBLISHED runs as known answers.  example1 (``examples/out_example1``, LAML 0.0.2): the published
+likelihood is pinned in tests/test_oracle_golden.py / tests/test_gpu_solver.py; here its published annotation file.
+The reference's PUBLISHED example2 run (``examples/out_example2``: LAML 1.0.0 with MOSEK and treeswift, topology
+search, de-duplication) as known answers (tests/golden/make_published_goldens.py): the published negative
+log-likelihood 1124.4446364799137 at the published trees / phi / nu, and the published posterior annotation file,
+byte for byte.  CPU: oracle, numpy models of both engines, the solver class and the annotation writer on the
+oracle-backed stand-in; tests/test_zz_gpu_annotate.py and tests/test_zz_gpu_case_tests.py run the engine."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import laml_b200.solver as solver_mod
+from helpers import GOLDEN, load_npz_case
+from oracle_engine import OracleEngine
+
+PUBLISHED_NLLH = 1124.4446364799137
+
+
+def annotation_case():
+    rec = json.load(open(os.path.join(GOLDEN, "example2_annotation_case.json")))
+    Q = [{int(k): v for k, v in q.items()} for q in rec["Q"]]
+    return rec["trees"], rec["msa"], Q, rec["published"]
+
+
+def test_published_likelihood_oracle_and_models():
+    case, z = load_npz_case("ref_example2_published")
+    out = case.oracle().estep(case.d, case.nu, case.phi)
+    assert abs(-out["llh"] - PUBLISHED_NLLH) <= 1e-12 * PUBLISHED_NLLH
+    from fullstate_model import estep as full_estep
+    from lumped_model import estep as lumped_estep
+    for model in (lumped_estep, full_estep):
+        m = model(case.forest, case.leaf_row, case.enc.codes, case.enc.qptr, case.enc.qval, case.d, case.nu, case.phi)
+        assert abs(-m["llh"] - PUBLISHED_NLLH) <= 1e-11 * PUBLISHED_NLLH
+        ids = case.ids(z["labels"], z["tree_of"])
+        np.testing.assert_allclose(m["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * case.enc.n_sites)
+
+
+def test_published_annotation_file_byte_for_byte(tmp_path, monkeypatch):
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    from laml_b200.annotate import annotate
+    trees, msa, Q, pub = annotation_case()
+    out = tmp_path / "annot.txt"
+    annotate(trees, msa, Q, {"phi": pub["phi"], "nu": pub["nu"]}, str(out))
+    assert out.read_text() == open(os.path.join(GOLDEN, "annot_example2_published.txt")).read()
+
+
+def test_published_optimum_is_a_fixed_point_of_the_em(monkeypatch):
+    """EM from the published point (the reference's MOSEK optimum; the published tree is not ultrametric, so the
+    run's final optimisation was the unconstrained one) stops at once: the likelihood moves by < 1e-8 relative, phi
+    and nu by < 1e-5 -- the north-star tolerance for converged parameters -- and no branch by more than 5e-4"""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    case, z = load_npz_case("ref_example2_published")
+    s = solver_mod.GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': case.phi, 'nu': case.nu})
+    start = s.negative_llh()
+    s._ensure()
+    d0 = s._d().copy()
+    nllh, iters, status = s.EM_optimization(verbose=-1, ultra_constr=False)
+    assert status == "optimal" and iters <= 2
+    assert nllh <= start and abs(nllh - start) <= 1e-8 * start
+    assert abs(s.params.phi - case.phi) < 1e-5 and abs(s.params.nu - case.nu) < 1e-5
+    assert np.abs(s._d() - d0).max() < 5e-4
+
+
+def test_published_example1_annotation_file_byte_for_byte(tmp_path, monkeypatch):
+    """examples/out_example1/example1_annotations.txt (501 lines; 250 cells x 30 sites) from the published trees
+    (time-scaled lengths x mutation rate = ref_example1_optimum.npz) and the published phi / nu"""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    from laml_b200.annotate import annotate
+    case, z = load_npz_case("ref_example1_optimum")
+    trees = [t.replace("[&R] ", "") for t in case.newicks]      # the published input carried no rooting comment
+    out = tmp_path / "annot.txt"
+    annotate(trees, case.msa, case.Q, {"phi": case.phi, "nu": case.nu}, str(out))
+    assert out.read_text() == open(os.path.join(GOLDEN, "annot_example1_published.txt")).read()

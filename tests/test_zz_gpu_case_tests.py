@@ -29,3 +29,16 @@ def test_case_test_known_answers(name, engine):
     stored = rec["stored_nllh"]
     assert min(abs(ml - stored), abs(-out["llh"] - stored)) <= (1e-9 if name == "test6" else 1e-8) * stored
     eng.close()
+
+
+@pytest.mark.parametrize("engine", ["lumped", "fullstate"])
+def test_published_example2_likelihood(engine):
+    """examples/out_example2/example2_params.txt: 1124.4446364799137 at the published trees / phi / nu"""
+    case, z = load_npz_case("ref_example2_published")
+    with env_override(PMM_ENGINE=engine):
+        eng = make_engine(case)
+    out = eng.estep(case.d, case.nu, case.phi)
+    assert abs(-out["llh"] - 1124.4446364799137) <= 1e-9 * 1124.4446364799137
+    ids = case.ids(z["labels"], z["tree_of"])
+    np.testing.assert_allclose(out["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * case.enc.n_sites)
+    eng.close()
