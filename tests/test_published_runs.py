@@ -73,3 +73,63 @@ def test_published_example1_annotation_file_byte_for_byte(tmp_path, monkeypatch)
     out = tmp_path / "annot.txt"
     annotate(trees, case.msa, case.Q, {"phi": case.phi, "nu": case.nu}, str(out))
     assert out.read_text() == open(os.path.join(GOLDEN, "annot_example1_published.txt")).read()
+
+
+# ---- the other published example2 runs: run_laml_api.py (ultrametric, MOSEK) and the two fastEM-cpu runs -------------------
+RUNS = json.load(open(os.path.join(GOLDEN, "published_runs.json")))
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_other_published_likelihoods(name):
+    """the ``Negative-llh`` each run printed (examples/<run>/*_params.txt) at its published trees / phi / nu, on the
+    de-duplicated data it refers to: reproduced to 1e-12 by the oracle and by the numpy model of the lumped engine"""
+    case, z = load_npz_case(name)
+    out = case.oracle().inside(case.d, case.nu, case.phi)
+    assert abs(-out["llh"] - RUNS[name]["nllh"]) <= 1e-12 * RUNS[name]["nllh"]
+    from lumped_model import estep
+    m = estep(case.forest, case.leaf_row, case.enc.codes, case.enc.qptr, case.enc.qval, case.d, case.nu, case.phi)
+    assert abs(-m["llh"] - RUNS[name]["nllh"]) <= 1e-11 * RUNS[name]["nllh"]
+
+
+def _tip_spread(tree):
+    dist = {}
+    for nd in tree.traverse_preorder():
+        dist[nd] = (dist[nd.parent] if nd.parent is not None else 0.0) + (nd.edge_length or 0.0)
+    tips = np.array([dist[nd] for nd in tree.traverse_leaves()])
+    return float(np.ptp(tips))
+
+
+@pytest.mark.parametrize("name", ["ref_example2_api", "ref_example2_fastem"])
+def test_published_ultrametric_optima_are_fixed_points(name, monkeypatch):
+    """``run_laml_api.py`` ran the default, ultrametric mode with MOSEK: its published tree is ultrametric (tips level
+    to 3e-8) and is a fixed point of the ultrametric EM here -- pmm_ultrametric_solve against a real MOSEK optimum:
+    one iteration, likelihood unchanged to 1e-9 relative, phi and nu to 1e-5 (the north-star tolerance), branches
+    to 1e-4.  Likewise the fastEM-cpu run's tree (its M-step is a float32 gradient method: 2e-5 on nu)."""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    case, z = load_npz_case(name)
+    s = solver_mod.GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': case.phi, 'nu': case.nu})
+    assert _tip_spread(s.trees[0]) < 1e-7
+    start = s.negative_llh()
+    d0 = s._d().copy()
+    nllh, iters, status = s.EM_optimization(verbose=-1, ultra_constr=True)
+    assert status == "optimal" and iters <= 2
+    assert abs(nllh - start) <= 1e-8 * start
+    tol_nu = 1e-5 if name == "ref_example2_api" else 2e-5
+    assert abs(s.params.phi - case.phi) < 1e-5 and abs(s.params.nu - case.nu) < tol_nu
+    assert np.abs(s._d() - d0).max() < 1e-4 and _tip_spread(s.trees[0]) < 1e-9
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_other_published_annotation_files(name, tmp_path, monkeypatch):
+    """the annotation files those runs wrote, from their published trees (with the re-inserted duplicates) and
+    parameters"""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    from annot_compare import assert_annotations_match
+    from laml_b200.annotate import annotate
+    _, msa, Q, _ = annotation_case()
+    run = RUNS[name]
+    out = tmp_path / "annot.txt"
+    annotate(run["annotation_trees"], msa, Q, {"phi": run["phi"], "nu": run["nu"]}, str(out))
+    ref = open(os.path.join(GOLDEN, run["annotation"])).read()
+    assert_annotations_match(out.read_text(), ref, exact=False)
+    assert out.read_text() == ref

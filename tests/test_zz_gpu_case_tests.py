@@ -42,3 +42,31 @@ def test_published_example2_likelihood(engine):
     ids = case.ids(z["labels"], z["tree_of"])
     np.testing.assert_allclose(out["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * case.enc.n_sites)
     eng.close()
+
+
+@pytest.mark.parametrize("engine", ["lumped", "fullstate"])
+@pytest.mark.parametrize("name", ["ref_example2_api", "ref_example2_fastem", "ref_example2_fastem_nostart"])
+def test_other_published_example2_likelihoods(name, engine):
+    """the likelihoods the other published example2 runs printed (tests/test_published_runs.py)"""
+    runs = load_json("published_runs.json")
+    case, z = load_npz_case(name)
+    with env_override(PMM_ENGINE=engine):
+        eng = make_engine(case)
+    llh = eng.inside(case.d, case.nu, case.phi)
+    assert abs(-llh - runs[name]["nllh"]) <= 1e-9 * runs[name]["nllh"]
+    eng.close()
+
+
+def test_published_ultrametric_optimum_is_a_fixed_point():
+    """MOSEK's ultrametric optimum of the published run_laml_api.py run is a fixed point of the ultrametric EM:
+    E-step on the GPU, pmm_ultrametric_solve on the host (same assertions as tests/test_published_runs.py)"""
+    from laml_b200.solver import GPU_EM_solver
+    case, z = load_npz_case("ref_example2_api")
+    s = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': case.phi, 'nu': case.nu})
+    start = s.negative_llh()
+    d0 = s._d().copy()
+    nllh, iters, status = s.EM_optimization(verbose=-1, ultra_constr=True)
+    assert status == "optimal" and iters <= 2 and abs(nllh - start) <= 1e-8 * start
+    assert abs(s.params.phi - case.phi) < 1e-5 and abs(s.params.nu - case.nu) < 1e-5
+    assert np.abs(s._d() - d0).max() < 1e-4
+    s.close()
