@@ -133,3 +133,21 @@ def test_other_published_annotation_files(name, tmp_path, monkeypatch):
     ref = open(os.path.join(GOLDEN, run["annotation"])).read()
     assert_annotations_match(out.read_text(), ref, exact=False)
     assert out.read_text() == ref
+
+
+def test_published_example1_optimum_under_the_ultrametric_em(monkeypatch):
+    """example1's published run (LAML 0.0.2, ultrametric, MOSEK; nllh 6987.352449704049): its tree is ultrametric to
+    5e-7; the ultrametric EM here from that point finds a slightly better one within the reference's own convergence
+    slack (2e-4 in nllh after two iterations) and moves phi by < 1e-5, nu by < 3e-5, no branch by more than 5e-4"""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    case, z = load_npz_case("ref_example1_optimum")
+    s = solver_mod.GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': case.phi, 'nu': case.nu})
+    assert _tip_spread(s.trees[0]) < 1e-6
+    start = s.negative_llh()
+    assert abs(start - 6987.352449704049) <= 1e-12 * start
+    d0 = s._d().copy()
+    nllh, iters, status = s.EM_optimization(verbose=-1, ultra_constr=True)
+    assert status == "optimal" and iters <= 3
+    assert start - 5e-4 < nllh <= start
+    assert abs(s.params.phi - case.phi) < 1e-5 and abs(s.params.nu - case.nu) < 3e-5
+    assert np.abs(s._d() - d0).max() < 5e-4
