@@ -22,16 +22,22 @@ CASES = {
     2: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),
     3: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),
     6: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),
+    4: ("n64_d0_r1_character_matrix.csv", "n64_d0_priors.csv"),                   # --resolve_search
+    5: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),             # topology search on a polytomous start
+    7: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),
+    9: ("bar10_character_matrix_without_cluster.csv", "bar10_mutation_prior.csv"),   # real data, polytomies
+    10: ("3724_NT_All_dedup_mtx.txt", "3724_NT_All_priors_norm.pkl"),             # real data, 3 724 cells, --ultrametric
 }
 
 
 def parse_output(path):
     text = open(path).read()
-    tree = re.search(r"Newick tree: (.*)", text).group(1).strip()
+    m = re.search(r"Newick tree: (.*)", text) or re.search(r"Newick tree \(s\):\s*\n(.*)", text)
+    tree = m.group(1).strip()
     num = r"([-+0-9.eE]+)"
-    nllh = float(re.search(r"negative-llh: \(?" + num, text).group(1))
-    phi = float(re.search(r"dropout rate: " + num, text).group(1))
-    nu = float(re.search(r"silencing rate: " + num, text).group(1))
+    nllh = float(re.search(r"[Nn]egative-llh: \(?" + num, text).group(1))
+    phi = float(re.search(r"[Dd]ropout rate: " + num, text).group(1))
+    nu = float(re.search(r"[Ss]ilencing rate: " + num, text).group(1))
     return tree, nllh, phi, nu
 
 
@@ -43,7 +49,7 @@ def main():
         msa, _ = sl.read_sequences(os.path.join(d, mtx), filetype="charMtrx", delimiter=",", masked_symbol="?")
         Q = sl.read_priors(os.path.join(d, pri), msa)
         tree, nllh, phi, nu = parse_output(os.path.join(d, "sample_output.txt"))
-        ml = R.ML_solver([tree], {"charMtrx": msa}, {"Q": Q}, {"phi": phi, "nu": nu}).negative_llh()
+        ml = R.ML_solver([tree], {"charMtrx": msa}, {"Q": Q}, {"phi": phi, "nu": nu}).negative_llh() if k != 10 else None      # test10: ML_solver's Python recursion is slow at 2 919 nodes; the stored value is EM_solver's
         ref = G.save_case("ref_case_test%d" % k, [tree], msa, Q, phi, nu, full=False)
         rec["test%d" % k] = dict(source="case_tests/old/test%d/sample_output.txt" % k, fixture="ref_case_test%d" % k,
                                  stored_nllh=nllh, phi=phi, nu=nu, ml_solver_nllh=ml, em_solver_nllh=ref["nllh"])

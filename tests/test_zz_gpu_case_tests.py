@@ -12,7 +12,7 @@ CASES = load_json("case_tests.json")
 
 
 @pytest.mark.parametrize("engine", ["lumped", "fullstate"])
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES, key=lambda s: int(s[4:])))
 def test_case_test_known_answers(name, engine):
     rec = CASES[name]
     case, z = load_npz_case(rec["fixture"])
@@ -25,9 +25,11 @@ def test_case_test_known_answers(name, engine):
     np.testing.assert_allclose(out["S"][ids].T, z["Ssum"], rtol=1e-8, atol=1e-10 * K)
     assert abs(out["Rtilde"] - float(z["Rtilde"])) <= 1e-8 * max(1.0, float(z["Rtilde"]))
     ml = -eng.inside(_em_binarised_to_polytomy(case), case.nu, case.phi)
-    assert abs(ml - rec["ml_solver_nllh"]) <= 1e-9 * rec["ml_solver_nllh"]
+    if rec["ml_solver_nllh"] is not None:
+        assert abs(ml - rec["ml_solver_nllh"]) <= 1e-9 * rec["ml_solver_nllh"]
     stored = rec["stored_nllh"]
-    assert min(abs(ml - stored), abs(-out["llh"] - stored)) <= (1e-9 if name == "test6" else 1e-8) * stored
+    exact = name in ("test5", "test6", "test9", "test10")
+    assert min(abs(ml - stored), abs(-out["llh"] - stored)) <= (1e-9 if exact else 1e-8) * stored
     eng.close()
 
 
