@@ -151,3 +151,25 @@ def test_published_example1_optimum_under_the_ultrametric_em(monkeypatch):
     assert start - 5e-4 < nllh <= start
     assert abs(s.params.phi - case.phi) < 1e-5 and abs(s.params.nu - case.nu) < 3e-5
     assert np.abs(s._d() - d0).max() < 5e-4
+
+
+def test_published_uninformative_sites_case(tmp_path, monkeypatch):
+    """case_tests/test1 (LAML 1.0.0, "testcase with uninformative sites"): three columns, a prior for one of them; the
+    two uninformative columns are dropped (ML_solver.py:47-67).  Published: nllh 3.3033497524754867, phi 0,
+    nu 2.481710016212404e-06, mutation rate 1.1061115018134888, and the annotation file below."""
+    monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
+    from laml_b200.annotate import annotate
+    from laml_b200.tree import read_tree_newick
+    msa = {'a': [0, 0, '?'], 'b': [0, 1, '?'], 'c': [0, 2, '?']}
+    Q = [{1: 0.5, 2: 0.5}]
+    t = read_tree_newick("(((a:0.9909593184497377,b:0.9909593184497377):0.004520341420182489,c:0.9954796598699202):0.004520340130079882);")
+    for nd in t.traverse_preorder():
+        if nd.edge_length is not None:
+            nd.edge_length *= 1.1061115018134888
+    params = {'phi': 0, 'nu': 2.481710016212404e-06}
+    s = solver_mod.GPU_EM_solver([t.newick()], {'charMtrx': msa}, {'Q': Q}, params)
+    assert s.numsites == 1
+    assert abs(s.negative_llh() - 3.3033497524754867) <= 1e-14
+    out = tmp_path / "annot.txt"
+    annotate([t.newick()], msa, Q, params, str(out))
+    assert out.read_text() == "(((a:0,b:1)I2:0,c:1)I1:0)I0;\nI0,0\nI1,0\nc,2\nI2,0\nb,1\na,0\n"
