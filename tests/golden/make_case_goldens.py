@@ -27,6 +27,8 @@ CASES = {
     7: ("n64_d0s32_r1_character_matrix.csv", "n64_d0s32_priors.csv"),
     9: ("bar10_character_matrix_without_cluster.csv", "bar10_mutation_prior.csv"),   # real data, polytomies
     10: ("3724_NT_All_dedup_mtx.txt", "3724_NT_All_priors_norm.pkl"),             # real data, 3 724 cells, --ultrametric
+    "8": ("character_matrix.csv", "prior_k30_r01.csv", "problin_output.txt"),       # 250 cells, topology search
+    "8u": ("character_matrix.csv", "prior_k30_r01.csv", "problin_output_ultr.txt"),  # ... --ultrametric --parallel
 }
 
 
@@ -44,14 +46,16 @@ def parse_output(path):
 def main():
     sl = R.sequence_lib
     rec = {}
-    for k, (mtx, pri) in CASES.items():
-        d = os.path.join(BASE, "test%d" % k)
+    for k, spec in CASES.items():
+        mtx, pri = spec[0], spec[1]
+        output = spec[2] if len(spec) > 2 else "sample_output.txt"
+        d = os.path.join(BASE, "test%s" % str(k).rstrip("u"))
         msa, _ = sl.read_sequences(os.path.join(d, mtx), filetype="charMtrx", delimiter=",", masked_symbol="?")
         Q = sl.read_priors(os.path.join(d, pri), msa)
-        tree, nllh, phi, nu = parse_output(os.path.join(d, "sample_output.txt"))
+        tree, nllh, phi, nu = parse_output(os.path.join(d, output))
         ml = R.ML_solver([tree], {"charMtrx": msa}, {"Q": Q}, {"phi": phi, "nu": nu}).negative_llh() if k != 10 else None      # test10: ML_solver's Python recursion is slow at 2 919 nodes; the stored value is EM_solver's
-        ref = G.save_case("ref_case_test%d" % k, [tree], msa, Q, phi, nu, full=False)
-        rec["test%d" % k] = dict(source="case_tests/old/test%d/sample_output.txt" % k, fixture="ref_case_test%d" % k,
+        ref = G.save_case("ref_case_test%s" % k, [tree], msa, Q, phi, nu, full=False)
+        rec["test%s" % k] = dict(source="case_tests/old/test%s/%s" % (str(k).rstrip("u"), output), fixture="ref_case_test%s" % k,
                                  stored_nllh=nllh, phi=phi, nu=nu, ml_solver_nllh=ml, em_solver_nllh=ref["nllh"])
         print(k, "stored", nllh, "ML_solver", ml, "EM_solver", ref["nllh"])
     json.dump(rec, open(os.path.join(HERE, "case_tests.json"), "w"), indent=1)
