@@ -144,7 +144,9 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "cell*site/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "em_iter_per_s_full_workload": value / (N * spec["n_sites"]),
         "note": "reference is pure Python (cannot travel); this arm is its C restatement oracle/pmm_oracle.c, "
-                "pinned to the reference's golden vectors (tests/test_oracle_golden.py)",
+                "pinned to the reference's golden vectors (tests/test_oracle_golden.py); the Python reference itself "
+                "(EM_solver.Estep, single-threaded) runs 5.6e4 cell*site/s on one core at 1k x 30, 52x slower than one "
+                "thread of this port (measured in the build container, DESIGN.md section 7)",
     }
     print(json.dumps(line), flush=True)
 
