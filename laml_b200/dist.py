@@ -140,6 +140,44 @@ class ShardedEngine:
         return {"nllh": -cur, "d": d_out, "nu": nu_out, "phi": phi_out, "iters": it, "status": "optimal"}
 
 
+    def em_ultrametric(self, problem, d, nu, phi, R, n_cells, free_mask, optimize_nu=True, optimize_phi=True,
+                       conv_eps=1e-8, max_iter=1000, eps_nu=1e-5, eps_s=1e-6):
+        """``EM_solver.EM_optimization`` with ``ultra_constr=True`` (EM_solver.py:461-512) on site shards.
+        The branch-length program under the ultrametric equalities runs on the host
+        (``laml_b200.ultrametric.mstep``), a pure function of the all-reduced statistics, so every rank
+        computes the same lengths and no second exchange is needed: per iteration one E-step +
+        all-reduce, one replicated host M-step, one inside pass + all-reduce for the convergence test
+        (the same engine calls as ``GPU_EM_solver.EM_optimization``).  ``problem`` is the
+        topology-dependent :class:`laml_b200.ultrametric.UltrametricProblem`."""
+        from . import ultrametric as um
+        fm = np.asarray(free_mask, np.uint8)
+        free = fm.astype(bool)
+        d = np.array(d, np.float64, copy=True)
+        self.eng.upload_params(d, nu, phi)
+        self.inside_dev()
+        pre = cur = self.llh()
+        it, H, status, converged = 1, None, "optimal", False
+        while it <= max_iter:
+            est = self.estep(d, nu, phi)
+            d_new, nu, phi, H_new, status_d = um.mstep(problem, est["S"], est["Rtilde"], R, n_cells, self.K_total, fm, d,
+                                                       nu, phi, H_prev=H, optimize_phi=optimize_phi,
+                                                       optimize_nu=optimize_nu, eps_nu=eps_nu, eps_s=eps_s)
+            if status_d == "infeasible":                          # EM_solver.py:425-426, :497-499
+                return {"nllh": -pre, "d": d, "nu": nu, "phi": phi, "iters": it, "status": "d_infeasible"}
+            H = H_new
+            status = "optimal" if status_d == "optimal" else "failed_d"
+            d = np.where(free, d_new, d)
+            self.eng.upload_params(d, nu, phi)
+            self.inside_dev()
+            cur = self.llh()
+            if abs((cur - pre) / pre) < conv_eps:
+                converged = True
+                break
+            pre = cur
+            it += 1
+        return {"nllh": -cur, "d": d, "nu": nu, "phi": phi, "iters": it, "status": status, "converged": converged}
+
+
 def score_nni_sharded(engine, cand_u, cand_k, d, nu, phi, group=None, device=None, **kw):
     """Candidate-sharded NNI scoring (BASELINE config 5): candidate trees are independent units, so
     every rank -- each holding ALL sites of the data set -- scores the slice ``rank::world`` with

@@ -278,36 +278,13 @@ class GPU_EM_solver:
             d_new, nu_new, phi_new = self._engine.mstep(S, Rt, self._R, n_cells, d, nu, phi, fm,
                                                         optimize_nu, optimize_phi, self.dmin, self.dmax, eps_s, eps_nu)
             return d_new, nu_new, phi_new, "optimal"
-        d_new, status_d = self._host_brlen(S, fm, d, nu, eps_nu, eps_s, cache)
-        if status_d == "infeasible":
-            return d, nu, phi, status_d
-        # nu with d fixed at d_new (EM_solver.py:427-433) and phi in closed form (:318-326): scalar
-        # problems on O(n) statistics, solved here because d_new only exists on the host
-        nu_new = _nu_given_d(S, fm, d_new, self.numsites, eps_s) if optimize_nu else nu
-        phi_new = phi
-        if optimize_phi:
-            phi_new = Rt / (self._R + Rt)
-            if abs(phi_new) < 1 / (self.numsites * n_cells):
-                phi_new = 0
-        return d_new, nu_new, phi_new, status_d
-
-    def _host_brlen(self, S, fm, d, nu, eps_nu, eps_s, cache):
-        """argmax of EM_solver.py:351-357 subject to the box and the ultrametric equalities, from the
-        GPU's statistics: node-height re-parametrisation + tree-structured barrier Newton
-        (``laml_b200/ultrametric.py``; exact, O(n) memory).  ``cache`` is the topology-dependent
-        :class:`UltrametricProblem`."""
         from . import ultrametric as um
-        s = np.maximum(S, eps_s)                                     # EM_solver.py:343-346
-        s = s / s.sum(axis=1, keepdims=True) * self.numsites
-        H0 = getattr(self, "_H_prev", None)
-        d_new, H, info = um.solve(cache, s, nu, eps_nu=eps_nu, H0=H0)
-        if d_new is None:
-            return d, "infeasible"
-        self._H_prev = H
-        out = d.copy()
-        free = fm.astype(bool)
-        out[free] = d_new[free]
-        return out, info["status"]
+        d_new, nu_new, phi_new, H, status_d = um.mstep(cache, S, Rt, self._R, n_cells, self.numsites, fm, d, nu, phi,
+                                                       H_prev=getattr(self, "_H_prev", None), optimize_phi=optimize_phi,
+                                                       optimize_nu=optimize_nu, eps_nu=eps_nu, eps_s=eps_s)
+        if status_d != "infeasible":
+            self._H_prev = H
+        return d_new, nu_new, phi_new, status_d
 
     def _ultrametric_problem(self, local_brlen_opt=True):
         """edge kinds for the height re-parametrisation: free / fixed length / counts as zero (polytomy mark),
@@ -502,46 +479,3 @@ class GPU_EM_solver:
             return None, "failed"
         nllh, status = out
         return (None if nllh is None else -nllh), status
-
-
-def _nu_given_d(S, fm, d, numsites, eps_s):
-    """argmax over nu in [0,1] of EM_solver.py:394-399 with d fixed (host, ultrametric path only)."""
-    idx = np.nonzero(fm)[0]
-    s = np.maximum(S[idx], eps_s)
-    s = s / s.sum(axis=1, keepdims=True) * numsites
-    dd = d[idx]
-    lin = float(((s[:, 0] + s[:, 1] + s[:, 3]) * dd).sum())
-    w = s[:, 2] + s[:, 4]
-
-    def grad(x):
-        return float((w * dd / np.expm1(x * dd)).sum()) - lin
-
-    def grad2(x):
-        em = np.expm1(x * dd)
-        return -float((w * dd * dd * (em + 1.0) / (em * em)).sum())
-
-    if grad(1.0) >= 0:
-        return 1.0
-    lo, hi = 0.5, 1.0
-    while grad(lo) <= 0:
-        hi, lo = lo, lo * 0.5
-        if lo < 1e-300:
-            return 0.0
-    # grad is decreasing and convex on (0, 1]: Newton from the left end of the bracket rises monotonically to
-    # the root; the bracket is kept only as a safeguard
-    x = lo
-    for _ in range(100):
-        g = grad(x)
-        if g > 0:
-            lo = x
-        else:
-            hi = x
-        step = -g / grad2(x)
-        nx = x + step
-        if not (lo < nx < hi):
-            nx = 0.5 * (lo + hi)
-        if abs(nx - x) <= 4e-16 * x:
-            x = nx
-            break
-        x = nx
-    return x

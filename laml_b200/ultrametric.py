@@ -250,3 +250,71 @@ def solve_numpy(problem: UltrametricProblem, S, nu, eps_nu=1e-5, H0=None, mu_fin
     d[P.kind == FIXED] = P.fixed_len[P.kind == FIXED]
     d[free] = np.clip(d[free], lo, hi)
     return d, H, {"status": status, "newton_iters": iters, "mu": mu}
+
+
+def nu_given_d(S, fm, d, numsites, eps_s=1e-6):
+    """argmax over nu in [0,1] of EM_solver.py:394-399 with d fixed: a scalar concave program on O(n) sums.
+    ``S`` (n,5) raw statistics; rows are clamped and rescaled as EM_solver.py:343-346."""
+    idx = np.nonzero(fm)[0]
+    s = np.maximum(S[idx], eps_s)
+    s = s / s.sum(axis=1, keepdims=True) * numsites
+    dd = d[idx]
+    lin = float(((s[:, 0] + s[:, 1] + s[:, 3]) * dd).sum())
+    w = s[:, 2] + s[:, 4]
+
+    def grad(x):
+        return float((w * dd / np.expm1(x * dd)).sum()) - lin
+
+    def grad2(x):
+        em = np.expm1(x * dd)
+        return -float((w * dd * dd * (em + 1.0) / (em * em)).sum())
+
+    if grad(1.0) >= 0:
+        return 1.0
+    lo, hi = 0.5, 1.0
+    while grad(lo) <= 0:
+        hi, lo = lo, lo * 0.5
+        if lo < 1e-300:
+            return 0.0
+    # grad is decreasing and convex on (0, 1]: Newton from the left end of the bracket rises monotonically to
+    # the root; the bracket is kept only as a safeguard
+    x = lo
+    for _ in range(100):
+        g = grad(x)
+        if g > 0:
+            lo = x
+        else:
+            hi = x
+        nx = x - g / grad2(x)
+        if not (lo < nx < hi):
+            nx = 0.5 * (lo + hi)
+        if abs(nx - x) <= 4e-16 * x:
+            x = nx
+            break
+        x = nx
+    return x
+
+
+def mstep(problem: UltrametricProblem, S, Rtilde, R, n_cells, numsites, fm, d, nu, phi, H_prev=None, optimize_phi=True,
+          optimize_nu=True, eps_nu=1e-5, eps_s=1e-6):
+    """One M-step under the ultrametric constraint from all-reduced statistics (``EM_solver.Mstep`` with
+    ``ultra_constr_cache``, EM_solver.py:307-459): branch lengths by :func:`solve`, then nu with the new lengths
+    fixed (:427-433) and phi in closed form (:318-326).  Pure function of its arguments -- every rank of a
+    site-sharded run computes the same result from the same reduced statistics.
+    Returns ``(d_new, nu_new, phi_new, H, status)`` with status "optimal" / "failed_d" / "infeasible"."""
+    S = np.asarray(S, np.float64)
+    s = np.maximum(S, eps_s)                                         # EM_solver.py:343-346
+    s = s / s.sum(axis=1, keepdims=True) * numsites
+    d_sol, H, info = solve(problem, s, nu, eps_nu=eps_nu, H0=H_prev)
+    if d_sol is None:
+        return d, nu, phi, H_prev, "infeasible"
+    free = np.asarray(fm).astype(bool)
+    d_new = np.array(d, np.float64, copy=True)
+    d_new[free] = d_sol[free]
+    nu_new = nu_given_d(S, fm, d_new, numsites, eps_s) if optimize_nu else nu
+    phi_new = phi
+    if optimize_phi:
+        phi_new = Rtilde / (R + Rtilde)
+        if abs(phi_new) < 1 / (numsites * n_cells):
+            phi_new = 0
+    return d_new, nu_new, phi_new, H, info["status"]

@@ -43,6 +43,10 @@ class OracleBackedEngine:
         self.stats[5 * self.n_nodes] = out["Rtilde"]
         self.stats[5 * self.n_nodes + 1] = out["llh"]
 
+    def inside_dev(self):
+        out = self.orc.inside(self.d, self.nu, self.phi)
+        self.stats[5 * self.n_nodes + 1] = out["llh"]
+
     def mstep_dev(self, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
                   eps_s=1e-6, eps_nu=1e-5):
         from oracle.pmm_oracle import lib
@@ -96,6 +100,57 @@ def test_sharded_matches_unsharded():
     assert abs(nllh - ref_em["nllh"]) <= 1e-9 * ref_em["nllh"]
     np.testing.assert_allclose(d, ref_em["d"], rtol=1e-9, atol=1e-11)
     assert abs(nu - ref_em["nu"]) < 1e-10 and abs(phi - ref_em["phi"]) < 1e-12
+
+
+def _ultra_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laml_b200 import ultrametric as um
+    from laml_b200.dist import ShardedEngine, partition_sites
+    from laml_b200.synth import make_workload
+    w = make_workload(48, 20, 2, 10, 0.15, 0.1, seed=33)
+    lo, hi = partition_sites(w.qptr, world)[rank]
+    qptr = (w.qptr[lo:hi + 1] - w.qptr[lo]).astype(np.int32)
+    qval = w.qval[w.qptr[lo]:w.qptr[hi]]
+    eng = OracleBackedEngine(w.forest, w.codes[:, lo:hi], qptr, qval, 48)
+    sh = ShardedEngine(eng, 20, stats_tensor=eng.stats)
+    n = w.forest.n_nodes
+    prob = um.UltrametricProblem(w.forest.parent, np.zeros(n, np.int8), np.zeros(n), 0.005, 10.0)
+    R = float((w.codes != -1).sum())
+    fm = np.ones(n, np.uint8)
+    em = sh.em_ultrametric(prob, np.maximum(w.d, 0.01), 0.15, 0.1, R, 48, fm, max_iter=8)
+    ret[rank] = (em["nllh"], em["nu"], em["phi"], em["d"].copy(), em["iters"], em["status"])
+    dist.destroy_process_group()
+
+
+def test_sharded_ultrametric_em_matches_unsharded():
+    """site-sharded EM under the ultrametric constraint: two ranks end on the same lengths / nu / phi as one rank
+    holding all sites (the host M-step is a pure function of the all-reduced statistics), and the lengths are
+    ultrametric"""
+    mgr = mp.Manager()
+    ret2, ret1 = mgr.dict(), mgr.dict()
+    port = 29400 + os.getpid() % 90
+    mp.spawn(_ultra_worker, args=(2, port, ret2), nprocs=2, join=True)
+    mp.spawn(_ultra_worker, args=(1, port + 100, ret1), nprocs=1, join=True)
+    for a, b in ((ret2[0], ret2[1]), (ret2[0], ret1[0])):
+        assert a[4] == b[4] and a[5] == b[5]
+        assert abs(a[0] - b[0]) <= 1e-9 * abs(b[0])
+        np.testing.assert_allclose(a[3], b[3], rtol=1e-7, atol=1e-9)
+        assert abs(a[1] - b[1]) < 1e-8 and abs(a[2] - b[2]) < 1e-12
+    # identical on the two ranks of one run, to the bit: both ran the same M-step on the same reduced statistics
+    np.testing.assert_array_equal(ret2[0][3], ret2[1][3])
+    from laml_b200.synth import make_workload
+    w = make_workload(48, 20, 2, 10, 0.15, 0.1, seed=33)
+    d, parent = ret2[0][3], w.forest.parent
+    depth = []
+    for leaf in range(w.forest.n_leaves):
+        x, t = leaf, 0.0
+        while parent[x] >= 0:
+            t += d[x]
+            x = parent[x]
+        depth.append(t)
+    assert max(depth) - min(depth) < 1e-6
 
 
 class _FakeNniEngine:
