@@ -152,6 +152,35 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
                         int32_t *out_nodes);
 
 /*
+ * The same under the ultrametric constraint -- strategy['ultra_constr'] of Topology_search.apply_nni, the
+ * runner's default (runner.py:91,287): every M-step of a candidate's local EM solves EM_solver.py:351-357 for the
+ * five free branches subject to the box and the root-to-leaf equalities (EM_solver.py:53-89,359-361).  With the
+ * rest of the tree fixed a candidate has two unknown node heights (three when v is the root of the only tree);
+ * the kernel's M-step is pmm_ultrametric_solve specialised to that five-edge tree
+ * (laml_b200/csrc/pmm_nni_ultra.cuh).  d[n] must be ultrametric already (leaf paths below every node equal to
+ * 1e-9, trees of a forest equally high): otherwise the call fails.  A candidate whose constrained M-step is
+ * infeasible or fails (the reference's "d_infeasible" / "failed_d" -> its retry with every branch free,
+ * Topology_search.py:301-306) gets out_nllh = NaN and out_iters = -1 and is left to the caller.
+ * Lumped-state engine only.
+ */
+int pmm_score_nni_batch_ultra(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k,
+                              const double *d, double nu, double phi, double dmin, double dmax, double conv_eps,
+                              int32_t max_iter, double *out_nllh, double *out_d5, int32_t *out_iters,
+                              int32_t *out_nodes);
+
+/*
+ * Test hook, pure host code (works without a GPU): the host instance of the constrained M-step the kernel behind
+ * pmm_score_nni_batch_ultra runs per candidate and EM iteration.  S25: clamped / rescaled statistics of the
+ * branches (v, u, moved child, other child, former sibling), [5][5]; hA / hB / hC: heights of the other child,
+ * the former sibling and the moved child; hTop: height of v's parent (ignored when top_free).  H3 (heights of u,
+ * v and the top): previous iteration's on input when warm, the optimum on output; d5: the five lengths.
+ * Returns 0 = optimal, 1 = infeasible, 2 = failed, -1 = bad arguments.
+ */
+int pmm_debug_nni_ultra_mstep(const double *S25, double nu, double eps_nu, double lo, double hi, double hA,
+                              double hB, double hC, double hTop, int32_t top_free, int32_t warm, double *H3,
+                              double *d5, int32_t *newton_iters);
+
+/*
  * Runtime options.  "slices" (1..4, default 2 or PMM_SLICES): the sites of a handle are processed as this many
  * slices on separate CUDA streams so that the latency-bound top-of-the-tree launches of one slice overlap the
  * big launch of another; with 1 the passes run back to back on the handle's stream and pmm_last_timing can

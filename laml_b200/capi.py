@@ -21,8 +21,22 @@ SYMBOLS = [
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
-    "pmm_ultrametric_solve",
+    "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep",
 ]
+
+
+def nni_ultra_mstep(S25, nu, lo, hi, hA, hB, hC, hTop, top_free=False, H=None, eps_nu=1e-5):
+    """``pmm_debug_nni_ultra_mstep`` (host instance of the batch kernel's constrained M-step; no GPU needed):
+    ``(d5, H3, status, newton_iters)``; ``H`` = the previous heights (warm start) or None."""
+    L = load_library()
+    S = np.ascontiguousarray(S25, np.float64).reshape(25)
+    H3 = np.zeros(3) if H is None else np.array(H, np.float64, copy=True)
+    d5 = np.zeros(5)
+    it = C.c_int32()
+    rc = L.pmm_debug_nni_ultra_mstep(S.ctypes.data, float(nu), float(eps_nu), float(lo), float(hi), float(hA), float(hB),
+                                     float(hC), float(hTop), int(bool(top_free)), int(H is not None), H3.ctypes.data,
+                                     d5.ctypes.data, C.byref(it))
+    return d5, H3, rc, it.value
 
 
 class PMMError(RuntimeError):
@@ -81,6 +95,8 @@ def load_library():
     L.pmm_stats_len.restype = i64
     L.pmm_mstep_dev.argtypes = [vp, f64, i32, vp, i32, i32, f64, f64, f64, f64]
     L.pmm_score_nni_batch.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
+    L.pmm_score_nni_batch_ultra.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
+    L.pmm_debug_nni_ultra_mstep.argtypes = [vp, f64, f64, f64, f64, f64, f64, f64, f64, i32, i32, vp, vp, P(i32)]
     L.pmm_sync.argtypes = [vp]
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
@@ -239,15 +255,19 @@ class Engine:
         return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
                 "status": "optimal" if status.value == 0 else "failed"}
 
-    def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000):
-        """Score NNI candidates (``Topology_search.apply_nni``, one local 5-branch EM each) in one call."""
+    def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000, ultra=False):
+        """Score NNI candidates (``Topology_search.apply_nni``, one local 5-branch EM each) in one call.
+        ``ultra=True``: the local M-steps under the ultrametric constraint (``pmm_score_nni_batch_ultra``);
+        ``d`` must be ultrametric; candidates the constraint leaves no room for come back with ``nllh`` NaN
+        and ``iters`` -1."""
         cu, ck = _i32(cand_u), _i32(cand_k)
         m = int(cu.shape[0])
         d = _f64(d)
         nllh = np.empty(m); d5 = np.empty((m, 5)); iters = np.empty(m, np.int32); nodes = np.empty((m, 5), np.int32)
-        self._ck(self._L.pmm_score_nni_batch(self._h, m, cu.ctypes.data, ck.ctypes.data, d.ctypes.data, float(nu), float(phi),
-                                             dmin, dmax, conv_eps, int(max_iter), nllh.ctypes.data, d5.ctypes.data,
-                                             iters.ctypes.data, nodes.ctypes.data))
+        fn = self._L.pmm_score_nni_batch_ultra if ultra else self._L.pmm_score_nni_batch
+        self._ck(fn(self._h, m, cu.ctypes.data, ck.ctypes.data, d.ctypes.data, float(nu), float(phi),
+                    dmin, dmax, conv_eps, int(max_iter), nllh.ctypes.data, d5.ctypes.data,
+                    iters.ctypes.data, nodes.ctypes.data))
         return {"nllh": nllh, "d5": d5, "iters": iters, "nodes": nodes}
 
     # -- device-resident entry points ----------------------------------------

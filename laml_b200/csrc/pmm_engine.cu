@@ -1217,19 +1217,24 @@ int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *fre
 }
 
 
-int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k, const double *d, double nu,
-                        double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh, double *out_d5,
-                        int32_t *out_iters, int32_t *out_nodes) {
+}  // extern "C"
+
+// ultra: every candidate's local M-step under the ultrametric equalities (pmm_nni_ultra.cuh); needs lengths that
+// are ultrametric already, because everything outside the five free branches is a constant of the candidate
+static int score_nni_impl(pmm_handle *h, bool ultra, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k, const double *d,
+                          double nu, double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh,
+                          double *out_d5, int32_t *out_iters, int32_t *out_nodes) {
     if (n_cand <= 0) return 0;
     if (pmm_upload_params(h, d, nu, phi)) return 1;
     const bool lumped_nni = h->engine == 0 && !env_int("PMM_NNI_ROWS", 0);
+    if (ultra && !lumped_nni) return fail(h, "pmm_score_nni_batch_ultra runs on the lumped-state engine only");
     if (lumped_nni && h->lKc < h->K) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk)");
     if (!lumped_nni && ensure_fullstate(h)) return 1;       // PMM_NNI_ROWS=1 / PMM_ENGINE=fullstate: cached full-state rows (pmm_nni.cuh)
     if (!lumped_nni && h->chunks.size() != 1) return fail(h, "pmm_score_nni_batch needs all sites resident (1 site chunk, have %zu)", h->chunks.size());
     const int N = h->n_leaves, n = h->n;
     std::vector<int> root_index(n, 0);
+    std::vector<int> order; order.reserve(n);                    // parents before children
     {   // root index per node (host copy of the tree)
-        std::vector<int> order; order.reserve(n);
         int nr = 0;
         for (int v = 0; v < n; v++) if (h->parent[v] < 0) { root_index[v] = nr++; order.push_back(v); }
         for (size_t i = 0; i < order.size(); i++) {
@@ -1237,6 +1242,32 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
             if (h->left[v] >= 0) for (int c : {h->left[v], h->right[v]}) { root_index[c] = root_index[v]; order.push_back(c); }
         }
     }
+    // heights above the leaves (ultra): longest and shortest leaf path below every node must agree
+    std::vector<double> height;
+    double super_height = 0.0;
+    if (ultra) {
+        const double tol = 1e-9;
+        std::vector<double> hmin(n, 0.0);
+        height.assign(n, 0.0);
+        for (size_t i = order.size(); i-- > 0;) {
+            const int v = order[i];
+            if (h->left[v] < 0) continue;
+            const int a = h->left[v], b = h->right[v];
+            height[v] = std::fmax(height[a] + d[a], height[b] + d[b]);
+            hmin[v] = std::fmin(hmin[a] + d[a], hmin[b] + d[b]);
+            if (!(height[v] - hmin[v] <= tol))
+                return fail(h, "pmm_score_nni_batch_ultra: the current lengths are not ultrametric (node %d: leaf paths differ by %.3g)",
+                            v, height[v] - hmin[v]);
+        }
+        double lo_s = INFINITY;
+        for (int v = 0; v < n; v++) if (h->parent[v] < 0) {
+            super_height = std::fmax(super_height, height[v] + d[v]);
+            lo_s = std::fmin(lo_s, height[v] + d[v]);
+        }
+        if (h->n_roots > 1 && !(super_height - lo_s <= tol))
+            return fail(h, "pmm_score_nni_batch_ultra: the trees of the forest are not equally high (%.3g)", super_height - lo_s);
+    }
+    std::vector<NniUltra> ultras(ultra ? n_cand : 0);
     std::vector<NniCand> cands(n_cand);
     std::vector<NniState> st(n_cand);
     for (int i = 0; i < n_cand; i++) {
@@ -1257,6 +1288,14 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         z.llh_prev = z.llh_cur = 0.0; z.iters = 0; z.done = 0;
         st[i] = z;
         if (out_nodes) { int32_t *o = out_nodes + (size_t)5 * i; o[0] = v; o[1] = u; o[2] = ck; o[3] = co; o[4] = w; }
+        if (ultra) {
+            NniUltra q;
+            q.hA = height[co]; q.hB = height[w]; q.hC = height[ck];
+            q.top_free = (c.g < 0 && h->n_roots == 1) ? 1 : 0;
+            q.hTop = (c.g >= 0) ? height[c.g] : super_height;     // a root of a forest hangs from the common top
+            q.pad = 0;
+            ultras[i] = q;
+        }
     }
     if (lumped_nni) {
         // ---- lumped records: one E-step that stores every out-record, then ONE launch, one CTA per candidate
@@ -1266,12 +1305,15 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         if (rc) return 1;
         double llh_total = 0.0;
         CK(cudaMemcpyAsync(&llh_total, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        NniCand *d_c = nullptr; NniState *d_s = nullptr; double *d_rsum = nullptr;
-        auto cleanup = [&]() { dfree(d_c); dfree(d_s); dfree(d_rsum); };
+        NniCand *d_c = nullptr; NniState *d_s = nullptr; double *d_rsum = nullptr; NniUltra *d_u = nullptr;
+        auto cleanup = [&]() { dfree(d_c); dfree(d_s); dfree(d_rsum); dfree(d_u); };
         const size_t keep = h->device_bytes;
-        if (dalloc(h, &d_c, n_cand) || dalloc(h, &d_s, n_cand) || dalloc(h, &d_rsum, h->n_roots)) { cleanup(); h->device_bytes = keep; return 1; }
+        if (dalloc(h, &d_c, n_cand) || dalloc(h, &d_s, n_cand) || dalloc(h, &d_rsum, h->n_roots) || (ultra && dalloc(h, &d_u, n_cand))) {
+            cleanup(); h->device_bytes = keep; return 1;
+        }
         h->device_bytes = keep;     // scratch of this call only
         cudaError_t e = cudaMemcpyAsync(d_c, cands.data(), sizeof(NniCand) * n_cand, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess && ultra) e = cudaMemcpyAsync(d_u, ultras.data(), sizeof(NniUltra) * n_cand, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, st.data(), sizeof(NniState) * n_cand, cudaMemcpyHostToDevice, h->stream);
         for (int r = 0; r < h->n_roots && e == cudaSuccess; r++)
             pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Lroot_llh + (size_t)r * h->K, h->K, d_rsum + r, 0);
@@ -1279,8 +1321,12 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         if (e == cudaSuccess) {
             const LParams P = make_lparams(h, 0, false);
             const int K_total = h->K_total > 0 ? h->K_total : h->K;
-            pmm_nni_lumped<<<(unsigned)n_cand, NNIL_THREADS, 0, h->stream>>>(P, d_c, d_s, d_rsum, llh_total, K_total, dmin, dmax, 1e-6, 1e-5,
-                                                                            conv_eps, max_iter);
+            if (ultra)
+                pmm_nni_lumped<true><<<(unsigned)n_cand, NNIL_THREADS, 0, h->stream>>>(P, d_c, d_s, d_rsum, llh_total, K_total, dmin, dmax, 1e-6,
+                                                                                      1e-5, conv_eps, max_iter, d_u);
+            else
+                pmm_nni_lumped<false><<<(unsigned)n_cand, NNIL_THREADS, 0, h->stream>>>(P, d_c, d_s, d_rsum, llh_total, K_total, dmin, dmax, 1e-6,
+                                                                                       1e-5, conv_eps, max_iter, nullptr);
             h->launches += 1 + h->n_roots;
             e = cudaGetLastError();
         }
@@ -1289,8 +1335,9 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         cleanup();
         if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(h, "pmm_score_nni_batch: %s", cudaGetErrorString(e)); }
         for (int i = 0; i < n_cand; i++) {
-            if (out_nllh) out_nllh[i] = -st[i].llh_cur;
-            if (out_iters) out_iters[i] = st[i].iters;
+            const bool bad = st[i].done == 2;               // constrained M-step infeasible / failed: no score
+            if (out_nllh) out_nllh[i] = bad ? NAN : -st[i].llh_cur;
+            if (out_iters) out_iters[i] = bad ? -1 : st[i].iters;
             if (out_d5) for (int b = 0; b < 5; b++) out_d5[(size_t)5 * i + b] = st[i].d[b];
         }
         return 0;
@@ -1340,6 +1387,32 @@ int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, co
         if (out_d5) for (int b = 0; b < 5; b++) out_d5[(size_t)5 * i + b] = st[i].d[b];
     }
     return 0;
+}
+
+extern "C" {
+
+int pmm_score_nni_batch(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k, const double *d, double nu,
+                        double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh, double *out_d5,
+                        int32_t *out_iters, int32_t *out_nodes) {
+    return score_nni_impl(h, false, n_cand, cand_u, cand_k, d, nu, phi, dmin, dmax, conv_eps, max_iter, out_nllh, out_d5, out_iters, out_nodes);
+}
+
+int pmm_score_nni_batch_ultra(pmm_handle *h, int32_t n_cand, const int32_t *cand_u, const int32_t *cand_k, const double *d, double nu,
+                              double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh,
+                              double *out_d5, int32_t *out_iters, int32_t *out_nodes) {
+    return score_nni_impl(h, true, n_cand, cand_u, cand_k, d, nu, phi, dmin, dmax, conv_eps, max_iter, out_nllh, out_d5, out_iters, out_nodes);
+}
+
+// host instance of the batch kernel's constrained M-step (pmm_nni_ultra.cuh), for tests on machines without a GPU
+int pmm_debug_nni_ultra_mstep(const double *S25, double nu, double eps_nu, double lo, double hi, double hA, double hB, double hC,
+                              double hTop, int32_t top_free, int32_t warm, double *H3, double *d5, int32_t *newton_iters) {
+    if (!S25 || !H3 || !d5) return -1;
+    NniUltra c;
+    c.hA = hA; c.hB = hB; c.hC = hC; c.hTop = hTop; c.top_free = top_free; c.pad = 0;
+    int it = 0;
+    const int rc = ultra2_solve(c, S25, nu, eps_nu, lo, hi, warm != 0, H3, d5, &it);
+    if (newton_iters) *newton_iters = it;
+    return rc;
 }
 
 int pmm_get_info(const pmm_handle *h, pmm_info *info) {

@@ -14,8 +14,15 @@
 #pragma once
 #include "pmm_lumped.cuh"
 #include "pmm_nni.cuh"
+#include "pmm_nni_ultra.cuh"
 
 namespace pmm {
+
+// out of line: the barrier Newton loop must not compete for registers with the site loop of the kernel
+__device__ __noinline__ int ultra2_solve_dev(const NniUltra *c, const double *S, double nu, double eps_nu, double lo, double hi,
+                                             bool warm, double *H, double *d5) {
+    return ultra2_solve(*c, S, nu, eps_nu, lo, hi, warm, H, d5, nullptr);
+}
 
 constexpr int NNIL_THREADS = 128;
 
@@ -33,10 +40,14 @@ __device__ __forceinline__ Opd merge_children(const Child &v, const Child &w) {
     return r;
 }
 
+// ULTRA: the M-step of the five branches under the ultrametric equalities (pmm_nni_ultra.cuh) instead of five
+// independent 1-D problems; `ultra` holds the fixed heights around each candidate.  A candidate whose M-step is
+// infeasible (or fails) ends with done = 2 and is left to the caller.
+template <bool ULTRA>
 __global__ void __launch_bounds__(NNIL_THREADS, 3) pmm_nni_lumped(LParams P, const NniCand *__restrict__ cands, NniState *__restrict__ state,
                                                                 const double *__restrict__ root_llh_sum, double llh_total, int K_total,
                                                                 double dmin, double dmax, double eps_s, double eps_nu, double conv_eps,
-                                                                int max_iter) {
+                                                                int max_iter, const NniUltra *__restrict__ ultra) {
     __shared__ double s_d[5];
     __shared__ double4 s_bc[5];
     __shared__ double s_red[NNIL_THREADS / 32][26];
@@ -44,6 +55,7 @@ __global__ void __launch_bounds__(NNIL_THREADS, 3) pmm_nni_lumped(LParams P, con
     __shared__ double s_end[4];
     __shared__ double4 s_lut[4];
     __shared__ int s_done;
+    __shared__ double s_S[ULTRA ? 25 : 1], s_H[3];
     const int ci = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const NniCand cd = cands[ci];
     NniState st = state[ci];
@@ -155,20 +167,42 @@ __global__ void __launch_bounds__(NNIL_THREADS, 3) pmm_nni_lumped(LParams P, con
         }
         __syncthreads();
         if (s_done) break;
-        if (tid < 5) {
-            double x[5], tot = 0.0;
+        if (ULTRA) {
+            if (tid < 5) {                                  // statistics clamp / rescale, EM_solver.py:343-346
+                double tot = 0.0;
 #pragma unroll
-            for (int k = 0; k < 5; k++) { x[k] = fmax(s_tot[tid * 5 + k], eps_s); tot += x[k]; }
+                for (int k = 0; k < 5; k++) { s_S[tid * 5 + k] = fmax(s_tot[tid * 5 + k], eps_s); tot += s_S[tid * 5 + k]; }
 #pragma unroll
-            for (int k = 0; k < 5; k++) x[k] = x[k] / tot * (double)K_total;
-            s_d[tid] = mstep_branch_length(x, nu, use_nu, dmin, dmax, s_d[tid], s_end);
+                for (int k = 0; k < 5; k++) s_S[tid * 5 + k] = s_S[tid * 5 + k] / tot * (double)K_total;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double d5[5];
+                const int rc = ultra2_solve_dev(ultra + ci, s_S, nu, eps_nu, dmin, dmax, st.iters > 1, s_H, d5);   // first M-step cold
+                if (rc != 0) s_done = 2;
+                else {
+#pragma unroll
+                    for (int b = 0; b < 5; b++) s_d[b] = d5[b];
+                }
+            }
+            __syncthreads();
+            if (s_done) break;
+        } else {
+            if (tid < 5) {
+                double x[5], tot = 0.0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { x[k] = fmax(s_tot[tid * 5 + k], eps_s); tot += x[k]; }
+#pragma unroll
+                for (int k = 0; k < 5; k++) x[k] = x[k] / tot * (double)K_total;
+                s_d[tid] = mstep_branch_length(x, nu, use_nu, dmin, dmax, s_d[tid], s_end);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < 5; b++) st.d[b] = s_d[b];
-        st.done = 1;
+        st.done = s_done;
         state[ci] = st;
     }
 }

@@ -1,0 +1,153 @@
+// pmm_nni_ultra.cuh -- the local M-step of an NNI candidate under the ultrametric constraint.
+//
+// Reference behaviour: Topology_search.apply_nni with strategy['ultra_constr'] (the runner's default,
+// runner.py:91,287) frees the five branches around the move (Topology_search.py:259) and every M-step of the
+// candidate's EM solves EM_solver.py:351-357 subject to the box AND the root-to-leaf equalities
+// (EM_solver.py:53-89,359-361; cvxpy -> MOSEK).  With everything else fixed the heights of the three subtrees
+// below the move (hA, hB, hC) and of v's parent (hTop) are constants, so in the height parametrisation of
+// pmm_ultrametric.cpp the candidate has TWO unknowns, the heights of u' and v':
+//     d_v = hTop - Hv   d_u = Hv - Hu   d_C = Hv - hC   d_A = Hu - hA   d_B = Hu - hB        (order of NniState.d)
+// (when v is the root of the only tree its branch hangs from nothing: d_v is a third, separable unknown).
+// ultra2_solve is pmm_ultrametric_solve specialised to this five-edge tree, statement by statement: same
+// interior point and margin, same warm start, same barrier schedule, step rule, line search and stopping
+// tests -- so a candidate scored in the batch kernel walks the same EM trajectory as one scored by the
+// host M-step on the whole tree.  Plain fp64 arithmetic, __host__ __device__: the host instance is exported as
+// pmm_debug_nni_ultra_mstep and tested against pmm_ultrametric_solve on CPU (tests/test_nni_ultra_host.py).
+#pragma once
+#include <math.h>
+
+#ifndef PMM_HD
+#ifdef __CUDACC__
+#define PMM_HD __host__ __device__ __forceinline__
+#else
+#define PMM_HD inline
+#endif
+#endif
+
+namespace pmm {
+
+struct NniUltra { double hA, hB, hC, hTop; int top_free, pad; };
+
+// per-edge objective pieces: k = (nu+1) S0 + nu (S1+S3), S1, S24 = S2 + S4
+struct Ultra2Stats { double k[5], S1[5], S24[5]; double nu; bool use_nu; };
+
+PMM_HD void ultra2_f(const Ultra2Stats &T, int e, double x, double &val, double &g, double &h) {
+    const double em = expm1(x);
+    val = -T.k[e] * x + T.S1[e] * log(-expm1(-x));
+    g = -T.k[e] + T.S1[e] / em;
+    h = -T.S1[e] * (em + 1.0) / (em * em);
+    if (T.use_nu) {
+        const double emn = expm1(T.nu * x);
+        val += T.S24[e] * log(-expm1(-T.nu * x));
+        g += T.nu * T.S24[e] / emn;
+        h -= T.nu * T.nu * T.S24[e] * (emn + 1.0) / (emn * emn);
+    }
+}
+
+// edge lengths (v, u, C, A, B) of heights H = (Hu, Hv, Ht)
+PMM_HD void ultra2_edges(const NniUltra &c, const double *H, double *x) {
+    x[0] = H[2] - H[1]; x[1] = H[1] - H[0]; x[2] = H[1] - c.hC; x[3] = H[0] - c.hA; x[4] = H[0] - c.hB;
+}
+
+PMM_HD double ultra2_objective(const NniUltra &c, const Ultra2Stats &T, const double *H, double mu, double lo, double hi) {
+    double x[5], s = 0.0, b = 0.0;
+    ultra2_edges(c, H, x);
+    for (int e = 0; e < 5; e++) {
+        if (x[e] <= lo || x[e] >= hi) return -INFINITY;
+        double val, g, h;
+        ultra2_f(T, e, x[e], val, g, h);
+        s += val;
+        b += log(x[e] - lo) + log(hi - x[e]);
+    }
+    return s + mu * b;
+}
+
+// returns 0 = optimal, 1 = infeasible, 2 = failed (non-finite slope).  S: clamped / rescaled statistics of the
+// five branches, [5][5] branch-major.  H (Hu, Hv, Ht): in = previous iteration's heights when `warm`, out = the
+// optimum; d5 = the five lengths.
+PMM_HD int ultra2_solve(const NniUltra &c, const double *S, double nu, double eps_nu, double lo, double hi, bool warm,
+                        double *H, double *d5, int *newton_iters, double mu_final = 1e-11, double warm_theta = 1e-6,
+                        double warm_mu = 1e-9) {
+    Ultra2Stats T;
+    T.nu = nu; T.use_nu = nu > eps_nu;
+    for (int e = 0; e < 5; e++) {
+        const double *s = S + 5 * e;
+        T.k[e] = (nu + 1.0) * s[0] + nu * (s[1] + s[3]);
+        T.S1[e] = s[1];
+        T.S24[e] = s[2] + s[4];
+    }
+    // interior point: every parent as low as its children allow, plus the margin (interior_heights)
+    const double margin = fmax(1e-3, 0.5 * lo);
+    double Hint[3];
+    Hint[0] = fmax(c.hA, c.hB) + lo + margin;
+    Hint[1] = fmax(Hint[0], c.hC) + lo + margin;
+    Hint[2] = c.top_free ? Hint[1] + lo + margin : c.hTop;
+    // a fixed top that the interior point would have to lift is infeasible: the lift propagates to a leaf
+    if (!c.top_free && Hint[1] + lo + margin > c.hTop) { if (newton_iters) *newton_iters = 0; return 1; }
+    double Hc[3], Hn[3], x[5];
+    if (warm) {
+        ultra2_edges(c, H, x);
+        for (int e = 0; e < 5; e++) if (!(x[e] >= lo - 1e-12 && x[e] <= hi + 1e-12)) warm = false;
+    }
+    for (int i = 0; i < 3; i++) Hc[i] = warm ? (1.0 - warm_theta) * H[i] + warm_theta * Hint[i] : Hint[i];
+    if (!c.top_free) Hc[2] = c.hTop;
+    ultra2_edges(c, Hc, x);
+    int iters = 0, status = 0;
+    if (newton_iters) *newton_iters = 0;
+    for (int e = 0; e < 5; e++) if (!(x[e] > lo && x[e] < hi)) return 1;
+    const double n_free = 5.0;
+    double mu = warm ? warm_mu : 1.0;
+    for (;;) {
+        for (int it = 0; it < 60; it++) {
+            double g[5], w[5];
+            ultra2_edges(c, Hc, x);
+            for (int e = 0; e < 5; e++) {
+                double val, ge, he;
+                ultra2_f(T, e, x[e], val, ge, he);
+                g[e] = ge + mu * (1.0 / (x[e] - lo) - 1.0 / (hi - x[e]));
+                w[e] = he - mu * (1.0 / ((x[e] - lo) * (x[e] - lo)) + 1.0 / ((hi - x[e]) * (hi - x[e])));
+            }
+            // Newton direction in (Hu, Hv[, Ht]).  A free top is separable: its edge drops out of the (u, v) system
+            const double g0 = c.top_free ? 0.0 : g[0], w0 = c.top_free ? 0.0 : w[0];
+            const double gu = -g[1] + g[3] + g[4], gv = -g0 + g[1] + g[2];
+            const double a11 = w[1] + w[3] + w[4], a22 = w0 + w[1] + w[2], a12 = -w[1];
+            const double det = a11 * a22 - a12 * a12;
+            double dl[3];
+            dl[0] = -(a22 * gu - a12 * gv) / det;
+            dl[1] = -(a11 * gv - a12 * gu) / det;
+            dl[2] = c.top_free ? dl[1] - g[0] / w[0] : 0.0;
+            double dx[5];
+            dx[0] = dl[2] - dl[1]; dx[1] = dl[1] - dl[0]; dx[2] = dl[1]; dx[3] = dl[0]; dx[4] = dl[0];
+            double slope = 0.0;
+            for (int e = 0; e < 5; e++) slope += g[e] * dx[e];
+            iters++;
+            if (!isfinite(slope)) { status = 2; break; }
+            if (slope <= 1e-13 * n_free * fmax(mu, 1e-12) + 1e-15) break;
+            double tmax = INFINITY;
+            for (int e = 0; e < 5; e++) {
+                if (dx[e] < 0) tmax = fmin(tmax, (x[e] - lo) / (-dx[e]));
+                else if (dx[e] > 0) tmax = fmin(tmax, (hi - x[e]) / dx[e]);
+            }
+            double t = fmin(1.0, 0.99 * tmax);
+            const double f0 = ultra2_objective(c, T, Hc, mu, lo, hi);
+            bool found = false;
+            while (t > 1e-14) {
+                for (int i = 0; i < 3; i++) Hn[i] = Hc[i] + t * dl[i];
+                if (ultra2_objective(c, T, Hn, mu, lo, hi) >= f0 + 1e-4 * t * slope) { found = true; break; }
+                t *= 0.5;
+            }
+            if (!found) break;
+            for (int i = 0; i < 3; i++) Hc[i] = Hn[i];
+            if (t * slope < 1e-14 * n_free) break;
+        }
+        if (status != 0 || mu <= mu_final) break;
+        mu = fmax(mu * 0.1, mu_final);
+    }
+    ultra2_edges(c, Hc, x);
+    for (int e = 0; e < 5; e++) d5[e] = fmin(fmax(x[e], lo), hi);
+    for (int i = 0; i < 3; i++) H[i] = Hc[i];
+    if (newton_iters) *newton_iters = iters;
+    return status;
+}
+
+}  // namespace pmm
