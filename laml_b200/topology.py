@@ -70,8 +70,23 @@ def start_lengths(solver: GPU_EM_solver) -> np.ndarray:
     return np.maximum(solver._d(), 2 * solver.dmin)
 
 
+def is_ultrametric(forest, d, tol: float = 1e-9) -> bool:
+    """leaf paths below every node equal to ``tol`` and all trees equally high: what ``pmm_score_nni_batch_ultra``
+    requires of the current lengths (everything outside a candidate's five branches is a constant of its problem)"""
+    n = forest.n_nodes
+    parent = np.asarray(forest.parent)
+    depth = np.zeros(n)                                            # root-to-node path including the root branch
+    order = [int(r) for r in np.nonzero(parent < 0)[0]]
+    for v in order:                                                # parents before children
+        depth[v] = d[v] + (depth[parent[v]] if parent[v] >= 0 else 0.0)
+        if forest.left[v] >= 0:
+            order += [int(forest.left[v]), int(forest.right[v])]
+    tips = depth[: forest.n_leaves]
+    return bool(tips.max() - tips.min() <= tol)
+
+
 def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp: bool = True, shard: bool = False,
-                        group=None, device=None) -> Neighbourhood:
+                        group=None, device=None, ultra: bool = False) -> Neighbourhood:
     """One batched call for all candidates ``Topology_search.single_nni`` could try on ``solver``'s trees
     (``:221-231``: every internal non-root node; with ``only_marked`` those carrying ``node.mark``), each
     scored as ``apply_nni`` does with ``local_brlen_opt`` (``:253-300``): nu, phi and all lengths fixed
@@ -83,7 +98,10 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
 
     ``shard=True`` under ``torch.distributed``: candidate trees are independent units, so every rank -- each
     holding all sites -- scores the candidates ``rank::world`` and one ``all_gather`` gives every rank the full
-    result (``dist.score_nni_sharded``, BASELINE config 5 on 8 GPUs)."""
+    result (``dist.score_nni_sharded``, BASELINE config 5 on 8 GPUs).
+
+    ``ultra=True``: the local EM of every candidate under the ultrametric constraint
+    (``pmm_score_nni_batch_ultra``); candidates it leaves no room for have score NaN."""
     forest = solver._ensure()
     if solver.num_polytomy_mark and any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
         raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
@@ -97,12 +115,13 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
     if len(cu) == 0:
         z = np.zeros(0)
         return Neighbourhood(cu, ck, z, np.zeros((0, 5)), np.zeros((0, 5), np.int32), np.zeros(0, np.int32), d0, d_raw)
+    kw = {"ultra": True} if ultra else {}
     if shard:
         from .dist import score_nni_sharded
         res = score_nni_sharded(solver._engine, cu, ck, d0, solver.params.nu, solver.params.phi, group=group, device=device,
-                                dmin=solver.dmin, dmax=solver.dmax)
+                                dmin=solver.dmin, dmax=solver.dmax, **kw)
     else:
-        res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax)
+        res = solver._engine.score_nni_batch(cu, ck, d0, solver.params.nu, solver.params.phi, solver.dmin, solver.dmax, **kw)
     return Neighbourhood(cu, ck, -res["nllh"], res["d5"], res["nodes"], res["iters"], d0, d_raw)
 
 
@@ -148,10 +167,16 @@ class GPU_Topology_search:
     ``clamp_start=True`` gives the reference's literal behaviour."""
 
     def __init__(self, treeTopoList, solver=GPU_EM_solver, data={}, prior={}, params={}, T_cooldown=20, alpha_cooldown=0.9,
-                 device: int = 0, clamp_start: bool = False, shard_candidates: bool = False, group=None, gather_device=None):
+                 device: int = 0, clamp_start: bool = False, shard_candidates: bool = False, group=None, gather_device=None,
+                 batch_ultra: Optional[bool] = None):
         # shard_candidates: one process per GPU (torchrun), every rank runs this same search with the same
         # ``random`` seed -- the policy is replayed identically everywhere -- and scores 1/world of each
         # neighbourhood (``dist.score_nni_sharded``)
+        # batch_ultra: score the neighbourhood in one launch under ``ultra_constr`` too (the two-height M-step of
+        # pmm_nni_ultra.cuh).  Off unless asked for (argument or PMM_NNI_ULTRA_BATCH=1): the kernel variant was written
+        # after this round's GPU budget was spent, so its first GPU run is tests/test_zzz_gpu_nni_ultra.py
+        import os
+        self.batch_ultra = bool(int(os.environ.get("PMM_NNI_ULTRA_BATCH", "0"))) if batch_ultra is None else bool(batch_ultra)
         self.clamp_start = clamp_start
         self.shard_candidates, self.group, self.gather_device = shard_candidates, group, gather_device
         self.treeTopoList = list(treeTopoList)
@@ -250,6 +275,14 @@ class GPU_Topology_search:
     def single_nni(self, curr_score, nni_iter, strategy, only_marked=False, verbose=False, sync=True):
         """``single_nni`` + ``apply_nni`` (``:221-322``): returns ``(score, n_attempts, took)``."""
         s = self._solver
+        ultra = bool(strategy.get('ultra_constr', False))
+        batch = self._batched(strategy) and not (ultra and not self._can_batch_ultra())
+        if batch and ultra:
+            # candidates the constraint leaves no room for go through score_tree, which re-reads the trees from
+            # newick: start from node ids that ARE those of the current newick, so that the neighbourhood's ids
+            # survive such a round trip (ids drift from the traversal order with every array-level move)
+            marks0 = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+            self._restore(s.get_tree_newick(), (s.params.nu, s.params.phi), marks0)
         forest = s._ensure()
         branches = np.nonzero((forest.left >= 0) & (forest.parent >= 0))[0]
         if only_marked:
@@ -258,12 +291,13 @@ class GPU_Topology_search:
         # generator seeded by ``random`` is the same policy (and stays reproducible under ``random.seed``) without
         # a Python-level pass over 10^4 branches per iteration
         branches = np.random.default_rng(getrandbits(63)).permutation(branches).tolist()
-        if self._batched(strategy):
+        if batch:
             nb = score_neighbourhood(s, only_marked=only_marked, clamp=self.clamp_start, shard=self.shard_candidates,
-                                     group=self.group, device=self.gather_device)
+                                     group=self.group, device=self.gather_device, ultra=ultra)
             self.trees_scored += len(nb.score)
             first = nb.first_of(forest.n_nodes)
             n_attempts = 0
+            seq = None                                # state of the one-at-a-time path, set up on first use
             while branches:
                 u = branches.pop()
                 moves = [0, 1]
@@ -272,6 +306,17 @@ class GPU_Topology_search:
                 for k in moves:
                     i = int(first[u]) + k
                     new_score = float(nb.score[i])
+                    if new_score != new_score:
+                        # the constrained local M-step had no room (or failed): the reference's sequence for such a
+                        # candidate -- local attempt, then every branch free (:301-306) -- on the live solver
+                        if seq is None:
+                            seq = (s.get_tree_newick(), (s.params.nu, s.params.phi),
+                                   [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees])
+                        new_score, took = self._sequential_candidate(u, k, strategy, curr_score, nni_iter, *seq)
+                        if took:
+                            return new_score, n_attempts, True
+                        s._ensure()                   # node ids are those of the same newick: nb stays valid
+                        continue
                     if self.__accept_proposal__(curr_score, new_score, nni_iter):
                         apply_move(s, nb, i)
                         if sync:                      # ``sync=False``: the caller tracks snapshots (__search_one__)
@@ -279,13 +324,10 @@ class GPU_Topology_search:
                         return new_score, n_attempts, True
             return curr_score, n_attempts, False
         # One candidate at a time -- the reference's own call sequence (:246-306) on the live solver and handle --
-        # for what the batch kernel does not cover: the ultrametric equalities (its local EM is unconstrained) and
-        # local_brlen_opt = False (every parameter re-optimised per candidate).  ``score_tree`` replaces the
-        # solver's node objects; a rejected candidate is undone by re-reading the trees it started from (same
-        # newick => same node ids after flattening).
+        # for what the batch kernel does not cover: local_brlen_opt = False (every parameter re-optimised per
+        # candidate) and, unless ``batch_ultra``, the ultrametric equalities.
         before, params0 = s.get_tree_newick(), (s.params.nu, s.params.phi)
         marks = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
-        local = bool(strategy.get('local_brlen_opt', True))
         n_attempts = 0
         while branches:
             u_id = branches.pop()
@@ -293,57 +335,80 @@ class GPU_Topology_search:
             shuffle(moves)
             n_attempts += 2
             for k in moves:
-                forest = s._ensure()
-                u = forest.nodes[u_id]
-                v = u.parent
-                w = next(c for c in v.children if c is not u)
-                child = u.children[k]
-                st = deepcopy(strategy)
-                st['fixed_brlen'] = None
-                st['nodes_to_recompute'] = None
-                if local:                                                   # :253-277
-                    st['fixed_nu'], st['fixed_phi'] = s.params.nu, s.params.phi
-                    free = {id(x) for x in (u.children + v.children + [v])}
-                    fixed_brlen = []
-                    for tree in s.trees:
-                        fb = {}
-                        for nd in tree.traverse_postorder():
-                            nd.anchors = (nd.label, nd.label) if not nd.children else \
-                                (nd.children[0].anchors[0], nd.children[-1].anchors[0])
-                            if id(nd) not in free:
-                                fb[nd.anchors] = nd.edge_length
-                        fixed_brlen.append(fb)
-                    st['fixed_brlen'] = fixed_brlen
-                u.remove_child(child); v.add_child(child)
-                v.remove_child(w); u.add_child(w)
-                s._forest = None
-                marks_moved = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
-                new_score, status = s.score_tree(strategy=st)
-                self.trees_scored += 1
-                if local and status != "optimal":                           # :301-306: retry with everything free
-                    self._restore(before, params0, marks)
-                    forest = s._ensure()
-                    u = forest.nodes[u_id]; v = u.parent
-                    w = next(c for c in v.children if c is not u); child = u.children[k]
-                    u.remove_child(child); v.add_child(child)
-                    v.remove_child(w); u.add_child(w)
-                    s._forest = None
-                    st['fixed_brlen'] = None
-                    new_score, status = s.score_tree(strategy=st)
-                    self.trees_scored += 1
-                if new_score is not None and self.__accept_proposal__(curr_score, new_score, nni_iter):
-                    for t, ms in zip(s.trees, marks_moved):                 # score_tree re-read the moved trees: marks by position
-                        nodes = list(t.traverse_preorder())
-                        for nd, m in zip(nodes, ms if len(ms) == len(nodes) else [False] * len(nodes)):
-                            nd.mark = m
-                    self._sync_from_solver()
+                new_score, took = self._sequential_candidate(u_id, k, strategy, curr_score, nni_iter, before, params0, marks)
+                if took:
                     return new_score, n_attempts, True
-                self._restore(before, params0, marks)
         return curr_score, n_attempts, False
+
+    def _sequential_candidate(self, u_id, k, strategy, curr_score, nni_iter, before, params0, marks):
+        """``apply_nni`` (``:242-322``) for one candidate on the live solver: ``(new_score, accepted)``.  ``score_tree``
+        replaces the solver's node objects; a rejected candidate is undone by re-reading the trees it started from
+        (same newick => same node ids after flattening)."""
+        s = self._solver
+        local = bool(strategy.get('local_brlen_opt', True))
+        forest = s._ensure()
+        u = forest.nodes[u_id]
+        v = u.parent
+        w = next(c for c in v.children if c is not u)
+        child = u.children[k]
+        st = deepcopy(strategy)
+        st['fixed_brlen'] = None
+        st['nodes_to_recompute'] = None
+        if local:                                                   # :253-277
+            st['fixed_nu'], st['fixed_phi'] = s.params.nu, s.params.phi
+            free = {id(x) for x in (u.children + v.children + [v])}
+            fixed_brlen = []
+            for tree in s.trees:
+                fb = {}
+                for nd in tree.traverse_postorder():
+                    nd.anchors = (nd.label, nd.label) if not nd.children else \
+                        (nd.children[0].anchors[0], nd.children[-1].anchors[0])
+                    if id(nd) not in free:
+                        fb[nd.anchors] = nd.edge_length
+                fixed_brlen.append(fb)
+            st['fixed_brlen'] = fixed_brlen
+        u.remove_child(child); v.add_child(child)
+        v.remove_child(w); u.add_child(w)
+        s._forest = None
+        marks_moved = [[getattr(nd, "mark", False) for nd in t.traverse_preorder()] for t in s.trees]
+        new_score, status = s.score_tree(strategy=st)
+        self.trees_scored += 1
+        if local and status != "optimal":                           # :301-306: retry with everything free
+            self._restore(before, params0, marks)
+            forest = s._ensure()
+            u = forest.nodes[u_id]; v = u.parent
+            w = next(c for c in v.children if c is not u); child = u.children[k]
+            u.remove_child(child); v.add_child(child)
+            v.remove_child(w); u.add_child(w)
+            s._forest = None
+            st['fixed_brlen'] = None
+            new_score, status = s.score_tree(strategy=st)
+            self.trees_scored += 1
+        if new_score is not None and self.__accept_proposal__(curr_score, new_score, nni_iter):
+            for t, ms in zip(s.trees, marks_moved):                 # score_tree re-read the moved trees: marks by position
+                nodes = list(t.traverse_preorder())
+                for nd, m in zip(nodes, ms if len(ms) == len(nodes) else [False] * len(nodes)):
+                    nd.mark = m
+            self._sync_from_solver()
+            return new_score, True
+        self._restore(before, params0, marks)
+        return new_score, False
+
+    def _can_batch_ultra(self) -> bool:
+        """the batch kernel's constrained M-step treats everything outside the five free branches as constants of
+        an ultrametric tree: usable when asked for and the current lengths (as the candidates will see them) are"""
+        if not self.batch_ultra:
+            return False
+        s = self._solver
+        forest = s._ensure()
+        d = s._d()
+        if self.clamp_start:
+            d = np.maximum(d, 2 * s.dmin)
+        return is_ultrametric(forest, d)
 
     @staticmethod
     def _batched(strategy) -> bool:
-        return bool(strategy.get('local_brlen_opt', True)) and not strategy.get('ultra_constr', False)
+        return bool(strategy.get('local_brlen_opt', True))
 
     def _restore(self, newicks, params, marks):
         from .tree import read_tree_newick
@@ -393,7 +458,9 @@ class GPU_Topology_search:
         if verbose:
             print("Initial score: " + str(curr_score), flush=True)
         self._sync_from_solver()
-        lazy = self._batched(strategy)      # the one-at-a-time path replaces the node objects: no array snapshots
+        # the one-at-a-time path (all of ultra_constr without batch_ultra, its infeasible candidates with) replaces
+        # the node objects: no array snapshots there
+        lazy = self._batched(strategy) and not strategy.get('ultra_constr', False)
         best_score, best = curr_score, (self._snapshot() if lazy else (self.treeTopoList, self.params))
         for nni_iter in range(maxiter):
             if verbose:

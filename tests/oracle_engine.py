@@ -81,7 +81,52 @@ class OracleEngine:
         r["status"] = "optimal"
         return r
 
-    def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000):
+    def _check_ultrametric(self, d, tol=1e-9):
+        f = self._forest
+        hi, lo = np.zeros(f.n_nodes), np.zeros(f.n_nodes)
+        order = [int(r) for r in np.nonzero(f.parent < 0)[0]]
+        for v in order:
+            if f.left[v] >= 0:
+                order += [int(f.left[v]), int(f.right[v])]
+        for v in reversed(order):
+            if f.left[v] >= 0:
+                a, b = int(f.left[v]), int(f.right[v])
+                hi[v], lo[v] = max(hi[a] + d[a], hi[b] + d[b]), min(lo[a] + d[a], lo[b] + d[b])
+                if hi[v] - lo[v] > tol:
+                    raise ValueError("pmm_score_nni_batch_ultra: the current lengths are not ultrametric")
+        tops = [hi[r] + d[r] for r in np.nonzero(f.parent < 0)[0]]
+        if len(tops) > 1 and max(tops) - min(tops) > tol:
+            raise ValueError("pmm_score_nni_batch_ultra: the trees of the forest are not equally high")
+
+    def _ultra_em(self, prob, parent, five, d, nu, phi, dmin, dmax, conv_eps, max_iter):
+        """EM with the five branches free under the ultrametric equalities: whole-tree host M-step
+        (laml_b200.ultrametric.mstep, everything else FIXED) around the oracle's E-step -- the loop of
+        ``GPU_EM_solver.EM_optimization(ultra_constr=True)``"""
+        from laml_b200 import ultrametric as um
+        n = self.n_nodes
+        kind = np.full(n, um.FIXED, np.int8)
+        kind[five] = um.FREE
+        fm = (kind == um.FREE).astype(np.uint8)
+        P = um.UltrametricProblem(parent, kind, d, dmin, dmax)
+        d = np.array(d, np.float64, copy=True)
+        pre = prob.inside(d, nu, phi)["llh"]
+        H, it, cur = None, 1, None
+        while True:
+            r = prob.estep(d, nu, phi)
+            d_new, _, _, H_new, status = um.mstep(P, np.ascontiguousarray(r["S"].T), r["Rtilde"], 1.0, 1, self.n_sites, fm, d,
+                                                  nu, phi, H_prev=H, optimize_phi=False, optimize_nu=False)
+            if status != "optimal":
+                return None
+            H = H_new
+            d = np.where(fm.astype(bool), d_new, d)
+            cur = prob.inside(d, nu, phi)["llh"]
+            if abs((cur - pre) / pre) < conv_eps or it >= max_iter:
+                break
+            pre = cur
+            it += 1
+        return {"nllh": -cur, "d": d, "iters": it}
+
+    def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000, ultra=False):
         """Every candidate by a full-tree EM with the five local branches free on the explicitly
         re-wired topology -- what ``Topology_search.apply_nni`` does with ``local_brlen_opt``
         (``Topology_search.py:253-300``).  Same output layout as ``pmm_score_nni_batch``: ``nodes`` =
@@ -90,6 +135,8 @@ class OracleEngine:
         m = len(cand_u)
         nllh = np.empty(m); d5 = np.empty((m, 5)); iters = np.empty(m, np.int32); nodes = np.empty((m, 5), np.int32)
         d = np.asarray(d, np.float64)
+        if ultra:
+            self._check_ultrametric(d)
         for i, (u, k) in enumerate(zip(cand_u, cand_k)):
             u, k = int(u), int(k)
             v = int(f.parent[u])
@@ -100,9 +147,16 @@ class OracleEngine:
             prob = OracleProblem(forest_from_parent(p2, l2, r2), np.arange(self.n_leaves, dtype=np.int32), self.codes,
                                  self.qptr, self.qval)
             five = [v, u, moved, stay, w]
-            fm = np.zeros(self.n_nodes, np.uint8)
-            fm[five] = 1
-            r = prob.em(d, nu, phi, fm, False, False, dmin, dmax, conv_eps, max_iter)
+            nodes[i] = five
+            if ultra:
+                r = self._ultra_em(prob, p2, five, d, nu, phi, dmin, dmax, conv_eps, max_iter)
+                if r is None:                       # constrained M-step infeasible / failed: no score
+                    nllh[i], iters[i], d5[i] = np.nan, -1, d[five]
+                    continue
+            else:
+                fm = np.zeros(self.n_nodes, np.uint8)
+                fm[five] = 1
+                r = prob.em(d, nu, phi, fm, False, False, dmin, dmax, conv_eps, max_iter)
             nllh[i], iters[i] = r["nllh"], r["iters"]
             d5[i] = r["d"][five]
             nodes[i] = five

@@ -274,6 +274,100 @@ def test_ultrametric_search_goes_candidate_by_candidate():
     assert score >= -s0.optimize(initials=1, random_seeds=4, verbose=-1, ultra_constr=True)[0] - 1e-6
 
 
+@pytest.mark.parametrize("name", ["ref_rand_small", "ref_rand_forest"])
+def test_batch_ultra_scores_equal_the_unclamped_reference_call(name, monkeypatch):
+    """``score_neighbourhood(ultra=True)`` = the call the reference makes per candidate (new solver from the
+    re-wired newick, ``score_tree`` with ``fixed_brlen`` anchors and ``ultra_constr``) with ONE difference, the
+    same as ``clamp_start=False`` on the unconstrained path: lengths are not raised to ``2 dmin`` first.  (With the
+    raise, the fixed part of an ultrametric tree that has a branch below ``2 dmin`` stops being ultrametric and the
+    reference's local attempt is infeasible by construction -- it then re-optimises every branch,
+    Topology_search.py:301-306.)  Scores, and which candidates the constraint leaves no room for, agree."""
+    case, z = load_npz_case(name)
+    s = _solver(case)
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    score0, status0 = s.score_tree(strategy=st)                   # an ultrametric starting point
+    assert status0 == "optimal"
+    from laml_b200.topology import is_ultrametric
+    assert is_ultrametric(s._ensure(), s._d())
+    nb = score_neighbourhood(s, clamp=False, ultra=True)
+    # the clamped call is infeasible whenever a fixed branch sits below 2 dmin
+    if (s._d() < 2 * s.dmin - 1e-12).any():
+        _, status = score_candidate_like_the_reference(s, int(nb.cand_u[0]), int(nb.cand_k[0]), case, {'ultra_constr': True})
+        assert status == "d_infeasible"
+
+    def ini_unclamped(self):
+        return [nd.edge_length for tree in self.trees for nd in tree.traverse_postorder()]
+    monkeypatch.setattr(GPU_EM_solver, "ini_brlens", ini_unclamped)
+    n_nan = 0
+    for i in range(len(nb.score)):
+        ref_score, status = score_candidate_like_the_reference(s, int(nb.cand_u[i]), int(nb.cand_k[i]), case,
+                                                               {'ultra_constr': True})
+        if np.isnan(nb.score[i]):
+            assert status == "d_infeasible" and nb.iters[i] == -1
+            n_nan += 1
+        else:
+            assert status == "optimal"
+            assert abs(ref_score - nb.score[i]) <= 1e-9 * abs(ref_score), (i, ref_score, nb.score[i])
+    assert 0 < n_nan < len(nb.score)
+
+
+def test_batch_ultra_needs_ultrametric_lengths():
+    case, z = load_npz_case("ref_rand_small")
+    s = _solver(case)
+    with pytest.raises(ValueError, match="not ultrametric"):
+        score_neighbourhood(s, clamp=False, ultra=True)
+
+
+@pytest.mark.parametrize("no,T0", [(9, '((a,b),(c,d));'), (10, '(a,b,c,d);')])
+def test_reference_search_tests_ultrametric_batched(no, T0):
+    """tests 9 and 10 of unit_tests_TopoSearch.py with ``batch_ultra``: neighbourhoods scored in one call under the
+    constraint, candidates without room by the reference's sequence; same brute-force optimum to 4 places"""
+    from random import seed
+    seed(a=1000 + no)
+    Q = [dict(q) for q in Q5]
+    nllh_bf = _brute_force(MSA_B, Q, ultra_constr=True)
+    ts = GPU_Topology_search([T0], GPU_EM_solver, data={'charMtrx': MSA_B}, prior={'Q': Q}, params={'phi': 0, 'nu': 0},
+                             batch_ultra=True)
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    best_trees, max_score, best_params = ts.search(maxiter=200, verbose=False, strategy=st, nreps=1)
+    assert abs(nllh_bf + max_score) < 5e-5, (no, -max_score, nllh_bf, best_trees)
+
+
+@pytest.mark.parametrize("name,rseed,min_sequential", [("ref_rand_small", 77, 0), ("ref_rand_forest", 5, 1)])
+def test_batch_ultra_search_on_random_cases(name, rseed, min_sequential):
+    """the batched constrained search does not lose score, uses one handle, mixes batch calls with one-at-a-time
+    candidates (the forest case meets a candidate without room), and ends on ultrametric, equally high trees whose
+    fresh likelihood is the score"""
+    from random import seed
+    from laml_b200.tree import read_tree_newick
+    case, z = load_npz_case(name)
+    seed(a=rseed)
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    ts = GPU_Topology_search(case.newicks, GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
+                             params={'phi': case.phi, 'nu': case.nu}, batch_ultra=True)
+    OracleEngine.instances = 0
+    sequential, inner = [], ts._sequential_candidate
+    ts._sequential_candidate = lambda *a, **k: (sequential.append(a[:2]), inner(*a, **k))[1]
+    trees, score, params = ts.search(maxiter=6, nreps=1, strategy=st)
+    assert OracleEngine.instances == 1 and np.isfinite(score) and len(sequential) >= min_sequential
+    s0 = _solver(case)
+    start, _ = s0.score_tree(strategy=st)
+    assert score >= start - 1e-6
+    tips = []
+    for tr in trees:
+        t = read_tree_newick(tr)
+        dist = {}
+        for nd in t.traverse_preorder():
+            dist[nd] = (dist[nd.parent] if nd.parent is not None else 0.0) + (nd.edge_length or 0.0)
+        tips += [dist[nd] for nd in t.traverse_leaves()]
+    assert np.ptp(np.array(tips)) < 1e-6
+    fresh = GPU_EM_solver(trees, {'charMtrx': case.msa}, {'Q': case.Q}, params)
+    assert abs(-fresh.negative_llh() - score) <= 1e-6 * abs(score)
+
+
 def test_full_reoptimisation_per_candidate():
     """local_brlen_opt = False: every parameter re-optimised per candidate on the live handle"""
     from random import seed

@@ -1,0 +1,97 @@
+"""Batched NNI scoring under the ultrametric constraint (``pmm_score_nni_batch_ultra``) on the GPU against the
+CPU model of the same definition: a full-tree EM per candidate on the explicitly re-wired topology, oracle E-step,
+whole-tree host M-step with every branch but the five around the move fixed (tests/oracle_engine.py) -- which
+tests/test_topology_host.py shows to be the reference's per-candidate call without its ``2 dmin`` raise.
+
+The kernel variant was written after this round's GPU budget was spent: its arithmetic is covered on CPU through
+its host instance (tests/test_nni_ultra_host.py), but THIS file has not run on a GPU yet.  It sorts last so that
+nothing else depends on it, and it is marked xfail(strict=False) for that reason alone -- an XPASS is the expected
+outcome, and the marker goes once a GPU run is on record."""
+import numpy as np
+import pytest
+
+from laml_b200.capi import Engine, PMMError
+from laml_b200.nni import nni_candidates
+from laml_b200.synth import make_workload
+from oracle_engine import OracleEngine
+from test_nni_ultra_host import ultrametric_lengths
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="first GPU run of the ULTRA kernel variant is the driver's round-end pass")]
+
+
+@pytest.mark.parametrize("seed,n,K,amax,nu,phi,step", [(91, 40, 14, 12, 0.15, 0.1, (0.02, 0.3)), (92, 25, 9, 40, 0.0, 0.2, (0.006, 0.012)),
+                                                       (93, 60, 20, 6, 0.3, 0.0, (0.01, 0.2))])
+def test_batch_ultra_matches_the_cpu_model(seed, n, K, amax, nu, phi, step):
+    w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
+    f = w.forest
+    d, _ = ultrametric_lengths(f, np.random.default_rng(seed), step=step)
+    eng = Engine(n, w.qptr, w.qval, w.codes)
+    eng.set_tree(f.parent, f.left, f.right)
+    cu, ck = nni_candidates(f.parent, f.left, n)
+    got = eng.score_nni_batch(cu, ck, d, nu, phi, ultra=True)
+    model = OracleEngine(n, w.qptr, w.qval, w.codes)
+    model.set_tree(f.parent, f.left, f.right)
+    want = model.score_nni_batch(cu, ck, d, nu, phi, ultra=True)
+    bad = np.isnan(want["nllh"])
+    assert (np.isnan(got["nllh"]) == bad).all() and (got["iters"][bad] == -1).all()
+    assert (got["nodes"] == want["nodes"]).all()
+    ok = ~bad
+    assert ok.sum() > len(cu) // 3 and (seed != 92 or bad.sum() >= 5)      # case 92 has candidates without room
+    np.testing.assert_allclose(got["nllh"][ok], want["nllh"][ok], rtol=1e-9)
+    np.testing.assert_allclose(got["d5"][ok], want["d5"][ok], rtol=1e-5, atol=1e-7)
+    assert (np.abs(got["iters"][ok] - want["iters"][ok]) <= 1).all()
+    # the five lengths leave every candidate tree ultrametric
+    from laml_b200.nni import apply_nni
+    from laml_b200.flatten import forest_from_parent
+    from laml_b200.topology import is_ultrametric
+    for i in np.nonzero(ok)[0][:20]:
+        p2, l2, r2 = apply_nni(f.parent, f.left, f.right, int(cu[i]), int(ck[i]))
+        d2 = d.copy()
+        d2[got["nodes"][i]] = got["d5"][i]
+        assert is_ultrametric(forest_from_parent(p2, l2, r2), d2, tol=1e-9)
+    eng.close()
+
+
+def test_batch_ultra_refuses_lengths_that_are_not_ultrametric():
+    w = make_workload(20, 8, 2, 10, 0.2, 0.2, seed=95)
+    eng = Engine(20, w.qptr, w.qval, w.codes)
+    eng.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    cu, ck = nni_candidates(w.forest.parent, w.forest.left, 20)
+    with pytest.raises(PMMError, match="not ultrametric"):
+        eng.score_nni_batch(cu, ck, np.maximum(w.d, 0.01), 0.2, 0.2, ultra=True)
+    # the handle survives the refusal, and the unconstrained batch still runs
+    res = eng.score_nni_batch(cu, ck, np.maximum(w.d, 0.01), 0.2, 0.2)
+    assert np.isfinite(res["nllh"]).all()
+    eng.close()
+
+
+def test_batch_ultra_search_on_the_gpu():
+    from copy import deepcopy
+    from random import seed
+    from helpers import load_npz_case
+    from laml_b200.solver import DEFAULT_STRATEGY, GPU_EM_solver
+    from laml_b200.topology import GPU_Topology_search
+    from laml_b200.tree import read_tree_newick
+    case, z = load_npz_case("ref_rand_forest")
+    st = deepcopy(DEFAULT_STRATEGY)
+    st['ultra_constr'] = True
+    out = {}
+    for batch in (True, False):
+        seed(a=5)
+        ts = GPU_Topology_search(case.newicks, GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
+                                 params={'phi': case.phi, 'nu': case.nu}, batch_ultra=batch)
+        out[batch] = ts.search(maxiter=4, nreps=1, strategy=st)
+    trees, score, params = out[True]
+    assert np.isfinite(score)
+    tips = []
+    for tr in trees:
+        t = read_tree_newick(tr)
+        dist = {}
+        for nd in t.traverse_preorder():
+            dist[nd] = (dist[nd.parent] if nd.parent is not None else 0.0) + (nd.edge_length or 0.0)
+        tips += [dist[nd] for nd in t.traverse_leaves()]
+    assert np.ptp(np.array(tips)) < 1e-6
+    fresh = GPU_EM_solver(trees, {'charMtrx': case.msa}, {'Q': case.Q}, params)
+    assert abs(-fresh.negative_llh() - score) <= 1e-6 * abs(score)
+    fresh.close()

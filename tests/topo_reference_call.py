@@ -6,7 +6,7 @@ from laml_b200.solver import DEFAULT_STRATEGY, GPU_EM_solver
 from laml_b200.tree import read_tree_newick
 
 
-def score_candidate_like_the_reference(solver, u_id, k, case):
+def score_candidate_like_the_reference(solver, u_id, k, case, strategy_extra=None):
     forest = solver._ensure()
     trees = [read_tree_newick(t) for t in solver.get_tree_newick()]          # treeList_obj
     # locate u in the copy by traversal position
@@ -34,6 +34,7 @@ def score_candidate_like_the_reference(solver, u_id, k, case):
     v.remove_child(w); u.add_child(w)
     st = dict(DEFAULT_STRATEGY)
     st.update(fixed_brlen=fixed_brlen, fixed_nu=solver.params.nu, fixed_phi=solver.params.phi)
+    st.update(strategy_extra or {})
     new = GPU_EM_solver([t.newick() for t in trees], {'charMtrx': case.msa}, {'Q': case.Q}, solver.get_params())
     score, status = new.score_tree(strategy=st)
     new.close()
