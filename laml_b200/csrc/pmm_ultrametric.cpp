@@ -114,20 +114,29 @@ bool feasible(const Problem &P, const std::vector<double> &H, bool strict) {
 
 struct Stats { std::vector<double> k, S1, S24; double nu; bool use_nu; };
 
-inline void f_derivs(const Stats &T, int v, double x, double &val, double &g, double &h) {
+// per-branch objective of EM_solver.py:351-357: the value alone (expm1 + log per term) and the derivatives alone
+// (one expm1 per term), so that neither caller pays for what it does not use
+inline double f_value(const Stats &T, int v, double x) {
+    double val = -T.k[v] * x + T.S1[v] * std::log(-std::expm1(-x));
+    if (T.use_nu) val += T.S24[v] * std::log(-std::expm1(-T.nu * x));
+    return val;
+}
+inline void f_grad_hess(const Stats &T, int v, double x, double &g, double &h) {
     const double em = std::expm1(x);
-    val = -T.k[v] * x + T.S1[v] * std::log(-std::expm1(-x));
     g = -T.k[v] + T.S1[v] / em;
     h = -T.S1[v] * (em + 1.0) / (em * em);
     if (T.use_nu) {
         const double emn = std::expm1(T.nu * x);
-        val += T.S24[v] * std::log(-std::expm1(-T.nu * x));
         g += T.nu * T.S24[v] / emn;
         h -= T.nu * T.nu * T.S24[v] * (emn + 1.0) / (emn * emn);
     }
 }
 
-double objective(const Problem &P, const Stats &T, const std::vector<double> &H, double mu) {
+// objective = fsum + mu * bsum; the two sums are returned separately so that the value at an accepted point can be
+// carried to the next Newton step (and re-weighted when mu changes) instead of being evaluated again
+struct ObjParts { double fsum, bsum; bool inside; };
+
+ObjParts objective_parts(const Problem &P, const Stats &T, const std::vector<double> &H) {
     const int m = (int)P.fidx.size(), nchunks = (m + CHUNK - 1) / CHUNK;
     std::vector<double> sum(nchunks, 0.0), bar(nchunks, 0.0);
     std::atomic<bool> outside(false);
@@ -137,17 +146,19 @@ double objective(const Problem &P, const Stats &T, const std::vector<double> &H,
             const int v = P.fidx[i];
             const double x = H[P.par[v]] - H[v];
             if (x <= P.lo || x >= P.hi) { outside = true; return; }
-            double val, g, h;
-            f_derivs(T, v, x, val, g, h);
-            s += val;
+            s += f_value(T, v, x);
             b += std::log(x - P.lo) + std::log(P.hi - x);
         }
         sum[c] = s; bar[c] = b;
     });
-    if (outside) return -std::numeric_limits<double>::infinity();
+    if (outside) return {0.0, 0.0, false};
     double s = 0.0, b = 0.0;
     for (int c = 0; c < nchunks; c++) { s += sum[c]; b += bar[c]; }
-    return s + mu * b;
+    return {s, b, true};
+}
+
+inline double objective_of(const ObjParts &o, double mu) {
+    return o.inside ? o.fsum + mu * o.bsum : -std::numeric_limits<double>::infinity();
 }
 
 struct Work { std::vector<double> g, w, a, b, alpha, beta, delta; std::vector<char> grounded; };
@@ -161,8 +172,8 @@ double newton_direction(const Problem &P, const Stats &T, const std::vector<doub
         for (int i = c * CHUNK, e = std::min(m, (c + 1) * CHUNK); i < e; i++) {
             const int v = P.fidx[i];
             const double x = H[P.par[v]] - H[v];
-            double val, g, h;
-            f_derivs(T, v, x, val, g, h);
+            double g, h;
+            f_grad_hess(T, v, x, g, h);
             W.g[v] = g + mu * (1.0 / (x - P.lo) - 1.0 / (P.hi - x));
             W.w[v] = h - mu * (1.0 / ((x - P.lo) * (x - P.lo)) + 1.0 / ((P.hi - x) * (P.hi - x)));
         }
@@ -236,6 +247,8 @@ extern "C" int pmm_ultrametric_solve(int32_t n, const int32_t *parent, const int
     Work W;
     double mu = warm ? warm_mu : 1.0;
     int iters = 0, status = 0;
+    ObjParts at_H = {0.0, 0.0, false};                                          // objective sums at the current H
+    bool have_at_H = false;
     for (;;) {
         for (int it = 0; it < 60; it++) {
             const double slope = newton_direction(P, T, H, mu, W);
@@ -250,15 +263,19 @@ extern "C" int pmm_ultrametric_solve(int32_t n, const int32_t *parent, const int
                 else if (dx > 0) tmax = std::fmin(tmax, (hi - x) / dx);
             }
             double t = std::fmin(1.0, 0.99 * tmax);
-            const double f0 = objective(P, T, H, mu);
+            if (!have_at_H) { at_H = objective_parts(P, T, H); have_at_H = true; }
+            const double f0 = objective_of(at_H, mu);
             bool found = false;
+            ObjParts trial = at_H;
             while (t > 1e-14) {
                 for (int v = 0; v <= n; v++) Hn[v] = H[v] + t * W.delta[v];
-                if (objective(P, T, Hn, mu) >= f0 + 1e-4 * t * slope) { found = true; break; }
+                trial = objective_parts(P, T, Hn);
+                if (objective_of(trial, mu) >= f0 + 1e-4 * t * slope) { found = true; break; }
                 t *= 0.5;
             }
             if (!found) break;
             H.swap(Hn);
+            at_H = trial;                                                        // the accepted point's sums
             if (t * slope < 1e-14 * n_free) break;
         }
         if (status != 0 || mu <= mu_final) break;
