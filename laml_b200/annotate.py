@@ -91,10 +91,12 @@ def _row_text(tag_row, p0_row, p1_row, alpha_names: Sequence[Sequence[str]], Q) 
     return ",".join(out)
 
 
-def write_annotations(solver, Q, out_annotate) -> None:
+def write_annotations(solver, Q, out_annotate) -> List[str]:
     """Write the reference's annotation file for ``solver`` (a ``GPU_EM_solver`` at the parameters to
     annotate).  ``Q`` is the prior as the caller holds it (list of dicts; the runner passes its raw, possibly
-    un-normalised one, ``runner.py:433``).  The solver's trees are left as they were."""
+    un-normalised one, ``runner.py:433``).  The solver's trees are left as they were.  Returns the annotated
+    newick strings (labelled nodes, branch lengths = expected mutations): what the runner reads off
+    ``my_solver.trees`` for its return value (``runner.py:450-451``)."""
     from .tree import Node
     forest = solver._ensure().derived()
     enc = solver._enc
@@ -113,6 +115,7 @@ def write_annotations(solver, Q, out_annotate) -> None:
     saved = [(nd, nd.label, nd.edge_length) for nd in forest.nodes]
     old_roots = [tree.root for tree in solver.trees]
     idx = 0
+    annotated: List[str] = []
     try:
         with open(out_annotate, 'w') as fout:
             for tree in solver.trees:
@@ -132,7 +135,8 @@ def write_annotations(solver, Q, out_annotate) -> None:
                         idx += 1
                     all_labels.add(node.label)
                     node.edge_length = round(float(expected_mutations[node_id[id(node)]]), 3)
-                fout.write(tree.newick() + "\n")
+                annotated.append(tree.newick())
+                fout.write(annotated[-1] + "\n")
                 for node in tree.traverse_preorder():                         # runner.py:419-435
                     if node is added:
                         fout.write(node.label + "," + ",".join(['0'] * K) + "\n")
@@ -148,15 +152,17 @@ def write_annotations(solver, Q, out_annotate) -> None:
                 tree.root = root
         for nd, label, length in saved:
             nd.label, nd.edge_length = label, length
+    return annotated
 
 
-def annotate(opt_trees, msa, Q, opt_params, out_annotate, device: int = 0) -> None:
+def annotate(opt_trees, msa, Q, opt_params, out_annotate, device: int = 0) -> List[str]:
     """The whole annotation step of the runner (``runner.py:391-435``) in one call: a throw-away solver on
-    the optimised trees at the optimised parameters, one E-step on the GPU, the file."""
+    the optimised trees at the optimised parameters, one E-step on the GPU, the file.  Returns the annotated
+    newick strings (see :func:`write_annotations`)."""
     from .solver import GPU_EM_solver
     solver = GPU_EM_solver(opt_trees, {'charMtrx': msa}, {'Q': Q}, {'phi': opt_params['phi'], 'nu': opt_params['nu']},
                            device=device)
     try:
-        write_annotations(solver, Q, out_annotate)
+        return write_annotations(solver, Q, out_annotate)
     finally:
         solver.close()
