@@ -202,6 +202,10 @@ class GPU_Topology_search:
             return self.solver(self.treeTopoList, self.data, self.prior, self.params, device=self.device)
         return self.solver(self.treeTopoList, self.data, self.prior, self.params)
 
+    def update_from_solver(self, mySolver):                                    # :43-48 (called by runner.py:290)
+        self.treeTopoList = mySolver.get_tree_newick()
+        self.params = mySolver.get_params()
+
     def _open(self, resolve_polytomies: bool, eps_len: float = 1e-3) -> GPU_EM_solver:
         """the search's solver for ``self.treeTopoList``; polytomies are resolved and the inserted nodes marked
         BEFORE the solver sees the trees (``__mark_polytomies__``, ``:51-66``), so that they are ordinary,

@@ -24,8 +24,10 @@ import laml_b200.solver as solver_mod  # noqa: E402
 from oracle_engine import OracleEngine  # noqa: E402
 
 
-def integration_patch(src: str) -> str:
-    """the hunks of INTEGRATION.md section 1, as text substitutions that fail loudly if the runner changes"""
+def integration_patch(src: str, search: str = "reference") -> str:
+    """the hunks of INTEGRATION.md section 1, as text substitutions that fail loudly if the runner changes;
+    ``search``: keep the reference's Topology_search class ("reference"), or the optional hunk that swaps in
+    GPU_Topology_search ("batched" / "batched_ultra")"""
     def sub(old, new, count=1):
         nonlocal src
         assert src.count(old) >= 1, "runner.py no longer contains: " + old
@@ -53,11 +55,18 @@ def integration_patch(src: str) -> str:
     guarded = '    if str(canon["solver"]).lower() != "em-b200":\n' + "".join(
         ("    " + line if line.strip() else line) for line in block.splitlines(keepends=True))
     src = src[:a] + guarded + src[b:]
+    if search != "reference":
+        # optional hunk (runner.py:246-247): the search class
+        sub("    myTopoSearch = Topology_search(input_trees, selected_solver, data=data, prior=prior, params=params)\n",
+            "    from laml_b200.topology import GPU_Topology_search\n"
+            "    myTopoSearch = GPU_Topology_search(input_trees, selected_solver, data=data, prior=prior, params=params%s)\n"
+            % (", batch_ultra=True" if search == "batched_ultra" else ""))
     return src
 
 
 @pytest.fixture
-def runner(monkeypatch):
+def runner(monkeypatch, request):
+    search = getattr(request, "param", "reference")
     R = ref_loader.load()
     monkeypatch.setattr(solver_mod, "Engine", OracleEngine)
     pkg = sys.modules["laml_libs"]
@@ -77,7 +86,7 @@ def runner(monkeypatch):
             for k, v in attrs.items():
                 setattr(mod, k, v)
             monkeypatch.setitem(sys.modules, name, mod)
-    src = integration_patch(open(os.path.join(R.root, "laml_libs", "runner.py")).read())
+    src = integration_patch(open(os.path.join(R.root, "laml_libs", "runner.py")).read(), search)
     mod = types.ModuleType("laml_libs_runner_patched")
     exec(compile(src, "runner.py+INTEGRATION.md", "exec"), mod.__dict__)
     monkeypatch.delenv("MOSEKLM_LICENSE_FILE", raising=False)
@@ -86,6 +95,7 @@ def runner(monkeypatch):
     sys.stdout = stdout                       # the runner swaps stdout for its tee logger
 
 
+@pytest.mark.parametrize("runner", ["reference", "batched"], indirect=True)
 def test_example1_through_the_reference_runner(runner, tmp_path):
     mod, R = runner
     ex = os.path.join(R.root, "examples", "example1")
@@ -166,3 +176,47 @@ def _lengths_by_clade(t):
         if nd.edge_length is not None:
             out[below[nd]] = nd.edge_length
     return out
+
+
+_EXAMPLE2_INITIAL = []
+
+
+@pytest.mark.parametrize("runner", ["reference", "batched", "batched_ultra"], indirect=True)
+def test_example2_topology_search_through_the_reference_runner(runner, tmp_path):
+    """the published example2 command line (``--topology_search``, 64 cells of which 2 are duplicates, ultrametric
+    constraint on) cut to two NNI iterations: with the reference's own search class driving GPU_EM_solver, and with
+    the search-class hunk (candidate by candidate, and neighbourhoods batched under the constraint)"""
+    from random import seed
+    mod, R = runner
+    ex = os.path.join(R.root, "examples", "example2")
+    prefix = str(tmp_path / "example2")
+    stdout = sys.stdout
+    seed(a=4242)
+    try:
+        tree, params, ann_path, _, log_path = mod.run_from_namespace(dict(
+            character_matrix=os.path.join(ex, "character_matrix.csv"), tree_topology=os.path.join(ex, "starting.tree"),
+            priors=os.path.join(ex, "priors.csv"), output=prefix, nInitials=1, randomreps=1, topology_search=True,
+            timescale=10, solver="em-b200", maxIters=2, verbose=True))
+    finally:
+        if hasattr(sys.stdout, "log"):
+            sys.stdout.log.close()
+        sys.stdout = stdout
+    log = open(prefix + ".log").read()
+    assert "Started with 64 sequences. Deduplication removes 2 sequences." in log and "Starting topology search" in log
+    # the score of the starting topology after numerical optimisation under the constraint (the published log's
+    # -1126.92 is LAML 1.0.0's unconstrained one; 1.0.5's runner forces ultra_constr, runner.py:91): the same in all
+    # three modes, and above the unconstrained optimum
+    ini = float(re.search(r"Initial score: (-[0-9.]+)", log).group(1))
+    _EXAMPLE2_INITIAL.append(ini)
+    assert abs(ini - _EXAMPLE2_INITIAL[0]) <= 1e-6 * abs(ini) and -ini > 1126.9195350702505
+    nll = params["nll"]
+    assert np.isfinite(nll) and nll <= -ini + 1e-3            # the search never returns worse than its start
+    assert "Optimal topology found. Re-optimizing other parameters" in log or "Optimal score for this search" in log
+    from laml_b200.tree import read_tree_newick
+    out_t = read_tree_newick(open(prefix + "_trees.nwk").readline().strip())
+    assert len(list(out_t.traverse_leaves())) == 64           # duplicates are put back (add_dup)
+    assert abs(out_t.height(weighted=True) - 10.0) < 1e-9
+    ann = open(str(ann_path)).read().splitlines()
+    assert ann[0] == tree and len(ann) > 100
+    for f in ("_params.txt", "_trees.collapsed.nwk"):
+        assert os.path.isfile(prefix + f)
