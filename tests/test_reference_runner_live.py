@@ -90,8 +90,11 @@ def runner(monkeypatch, request):
     mod = types.ModuleType("laml_libs_runner_patched")
     exec(compile(src, "runner.py+INTEGRATION.md", "exec"), mod.__dict__)
     monkeypatch.delenv("MOSEKLM_LICENSE_FILE", raising=False)
+    monkeypatch.setitem(sys.modules, "laml_libs.runner", mod)       # what laml_libs/api.py imports
+    monkeypatch.delitem(sys.modules, "laml_libs.api", raising=False)
     stdout = sys.stdout
     yield mod, R
+    sys.modules.pop("laml_libs.api", None)
     sys.stdout = stdout                       # the runner swaps stdout for its tee logger
 
 
@@ -220,3 +223,30 @@ def test_example2_topology_search_through_the_reference_runner(runner, tmp_path)
     assert ann[0] == tree and len(ann) > 100
     for f in ("_params.txt", "_trees.collapsed.nwk"):
         assert os.path.isfile(prefix + f)
+
+
+def test_api_run_laml_infer(runner, tmp_path):
+    """``laml_libs.api.run_laml_infer`` (the programmatic entry point, api.py:39-131; imported verbatim) on top of
+    the patched runner: example1, published command line"""
+    mod, R = runner
+    from laml_libs.api import LAMLOutput, run_laml_infer
+    ex = os.path.join(R.root, "examples", "example1")
+    stdout = sys.stdout
+    from random import seed
+    seed(a=7)
+    try:
+        out = run_laml_infer(character_matrix=os.path.join(ex, "character_matrix.csv"),
+                             tree_topology=os.path.join(ex, "starting.tree"), priors=os.path.join(ex, "priors.csv"),
+                             solver="em-b200", nInitials=1, randomreps=1, timescale=10, output_prefix=str(tmp_path / "api"))
+    finally:
+        if hasattr(sys.stdout, "log"):
+            sys.stdout.log.close()
+        sys.stdout = stdout
+    assert isinstance(out, LAMLOutput) and out.tree_newick.endswith(";")
+    # another random start, the same optimum (published: phi 0.14378501771164973, nu 0.13359737967697907, rate 0.1034192687776938)
+    assert abs(out.params.phi_dropout - 0.14378501771164973) < 3e-4
+    assert abs(out.params.nu_silence - 0.13359737967697907) < 3e-4
+    assert abs(out.params.lambda_edit - 0.1034192687776938) < 5e-4 * 0.1034192687776938
+    assert out.annotations_path.is_file() and out.log_path.is_file()
+    nllh = float(open(str(tmp_path / "api_params.txt")).read().split("Negative-llh: (")[1].split(",")[0])
+    assert abs(nllh - 6987.352449704049) < 1e-6 * 6987.35
