@@ -192,7 +192,7 @@ def test_nni_candidate_sharding():
         np.testing.assert_array_equal(iters, want["iters"]); np.testing.assert_array_equal(nodes, want["nodes"])
 
 
-def _search_worker(rank, world, port, ret):
+def _search_worker(rank, world, port, ret, ultra=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -207,8 +207,11 @@ def _search_worker(rank, world, port, ret):
     case, z = load_npz_case("ref_rand_small")
     seed(a=21)                                       # the same policy stream on every rank
     ts = GPU_Topology_search(case.newicks, solver_mod.GPU_EM_solver, data={'charMtrx': case.msa}, prior={'Q': case.Q},
-                             params={'phi': case.phi, 'nu': case.nu}, shard_candidates=world > 1, gather_device="cpu")
-    trees, score, params = ts.search(maxiter=4, nreps=1)
+                             params={'phi': case.phi, 'nu': case.nu}, shard_candidates=world > 1, gather_device="cpu",
+                             batch_ultra=ultra)
+    strategy = dict(solver_mod.DEFAULT_STRATEGY)
+    strategy['ultra_constr'] = ultra
+    trees, score, params = ts.search(maxiter=4, nreps=1, strategy=strategy)
     ret[rank] = (trees, score, params, ts.trees_scored)
     dist.destroy_process_group()
 
@@ -221,6 +224,19 @@ def test_candidate_sharded_search_matches_single_process():
     port = 29700 + os.getpid() % 90
     mp.spawn(_search_worker, args=(2, port, ret2), nprocs=2, join=True)
     mp.spawn(_search_worker, args=(1, port + 100, ret1), nprocs=1, join=True)
+    assert ret2[0][0] == ret2[1][0] == ret1[0][0]
+    assert ret2[0][1] == ret2[1][1] == ret1[0][1]
+    assert ret2[0][2] == ret1[0][2] and ret2[0][3] == ret1[0][3]
+
+
+def test_candidate_sharded_ultrametric_search_matches_single_process():
+    """the same under ``ultra_constr`` with ``batch_ultra``: neighbourhoods scored under the constraint, sharded
+    ``rank::world``; NaN scores (candidates without room) travel through the all_gather like any other"""
+    mgr = mp.Manager()
+    ret2, ret1 = mgr.dict(), mgr.dict()
+    port = 29500 + os.getpid() % 90
+    mp.spawn(_search_worker, args=(2, port, ret2, True), nprocs=2, join=True)
+    mp.spawn(_search_worker, args=(1, port + 100, ret1, True), nprocs=1, join=True)
     assert ret2[0][0] == ret2[1][0] == ret1[0][0]
     assert ret2[0][1] == ret2[1][1] == ret1[0][1]
     assert ret2[0][2] == ret1[0][2] and ret2[0][3] == ret1[0][3]
