@@ -408,7 +408,7 @@ class GPU_Topology_search:
         d = s._d()
         if self.clamp_start:
             d = np.maximum(d, 2 * s.dmin)
-        return is_ultrametric(forest, d)
+        return is_ultrametric(forest, d, tol=5e-10)            # inside the library's own 1e-9 whatever the summation order
 
     @staticmethod
     def _batched(strategy) -> bool:
