@@ -37,7 +37,11 @@
 // warp's sites through a transposed shared-memory tile and written once per (warp, node) into
 // Spart[site group][node][5]; pmm_reduce_S sums the site groups in a fixed order (bit-reproducible).
 #pragma once
+#ifdef PMM_HOST_EMU                      // host build of the kernels under tests/native/cuda_host_shim.h
+#include "pmm_common.cuh"
+#else
 #include "pmm_kernels.cuh"
+#endif
 #include <type_traits>
 
 namespace pmm {
@@ -120,11 +124,17 @@ __device__ __forceinline__ double4 ld_bc(const double *__restrict__ bc, int v) {
     const double2 hi = __ldg(reinterpret_cast<const double2 *>(bc) + 2 * (size_t)v + 1);
     return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
+#ifdef PMM_HOST_EMU
+__device__ __forceinline__ void prefetch_l2(const void *) {}
+__device__ __forceinline__ void grid_dependency_wait() {}
+__device__ __forceinline__ void grid_launch_dependents() {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // programmatic dependent launch: the next launch of the stream may start (and stage its clade) while this grid
 // drains; it must not touch records before grid_dependency_wait() (no-ops without the launch attribute)
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // the clade's steps, the branch constants of every step's two children and the four leaf vectors
 // (EM_solver.py:103-116 in full-state form, indexed by min(code, 1) + 2:

@@ -26,15 +26,7 @@ constexpr int NNI_THREADS = 128;
 constexpr int NNI_G = 4;
 constexpr int NNI_NG = NNI_THREADS / NNI_G;
 
-struct NniCand { int g, s, A, B, C, v, u, root; };    // node ids (g = -1: v is a root), root index of the tree
-
-// per-candidate state: d5 = lengths of (v, u, C, A, B)
-struct NniState { double d[5]; double llh_prev, llh_cur; int iters, done; };
-
-__device__ __forceinline__ double4 consts_of(double dv, double nu) {
-    const double c = exp(-nu * dv);
-    return make_double4(fabs(exp(-(1.0 + nu) * dv)), fabs(c * (-expm1(-dv))), fabs(c), fabs(-expm1(-nu * dv)));
-}
+// NniCand, NniState, consts_of: pmm_common.cuh
 
 __device__ __forceinline__ double gsum4(double x, unsigned m) {
     x += __shfl_xor_sync(m, x, 2);

@@ -13,7 +13,9 @@
 // the convergence test (:503).  One launch scores every candidate; nothing but the records is read.
 #pragma once
 #include "pmm_lumped.cuh"
+#ifndef PMM_HOST_EMU
 #include "pmm_nni.cuh"
+#endif
 #include "pmm_nni_ultra.cuh"
 
 namespace pmm {
