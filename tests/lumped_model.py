@@ -54,7 +54,7 @@ def _message(view, bc, qsum):
     return E0, xm, Eb, Eh, sq, xb
 
 
-def estep(forest, leaf_row, codes, qptr, qval, d, nu, phi):
+def estep(forest, leaf_row, codes, qptr, qval, d, nu, phi, dump=False):
     n = forest.parent.shape[0]
     N = forest.n_leaves
     K = codes.shape[1]
@@ -98,10 +98,12 @@ def estep(forest, leaf_row, codes, qptr, qval, d, nu, phi):
 
     # ---------------- roots: site likelihood
     invL = {}
+    root_llh = {}
     for r in np.nonzero(parent < 0)[0]:
         E0, _, _, _, sq, _ = _message(rec[r], (A[r], B[r], C[r], G[r]), qsum)
         with np.errstate(divide="ignore"):
-            site_llh += np.where(E0 > 0, np.log(E0), -np.inf) + rec[r][5] * math.log(2.0)
+            root_llh[r] = np.where(E0 > 0, np.log(E0), -np.inf) + rec[r][5] * math.log(2.0)
+            site_llh += root_llh[r]
         inv = np.where(E0 > 0, 1.0 / np.where(E0 > 0, E0, 1.0), 0.0)
         invL[r] = inv
         S[r, 0] += (A[r] * rec[r][0] * inv).sum()
@@ -162,4 +164,7 @@ def estep(forest, leaf_row, codes, qptr, qval, d, nu, phi):
                 e = _expo(np.maximum(np.maximum(n0, nm), np.maximum(nB, nD)))
                 sc = np.ldexp(1.0, -e)
                 out[v] = (n0 * sc, nm * sc, nB * sc, nD * sc, nk, F + cumw + e)
-    return {"llh": float(site_llh.sum()), "site_llh": site_llh, "S": S, "Rtilde": float(Rt)}
+    res = {"llh": float(site_llh.sum()), "site_llh": site_llh, "S": S, "Rtilde": float(Rt)}
+    if dump:        # the records themselves, as the engine stores them (pmm_lumped.cuh): inside (x0, xm, xz, qh, h, cum), outside (o0, om, oB, oD, k, F)
+        res.update(rec=rec, out=out, invL=invL, root_llh=root_llh, bc=np.stack([A, B, C, G], axis=1), qsum=qsum)
+    return res

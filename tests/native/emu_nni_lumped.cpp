@@ -1,0 +1,50 @@
+// emu_nni_lumped.cpp -- TEST INFRASTRUCTURE: pmm_nni_lumped<ULTRA> (laml_b200/csrc/pmm_nni_lumped.cuh), the kernel
+// behind pmm_score_nni_batch / pmm_score_nni_batch_ultra, compiled for the host under cuda_host_shim.h and fed with
+// records built by the numpy model of the lumped engine (tests/lumped_model.py).  Built and driven by
+// tests/test_nni_kernel_emulated.py.
+#include "cuda_host_shim.h"
+#include "../../laml_b200/csrc/pmm_nni_lumped.cuh"
+
+using namespace pmm;
+
+extern "C" int emu_nni_lumped(int ultra, int n_cand, const int *cand8 /* [n_cand][8] = g,s,A,B,C,v,u,root */, const double *d5_in,
+                              const double *ultra5 /* [n_cand][5] = hA,hB,hC,hTop,top_free or null */,
+                              int K, int Kp, int n_leaves, int n_nodes, const int *codes /* [n_leaves][K] */, const int *site_ptr,
+                              const double *prior, const double *qsum, double nu, double phi, const double *bc /* [n][4] */,
+                              const double *X /* [n_int][Kp][4] */, const double *O /* [n_int][Kp][4] */, const int *OI /* [n_int][Kp][2] */,
+                              const double *invL /* [n_roots][K] */, const double *root_llh_sum, double llh_total, int K_total,
+                              double dmin, double dmax, double conv_eps, int max_iter,
+                              double *out_llh, double *out_d5, int *out_iters, int *out_done) {
+    LParams P;
+    memset(&P, 0, sizeof(P));
+    P.K = K; P.Kp = Kp; P.site0 = 0; P.code_stride = K; P.n_leaves = n_leaves; P.n_nodes = n_nodes; P.n_clades = 0;
+    P.codes = codes; P.site_ptr = site_ptr; P.prior = prior; P.qsum = qsum;
+    const double params[2] = {nu, phi};
+    P.params = params; P.bc = bc;
+    P.X = reinterpret_cast<double2 *>(const_cast<double *>(X));
+    P.O = reinterpret_cast<double4 *>(const_cast<double *>(O));
+    P.OI = reinterpret_cast<int2 *>(const_cast<int *>(OI));
+    P.invL = const_cast<double *>(invL);
+    P.K_total = K_total;
+    std::vector<NniCand> cands(n_cand);
+    std::vector<NniState> st(n_cand);
+    std::vector<NniUltra> ul(n_cand);
+    for (int i = 0; i < n_cand; i++) {
+        const int *c = cand8 + 8 * i;
+        cands[i] = NniCand{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]};
+        for (int b = 0; b < 5; b++) st[i].d[b] = d5_in[5 * i + b];
+        st[i].llh_prev = st[i].llh_cur = 0.0; st[i].iters = 0; st[i].done = 0;
+        if (ultra) { const double *u = ultra5 + 5 * i; ul[i] = NniUltra{u[0], u[1], u[2], u[3], (int)u[4], 0}; }
+    }
+    if (ultra)
+        emu::launch((unsigned)n_cand, NNIL_THREADS, pmm_nni_lumped<true>, P, cands.data(), st.data(), root_llh_sum, llh_total, K_total,
+                    dmin, dmax, 1e-6, 1e-5, conv_eps, max_iter, ul.data());
+    else
+        emu::launch((unsigned)n_cand, NNIL_THREADS, pmm_nni_lumped<false>, P, cands.data(), st.data(), root_llh_sum, llh_total, K_total,
+                    dmin, dmax, 1e-6, 1e-5, conv_eps, max_iter, (const NniUltra *)nullptr);
+    for (int i = 0; i < n_cand; i++) {
+        out_llh[i] = st[i].llh_cur; out_iters[i] = st[i].iters; out_done[i] = st[i].done;
+        for (int b = 0; b < 5; b++) out_d5[5 * i + b] = st[i].d[b];
+    }
+    return 0;
+}

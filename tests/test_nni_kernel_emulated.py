@@ -1,0 +1,139 @@
+"""The batch NNI kernel ITSELF -- ``pmm_nni_lumped<ULTRA>`` of laml_b200/csrc/pmm_nni_lumped.cuh, unchanged -- run on
+the CPU: compiled for the host under a small CUDA shim (tests/native/cuda_host_shim.h: one std::thread per CUDA
+thread, barriers for __syncthreads / warp primitives), fed with the inside / outside records of the numpy model of
+the lumped engine (tests/lumped_model.py), and compared with the definition (tests/oracle_engine.py: a full-tree EM
+per candidate on the re-wired topology).  Covers what a machine without a GPU otherwise cannot: the kernel's site
+loop (record decoding, local inside / outside recursion, counts), its reductions, the EM loop and convergence
+test, and both M-steps (five 1-D problems; the two-height constrained problem).  Says nothing about memory ordering
+or speed -- the ``-m gpu`` tests do."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from laml_b200.nni import nni_candidates            # noqa: E402
+from laml_b200.synth import make_workload           # noqa: E402
+from lumped_model import estep as lumped_estep      # noqa: E402
+from oracle_engine import OracleEngine              # noqa: E402
+from test_nni_ultra_host import ultrametric_lengths  # noqa: E402
+
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(CUDA_INC, "cuda_runtime.h")), reason="CUDA headers not found")
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libemu_nni.so")
+    src = os.path.join(HERE, "native", "emu_nni_lumped.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC, src, "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.emu_nni_lumped.restype = C.c_int
+    return lib
+
+
+def pack_records(forest, m, K):
+    """the model's records in the engine's memory layout: X [n_int][Kp] x (x0, xz, t, h|cum), O (o0, om, oB, oD), OI (k, F)"""
+    N, n = forest.n_leaves, forest.n_nodes
+    Kp = (K + 31) // 32 * 32
+    X = np.zeros((n - N, Kp, 4)); O = np.zeros((n - N, Kp, 4)); OI = np.zeros((n - N, Kp, 2), np.int32)
+    for u in range(N, n):
+        x0, xm, xz, qh, h, cum = m["rec"][u]
+        hot = h >= 0
+        assert np.all(xm[hot] == 0.0)                                  # x_m and q_h share a slot
+        X[u - N, :K, 0], X[u - N, :K, 1] = x0, xz
+        X[u - N, :K, 2] = np.where(hot, qh, xm)
+        packed = (np.asarray(cum, np.int64).astype(np.uint64) << np.uint64(32)) | (np.asarray(h, np.int64).astype(np.uint64) & np.uint64(0xffffffff))
+        X[u - N, :K, 3] = packed.view(np.float64)
+        o0, om, oB, oD, k, F = m["out"][u]
+        O[u - N, :K] = np.stack([o0, om, oB, oD], axis=1)
+        OI[u - N, :K, 0], OI[u - N, :K, 1] = k, F
+    return Kp, X, O, OI
+
+
+def run_kernel(emu, w, d, nu, phi, ultra, max_iter=1000):
+    f = w.forest
+    N, n, K = f.n_leaves, f.n_nodes, w.codes.shape[1]
+    m = lumped_estep(f, np.arange(N), w.codes, w.qptr, w.qval, d, nu, phi, dump=True)
+    Kp, X, O, OI = pack_records(f, m, K)
+    roots = [int(r) for r in np.nonzero(f.parent < 0)[0]]
+    root_index = np.zeros(n, np.int32)
+    order = list(roots)
+    for v in order:
+        if f.left[v] >= 0:
+            order += [int(f.left[v]), int(f.right[v])]
+    for i, r in enumerate(roots):
+        root_index[r] = i
+    for v in order:
+        if f.parent[v] >= 0:
+            root_index[v] = root_index[f.parent[v]]
+    invL = np.stack([m["invL"][r] for r in roots])
+    rsum = np.array([m["root_llh"][r].sum() for r in roots])
+    cu, ck = nni_candidates(f.parent, f.left, N)
+    nc = len(cu)
+    cand = np.zeros((nc, 8), np.int32); d5 = np.zeros((nc, 5)); ul = np.zeros((nc, 5)); nodes = np.zeros((nc, 5), np.int32)
+    height = np.zeros(n)
+    for v in reversed(order):
+        if f.left[v] >= 0:
+            height[v] = max(height[f.left[v]] + d[f.left[v]], height[f.right[v]] + d[f.right[v]])
+    top = max(height[r] + d[r] for r in roots)
+    for i, (u, k) in enumerate(zip(cu.tolist(), ck.tolist())):
+        v = int(f.parent[u]); wn = int(f.right[v] if f.left[v] == u else f.left[v])
+        c_k = int(f.right[u] if k else f.left[u]); c_o = int(f.left[u] if k else f.right[u])
+        g = int(f.parent[v]); s = -1 if g < 0 else int(f.right[g] if f.left[g] == v else f.left[g])
+        cand[i] = (g, s, c_o, wn, c_k, v, u, root_index[u])
+        nodes[i] = (v, u, c_k, c_o, wn)
+        d5[i] = d[nodes[i]]
+        ul[i] = (height[c_o], height[wn], height[c_k], height[g] if g >= 0 else top, float(g < 0 and len(roots) == 1))
+    codes = np.ascontiguousarray(w.codes, np.int32)
+    site_ptr = np.ascontiguousarray(w.qptr, np.int32); prior = np.ascontiguousarray(w.qval, np.float64)
+    qsum = np.ascontiguousarray(m["qsum"]); bc = np.ascontiguousarray(m["bc"])
+    out_llh = np.zeros(nc); out_d5 = np.zeros((nc, 5)); out_it = np.zeros(nc, np.int32); out_done = np.zeros(nc, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    rc = emu.emu_nni_lumped(int(ultra), nc, p(cand), p(d5), p(ul), K, Kp, N, n, p(codes), p(site_ptr), p(prior), p(qsum),
+                            C.c_double(nu), C.c_double(phi), p(bc), p(X), p(O), p(OI), p(np.ascontiguousarray(invL)), p(rsum),
+                            C.c_double(m["llh"]), K, C.c_double(0.005), C.c_double(10.0), C.c_double(1e-8), max_iter,
+                            p(out_llh), p(out_d5), p(out_it), p(out_done))
+    assert rc == 0
+    return cu, ck, nodes, -out_llh, out_d5, out_it, out_done
+
+
+@pytest.mark.parametrize("seed,n,K,amax,nu,phi", [(71, 12, 150, 12, 0.15, 0.1), (73, 10, 20, 6, 0.3, 0.0)])
+def test_unconstrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi):
+    """the kernel of pmm_score_nni_batch (already green on a B200) through the same emulation: validates the shim"""
+    w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
+    d = np.maximum(w.d, 0.01)
+    cu, ck, nodes, nllh, d5, iters, done = run_kernel(emu, w, d, nu, phi, ultra=False)
+    model = OracleEngine(n, w.qptr, w.qval, w.codes)
+    model.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    want = model.score_nni_batch(cu, ck, d, nu, phi)
+    assert (done == 1).all() and (nodes == want["nodes"]).all()
+    np.testing.assert_allclose(nllh, want["nllh"], rtol=1e-9)
+    np.testing.assert_allclose(d5, want["d5"], rtol=1e-6, atol=1e-8)
+    assert (iters == want["iters"]).all()
+
+
+@pytest.mark.parametrize("seed,n,K,amax,nu,phi,step", [(91, 12, 150, 12, 0.15, 0.1, (0.02, 0.3)), (92, 14, 9, 40, 0.0, 0.2, (0.006, 0.012))])
+def test_constrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi, step):
+    """pmm_nni_lumped<true> -- the kernel behind pmm_score_nni_batch_ultra, not yet run on a GPU -- against the
+    definition: scores to 1e-9, the five lengths, EM iteration counts, and which candidates have no room"""
+    w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
+    d, _ = ultrametric_lengths(w.forest, np.random.default_rng(seed), step=step)
+    cu, ck, nodes, nllh, d5, iters, done = run_kernel(emu, w, d, nu, phi, ultra=True)
+    model = OracleEngine(n, w.qptr, w.qval, w.codes)
+    model.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    want = model.score_nni_batch(cu, ck, d, nu, phi, ultra=True)
+    bad = np.isnan(want["nllh"])
+    assert ((done == 2) == bad).all() and (done[~bad] == 1).all()
+    if seed == 92:
+        assert bad.sum() >= 3
+    ok = ~bad
+    np.testing.assert_allclose(nllh[ok], want["nllh"][ok], rtol=1e-9)
+    np.testing.assert_allclose(d5[ok], want["d5"][ok], rtol=1e-5, atol=1e-7)
+    assert (np.abs(iters[ok] - want["iters"][ok]) <= 1).all()

@@ -3,8 +3,9 @@ CPU model of the same definition: a full-tree EM per candidate on the explicitly
 whole-tree host M-step with every branch but the five around the move fixed (tests/oracle_engine.py) -- which
 tests/test_topology_host.py shows to be the reference's per-candidate call without its ``2 dmin`` raise.
 
-The kernel variant was written after this round's GPU budget was spent: its arithmetic is covered on CPU through
-its host instance (tests/test_nni_ultra_host.py), but THIS file has not run on a GPU yet.  It sorts last so that
+The kernel variant was written after this round's GPU budget was spent: its M-step is covered on CPU through its
+host instance (tests/test_nni_ultra_host.py) and the whole kernel through a host build of its unchanged source
+(tests/test_nni_kernel_emulated.py), but THIS file has not run on a GPU yet.  It sorts last so that
 nothing else depends on it, and it is marked xfail(strict=False) for that reason alone -- an XPASS is the expected
 outcome, and the marker goes once a GPU run is on record."""
 import numpy as np
