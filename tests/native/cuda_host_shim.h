@@ -69,25 +69,28 @@ using std::max;
 using std::min;
 
 namespace emu {
-// kernel<<<grid, block>>>(args...) with a 1-D grid and block; the kernel is any callable
+// kernel<<<dim3(grid, grid_y), block>>>(args...) with a 1-D block; the kernel is any callable
 template <class K, class... A>
-void launch(unsigned grid, unsigned block, K kernel, A... args) {
+void launch2(unsigned grid, unsigned grid_y, unsigned block, K kernel, A... args) {
     Cta cta;
     current() = &cta;
     pthread_barrier_init(&cta.cta_bar, nullptr, block);
     for (unsigned w = 0; w < (block + 31) / 32; w++) pthread_barrier_init(&cta.warp_bar[w], nullptr, std::min(32u, block - 32 * w));
-    for (unsigned b = 0; b < grid; b++) {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < block; t++)
-            th.emplace_back([=] {
-                threadIdx = {t, 0, 0}; blockIdx = {b, 0, 0};
-                blockDim = dim3(block); gridDim = dim3(grid);
-                kernel(args...);
-            });
-        for (auto &x : th) x.join();
-    }
+    for (unsigned by = 0; by < grid_y; by++)
+        for (unsigned b = 0; b < grid; b++) {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < block; t++)
+                th.emplace_back([=] {
+                    threadIdx = {t, 0, 0}; blockIdx = {b, by, 0};
+                    blockDim = dim3(block); gridDim = dim3(grid, grid_y);
+                    kernel(args...);
+                });
+            for (auto &x : th) x.join();
+        }
     pthread_barrier_destroy(&cta.cta_bar);
     for (unsigned w = 0; w < (block + 31) / 32; w++) pthread_barrier_destroy(&cta.warp_bar[w]);
     current() = nullptr;
 }
+template <class K, class... A>
+void launch(unsigned grid, unsigned block, K kernel, A... args) { launch2(grid, 1u, block, kernel, args...); }
 }  // namespace emu

@@ -1,7 +1,7 @@
-// emu_nni_lumped.cpp -- TEST INFRASTRUCTURE: pmm_nni_lumped<ULTRA> (laml_b200/csrc/pmm_nni_lumped.cuh), the kernel
+// emu_lumped.cpp -- TEST INFRASTRUCTURE: pmm_nni_lumped<ULTRA> (laml_b200/csrc/pmm_nni_lumped.cuh), the kernel
 // behind pmm_score_nni_batch / pmm_score_nni_batch_ultra, compiled for the host under cuda_host_shim.h and fed with
 // records built by the numpy model of the lumped engine (tests/lumped_model.py).  Built and driven by
-// tests/test_nni_kernel_emulated.py.
+// tests/test_kernels_emulated.py.
 #include "cuda_host_shim.h"
 #include "../../laml_b200/csrc/pmm_nni_lumped.cuh"
 
@@ -45,6 +45,42 @@ extern "C" int emu_nni_lumped(int ultra, int n_cand, const int *cand8 /* [n_cand
     for (int i = 0; i < n_cand; i++) {
         out_llh[i] = st[i].llh_cur; out_iters[i] = st[i].iters; out_done[i] = st[i].done;
         for (int b = 0; b < 5; b++) out_d5[5 * i + b] = st[i].d[b];
+    }
+    return 0;
+}
+
+// The E-step kernels themselves: pmm_lumped_inside, then pmm_lumped_outside<false>, phase by phase as
+// pmm_engine.cu: run_lumped launches them (one launch per tier of the clade schedule, grid = clades x site blocks).
+extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_clades, const int *codes, const int *site_ptr,
+                                const double *prior, const double *qsum, double nu, double phi, const double *d /* [n] */,
+                                const int *in_steps, const int *in_clades, const int *in_phase_ptr, int n_in_phases,
+                                const int *out_steps, const int *out_clades, const int *out_phase_ptr, int n_out_phases, int store_all,
+                                double *X, double *O, int *OI, double *invL, double *root_site_llh, double *Spart, double *Rpart,
+                                double *bc_out /* [n][4] */) {
+    LParams P;
+    memset(&P, 0, sizeof(P));
+    P.K = K; P.Kp = Kp; P.site0 = 0; P.code_stride = K; P.n_leaves = n_leaves; P.n_nodes = n_nodes; P.n_clades = n_clades;
+    P.codes = codes; P.site_ptr = site_ptr; P.prior = prior; P.qsum = qsum;
+    const double params[2] = {nu, phi};
+    P.params = params;
+    for (int v = 0; v < n_nodes; v++) {                       // pmm_branch_consts
+        const double4 c = consts_of(d[v], nu);
+        bc_out[4 * v] = c.x; bc_out[4 * v + 1] = c.y; bc_out[4 * v + 2] = c.z; bc_out[4 * v + 3] = c.w;
+    }
+    P.bc = bc_out;
+    P.X = reinterpret_cast<double2 *>(X); P.O = reinterpret_cast<double4 *>(O); P.OI = reinterpret_cast<int2 *>(OI);
+    P.invL = invL; P.root_site_llh = root_site_llh; P.Spart = Spart; P.Rpart = Rpart;
+    P.K_total = K; P.store_all = store_all; P.sblk0 = 0;
+    const unsigned gy = (unsigned)((K + LT - 1) / LT);
+    for (int p = 0; p < n_in_phases; p++) {
+        const int c0 = in_phase_ptr[p], c1 = in_phase_ptr[p + 1];
+        if (c1 > c0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_inside, P, reinterpret_cast<const int4 *>(in_clades) + c0,
+                                  reinterpret_cast<const int4 *>(in_steps));
+    }
+    for (int p = 0; p < n_out_phases; p++) {
+        const int c0 = out_phase_ptr[p], c1 = out_phase_ptr[p + 1];
+        if (c1 > c0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
+                                  reinterpret_cast<const int4 *>(out_steps));
     }
     return 0;
 }

@@ -1,11 +1,17 @@
-"""The batch NNI kernel ITSELF -- ``pmm_nni_lumped<ULTRA>`` of laml_b200/csrc/pmm_nni_lumped.cuh, unchanged -- run on
-the CPU: compiled for the host under a small CUDA shim (tests/native/cuda_host_shim.h: one std::thread per CUDA
-thread, barriers for __syncthreads / warp primitives), fed with the inside / outside records of the numpy model of
-the lumped engine (tests/lumped_model.py), and compared with the definition (tests/oracle_engine.py: a full-tree EM
-per candidate on the re-wired topology).  Covers what a machine without a GPU otherwise cannot: the kernel's site
-loop (record decoding, local inside / outside recursion, counts), its reductions, the EM loop and convergence
-test, and both M-steps (five 1-D problems; the two-height constrained problem).  Says nothing about memory ordering
-or speed -- the ``-m gpu`` tests do."""
+"""The lumped-state kernels THEMSELVES on the CPU: the unchanged source of laml_b200/csrc/pmm_lumped.cuh and
+pmm_nni_lumped.cuh compiled for the host under a small CUDA shim (tests/native/cuda_host_shim.h: one std::thread
+per CUDA thread, ``__shared__`` as function-local statics, barriers for __syncthreads / warp primitives).
+
+* ``pmm_lumped_inside`` + ``pmm_lumped_outside`` -- the E-step, the hot path -- on the clade schedule the library
+  derives (``pmm_debug_lumped_schedule``), launch by launch as ``run_lumped`` issues them, against the CPU oracle at
+  the GPU parity tolerances;
+* ``pmm_nni_lumped<ULTRA>`` -- the batch NNI scorer, unconstrained and under the ultrametric constraint -- fed with
+  the inside / outside records of the numpy model of the lumped engine (tests/lumped_model.py), against the
+  definition (tests/oracle_engine.py: a full-tree EM per candidate on the re-wired topology).
+
+Covers what a machine without a GPU otherwise cannot: the kernels' own index arithmetic, record packing, closed
+forms, prefetch / register-set rotation, warp reductions, EM loop and M-steps.  Says nothing about memory ordering,
+registers or speed -- the ``-m gpu`` tests and the profiles do."""
 import ctypes as C
 import os
 import subprocess
@@ -31,7 +37,7 @@ pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(CUDA_INC, "cuda_
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libemu_nni.so")
-    src = os.path.join(HERE, "native", "emu_nni_lumped.cpp")
+    src = os.path.join(HERE, "native", "emu_lumped.cpp")
     subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC, src, "-o", so], check=True)
     lib = C.CDLL(so)
     lib.emu_nni_lumped.restype = C.c_int
@@ -137,3 +143,49 @@ def test_constrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi, step):
     np.testing.assert_allclose(nllh[ok], want["nllh"][ok], rtol=1e-9)
     np.testing.assert_allclose(d5[ok], want["d5"][ok], rtol=1e-5, atol=1e-7)
     assert (np.abs(iters[ok] - want["iters"][ok]) <= 1).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the E-step kernels themselves (pmm_lumped_inside / pmm_lumped_outside), on the clade schedule the library derives
+def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0):
+    from laml_b200.capi import lumped_schedule
+    f = w.forest
+    N, n, K = f.n_leaves, f.n_nodes, w.codes.shape[1]
+    sch = lumped_schedule(N, f.parent, f.left, f.right, clade_cap, clade_cap_top)
+    Kp, G = (K + 31) // 32 * 32, (K + 31) // 32
+    n_roots = int((f.parent < 0).sum())
+    qptr = np.asarray(w.qptr, np.int64)
+    qsum = np.array([w.qval[qptr[s]:qptr[s + 1]].sum() for s in range(K)])
+    X = np.zeros((n - N, Kp, 4)); O = np.zeros((n - N, Kp, 4)); OI = np.zeros((n - N, Kp, 2), np.int32)
+    invL = np.zeros((n_roots, K)); rllh = np.zeros((n_roots, K))
+    Spart = np.zeros((G, n, 5)); Rpart = np.zeros((G, max(sch["n_clades"], 1))); bc = np.zeros((n, 4))
+    codes = np.ascontiguousarray(w.codes, np.int32)
+    site_ptr = np.ascontiguousarray(w.qptr, np.int32); prior = np.ascontiguousarray(w.qval, np.float64)
+    dd = np.ascontiguousarray(d, np.float64)
+    arrs = {k: np.ascontiguousarray(sch[k], np.int32) for k in ("in_steps", "in_clades", "in_phase_ptr", "out_steps", "out_clades", "out_phase_ptr")}
+    p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    rc = emu.emu_lumped_estep(K, Kp, N, n, sch["n_clades"], p(codes), p(site_ptr), p(prior), p(qsum), C.c_double(nu), C.c_double(phi),
+                              p(dd), p(arrs["in_steps"]), p(arrs["in_clades"]), p(arrs["in_phase_ptr"]), len(arrs["in_phase_ptr"]) - 1,
+                              p(arrs["out_steps"]), p(arrs["out_clades"]), p(arrs["out_phase_ptr"]), len(arrs["out_phase_ptr"]) - 1,
+                              store_all, p(X), p(O), p(OI), p(invL), p(rllh), p(Spart), p(Rpart), p(bc))
+    assert rc == 0
+    return {"S": Spart.sum(axis=0), "llh": float(rllh.sum()), "Rtilde": float(Rpart.sum()), "site_llh": rllh.sum(axis=0),
+            "n_phases": sch["n_phases"], "n_clades": sch["n_clades"]}
+
+
+@pytest.mark.parametrize("seed,n,K,amax,nu,phi,caps", [(31, 40, 70, 12, 0.2, 0.15, (6, 4)), (32, 24, 33, 40, 0.0, 0.3, (127, 127)),
+                                                       (33, 30, 140, 5, 0.4, 0.0, (3, 3))])
+def test_estep_kernels_on_the_host(emu, seed, n, K, amax, nu, phi, caps):
+    """pmm_lumped_inside + pmm_lumped_outside, unchanged source, on the host: expected counts, likelihood and R~
+    against the CPU oracle at the GPU parity tolerances (several launches per pass with small clade capacities,
+    one with 127; K not a multiple of 32 or 128: idle lanes, a second site block)"""
+    from oracle.pmm_oracle import OracleProblem
+    w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
+    got = run_estep_kernels(emu, w, w.d, nu, phi, *caps)
+    ref = OracleProblem(w.forest, np.arange(n, dtype=np.int32), w.codes, w.qptr, w.qval).estep(w.d, nu, phi)
+    assert abs(got["llh"] - ref["llh"]) <= 1e-9 * abs(ref["llh"])
+    np.testing.assert_allclose(got["S"], ref["S"].T, rtol=1e-8, atol=1e-10 * K)
+    assert abs(got["Rtilde"] - ref["Rtilde"]) <= 1e-8 * max(1.0, abs(ref["Rtilde"]))
+    np.testing.assert_allclose(got["site_llh"], ref["site_llh"], rtol=1e-9, atol=1e-12)
+    if caps[0] < 10:
+        assert got["n_phases"] > 1 and got["n_clades"] > 3

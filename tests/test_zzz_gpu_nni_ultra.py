@@ -5,7 +5,7 @@ tests/test_topology_host.py shows to be the reference's per-candidate call witho
 
 The kernel variant was written after this round's GPU budget was spent: its M-step is covered on CPU through its
 host instance (tests/test_nni_ultra_host.py) and the whole kernel through a host build of its unchanged source
-(tests/test_nni_kernel_emulated.py), but THIS file has not run on a GPU yet.  It sorts last so that
+(tests/test_kernels_emulated.py), but THIS file has not run on a GPU yet.  It sorts last so that
 nothing else depends on it, and it is marked xfail(strict=False) for that reason alone -- an XPASS is the expected
 outcome, and the marker goes once a GPU run is on record."""
 import numpy as np
