@@ -56,7 +56,7 @@ extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_
                                 const int *in_steps, const int *in_clades, const int *in_phase_ptr, int n_in_phases,
                                 const int *out_steps, const int *out_clades, const int *out_phase_ptr, int n_out_phases, int store_all,
                                 double *X, double *O, int *OI, double *invL, double *root_site_llh, double *Spart, double *Rpart,
-                                double *bc_out /* [n][4] */) {
+                                double *bc_out /* [n][4] */, double *post0 /* [n][K] or null: the annotation variant */, double *post1) {
     LParams P;
     memset(&P, 0, sizeof(P));
     P.K = K; P.Kp = Kp; P.site0 = 0; P.code_stride = K; P.n_leaves = n_leaves; P.n_nodes = n_nodes; P.n_clades = n_clades;
@@ -71,6 +71,7 @@ extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_
     P.X = reinterpret_cast<double2 *>(X); P.O = reinterpret_cast<double4 *>(O); P.OI = reinterpret_cast<int2 *>(OI);
     P.invL = invL; P.root_site_llh = root_site_llh; P.Spart = Spart; P.Rpart = Rpart;
     P.K_total = K; P.store_all = store_all; P.sblk0 = 0;
+    P.post0 = post0; P.post1 = post1;
     const unsigned gy = (unsigned)((K + LT - 1) / LT);
     for (int p = 0; p < n_in_phases; p++) {
         const int c0 = in_phase_ptr[p], c1 = in_phase_ptr[p + 1];
@@ -79,8 +80,11 @@ extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_
     }
     for (int p = 0; p < n_out_phases; p++) {
         const int c0 = out_phase_ptr[p], c1 = out_phase_ptr[p + 1];
-        if (c1 > c0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
-                                  reinterpret_cast<const int4 *>(out_steps));
+        if (c1 <= c0) continue;
+        if (post0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<true>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
+                                reinterpret_cast<const int4 *>(out_steps));
+        else emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
+                          reinterpret_cast<const int4 *>(out_steps));
     }
     return 0;
 }

@@ -63,12 +63,21 @@ def pack_records(forest, m, K):
     return Kp, X, O, OI
 
 
-def run_kernel(emu, w, d, nu, phi, ultra, max_iter=1000):
+def run_kernel(emu, w, d, nu, phi, ultra, max_iter=1000, records=None):
+    """``records``: the output of :func:`run_estep_kernels` with ``store_all`` -- the NNI kernel then reads what the
+    emulated E-step kernels wrote, as on the GPU; default: records laid out from the numpy model"""
     f = w.forest
     N, n, K = f.n_leaves, f.n_nodes, w.codes.shape[1]
-    m = lumped_estep(f, np.arange(N), w.codes, w.qptr, w.qval, d, nu, phi, dump=True)
-    Kp, X, O, OI = pack_records(f, m, K)
     roots = [int(r) for r in np.nonzero(f.parent < 0)[0]]
+    if records is None:
+        m = lumped_estep(f, np.arange(N), w.codes, w.qptr, w.qval, d, nu, phi, dump=True)
+        Kp, X, O, OI = pack_records(f, m, K)
+        invL = np.stack([m["invL"][r] for r in roots])
+        rsum = np.array([m["root_llh"][r].sum() for r in roots])
+    else:
+        Kp, X, O, OI, invL = (K + 31) // 32 * 32, records["X"], records["O"], records["OI"], records["invL"]
+        rsum = records["root_llh"].sum(axis=1)
+        m = {"llh": records["llh"], "qsum": records["qsum"], "bc": records["bc"]}
     root_index = np.zeros(n, np.int32)
     order = list(roots)
     for v in order:
@@ -79,8 +88,6 @@ def run_kernel(emu, w, d, nu, phi, ultra, max_iter=1000):
     for v in order:
         if f.parent[v] >= 0:
             root_index[v] = root_index[f.parent[v]]
-    invL = np.stack([m["invL"][r] for r in roots])
-    rsum = np.array([m["root_llh"][r].sum() for r in roots])
     cu, ck = nni_candidates(f.parent, f.left, N)
     nc = len(cu)
     cand = np.zeros((nc, 8), np.int32); d5 = np.zeros((nc, 5)); ul = np.zeros((nc, 5)); nodes = np.zeros((nc, 5), np.int32)
@@ -147,7 +154,7 @@ def test_constrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi, step):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the E-step kernels themselves (pmm_lumped_inside / pmm_lumped_outside), on the clade schedule the library derives
-def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0):
+def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0, posteriors=False):
     from laml_b200.capi import lumped_schedule
     f = w.forest
     N, n, K = f.n_leaves, f.n_nodes, w.codes.shape[1]
@@ -163,14 +170,17 @@ def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0)
     site_ptr = np.ascontiguousarray(w.qptr, np.int32); prior = np.ascontiguousarray(w.qval, np.float64)
     dd = np.ascontiguousarray(d, np.float64)
     arrs = {k: np.ascontiguousarray(sch[k], np.int32) for k in ("in_steps", "in_clades", "in_phase_ptr", "out_steps", "out_clades", "out_phase_ptr")}
-    p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    post0 = np.full((n, K), np.nan) if posteriors else None
+    post1 = np.full((n, K), np.nan) if posteriors else None
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)   # noqa: E731
     rc = emu.emu_lumped_estep(K, Kp, N, n, sch["n_clades"], p(codes), p(site_ptr), p(prior), p(qsum), C.c_double(nu), C.c_double(phi),
                               p(dd), p(arrs["in_steps"]), p(arrs["in_clades"]), p(arrs["in_phase_ptr"]), len(arrs["in_phase_ptr"]) - 1,
                               p(arrs["out_steps"]), p(arrs["out_clades"]), p(arrs["out_phase_ptr"]), len(arrs["out_phase_ptr"]) - 1,
-                              store_all, p(X), p(O), p(OI), p(invL), p(rllh), p(Spart), p(Rpart), p(bc))
+                              store_all, p(X), p(O), p(OI), p(invL), p(rllh), p(Spart), p(Rpart), p(bc), p(post0), p(post1))
     assert rc == 0
     return {"S": Spart.sum(axis=0), "llh": float(rllh.sum()), "Rtilde": float(Rpart.sum()), "site_llh": rllh.sum(axis=0),
-            "n_phases": sch["n_phases"], "n_clades": sch["n_clades"]}
+            "n_phases": sch["n_phases"], "n_clades": sch["n_clades"], "X": X, "O": O, "OI": OI, "invL": invL, "root_llh": rllh,
+            "bc": bc, "qsum": qsum, "post0": post0, "post1": post1}
 
 
 @pytest.mark.parametrize("seed,n,K,amax,nu,phi,caps", [(31, 40, 70, 12, 0.2, 0.15, (6, 4)), (32, 24, 33, 40, 0.0, 0.3, (127, 127)),
@@ -189,3 +199,82 @@ def test_estep_kernels_on_the_host(emu, seed, n, K, amax, nu, phi, caps):
     np.testing.assert_allclose(got["site_llh"], ref["site_llh"], rtol=1e-9, atol=1e-12)
     if caps[0] < 10:
         assert got["n_phases"] > 1 and got["n_clades"] > 3
+
+
+def test_posterior_variant_on_the_host(emu):
+    """pmm_lumped_outside<true> (the annotation path, pmm_posteriors): log posteriors of state 0 / silenced per
+    (node, site) against the oracle's dump of the reference's ``post0`` / ``post1`` (EM_solver.py:276-277)"""
+    from oracle.pmm_oracle import OracleProblem
+    w = make_workload(26, 45, 1, 9, 0.25, 0.2, seed=41)
+    got = run_estep_kernels(emu, w, w.d, 0.25, 0.2, 5, 5, posteriors=True)
+    ref = OracleProblem(w.forest, np.arange(26, dtype=np.int32), w.codes, w.qptr, w.qval).estep(w.d, 0.25, 0.2, dump=True)
+    assert not np.isnan(got["post0"]).any() and not np.isnan(got["post1"]).any()     # every (node, site) was written
+    for name in ("post0", "post1"):
+        a, b = np.exp(got[name]), np.exp(np.asarray(ref[name]))
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-12)
+
+
+def test_whole_batch_call_on_the_host(emu):
+    """pmm_score_nni_batch_ultra end to end as the library runs it: E-step kernels with every out-record stored
+    (``store_all``), then the NNI kernel on THOSE records -- every kernel of the call emulated -- against the definition"""
+    seed, n, K, nu, phi = 95, 14, 40, 0.2, 0.1
+    w = make_workload(n, K, 1, 10, nu, phi, seed=seed)
+    d, _ = ultrametric_lengths(w.forest, np.random.default_rng(seed), step=(0.01, 0.2))
+    rec = run_estep_kernels(emu, w, d, nu, phi, 4, 3, store_all=1)
+    cu, ck, nodes, nllh, d5, iters, done = run_kernel(emu, w, d, nu, phi, ultra=True, records=rec)
+    model = OracleEngine(n, w.qptr, w.qval, w.codes)
+    model.set_tree(w.forest.parent, w.forest.left, w.forest.right)
+    want = model.score_nni_batch(cu, ck, d, nu, phi, ultra=True)
+    bad = np.isnan(want["nllh"])
+    assert ((done == 2) == bad).all() and (~bad).sum() > len(cu) // 2
+    np.testing.assert_allclose(nllh[~bad], want["nllh"][~bad], rtol=1e-9)
+    np.testing.assert_allclose(d5[~bad], want["d5"][~bad], rtol=1e-5, atol=1e-7)
+
+
+def _check_estep(emu, forest, codes, qptr, qval, d, nu, phi, caps):
+    from types import SimpleNamespace
+    from oracle.pmm_oracle import OracleProblem
+    w = SimpleNamespace(forest=forest, codes=codes, qptr=qptr, qval=qval)
+    got = run_estep_kernels(emu, w, d, nu, phi, *caps)
+    N, K = forest.n_leaves, codes.shape[1]
+    ref = OracleProblem(forest, np.arange(N, dtype=np.int32), codes, qptr, qval).estep(d, nu, phi)
+    assert abs(got["llh"] - ref["llh"]) <= 1e-9 * abs(ref["llh"])
+    np.testing.assert_allclose(got["S"], ref["S"].T, rtol=1e-8, atol=1e-10 * K)
+    assert abs(got["Rtilde"] - ref["Rtilde"]) <= 1e-8 * max(1.0, abs(ref["Rtilde"]))
+    return got
+
+
+def test_estep_kernels_larger_and_edge_shapes(emu):
+    """the shapes the GPU edge-case tests use, through the emulated kernels: a larger tree at the engine's default
+    clade capacities, a caterpillar-biased (deep) tree, a forest of two trees over the same cells, the smallest
+    trees, a site with a single state"""
+    from laml_b200.flatten import forest_from_parent
+    from laml_b200.synth import lognormal_branch_lengths, random_priors, random_tree, simulate_codes
+    w = make_workload(400, 200, 2, 60, 0.3, 0.3, seed=61)
+    got = _check_estep(emu, w.forest, w.codes, w.qptr, w.qval, w.d, 0.3, 0.3, (64, 16))
+    assert got["n_clades"] > 5
+    w = make_workload(120, 40, 1, 8, 0.1, 0.2, seed=62, caterpillar_bias=0.85)
+    _check_estep(emu, w.forest, w.codes, w.qptr, w.qval, w.d, 0.1, 0.2, (16, 16))
+    # forest (layout as tests/test_gpu_edge_cases.py::test_forest_of_two_trees)
+    N = 30
+    f1, f2 = random_tree(N, seed=51), random_tree(N, seed=52)
+    n1 = f1.n_nodes
+
+    def shift(f, leaf_off, int_off):
+        def m(a):
+            return np.where(a < 0, -1, np.where(a < N, a + leaf_off, a - N + int_off))
+        return m(f.parent), m(f.left), m(f.right)
+    p1, l1, r1 = shift(f1, 0, 2 * N)
+    p2, l2, r2 = shift(f2, N, 2 * N + (n1 - N))
+    forest = forest_from_parent(*(np.concatenate([a[:N], b[:N], a[N:], b[N:]]).astype(np.int32)
+                                  for a, b in ((p1, p2), (l1, l2), (r1, r2))))
+    d = lognormal_branch_lengths(forest, seed=53)
+    qptr, qval = random_priors(10, 2, 15, seed=54)
+    c1 = simulate_codes(f1, lognormal_branch_lengths(f1, seed=55), qptr, qval, 0.2, 0.2, seed=56)
+    _check_estep(emu, forest, np.concatenate([c1, c1]), qptr, qval, d, 0.2, 0.2, (8, 4))
+    for n_leaves in (2, 3):
+        f = random_tree(n_leaves, seed=91)
+        d = lognormal_branch_lengths(f, seed=92)
+        for codes in ([1, 0, -1], [-1, -1, -1], [1, 1, 1], [0, -2, 1]):
+            c = np.array(codes[:n_leaves], np.int32).reshape(n_leaves, 1)
+            _check_estep(emu, f, c, np.array([0, 1], np.int32), np.array([1.0]), d, 0.2, 0.1, (16, 16))
