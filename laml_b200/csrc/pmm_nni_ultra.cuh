@@ -31,14 +31,18 @@ struct NniUltra { double hA, hB, hC, hTop; int top_free, pad; };
 // per-edge objective pieces: k = (nu+1) S0 + nu (S1+S3), S1, S24 = S2 + S4
 struct Ultra2Stats { double k[5], S1[5], S24[5]; double nu; bool use_nu; };
 
-PMM_HD void ultra2_f(const Ultra2Stats &T, int e, double x, double &val, double &g, double &h) {
+// value alone (expm1 + log per term) and derivatives alone (one expm1 per term): neither caller pays for the other
+PMM_HD double ultra2_value(const Ultra2Stats &T, int e, double x) {
+    double val = -T.k[e] * x + T.S1[e] * log(-expm1(-x));
+    if (T.use_nu) val += T.S24[e] * log(-expm1(-T.nu * x));
+    return val;
+}
+PMM_HD void ultra2_grad_hess(const Ultra2Stats &T, int e, double x, double &g, double &h) {
     const double em = expm1(x);
-    val = -T.k[e] * x + T.S1[e] * log(-expm1(-x));
     g = -T.k[e] + T.S1[e] / em;
     h = -T.S1[e] * (em + 1.0) / (em * em);
     if (T.use_nu) {
         const double emn = expm1(T.nu * x);
-        val += T.S24[e] * log(-expm1(-T.nu * x));
         g += T.nu * T.S24[e] / emn;
         h -= T.nu * T.nu * T.S24[e] * (emn + 1.0) / (emn * emn);
     }
@@ -49,18 +53,22 @@ PMM_HD void ultra2_edges(const NniUltra &c, const double *H, double *x) {
     x[0] = H[2] - H[1]; x[1] = H[1] - H[0]; x[2] = H[1] - c.hC; x[3] = H[0] - c.hA; x[4] = H[0] - c.hB;
 }
 
-PMM_HD double ultra2_objective(const NniUltra &c, const Ultra2Stats &T, const double *H, double mu, double lo, double hi) {
-    double x[5], s = 0.0, b = 0.0;
+// objective = fsum + mu * bsum, the sums kept apart so that the value at an accepted point is carried to the next
+// Newton step (and re-weighted when mu changes) instead of being evaluated again -- as pmm_ultrametric.cpp does
+struct Ultra2Obj { double fsum, bsum; bool inside; };
+PMM_HD Ultra2Obj ultra2_objective(const NniUltra &c, const Ultra2Stats &T, const double *H, double lo, double hi) {
+    double x[5];
+    Ultra2Obj o;
+    o.fsum = 0.0; o.bsum = 0.0; o.inside = true;
     ultra2_edges(c, H, x);
     for (int e = 0; e < 5; e++) {
-        if (x[e] <= lo || x[e] >= hi) return -INFINITY;
-        double val, g, h;
-        ultra2_f(T, e, x[e], val, g, h);
-        s += val;
-        b += log(x[e] - lo) + log(hi - x[e]);
+        if (x[e] <= lo || x[e] >= hi) { o.inside = false; return o; }
+        o.fsum += ultra2_value(T, e, x[e]);
+        o.bsum += log(x[e] - lo) + log(hi - x[e]);
     }
-    return s + mu * b;
+    return o;
 }
+PMM_HD double ultra2_obj_at(const Ultra2Obj &o, double mu) { return o.inside ? o.fsum + mu * o.bsum : -INFINITY; }
 
 // returns 0 = optimal, 1 = infeasible, 2 = failed (non-finite slope).  S: clamped / rescaled statistics of the
 // five branches, [5][5] branch-major.  H (Hu, Hv, Ht): in = previous iteration's heights when `warm`, out = the
@@ -97,13 +105,14 @@ PMM_HD int ultra2_solve(const NniUltra &c, const double *S, double nu, double ep
     for (int e = 0; e < 5; e++) if (!(x[e] > lo && x[e] < hi)) return 1;
     const double n_free = 5.0;
     double mu = warm ? warm_mu : 1.0;
+    Ultra2Obj at_H = ultra2_objective(c, T, Hc, lo, hi);          // objective sums at the current point
     for (;;) {
         for (int it = 0; it < 60; it++) {
             double g[5], w[5];
             ultra2_edges(c, Hc, x);
             for (int e = 0; e < 5; e++) {
-                double val, ge, he;
-                ultra2_f(T, e, x[e], val, ge, he);
+                double ge, he;
+                ultra2_grad_hess(T, e, x[e], ge, he);
                 g[e] = ge + mu * (1.0 / (x[e] - lo) - 1.0 / (hi - x[e]));
                 w[e] = he - mu * (1.0 / ((x[e] - lo) * (x[e] - lo)) + 1.0 / ((hi - x[e]) * (hi - x[e])));
             }
@@ -129,15 +138,18 @@ PMM_HD int ultra2_solve(const NniUltra &c, const double *S, double nu, double ep
                 else if (dx[e] > 0) tmax = fmin(tmax, (hi - x[e]) / dx[e]);
             }
             double t = fmin(1.0, 0.99 * tmax);
-            const double f0 = ultra2_objective(c, T, Hc, mu, lo, hi);
+            const double f0 = ultra2_obj_at(at_H, mu);
             bool found = false;
+            Ultra2Obj trial = at_H;
             while (t > 1e-14) {
                 for (int i = 0; i < 3; i++) Hn[i] = Hc[i] + t * dl[i];
-                if (ultra2_objective(c, T, Hn, mu, lo, hi) >= f0 + 1e-4 * t * slope) { found = true; break; }
+                trial = ultra2_objective(c, T, Hn, lo, hi);
+                if (ultra2_obj_at(trial, mu) >= f0 + 1e-4 * t * slope) { found = true; break; }
                 t *= 0.5;
             }
             if (!found) break;
             for (int i = 0; i < 3; i++) Hc[i] = Hn[i];
+            at_H = trial;
             if (t * slope < 1e-14 * n_free) break;
         }
         if (status != 0 || mu <= mu_final) break;
