@@ -38,7 +38,10 @@ pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(CUDA_INC, "cuda_
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libemu_nni.so")
     src = os.path.join(HERE, "native", "emu_lumped.cpp")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC, src, "-o", so], check=True)
+    # PMM_EMU_CXXFLAGS="-fsanitize=address,undefined -fno-omit-frame-pointer -g" (with libasan preloaded) turns this file into
+    # a memory / UB checker of the kernels' source on the numpy-owned record arrays: scripts/native/sanitize_emulated_kernels.sh
+    extra = os.environ.get("PMM_EMU_CXXFLAGS", "").split()
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC] + extra + [src, "-o", so], check=True)
     lib = C.CDLL(so)
     lib.emu_nni_lumped.restype = C.c_int
     return lib
