@@ -277,6 +277,28 @@ def run_ours(args, rank, local_rank, world):
     h2d = 8 * n + 16 + 8 * (5 * n + 1) + 8 * n + 16        # estep: d,nu,phi; mstep: S,Rtilde,d,nu,phi
     d2h = 8 * (5 * n + 2) + 8 * n + 16                      # estep: S,Rtilde,llh; mstep: d,nu,phi
 
+    # ---- one EM iteration, parameters in / parameters out (ShardedEngine.em_step: the statistics stay on the
+    # device, only d / nu / phi go up and d / nu / phi / llh come down).  Reported BESIDE "e2e" (the split
+    # Estep / Mstep protocol above), never instead of it; any failure here is recorded and leaves the line intact.
+    em_step = None
+    try:
+        cur2 = (d_pin, nu0, phi0)
+        for _ in range(max(1, args.warmup // 2)):
+            cur2 = sh.em_step(cur2[0], cur2[1], cur2[2], R, N)[:3]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cur2 = sh.em_step(cur2[0], cur2[1], cur2[2], R, N)[:3]
+        barrier()
+        em_step = (time.perf_counter() - t0) / args.steps
+    except Exception as exc:                                    # noqa: BLE001 -- same code on every rank: all fail or none
+        em_step = repr(exc)
+    t_es = torch.tensor([float("inf") if isinstance(em_step, str) else em_step], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if world > 1:
+        dist.all_reduce(t_es, op=dist.ReduceOp.MAX)             # every rank takes part, failed or not
+    if not isinstance(em_step, str):
+        em_step = float(t_es.item()) if np.isfinite(float(t_es.item())) else "failed on another rank"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -377,6 +399,11 @@ def run_ours(args, rank, local_rank, world):
         "node_site_per_s": n * Ktot / (estep_ms * 1e-3),
         "e2e": {"value": N * Ktot / e2e_s, "unit": "cell*site/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3},
+        "e2e_em_step": ({"error": em_step} if isinstance(em_step, str) else
+                        {"value": N * Ktot / em_step, "unit": "cell*site/s", "ms_per_step": em_step * 1e3,
+                         "h2d_bytes_per_step": 8 * n + 16, "d2h_bytes_per_step": 8 * n + 24,
+                         "note": "one EM iteration through ShardedEngine.em_step: host d/nu/phi in, host d/nu/phi/llh out, "
+                                 "statistics stay on the device; 'e2e' above is the split Estep/Mstep protocol"}),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "device_bytes": info["device_bytes"],
     }

@@ -120,6 +120,18 @@ class ShardedEngine:
         with self._on_stream():
             return float(self.stats[5 * self.n_nodes + 1].item())
 
+    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0):
+        """ONE EM iteration from host parameters to host parameters (the body of the loop at EM_solver.py:483-499:
+        ``Estep`` then ``Mstep``) with the statistics left on the device: parameters up, E-step + all-reduce,
+        M-step, parameters down.  Returns ``(d, nu, phi, llh)``; ``llh`` is the log-likelihood AT THE INPUT point
+        (what the E-step's inside pass evaluates)."""
+        self.eng.upload_params(d, nu, phi)
+        self.estep_dev()
+        llh = self.llh()
+        self.eng.mstep_dev(R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)
+        d_out, nu_out, phi_out = self.eng.download_params()
+        return d_out, nu_out, phi_out, llh
+
     def em(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
            conv_eps=1e-8, max_iter=1000):
         """``EM_solver.EM_optimization`` (EM_solver.py:461-512, ultra_constr=False) on

@@ -76,9 +76,11 @@ def _worker(rank, world, port, ret):
     R = float((w.codes != -1).sum())
     est = sh.estep(w.d, w.nu, w.phi)
     em = sh.em(np.maximum(w.d, 0.01), 0.2, 0.15, R, 60, max_iter=6)
+    one = sh.em_step(np.maximum(w.d, 0.01), 0.2, 0.15, R, 60)
     if rank == 0:
         ret["S"], ret["llh"], ret["Rt"] = est["S"].copy(), est["llh"], est["Rtilde"]
         ret["em"] = (em["nllh"], em["nu"], em["phi"], em["d"].copy(), em["iters"])
+        ret["one"] = (one[0].copy(), one[1], one[2], one[3])
     dist.destroy_process_group()
 
 
@@ -100,6 +102,15 @@ def test_sharded_matches_unsharded():
     assert abs(nllh - ref_em["nllh"]) <= 1e-9 * ref_em["nllh"]
     np.testing.assert_allclose(d, ref_em["d"], rtol=1e-9, atol=1e-11)
     assert abs(nu - ref_em["nu"]) < 1e-10 and abs(phi - ref_em["phi"]) < 1e-12
+    # one EM iteration, parameters in / parameters out: the first iteration of the oracle's loop
+    d1, nu1, phi1, llh1 = ret["one"]
+    d0 = np.maximum(w.d, 0.01)
+    e0 = orc.estep(d0, 0.2, 0.15)
+    assert abs(llh1 - e0["llh"]) <= 1e-9 * abs(e0["llh"])
+    ref1 = orc.em(d0, 0.2, 0.15, max_iter=1)
+    if ref1["iters"] <= 2:                                  # the oracle's loop also stops after one M-step (+ the check)
+        np.testing.assert_allclose(d1, ref1["d"], rtol=1e-9, atol=1e-11)
+        assert abs(nu1 - ref1["nu"]) < 1e-10 and abs(phi1 - ref1["phi"]) < 1e-12
 
 
 def _ultra_worker(rank, world, port, ret):
