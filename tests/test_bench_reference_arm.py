@@ -1,0 +1,38 @@
+"""``bench.py --impl reference`` (the CPU arm the driver runs beside the GPU arm): the JSON contract of its line, and
+that under a multi-rank launch only rank 0 works and prints.  Small workload; no GPU involved."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env, *args):
+    env = dict(os.environ, **extra_env)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        if k not in extra_env:
+            env.pop(k, None)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--workload", "config2_1k_x_30"] + list(args), env=env, capture_output=True, text=True, timeout=300)
+
+
+def test_reference_arm_line():
+    res = _run({})
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                       # ONE JSON line on stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0
+    assert line["metric"] == "em_iteration_cell_site_per_s" and line["unit"] == "cell*site/s" and line["higher_is_better"] is True
+    assert line["config"]["workload"] == "config2_1k_x_30" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    cpu, e2e = line["cpu_baseline"], line["e2e"]
+    assert cpu["kind"] in ("port", "reference") and cpu["cores"] >= 1 and cpu["sample"] and cpu["value"] == line["value"]
+    assert e2e == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2")
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip() == ""
