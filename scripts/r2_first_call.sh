@@ -3,8 +3,8 @@
 #   gpurun --timeout 1500 -- 'bash scripts/r2_first_call.sh'
 # Writes gpurun_out/r2_*.{log,json,csv}; copy what matters to profiles/.
 mkdir -p gpurun_out
-# 1. the ULTRA variant of the NNI batch kernel and the fast_em boundary: first GPU runs (XPASS expected)
-timeout 900 python -m pytest tests/test_zzz_gpu_nni_ultra.py tests/test_zz_gpu_fast_em.py -m gpu -q -rxX > gpurun_out/r2_late_tests.log 2>&1
+# 1. the ULTRA variant of the NNI batch kernel, the fast_em boundary and ShardedEngine.em_step: first GPU runs (XPASS expected)
+timeout 900 python -m pytest tests/test_zzz_gpu_nni_ultra.py tests/test_zz_gpu_fast_em.py tests/test_zzzz_gpu_em_step.py -m gpu -q -rxX > gpurun_out/r2_late_tests.log 2>&1
 tail -5 gpurun_out/r2_late_tests.log
 # 2. memory checker on the new kernel path (small case)
 timeout 600 compute-sanitizer --tool memcheck python -m pytest "tests/test_zzz_gpu_nni_ultra.py::test_batch_ultra_matches_the_cpu_model" -m gpu -q -rxX > gpurun_out/r2_memcheck_nni_ultra.log 2>&1

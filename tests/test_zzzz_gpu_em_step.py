@@ -1,0 +1,47 @@
+"""``dist.ShardedEngine.em_step`` (one EM iteration, parameters in / parameters out, statistics on the device) on the
+GPU at world size 1, against the split protocol on the same engine (``pmm_estep`` -> host S -> ``pmm_mstep``: the
+GPU-verified path of tests/test_gpu_parity.py) and against the oracle.
+
+Written after this round's GPU budget was spent.  It only composes entry points that have run on the GPU, its host
+logic is covered by the world-size-2 gloo test (tests/test_sharded_gloo.py), but THIS file has not run on a GPU yet:
+it sorts last and is xfail(strict=False) for that reason alone -- XPASS is the expected outcome, and the marker goes
+once a GPU run is on record."""
+import numpy as np
+import pytest
+
+from laml_b200.capi import Engine
+from laml_b200.synth import make_workload
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="first GPU run of ShardedEngine.em_step is the driver's round-end pass")]
+
+
+@pytest.mark.parametrize("seed,n,K,amax,nu,phi", [(3, 300, 24, 40, 0.23, 0.17), (5, 90, 70, 6, 0.0, 0.3)])
+def test_em_step_matches_the_split_protocol_and_the_oracle(seed, n, K, amax, nu, phi):
+    from laml_b200.dist import ShardedEngine
+    from oracle.pmm_oracle import OracleProblem
+    w = make_workload(n_leaves=n, n_sites=K, a_lo=1, a_hi=amax, nu=max(nu, 0.1), phi=max(phi, 0.1), seed=seed)
+    f = w.forest
+    eng = Engine(n, w.qptr, w.qval, w.codes, device=0)
+    eng.set_tree(f.parent, f.left, f.right)
+    R = float((w.codes != -1).sum())
+    d0 = np.maximum(w.d, 0.01)
+    est = eng.estep(d0, nu, phi)
+    d_split, nu_split, phi_split = eng.mstep(est["S"], est["Rtilde"], R, n, d0, nu, phi)
+    sh = ShardedEngine(eng, K)
+    cur = (d0, nu, phi)
+    for _ in range(2):                                           # twice: the second call starts from downloaded parameters
+        first = cur
+        cur = sh.em_step(cur[0], cur[1], cur[2], R, n)
+        if first[0] is d0:
+            d1, nu1, phi1, llh1 = cur
+            assert abs(llh1 - est["llh"]) <= 1e-12 * abs(est["llh"])
+            np.testing.assert_allclose(d1, d_split, rtol=1e-12, atol=0)
+            assert abs(nu1 - nu_split) <= 1e-12 and abs(phi1 - phi_split) <= 1e-12
+        cur = cur[:3]
+    orc = OracleProblem(f, np.arange(n, dtype=np.int32), w.codes, w.qptr, w.qval)
+    ref = orc.em(d0, nu, phi, max_iter=2)                        # the oracle's loop stops after max_iter + 1 E-steps: 2 M-steps
+    if ref["iters"] == 3:
+        np.testing.assert_allclose(cur[0], ref["d"], rtol=1e-5, atol=1e-7)
+        assert abs(cur[1] - ref["nu"]) <= 1e-5 and abs(cur[2] - ref["phi"]) <= 1e-5
+    eng.close()
