@@ -83,6 +83,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def time_em_step(sh, d, nu, phi, R, n_cells, steps, warmup, barrier):
+    """seconds per ``ShardedEngine.em_step`` (host parameters in, host parameters out) over ``steps`` chained calls,
+    or the ``repr`` of the exception that stopped it -- the same code runs on every rank, so all fail or none"""
+    try:
+        cur = (d, nu, phi)
+        for _ in range(max(1, warmup // 2)):
+            cur = sh.em_step(cur[0], cur[1], cur[2], R, n_cells)[:3]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cur = sh.em_step(cur[0], cur[1], cur[2], R, n_cells)[:3]
+        barrier()
+        return (time.perf_counter() - t0) / steps
+    except Exception as exc:                                    # noqa: BLE001
+        return repr(exc)
+
+
 def workload_spec(name):
     from laml_b200.synth import CONFIGS
     if name not in CONFIGS:
@@ -280,19 +297,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- one EM iteration, parameters in / parameters out (ShardedEngine.em_step: the statistics stay on the
     # device, only d / nu / phi go up and d / nu / phi / llh come down).  Reported BESIDE "e2e" (the split
     # Estep / Mstep protocol above), never instead of it; any failure here is recorded and leaves the line intact.
-    em_step = None
-    try:
-        cur2 = (d_pin, nu0, phi0)
-        for _ in range(max(1, args.warmup // 2)):
-            cur2 = sh.em_step(cur2[0], cur2[1], cur2[2], R, N)[:3]
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cur2 = sh.em_step(cur2[0], cur2[1], cur2[2], R, N)[:3]
-        barrier()
-        em_step = (time.perf_counter() - t0) / args.steps
-    except Exception as exc:                                    # noqa: BLE001 -- same code on every rank: all fail or none
-        em_step = repr(exc)
+    em_step = time_em_step(sh, d_pin, nu0, phi0, R, N, args.steps, args.warmup, barrier)
     t_es = torch.tensor([float("inf") if isinstance(em_step, str) else em_step], dtype=torch.float64, device="cuda:%d" % local_rank)
     if world > 1:
         dist.all_reduce(t_es, op=dist.ReduceOp.MAX)             # every rank takes part, failed or not

@@ -36,3 +36,25 @@ def test_reference_arm_other_ranks_exit_quietly():
     res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2")
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip() == ""
+
+
+def test_time_em_step_helper():
+    """bench.time_em_step (the ``e2e_em_step`` leg of the GPU arm) on the oracle-backed stand-in engine: a time per
+    step when the calls work, the exception's repr -- not a raise -- when they do not"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from laml_b200.dist import ShardedEngine
+    from laml_b200.synth import make_workload
+    from test_sharded_gloo import OracleBackedEngine
+    w = make_workload(40, 10, 1, 8, 0.2, 0.15, seed=4)
+    eng = OracleBackedEngine(w.forest, w.codes, w.qptr, w.qval, 40)
+    sh = ShardedEngine(eng, 10, stats_tensor=eng.stats)
+    calls = []
+    t = bench.time_em_step(sh, np.maximum(w.d, 0.01), 0.2, 0.15, float((w.codes != -1).sum()), 40, 3, 3, lambda: calls.append(1))
+    assert isinstance(t, float) and t > 0 and len(calls) == 2
+
+    class Broken:
+        def em_step(self, *a):
+            raise RuntimeError("boom")
+    assert "boom" in bench.time_em_step(Broken(), None, 0.1, 0.1, 1.0, 1, 2, 2, lambda: None)
