@@ -102,7 +102,10 @@ int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double
  * rescale (:342-346), per-branch maximisation of (:351-357) over [dmin,dmax]
  * with nu fixed, then the 1-D problem in nu (:394-407).
  *   S[n*5], Rtilde: from pmm_estep;  R = number of non-'?' leaf entries (:322)
- *   free_mask[n]: 1 = branch enters the program (not polytomy-marked, not mark_fixed)
+ *   free_mask[n]: 1 = branch enters the program (not polytomy-marked, not mark_fixed);
+ *                 NULL = every branch is free (never "the mask of an earlier call": the handle
+ *                 resets it, and pmm_set_tree always does).  The same holds for pmm_em and
+ *                 pmm_mstep_dev; a mask equal to the previous one is not uploaded again.
  *   d in/out; nu, phi in/out.
  */
 int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n_cells,
@@ -117,6 +120,16 @@ int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n
 int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask,
            int32_t optimize_nu, int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax,
            double conv_eps, int32_t max_iter, double *nllh, int32_t *iters, int32_t *status);
+
+/*
+ * ONE iteration of that loop (EM_solver.py:483-499: Estep, then Mstep) from host parameters to host parameters:
+ * d / nu / phi in, the updated d / nu / phi out, llh = log-likelihood AT THE INPUT point (what the E-step's inside
+ * pass evaluates, i.e. the value the reference prints for the previous iteration).  The statistics never leave the
+ * device; one synchronisation per call.  This is the per-iteration protocol of a caller that wants to watch or
+ * steer the EM (GPU_EM_solver.EM_optimization with verbose output; bench.py's end-to-end step).
+ */
+int pmm_em_step(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask, int32_t optimize_nu,
+                int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax, double *llh);
 
 /* ---- device-resident variants (multi-GPU site sharding; see laml_b200/dist.py) ----
  * The statistics buffer is [S(n*5) | Rtilde | llh] fp64 on the device; the host

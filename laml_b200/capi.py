@@ -21,7 +21,7 @@ SYMBOLS = [
     "pmm_inside", "pmm_estep", "pmm_posteriors", "pmm_mstep", "pmm_em", "pmm_set_total_sites",
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
-    "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep",
+    "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep", "pmm_em_step",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     L.pmm_posteriors.argtypes = [vp, vp, f64, f64, vp, vp]
     L.pmm_mstep.argtypes = [vp, vp, f64, f64, i32, vp, i32, i32, f64, f64, f64, f64, vp, P(f64), P(f64)]
     L.pmm_em.argtypes = [vp, vp, P(f64), P(f64), vp, i32, i32, f64, i32, f64, f64, f64, i32, P(f64), P(i32), P(i32)]
+    L.pmm_em_step.argtypes = [vp, vp, P(f64), P(f64), vp, i32, i32, f64, i32, f64, f64, P(f64)]
     L.pmm_set_total_sites.argtypes = [vp, i32]
     L.pmm_upload_params.argtypes = [vp, vp, f64, f64]
     L.pmm_download_params.argtypes = [vp, vp, P(f64), P(f64)]
@@ -254,6 +255,16 @@ class Engine:
                                 C.byref(iters), C.byref(status)))
         return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
                 "status": "optimal" if status.value == 0 else "failed"}
+
+    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0):
+        """``pmm_em_step``: one EM iteration, host parameters in / out: ``(d, nu, phi, llh at the input point)``"""
+        d = np.array(d, np.float64, copy=True)
+        fm = np.ascontiguousarray(free_mask, np.uint8) if free_mask is not None else None
+        nu_c, phi_c, llh = C.c_double(nu), C.c_double(phi), C.c_double()
+        self._ck(self._L.pmm_em_step(self._h, d.ctypes.data, C.byref(nu_c), C.byref(phi_c),
+                                     fm.ctypes.data if fm is not None else None, int(optimize_nu), int(optimize_phi),
+                                     float(R), int(n_cells), dmin, dmax, C.byref(llh)))
+        return d, nu_c.value, phi_c.value, llh.value
 
     def score_nni_batch(self, cand_u, cand_k, d, nu, phi, dmin=0.005, dmax=10.0, conv_eps=1e-8, max_iter=1000, ultra=False):
         """Score NNI candidates (``Topology_search.apply_nni``, one local 5-branch EM each) in one call.

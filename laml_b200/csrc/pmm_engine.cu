@@ -74,6 +74,12 @@ struct pmm_handle {
     double *d_stats = nullptr;      // [5n | Rtilde | llh]
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
+    std::vector<unsigned char> free_host;   // the mask d_free holds (empty = all branches free)
+    // pinned staging for the parameter vectors (d | nu | phi): uploads and downloads of the per-iteration protocol
+    // (pmm_upload_params / pmm_download_params, i.e. ShardedEngine.em_step) are one DMA each, no pageable bounce
+    double *pin_up = nullptr, *pin_down = nullptr;
+    size_t pin_cap = 0;
+    cudaEvent_t ev_up = nullptr;            // the last upload has left pin_up
     NuState *d_nu_state = nullptr;
     unsigned *d_nu_bar = nullptr;
     double *d_nu_partial = nullptr;
@@ -757,6 +763,25 @@ int check_ready(pmm_handle *h) {
     return 0;
 }
 
+// free-branch mask of the M-step: NULL means "every branch is free" (never "whatever the last call left"); the
+// handle remembers what the device holds, so repeating a mask costs a memcmp and no copy
+int set_free_mask(pmm_handle *h, const uint8_t *free_mask) {
+    const size_t n = (size_t)h->n;
+    if (!free_mask) {
+        if (!h->free_host.empty()) {
+            CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
+            h->free_host.clear();
+        }
+        return 0;
+    }
+    if (h->free_host.size() == n && memcmp(h->free_host.data(), free_mask, n) == 0) return 0;
+    // pageable source: the copy is staged before the call returns, the caller's buffer is free afterwards
+    h->free_host.assign(free_mask, free_mask + n);
+    CK(cudaMemcpyAsync(h->d_free, h->free_host.data(), n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // inside (+ optionally outside/counts) over all chunks, parameters already on the device
 int run_passes(pmm_handle *h, bool outside, bool with_post, bool force_full = false) {
     if (h->engine == 0 && !force_full) { h->last_full = false; return run_lumped(h, outside, with_post); }
@@ -892,6 +917,9 @@ void pmm_destroy(pmm_handle *h) {
     free_tree_state(h);
     dfree(h->d_codes); dfree(h->d_params); dfree(h->d_site_ptr); dfree(h->d_prior); dfree(h->d_qsum);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->pin_up) cudaFreeHost(h->pin_up);
+    if (h->pin_down) cudaFreeHost(h->pin_down);
+    if (h->ev_up) cudaEventDestroy(h->ev_up);
     for (auto &st : h->aux) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto &row : h->ev_s) for (auto &e : row) if (e) cudaEventDestroy(e);
@@ -1006,7 +1034,13 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     CK(cudaMemcpy(h->d_out_items, out_items.data(), sizeof(int4) * out_items.size(), cudaMemcpyHostToDevice));
 
     if (build_lumped_schedule(h, order, root_index)) return 1;
-    if (reuse) return 0;
+    if (reuse) {
+        // node ids mean something else under the new topology: a mask of the old one must not survive
+        CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->free_host.clear();
+        return 0;
+    }
     // small per-node buffers first, then the records against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
         dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 8) || dalloc(h, &h->d_nu_bar, 1) || dalloc(h, &h->d_Rnode, h->n_int) ||
@@ -1016,6 +1050,7 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     if (h->engine == 1 && ensure_fullstate(h)) return 1;
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->free_host.clear();
     h->n = n;
     return 0;
 }
@@ -1061,26 +1096,54 @@ int pmm_set_total_sites(pmm_handle *h, int32_t n_sites_total) {
     return 0;
 }
 
+static int ensure_pinned(pmm_handle *h) {
+    const size_t need = (size_t)h->n + 4;
+    if (h->pin_cap >= need) return 0;
+    if (h->pin_up && h->stream) CK(cudaStreamSynchronize(h->stream));      // a copy may still be reading the old buffer
+    if (h->pin_up) { cudaFreeHost(h->pin_up); h->pin_up = nullptr; }
+    if (h->pin_down) { cudaFreeHost(h->pin_down); h->pin_down = nullptr; }
+    h->pin_cap = 0;
+    CK(cudaMallocHost((void **)&h->pin_up, sizeof(double) * need));
+    CK(cudaMallocHost((void **)&h->pin_down, sizeof(double) * need));
+    if (!h->ev_up) CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
+    h->pin_cap = need;
+    return 0;
+}
+
 int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi) {
     if (check_ready(h)) return 1;
+    if (!d) return fail(h, "pmm_upload_params: d is NULL");
     if (!(nu >= 0.0) || !(phi >= 0.0) || phi > 1.0) return fail(h, "need nu >= 0 and 0 <= phi <= 1 (got nu=%g phi=%g)", nu, phi);
-    for (int v = 0; v < h->n; v++)
-        if (!(d[v] >= 0.0) || !std::isfinite(d[v])) return fail(h, "branch length of node %d is %g; need finite, non-negative", v, d[v]);
-    double p[2] = {nu, phi};
-    CK(cudaMemcpyAsync(h->d_d, d, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_params, p, sizeof p, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // p lives on this stack frame
+    const bool had = h->pin_cap >= (size_t)h->n + 4;
+    if (ensure_pinned(h)) return 1;
+    if (had) CK(cudaEventSynchronize(h->ev_up));            // the previous upload has been read out of the staging buffer
+    // validate and stage in one pass; the call returns once the staging buffer holds the values (the caller's
+    // array is free), the DMA itself is ordered on the handle's stream like every kernel
+    const int n = h->n;
+    double *st = h->pin_up;
+    for (int v = 0; v < n; v++) {
+        const double x = d[v];
+        if (!(x >= 0.0) || !std::isfinite(x)) return fail(h, "branch length of node %d is %g; need finite, non-negative", v, x);
+        st[v] = x;
+    }
+    st[n] = nu; st[n + 1] = phi;
+    CK(cudaMemcpyAsync(h->d_d, st, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_params, st + n, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev_up, h->stream));
     return 0;
 }
 
 int pmm_download_params(pmm_handle *h, double *d, double *nu, double *phi) {
     if (check_ready(h)) return 1;
-    double p[2];
-    if (d) CK(cudaMemcpyAsync(d, h->d_d, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(p, h->d_params, sizeof p, cudaMemcpyDeviceToHost, h->stream));
+    if (ensure_pinned(h)) return 1;
+    const int n = h->n;
+    double *st = h->pin_down;
+    if (d) CK(cudaMemcpyAsync(st, h->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(st + n, h->d_params, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (nu) *nu = p[0];
-    if (phi) *phi = p[1];
+    if (d) memcpy(d, st, sizeof(double) * n);
+    if (nu) *nu = st[n];
+    if (phi) *phi = st[n + 1];
     return 0;
 }
 
@@ -1136,11 +1199,10 @@ int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double
     return 0;
 }
 
-int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi,
-                  double dmin, double dmax, double eps_s, double eps_nu) {
-    if (check_ready(h)) return 1;
+// the M-step on the device with the mask d_free holds
+static int mstep_dev_impl(pmm_handle *h, double R, int32_t n_cells, int32_t optimize_nu, int32_t optimize_phi,
+                          double dmin, double dmax, double eps_s, double eps_nu) {
     const int n = h->n;
-    if (free_mask) CK(cudaMemcpyAsync(h->d_free, free_mask, n, cudaMemcpyHostToDevice, h->stream));
     const int K_total = h->K_total > 0 ? h->K_total : h->K;
     pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
                                                                dmin, dmax, eps_s, eps_nu);
@@ -1175,6 +1237,13 @@ int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_
     return 0;
 }
 
+int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi,
+                  double dmin, double dmax, double eps_s, double eps_nu) {
+    if (check_ready(h)) return 1;
+    if (set_free_mask(h, free_mask)) return 1;
+    return mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, eps_s, eps_nu);
+}
+
 int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu,
               int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu, double *d, double *nu, double *phi) {
     if (pmm_upload_params(h, d, *nu, *phi)) return 1;
@@ -1186,13 +1255,33 @@ int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n
     return pmm_download_params(h, d, nu, phi);
 }
 
+int pmm_em_step(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask, int32_t optimize_nu,
+                int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax, double *llh) {
+    if (!nu || !phi) return fail(h, "pmm_em_step: nu / phi are NULL");
+    if (pmm_upload_params(h, d, *nu, *phi)) return 1;
+    if (set_free_mask(h, free_mask)) return 1;
+    if (run_passes(h, true, false)) return 1;
+    if (mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
+    // one synchronisation for everything that comes back: d | nu | phi | llh (at the INPUT point)
+    const int n = h->n;
+    double *st = h->pin_down;
+    CK(cudaMemcpyAsync(st, h->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(st + n, h->d_params, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(st + n + 2, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(d, st, sizeof(double) * n);
+    *nu = st[n]; *phi = st[n + 1];
+    if (llh) *llh = st[n + 2];
+    return 0;
+}
+
 int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask, int32_t optimize_nu, int32_t optimize_phi,
            double R, int32_t n_cells, double dmin, double dmax, double conv_eps, int32_t max_iter, double *nllh, int32_t *iters,
            int32_t *status) {
     if (pmm_upload_params(h, d, *nu, *phi)) return 1;
     const int n = h->n;
     const size_t n5 = (size_t)5 * n;
-    if (free_mask) CK(cudaMemcpyAsync(h->d_free, free_mask, n, cudaMemcpyHostToDevice, h->stream));
+    if (set_free_mask(h, free_mask)) return 1;
     double pre = 0, cur = 0;
     // EM_solver.py:467 pre_llh, then per iteration E, M, llh (:475-505).  The inside pass that
     // yields llh(p_k) is the same one the next E-step needs, so it is run once per iteration.
@@ -1202,7 +1291,7 @@ int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *fre
     cur = pre;
     int it = 1;
     while (it <= max_iter) {
-        if (pmm_mstep_dev(h, R, n_cells, nullptr, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
+        if (mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
         if (run_passes(h, true, false)) return 1;
         CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));

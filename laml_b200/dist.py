@@ -125,12 +125,13 @@ class ShardedEngine:
         ``Estep`` then ``Mstep``) with the statistics left on the device: parameters up, E-step + all-reduce,
         M-step, parameters down.  Returns ``(d, nu, phi, llh)``; ``llh`` is the log-likelihood AT THE INPUT point
         (what the E-step's inside pass evaluates)."""
+        if self.world == 1 and hasattr(self.eng, "em_step"):
+            return self.eng.em_step(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)   # pmm_em_step
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
-        llh = self.llh()
         self.eng.mstep_dev(R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)
-        d_out, nu_out, phi_out = self.eng.download_params()
-        return d_out, nu_out, phi_out, llh
+        d_out, nu_out, phi_out = self.eng.download_params()        # the one synchronisation of the step
+        return d_out, nu_out, phi_out, self.llh()
 
     def em(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
            conv_eps=1e-8, max_iter=1000):
@@ -141,7 +142,7 @@ class ShardedEngine:
         pre = cur = self.llh()
         it = 1
         while it <= max_iter:
-            self.eng.mstep_dev(R, n_cells, free_mask if it == 1 else None, optimize_nu, optimize_phi, dmin, dmax)
+            self.eng.mstep_dev(R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)   # an unchanged mask is not re-uploaded
             self.estep_dev()
             cur = self.llh()
             if abs((cur - pre) / pre) < conv_eps:

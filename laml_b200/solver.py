@@ -137,8 +137,32 @@ class GPU_EM_solver:
                     node.edge_length = eps_len
                     self.has_polytomy = True
 
+    def _resolve_new_polytomies(self):
+        """``optimize`` ends by re-reading its best trees with the solver-inserted branches collapsed
+        (``ML_solver.py:314-333``), so ``self.trees`` may be multifurcating again.  The reference never notices:
+        it builds a fresh solver -- whose constructor binarises and marks (``EM_solver.py:19-43``) -- for every
+        further call.  This class lives on (one handle per search), so the same binarisation is redone here
+        whenever the trees are about to be flattened: nodes that exist keep their marks, the inserted ones get
+        ``polytomy_mark`` and the constructor's length."""
+        if not any(len(nd.children) > 2 for tree in self.trees for nd in tree.traverse_preorder()):
+            return
+        for tree in self.trees:
+            known = {id(nd) for nd in tree.traverse_preorder()}
+            tree.resolve_polytomies()
+            for nd in tree.traverse_preorder():
+                if id(nd) not in known:
+                    nd.polytomy_mark, nd.mark_fixed = True, False
+                    nd.edge_length = self.dmin * 0.01
+                else:
+                    nd.polytomy_mark = bool(getattr(nd, 'polytomy_mark', False))
+                    nd.mark_fixed = bool(getattr(nd, 'mark_fixed', False))
+        self.has_polytomy = True
+        self.num_polytomy_mark = sum(1 for tree in self.trees for nd in tree.traverse_preorder() if nd.polytomy_mark)
+        self.num_edges = sum(len(list(tree.traverse_postorder())) for tree in self.trees)
+
     def _bind(self):
         """(re)build the flat forest and hand it to the engine"""
+        self._resolve_new_polytomies()
         row = {c: i for i, c in enumerate(self._enc.cells)}
         try:
             forest = flatten_trees(self.trees, leaf_key=row)      # leaf ids follow the matrix rows: stable across topologies
@@ -153,6 +177,7 @@ class GPU_EM_solver:
             self._leaf_row_bound = leaf_row
         self._engine.set_tree(forest.parent, forest.left, forest.right)
         self._forest = forest
+        self._um_for = None                                       # a cached ultrametric problem belongs to the old topology
         self._R = float((self._enc.codes[leaf_row] != -1).sum())  # EM_solver.py:322
         return forest
 
@@ -259,6 +284,16 @@ class GPU_EM_solver:
         if self._stats is None:
             raise RuntimeError("Mstep needs a preceding Estep")
         fm = self._free_mask(local_brlen_opt)
+        if ultra_constr_cache is not None:
+            from . import ultrametric as um
+            if not isinstance(ultra_constr_cache, um.UltrametricProblem):
+                # the reference hands Mstep what ultrametric_constr() returned, the dense (M, b) (EM_solver.py:470,489);
+                # the same equalities in the height parametrisation, built once per such object
+                key = id(ultra_constr_cache)
+                if getattr(self, "_um_for", None) != (key, bool(local_brlen_opt)):
+                    self._um_problem = self._ultrametric_problem(local_brlen_opt)
+                    self._um_for = (key, bool(local_brlen_opt))
+                ultra_constr_cache = self._um_problem
         d_new, nu_new, phi_new, status_d = self._mstep_arrays(self._stats["S"], self._stats["Rtilde"], fm, self._d(),
                                                               self.params.nu, self.params.phi, optimize_phi, optimize_nu,
                                                               eps_nu, eps_s, ultra_constr_cache)
@@ -307,6 +342,33 @@ class GPU_EM_solver:
     def EM_optimization(self, verbose=1, optimize_phi=True, optimize_nu=True, ultra_constr=False, maxIter=1000):
         """EM_solver.EM_optimization (``EM_solver.py:461-512``): returns ``(nllh, em_iter, status)``."""
         self._ensure()
+        if not ultra_constr and verbose > 0 and hasattr(self._engine, "em_step"):
+            # progress output as the reference's (EM_solver.py:468-505) needs the likelihood of every iterate on the host:
+            # one pmm_em_step per iteration -- parameters up, E-step + M-step on the device, parameters and the
+            # log-likelihood of the INPUT point down.  Call j turns p_{j-1} into p_j and reports llh(p_{j-1}), so the
+            # test of iteration j - 1 (:503) is applied one call later; the converged point is that call's input.
+            eng, fm, n_cells = self._engine, self._free_mask(True), len(self.charMtrx)
+            cur = (self._d(), self.params.nu, self.params.phi)
+            pre_llh, em_iter = None, 0
+            while True:
+                d_new, nu_new, phi_new, llh = eng.em_step(cur[0], cur[1], cur[2], self._R, n_cells, fm, optimize_nu, optimize_phi,
+                                                         self.dmin, self.dmax)
+                if pre_llh is None:
+                    print("Initial phi: " + str(cur[2]) + ". Initial nu: " + str(cur[1]) + ". Initial nllh: " + str(-llh))
+                else:
+                    print("Finished EM iter: " + str(em_iter) + ". Current nllh: " + str(-llh))
+                    if abs((llh - pre_llh) / pre_llh) < conv_eps or em_iter >= maxIter:
+                        if em_iter >= maxIter and not abs((llh - pre_llh) / pre_llh) < conv_eps:
+                            em_iter += 1
+                            print("Warning: exceeded maximum number of EM iterations (" + str(maxIter) + " iters)!")
+                        break
+                pre_llh = llh
+                em_iter += 1
+                cur = (d_new, nu_new, phi_new)
+            for nd, length in zip(self._forest.nodes, cur[0].tolist()):
+                nd.edge_length = length
+            self.params.nu, self.params.phi = cur[1], cur[2]
+            return -llh, em_iter, "optimal"
         if not ultra_constr:
             res = self._engine.em(self._d(), self.params.nu, self.params.phi, self._R, len(self.charMtrx),
                                   self._free_mask(True), optimize_nu, optimize_phi, self.dmin, self.dmax, conv_eps, maxIter)

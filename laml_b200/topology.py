@@ -103,13 +103,20 @@ def score_neighbourhood(solver: GPU_EM_solver, only_marked: bool = False, clamp:
     ``ultra=True``: the local EM of every candidate under the ultrametric constraint
     (``pmm_score_nni_batch_ultra``); candidates it leaves no room for have score NaN."""
     forest = solver._ensure()
-    if solver.num_polytomy_mark and any(getattr(nd, "polytomy_mark", False) for nd in forest.nodes):
-        raise ValueError("resolve polytomies before the search (Topology_search.__mark_polytomies__): "
-                         "a solver-inserted branch is never optimised and cannot take part in a move")
     cu, ck = nni_candidates(forest.parent, forest.left, forest.n_leaves)
     if only_marked:
         keep = np.array([bool(getattr(forest.nodes[u], "mark", False)) for u in cu], bool)
         cu, ck = cu[keep], ck[keep]
+    if solver.num_polytomy_mark:
+        # ``search(resolve_polytomies=False)`` on a polytomous input (runner.py:312, --keep_polytomies): the solver
+        # binarised the trees itself and its inserted branches are never optimised (EM_solver.py:39-43), so a move
+        # whose five branches include one is not a candidate -- the kernel would treat it as a free branch
+        pm = np.array([bool(getattr(nd, "polytomy_mark", False)) for nd in forest.nodes], bool)
+        if pm.any():
+            v = forest.parent[cu]
+            w = np.where(forest.left[v] == cu, forest.right[v], forest.left[v])
+            keep = ~(pm[cu] | pm[v] | pm[w] | pm[forest.left[cu]] | pm[forest.right[cu]])
+            cu, ck = cu[keep], ck[keep]
     d_raw = solver._d()
     d0 = np.maximum(d_raw, 2 * solver.dmin) if clamp else d_raw.copy()
     if len(cu) == 0:
@@ -291,6 +298,12 @@ class GPU_Topology_search:
         branches = np.nonzero((forest.left >= 0) & (forest.parent >= 0))[0]
         if only_marked:
             branches = np.array([i for i in branches if getattr(forest.nodes[i], "mark", False)], np.int64)
+        if s.num_polytomy_mark and len(branches):
+            # solver-inserted (never optimised) branches take no part in a move: see score_neighbourhood
+            pm = np.array([bool(getattr(nd, "polytomy_mark", False)) for nd in forest.nodes], bool)
+            v = forest.parent[branches]
+            w = np.where(forest.left[v] == branches, forest.right[v], forest.left[v])
+            branches = branches[~(pm[branches] | pm[v] | pm[w] | pm[forest.left[branches]] | pm[forest.right[branches]])]
         # the reference shuffles the branch list with ``random.shuffle`` (:231); a permutation drawn from a numpy
         # generator seeded by ``random`` is the same policy (and stays reproducible under ``random.seed``) without
         # a Python-level pass over 10^4 branches per iteration
@@ -418,6 +431,12 @@ class GPU_Topology_search:
         from .tree import read_tree_newick
         s = self._solver
         s.trees = [read_tree_newick(t) for t in newicks]
+        if s.num_polytomy_mark:
+            # the newicks may carry the branches the SOLVER inserted to binarise polytomies (never optimised, length
+            # dmin / 100): contract them as ``optimize`` does (ML_solver.py:317) -- the solver re-inserts and re-marks
+            # them when it binds the trees, exactly what a fresh reference solver would do with the polytomous tree
+            for t in s.trees:
+                t.collapse_short_branches(s.dmin * 0.01)
         for j, t in enumerate(s.trees):
             nodes = list(t.traverse_preorder())
             ms = marks[j] if marks is not None and len(marks[j]) == len(nodes) else [False] * len(nodes)

@@ -32,6 +32,30 @@ def test_reference_arm_line():
     assert line["value"] > 0 and line["ms_per_step"] > 0
 
 
+def test_reference_arm_under_torchrun_env_uses_every_core_and_no_gpu_library():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank: the arm must still use the cores the process may run on
+    (round 1's N >= 2 lines ran on one thread); and it must not touch the GPU library at all (PMM_LIB points nowhere)"""
+    res = _run({"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2", "OMP_NUM_THREADS": "1", "PMM_LIB": "/nonexistent/libpmm_b200.so"},
+               "--gpus", "2")
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip())
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and line["n_gpus"] == 2
+    assert "libpmm_b200" not in res.stderr
+
+
+def test_both_arms_print_the_same_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    from laml_b200.synth import random_priors
+    spec = bench.workload_spec("config2_1k_x_30")
+    qptr, _ = random_priors(spec["n_sites"], spec["a_lo"], spec["a_hi"], seed=5, uniform=True)
+    ref_cfg = json.loads(_run({}).stdout.strip())["config"]
+    assert ref_cfg == bench.config_dict("config2_1k_x_30", spec, qptr, 1)       # run_ours prints exactly config_dict(...)
+    import inspect
+    src = inspect.getsource(bench.run_ours)
+    assert '"config": config_dict(args.workload, spec, qptr, world),' in src
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2")
     assert res.returncode == 0, res.stderr[-2000:]
@@ -58,3 +82,8 @@ def test_time_em_step_helper():
         def em_step(self, *a):
             raise RuntimeError("boom")
     assert "boom" in bench.time_em_step(Broken(), None, 0.1, 0.1, 1.0, 1, 2, 2, lambda: None)
+    # a failure on ANOTHER rank: this rank's calls work, the collective AND says no -- no barrier is entered
+    calls.clear()
+    t = bench.time_em_step(sh, np.maximum(w.d, 0.01), 0.2, 0.15, float((w.codes != -1).sum()), 40, 3, 3, lambda: calls.append(1),
+                           all_ok=lambda ok: False)
+    assert t == "failed on another rank" and calls == []

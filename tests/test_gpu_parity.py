@@ -159,9 +159,9 @@ def test_site_slices_are_bit_identical(engine_mode):
 
 
 def test_engines_agree_at_config3_size(monkeypatch):
-    """BASELINE config 3 (10k cells x 500 sites, alphabets up to 100 states) is beyond what the oracle finishes in
-    seconds: the two independent GPU engines (lumped records vs full-state rows) must agree there, and the
-    size-independent properties of the counts must hold"""
+    """BASELINE config 3 (10k cells x 500 sites, alphabets up to 100 states): the two independent GPU engines (lumped
+    records vs full-state rows) must agree, and the size-independent properties of the counts must hold.  (Both are
+    compared with the threaded oracle on all 500 sites in tests/test_zz_gpu_parity_sizes.py.)"""
     from laml_b200.capi import Engine
     from laml_b200.synth import CONFIGS, make_workload
     w = make_workload(seed=3, **CONFIGS["config3_10k_x_500"])
@@ -210,6 +210,19 @@ def test_full_size_properties_config4():
 
     whole = run(0, K)
     a, b = run(0, 1000), run(1000, K)
+    # the oracle (the reference's algorithm) on a site sample of THIS 100k-cell tree: per-site likelihoods of the whole
+    # run, and the expected counts of an engine holding exactly those sites, at the north-star tolerances
+    import os
+    from oracle.pmm_oracle import OracleProblem
+    ks = 16
+    qp, qv = (w.qptr[:ks + 1] - w.qptr[0]).astype(np.int32), w.qval[:w.qptr[ks]].copy()
+    ref = OracleProblem(w.forest, np.arange(N, dtype=np.int32), np.ascontiguousarray(w.codes[:, :ks]), qp, qv).estep(
+        w.d, w.nu, w.phi, nthreads=max(1, len(os.sched_getaffinity(0))))
+    np.testing.assert_allclose(whole["site_llh"][:ks], ref["site_llh"], rtol=1e-9)
+    sample = run(0, ks)
+    assert abs(sample["llh"] - ref["llh"]) <= 1e-9 * abs(ref["llh"])
+    np.testing.assert_allclose(sample["S"], ref["S"].T, rtol=1e-8, atol=1e-10 * ks)
+    assert abs(sample["Rtilde"] - ref["Rtilde"]) <= 1e-8 * ref["Rtilde"]
     assert np.isfinite(whole["llh"]) and abs(whole["llh"] - whole["site_llh"].sum()) <= 1e-9 * abs(whole["llh"])
     assert abs((a["llh"] + b["llh"]) - whole["llh"]) <= 1e-12 * abs(whole["llh"])
     assert (np.concatenate([a["site_llh"], b["site_llh"]]) == whole["site_llh"]).all()       # per-site results are shard-independent

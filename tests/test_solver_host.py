@@ -210,3 +210,24 @@ def test_estep_leaves_statistics_and_posteriors_on_the_nodes():
     from helpers import assert_close_loginf
     assert_close_loginf(p0, z["post0"], 1e-10, 1e-12, "post0")
     assert abs(out["llh"] + float(z["nllh"])) <= 1e-12 * float(z["nllh"])
+
+
+def test_mstep_accepts_what_ultrametric_constr_returns():
+    """EM_solver.py:470,489: ``cache = self.ultrametric_constr()`` ... ``self.Mstep(ultra_constr_cache=cache)`` -- the
+    dense ``(M, b)`` the protocol method returns must be accepted by ``Mstep`` (same M-step as with the height
+    problem the EM loop uses internally)"""
+    case, z = load_npz_case("ref_rand_small")
+    out = []
+    for dense in (True, False):
+        s = _solver(case)
+        s._ensure()
+        s.Estep()
+        cache = s.ultrametric_constr() if dense else s._ultrametric_problem()
+        ok, status = s.Mstep(ultra_constr_cache=cache)
+        assert ok and status == "optimal"
+        out.append((s._d(), s.params.nu, s.params.phi))
+        if dense:                                    # a second M-step with the same object reuses the built problem
+            s.Estep()
+            assert s.Mstep(ultra_constr_cache=cache)[0]
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=0, atol=1e-12)
+    assert out[0][1:] == out[1][1:]

@@ -378,3 +378,43 @@ def test_full_reoptimisation_per_candidate():
     st['local_brlen_opt'] = False
     trees, score, params = ts.search(maxiter=20, nreps=1, strategy=st)
     assert abs(_brute_force(MSA_A, [dict(q) for q in Q5]) + score) < 5e-5
+
+
+@pytest.mark.parametrize("T0,msa", [('((a,b),c,d);', MSA_B), ('(a,b,c,d);', MSA_A), ('((a,b,c),d);', MSA_A)])
+def test_search_keeping_polytomies(T0, msa):
+    """``search(resolve_polytomies=False)`` on a polytomous input -- the call the runner makes under
+    ``--keep_polytomies`` (runner.py:312).  The reference survives it because every candidate gets a fresh solver,
+    whose constructor binarises and marks (EM_solver.py:19-43); here ONE solver lives through the search, so it must
+    re-resolve the polytomies ``optimize`` collapsed (ML_solver.py:314-333) whenever it re-reads its trees."""
+    from random import seed
+    seed(a=4242)
+    Q = [dict(q) for q in Q5]
+    ts = GPU_Topology_search([T0], GPU_EM_solver, data={'charMtrx': msa}, prior={'Q': Q}, params={'phi': 0, 'nu': 0})
+    best_trees, max_score, best_params = ts.search(resolve_polytomies=False, maxiter=20, verbose=False,
+                                                   strategy=deepcopy(DEFAULT_STRATEGY), nreps=1)
+    assert np.isfinite(max_score) and set(best_params) == {'phi', 'nu'}
+    # the score is the optimum of the tree that comes back, scored as the reference would: a fresh solver
+    s = GPU_EM_solver(best_trees, {'charMtrx': msa}, {'Q': Q}, best_params)
+    assert abs(-s.negative_llh() - max_score) <= 1e-6 * abs(max_score)
+    # and it is at least as good as the start tree's own optimum (the search only ever accepts or keeps)
+    s0 = GPU_EM_solver([T0], {'charMtrx': msa}, {'Q': Q})
+    nllh0, _ = s0.optimize(initials=1, verbose=-1)
+    assert -max_score <= nllh0 + 1e-4
+
+
+def test_solver_survives_optimize_on_a_polytomous_tree():
+    """negative_llh / score_tree / Estep on the SAME solver after ``optimize`` collapsed its inserted branches"""
+    msa = {"a": [1, 0], "b": [1, 2], "c": [0, 2], "d": [1, '?'], "e": [0, 0]}
+    Q = [{1: 1.0}, {2: 0.5, 3: 0.5}]
+    s = GPU_EM_solver(["((a:0.3,b:0.2,c:0.4)x:0.2,d:0.1,e:0.3)r:0.1;"], {'charMtrx': msa}, {'Q': Q}, {'phi': 0.1, 'nu': 0.1})
+    assert s.num_polytomy_mark == 2
+    nllh, status = s.optimize(initials=1, random_seeds=3, verbose=-1)
+    assert any(len(nd.children) > 2 for nd in s.trees[0].traverse_preorder())        # collapsed, as the reference's
+    again = s.negative_llh()                                                            # used to raise: needs binary trees
+    assert abs(again - nllh) <= 1e-9 * abs(nllh)
+    assert s.num_polytomy_mark == 2 and s.num_edges == 9
+    marked = [nd for nd in s.trees[0].traverse_postorder() if nd.polytomy_mark]
+    assert len(marked) == 2 and all(abs(nd.edge_length - 5e-5) < 1e-15 for nd in marked)
+    score, status = s.score_tree({'ultra_constr': False, 'fixed_phi': None, 'fixed_nu': None, 'fixed_brlen': None})
+    assert status == "optimal" and abs(-score - nllh) <= 1e-6 * abs(nllh)
+    s.Estep()

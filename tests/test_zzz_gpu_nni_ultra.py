@@ -3,11 +3,9 @@ CPU model of the same definition: a full-tree EM per candidate on the explicitly
 whole-tree host M-step with every branch but the five around the move fixed (tests/oracle_engine.py) -- which
 tests/test_topology_host.py shows to be the reference's per-candidate call without its ``2 dmin`` raise.
 
-The kernel variant was written after this round's GPU budget was spent: its M-step is covered on CPU through its
-host instance (tests/test_nni_ultra_host.py) and the whole kernel through a host build of its unchanged source
-(tests/test_kernels_emulated.py), but THIS file has not run on a GPU yet.  It sorts last so that
-nothing else depends on it, and it is marked xfail(strict=False) for that reason alone -- an XPASS is the expected
-outcome, and the marker goes once a GPU run is on record."""
+The kernel's M-step is also covered on CPU through its host instance (tests/test_nni_ultra_host.py) and the whole
+kernel through a host build of its unchanged source (tests/test_kernels_emulated.py).  First GPU run on record:
+the driver's round-1 pass (GPUTEST_r01.json: passed)."""
 import numpy as np
 import pytest
 
@@ -17,8 +15,7 @@ from laml_b200.synth import make_workload
 from oracle_engine import OracleEngine
 from test_nni_ultra_host import ultrametric_lengths
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="first GPU run of the ULTRA kernel variant is the driver's round-end pass")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.mark.parametrize("seed,n,K,amax,nu,phi,step", [(91, 40, 14, 12, 0.15, 0.1, (0.02, 0.3)), (92, 25, 9, 40, 0.0, 0.2, (0.006, 0.012)),

@@ -2,18 +2,15 @@
 GPU at world size 1, against the split protocol on the same engine (``pmm_estep`` -> host S -> ``pmm_mstep``: the
 GPU-verified path of tests/test_gpu_parity.py) and against the oracle.
 
-Written after this round's GPU budget was spent.  It only composes entry points that have run on the GPU, its host
-logic is covered by the world-size-2 gloo test (tests/test_sharded_gloo.py), but THIS file has not run on a GPU yet:
-it sorts last and is xfail(strict=False) for that reason alone -- XPASS is the expected outcome, and the marker goes
-once a GPU run is on record."""
+Its host logic is also covered by the world-size-2 gloo test (tests/test_sharded_gloo.py).  First GPU run on
+record: the driver's round-1 pass (GPUTEST_r01.json: passed)."""
 import numpy as np
 import pytest
 
 from laml_b200.capi import Engine
 from laml_b200.synth import make_workload
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="first GPU run of ShardedEngine.em_step is the driver's round-end pass")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.mark.parametrize("seed,n,K,amax,nu,phi", [(3, 300, 24, 40, 0.23, 0.17), (5, 90, 70, 6, 0.0, 0.3)])
@@ -45,3 +42,29 @@ def test_em_step_matches_the_split_protocol_and_the_oracle(seed, n, K, amax, nu,
         np.testing.assert_allclose(cur[0], ref["d"], rtol=1e-5, atol=1e-7)
         assert abs(cur[1] - ref["nu"]) <= 1e-5 and abs(cur[2] - ref["phi"]) <= 1e-5
     eng.close()
+
+
+def test_verbose_em_runs_on_em_step_and_equals_the_device_loop(capsys):
+    """``GPU_EM_solver.EM_optimization(verbose=1)`` prints the reference's progress lines (EM_solver.py:468-505) from one
+    ``pmm_em_step`` per iteration; it must stop at the same iteration, on the same parameters, as the silent run
+    (``pmm_em``, everything on the device)"""
+    from helpers import load_npz_case
+    from laml_b200.solver import GPU_EM_solver
+    case, z = load_npz_case("ref_rand_ragged")
+    out = []
+    for verbose in (-1, 1):
+        s = GPU_EM_solver(case.newicks, {'charMtrx': case.msa}, {'Q': case.Q}, {'phi': 0.2, 'nu': 0.15})
+        s._ensure()
+        for t in s.trees:
+            for nd in t.traverse_postorder():
+                nd.edge_length = max(0.01, nd.edge_length)
+        out.append(s.EM_optimization(verbose=verbose) + (s._d(), s.params.nu, s.params.phi))
+        s.close()
+    text = capsys.readouterr().out
+    quiet, loud = out
+    assert quiet[1] == loud[1] and quiet[2] == loud[2] == "optimal"
+    assert abs(quiet[0] - loud[0]) <= 1e-12 * abs(quiet[0])
+    np.testing.assert_allclose(loud[3], quiet[3], rtol=1e-12, atol=0)
+    assert abs(quiet[4] - loud[4]) <= 1e-14 and abs(quiet[5] - loud[5]) <= 1e-14
+    assert "Initial phi: 0.2. Initial nu: 0.15. Initial nllh: " in text
+    assert text.count("Finished EM iter: ") == loud[1] and ("Finished EM iter: %d. Current nllh: " % loud[1]) in text
