@@ -51,6 +51,7 @@ namespace pmm {
 #endif
 constexpr int LT = PMM_LT;               // threads (= sites) per CTA
 constexpr int STEP_CAP = 128;            // a clade has fewer steps than this (the host caps the clade size at 64)
+constexpr int STEP_PAD = 8;              // entries past the end of the staged step list (copies of the last step: look-ahead needs no guard)
 #ifndef PMM_LIN_MINB
 #define PMM_LIN_MINB 5
 #endif
@@ -68,6 +69,32 @@ constexpr int PF_DIST = PMM_PF_DIST;
 #define PMM_PF_DIST_OUT 3
 #endif
 constexpr int PF_DIST_OUT = PMM_PF_DIST_OUT;
+// tuning switches of the outside kernel (scripts/build_variants.sh builds one library per setting; defaults = the shipped kernel)
+#ifndef PMM_LD256
+#define PMM_LD256 1                      // records move as one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256) instead of two 128-bit ones
+#endif
+#ifndef PMM_RED_TREE
+#define PMM_RED_TREE 0                   // count reduction: pairwise adds (depth 4) instead of two serial chains of 8
+#endif
+#ifndef PMM_OUT_REGPF
+#define PMM_OUT_REGPF 1                  // 1: the next step's operands are loaded into a second register set one step ahead
+#endif
+#ifndef PMM_PF_O
+#define PMM_PF_O 0                       // 1: out-records a later step loads are pulled into L2 like its children's records
+#endif
+#ifndef PMM_OUT_BRFREE
+#define PMM_OUT_BRFREE 1                 // 1: the per-step fetch / prefetch / leaf-code prologue of the outside kernel is straight-line code:
+                                         //    predicated loads, clamped rows, a step list padded past its end -- no branches
+#endif
+#ifndef PMM_OUT_DESC_RELOAD
+#define PMM_OUT_DESC_RELOAD 1            // 1: step descriptors are re-read from shared memory every step instead of rotating through registers
+#endif
+#ifndef PMM_OUT_OCHAIN
+#define PMM_OUT_OCHAIN 0                 // 1: a loaded out[u] goes straight into the chain registers (they are dead once both T records exist)
+#endif
+#ifndef PMM_OUT_PIPE1
+#define PMM_OUT_PIPE1 0                  // 1: ONE operand register set, refilled for step i + 1 as soon as step i has decoded it
+#endif
 
 struct LParams {
     int K;                   // sites of this chunk
@@ -109,13 +136,33 @@ struct Opd { double4 r; int2 ri; };
 // An INSIDE operand is kept in the packed form of the 32-byte record: r = (x0, xz, t, h | cum) -- a record with a
 // hot state has x_m = 0 exactly and one without has no q_h, so the two share the slot t; h and cum ride in the
 // last 8 bytes.  Nothing is unpacked at load time (that would wait for the load): `decode` does it at the use.
-__device__ __forceinline__ void ld_xrec(Opd &p, const double2 *__restrict__ X, unsigned o) {
-    const double2 a = X[2 * (size_t)o], b = X[2 * (size_t)o + 1];
-    p.r = make_double4(a.x, a.y, b.x, b.y);
+#if PMM_LD256 && !defined(PMM_HOST_EMU)
+// 32-byte records are 32-byte aligned (cudaMalloc base, rows of whole warps): one 256-bit access each
+__device__ __forceinline__ double4 ld256(const void *p) {
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void st_xrec(double2 *__restrict__ X, unsigned o, const Opd &p) {
-    X[2 * (size_t)o] = make_double2(p.r.x, p.r.y);
-    X[2 * (size_t)o + 1] = make_double2(p.r.z, p.r.w);
+__device__ __forceinline__ void st256(void *p, const double4 r) {
+    asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w), "l"(p) : "memory");
+}
+#else
+__device__ __forceinline__ double4 ld256(const void *p) {
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st256(void *p, const double4 r) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(r.x, r.y);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(r.z, r.w);
+}
+#endif
+__device__ __forceinline__ void ld_xrec(Opd &p, const double2 *__restrict__ X, unsigned o) { p.r = ld256(X + 2 * (size_t)o); }
+__device__ __forceinline__ void st_xrec(double2 *__restrict__ X, unsigned o, const Opd &p) { st256(X + 2 * (size_t)o, p.r); }
+__device__ __forceinline__ void ld_orec(Opd &p, const double4 *__restrict__ O, const int2 *__restrict__ OI, unsigned o) {
+    p.r = ld256(O + o); p.ri = OI[o];
+}
+__device__ __forceinline__ void st_orec(double4 *__restrict__ O, int2 *__restrict__ OI, unsigned o, const Opd &p) {
+    st256(O + o, p.r); OI[o] = p.ri;
 }
 __device__ __forceinline__ double pack_hc(int h, int cum) { return __hiloint2double(cum, h); }
 
@@ -141,7 +188,7 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 //   known silenced (-2) -> e_m   '?' (-1) -> (phi, 1, phi..)   0 -> (1-phi) e_0   a -> (1-phi) e_a)
 __device__ __forceinline__ void stage_clade(int4 *s_steps, double4 *s_bc, double4 *s_lut, const LParams &P,
                                             const int4 *__restrict__ steps, int begin, int nsteps) {
-    for (int i = threadIdx.x; i < nsteps; i += LT) s_steps[i] = __ldg(steps + begin + i);
+    for (int i = threadIdx.x; i < nsteps + STEP_PAD; i += LT) s_steps[i] = __ldg(steps + begin + min(i, nsteps - 1));
     for (int i = threadIdx.x; i < 2 * nsteps; i += LT) {
         const int4 d = __ldg(steps + begin + (i >> 1));
         s_bc[i] = ld_bc(P.bc, (i & 1) ? d.z : d.y);
@@ -214,7 +261,7 @@ __device__ __forceinline__ void inside_fetch(const LParams &P, const int4 d, int
 }
 
 __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
-    __shared__ int4 s_steps[STEP_CAP + 2];
+    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
     __shared__ double4 s_bc[2 * STEP_CAP];
     __shared__ double4 s_lut[4];
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z
@@ -358,8 +405,22 @@ __device__ __forceinline__ void red_put5(const double *__restrict__ v, double *_
 __device__ __forceinline__ double red_finish(const double *__restrict__ red, int lane) {
     __syncwarp();
     double sum = 0.0;
+#if PMM_OUT_BRFREE
+    {   // every lane adds up half a row (lanes 20-31 repeat row 9): no divergent region in the step
+        const double2 *row = reinterpret_cast<const double2 *>(red + min(lane >> 1, 9) * RED_ROW + (lane & 1) * 18);
+#else
     if (lane < 20) {
         const double2 *row = reinterpret_cast<const double2 *>(red + (lane >> 1) * RED_ROW + (lane & 1) * 18);
+#endif
+#if PMM_RED_TREE
+        // 16 values, pairwise: dependent depth 4 (the serial form below has two chains of 8 at the end of every step)
+        double2 x[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) x[t] = row[t];
+        const double s0 = x[0].x + x[0].y, s1 = x[1].x + x[1].y, s2 = x[2].x + x[2].y, s3 = x[3].x + x[3].y;
+        const double s4 = x[4].x + x[4].y, s5 = x[5].x + x[5].y, s6 = x[6].x + x[6].y, s7 = x[7].x + x[7].y;
+        sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+#else
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int t = 0; t < 8; t += 2) {
@@ -367,6 +428,7 @@ __device__ __forceinline__ double red_finish(const double *__restrict__ red, int
             a += x.x; b += x.y; a += y.x; b += y.y;
         }
         sum = a + b;
+#endif
     }
     const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
     __syncwarp();                                    // readers done before the next step's writers
@@ -389,12 +451,49 @@ __device__ __forceinline__ void outside_fetch(const LParams &P, const int4 d, in
     else { const unsigned o = rec_index(P, d.y, s); ld_xrec(n.v, P.X, o); }
     if (d.w & 8) n.w.r.z = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
     else { const unsigned o = rec_index(P, d.z, s); ld_xrec(n.w, P.X, o); }
-    if ((d.w & 3) == KIND_LOAD) { const unsigned o = rec_index(P, d.x, s); n.o.r = P.O[o]; n.o.ri = P.OI[o]; }
+    if (!PMM_OUT_OCHAIN && (d.w & 3) == KIND_LOAD) { const unsigned o = rec_index(P, d.x, s); ld_orec(n.o, P.O, P.OI, o); }
+}
+
+// The same without branches: which access a child needs is a warp-uniform predicate (descriptor flag) or a per-lane one
+// (a leaf's code), so every load is issued under a predicate and the addresses are formed unconditionally.
+// pl: lane gathers the prior of its leaf's state into r.z; pi: lane loads the 32-byte inside record
+__device__ __forceinline__ void fetch_child_pred(Opd &n, bool leaf, int code, const double *__restrict__ prior_site,
+                                                 const double2 *__restrict__ X, unsigned o) {
+#ifdef PMM_HOST_EMU
+    if (leaf) { if (code > 0) n.r.z = prior_site[code - 1]; }
+    else ld_xrec(n, X, o);
+#else
+    const int pl = (leaf && code > 0) ? 1 : 0, pi = leaf ? 0 : 1;
+    const double *pq = prior_site + (code - 1);                   // dereferenced only under pl
+    const double2 *px = X + 2 * (size_t)o;                          // dereferenced only under pi
+    asm volatile("{\n\t.reg .pred pl, pi;\n\tsetp.ne.s32 pl, %4, 0;\n\tsetp.ne.s32 pi, %5, 0;\n\t"
+                 "@pl ld.global.nc.f64 %2, [%6];\n\t"
+                 "@pi ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t}"
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(pl), "r"(pi), "l"(pq), "l"(px));
+#endif
+}
+__device__ __forceinline__ void fetch_orec_pred(Opd &n, bool load, const double4 *__restrict__ O, const int2 *__restrict__ OI, unsigned o) {
+#ifdef PMM_HOST_EMU
+    if (load) ld_orec(n, O, OI, o);
+#else
+    const int p = load ? 1 : 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %6, 0;\n\t"
+                 "@p ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t"
+                 "@p ld.global.v2.s32 {%4,%5}, [%8];\n\t}"
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+r"(n.ri.x), "+r"(n.ri.y) : "r"(p), "l"(O + o), "l"(OI + o));
+#endif
+}
+__device__ __forceinline__ void outside_fetch_brfree(const LParams &P, const int4 d, int cv, int cw, OutSlot &n,
+                                                     const double *__restrict__ prior_site, int s) {
+    // record index of a leaf id would be negative: the address is formed anyway and never used
+    fetch_child_pred(n.v, d.w & 4, cv, prior_site, P.X, rec_index(P, d.y, s));
+    fetch_child_pred(n.w, d.w & 8, cw, prior_site, P.X, rec_index(P, d.z, s));
+    if (!PMM_OUT_OCHAIN) fetch_orec_pred(n.o, (d.w & 3) == KIND_LOAD, P.O, P.OI, rec_index(P, d.x, s));
 }
 
 template <bool POST>
 __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
-    __shared__ int4 s_steps[STEP_CAP + 2];
+    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
     __shared__ double4 s_bc[2 * STEP_CAP];
     __shared__ double4 s_lut[4];
     __shared__ __align__(16) double s_red[(LT / 32) * 10 * RED_ROW];
@@ -418,8 +517,18 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     double *Sg = P.Spart + (size_t)grp * P.n_nodes * 5;
 
     auto codes_of = [&](const int4 d, int &cv, int &cw) {
-        if (d.w & 4) cv = __ldg(codes_s + (size_t)d.y * P.code_stride);
-        if (d.w & 8) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
+        if (PMM_OUT_BRFREE) {
+            // always load: an internal child reads (and ignores) the code of the last leaf row, a line every lane keeps hot
+            cv = __ldg(codes_s + (size_t)min(d.y, N - 1) * P.code_stride);
+            cw = __ldg(codes_s + (size_t)min(d.z, N - 1) * P.code_stride);
+        } else {
+            if (d.w & 4) cv = __ldg(codes_s + (size_t)d.y * P.code_stride);
+            if (d.w & 8) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
+        }
+    };
+    auto fetch = [&](const int4 d, int cv, int cw, OutSlot &n) {
+        if (PMM_OUT_BRFREE) outside_fetch_brfree(P, d, cv, cw, n, prior_site, s_raw);
+        else outside_fetch(P, d, cv, cw, n, prior_site, s_raw, N);
     };
     Opd chain;                                           // out-record kept in registers for the next step
     chain.r = make_double4(0.0, 0.0, 0.0, 0.0); chain.ri = make_int2(-1, 0);
@@ -429,20 +538,39 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     int4 d0 = s_steps[0], d1 = (nsteps > 1) ? s_steps[1] : d0;
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(d0, c0v, c0w);
-    if (nsteps > 1) codes_of(d1, c1v, c1w);
-    outside_fetch(P, d0, c0v, c0w, A, prior_site, s_raw, N);
+    if (PMM_OUT_BRFREE || nsteps > 1) codes_of(d1, c1v, c1w);
+    if (PMM_OUT_REGPF) fetch(d0, c0v, c0w, A);
+    if (PMM_OUT_OCHAIN && (d0.w & 3) == KIND_LOAD) ld_orec(chain, P.O, P.OI, rec_index(P, d0.x, s_raw));
 
     auto step = [&](int i, OutSlot &cur, OutSlot &nxt) {
+        if (PMM_OUT_DESC_RELOAD) { d0 = s_steps[i]; d1 = s_steps[i + 1]; }       // s_steps has two entries of slack
         int4 d2 = d1;
         int c2v = 0, c2w = 0;
-        if (i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
-        if (i + 1 < nsteps) outside_fetch(P, d1, c1v, c1w, nxt, prior_site, s_raw, N);
-        if (PF_DIST_OUT > 0 && i + PF_DIST_OUT < nsteps) {
+        // the staged step list is padded with copies of its last step: looking ahead past the end re-reads that step's operands
+        if (PMM_OUT_BRFREE || i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
+        if (PMM_OUT_PIPE1) {}                                                   // refilled inside the step body, after the decode
+        else if (PMM_OUT_REGPF) { if (PMM_OUT_BRFREE || i + 1 < nsteps) fetch(d1, c1v, c1w, nxt); }
+        else fetch(d0, c0v, c0w, cur);                                          // no second register set: more warps hide the latency
+        if (PF_DIST_OUT > 0 && (PMM_OUT_BRFREE || i + PF_DIST_OUT < nsteps)) {
             const int4 dp = s_steps[i + PF_DIST_OUT];
-            if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.y, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
-            if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-            else { const unsigned o = rec_index(P, dp.z, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
+            if (PMM_OUT_BRFREE) {
+                // one prefetch per child, its address chosen by the (uniform) leaf flag
+                const char *cvp = reinterpret_cast<const char *>(codes_s + (size_t)min(dp.y, N - 1) * P.code_stride);
+                const char *cwp = reinterpret_cast<const char *>(codes_s + (size_t)min(dp.z, N - 1) * P.code_stride);
+                const char *xvp = reinterpret_cast<const char *>(P.X + 2 * (size_t)rec_index(P, max(dp.y, N), s_raw));
+                const char *xwp = reinterpret_cast<const char *>(P.X + 2 * (size_t)rec_index(P, max(dp.z, N), s_raw));
+                prefetch_l2((dp.w & 4) ? cvp : xvp);
+                prefetch_l2((dp.w & 8) ? cwp : xwp);
+                if (PMM_PF_O) {      // a loaded out[u] may come from an earlier launch; otherwise repeat a line just asked for
+                    const char *op = reinterpret_cast<const char *>(P.O + rec_index(P, dp.x, s_raw));
+                    prefetch_l2(((dp.w & 3) == KIND_LOAD) ? op : ((dp.w & 4) ? cvp : xvp));
+                }
+            } else {
+                if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
+                else { const unsigned o = rec_index(P, dp.y, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
+                if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
+                else { const unsigned o = rec_index(P, dp.z, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
+            }
         }
         const int u = d0.x, f = d0.w;
         const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
@@ -467,7 +595,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             Child r;
             decode(r, pr, cr, qsum);
             chain.r = make_double4(cr.x, cr.w, cr.y, 0.0); chain.ri = make_int2(-1, -r.cum);
-            if (P.store_all) { P.O[ou] = chain.r; P.OI[ou] = chain.ri; }      // the NNI scorer reads out[root] too
+            if (P.store_all) st_orec(P.O, P.OI, ou, chain);      // the NNI scorer reads out[root] too
             const double t0 = r.t0 * invL, t2 = r.gm * invL;
             double r10[10];
 #pragma unroll
@@ -481,7 +609,9 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
                 P.post1[gp] = (t2 > 0.0) ? log(t2) : -INFINITY;
             }
         }
-        if (how == KIND_LOAD) chain = cur.o;
+        if (!PMM_OUT_OCHAIN && how == KIND_LOAD) chain = cur.o;
+        // single register set: its contents are decoded, so the loads of step i + 1 can land in it while this step computes
+        if (PMM_OUT_PIPE1 && (PMM_OUT_BRFREE || i + 1 < nsteps)) fetch(d1, c1v, c1w, cur);
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
         const int F = chain.ri.y;
         const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
@@ -492,6 +622,8 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         red_put5(c5, red, lane, 5);                      // counts leave the registers at once
         child_outside<!vleaf>(chain, v, w, bcv, qsum, fac, ov, c5);
         red_put5(c5, red, lane, 0);
+        // out[u] is dead: if the next step loads its out-record, it lands in the chain registers while this step finishes
+        if (PMM_OUT_OCHAIN && !PMM_OUT_BRFREE && i + 1 < nsteps && (d1.w & 3) == KIND_LOAD) ld_orec(chain, P.O, P.OI, rec_index(P, d1.x, s_raw));
 #else
         child_outside(chain, w, v, bcw, qsum, fac, ow, c5);
         red_put5(c5, red, lane, 5);                      // counts leave the registers at once
@@ -512,13 +644,15 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
         if (!wleaf) {
             normalise_out(ow, F + v.cum);
-            if ((f & 32) || P.store_all) { const unsigned oo = rec_index(P, d0.z, s_raw); P.O[oo] = ow.r; P.OI[oo] = ow.ri; }
+            if ((f & 32) || P.store_all) st_orec(P.O, P.OI, rec_index(P, d0.z, s_raw), ow);
         }
         if (!vleaf) {
             normalise_out(ov, F + w.cum);
-            if ((f & 16) || P.store_all) { const unsigned oo = rec_index(P, d0.y, s_raw); P.O[oo] = ov.r; P.OI[oo] = ov.ri; }
-            chain = ov;
+            if ((f & 16) || P.store_all) st_orec(P.O, P.OI, rec_index(P, d0.y, s_raw), ov);
+            if (!PMM_OUT_OCHAIN || PMM_OUT_BRFREE || (f & 64)) chain = ov;
         }
+        // a step that loads its out-record gets it straight into the chain registers, under a predicate: nothing to select
+        if (PMM_OUT_OCHAIN && PMM_OUT_BRFREE) fetch_orec_pred(chain, (d1.w & 3) == KIND_LOAD, P.O, P.OI, rec_index(P, d1.x, s_raw));
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
         const double tot = red_finish(red, lane);
         if (lane < 20 && !(lane & 1)) {
@@ -534,11 +668,16 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             default: core(std::true_type{}, std::true_type{}); break;
         }
 #endif
-        d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
+        if (!PMM_OUT_DESC_RELOAD) { d0 = d1; d1 = d2; }
+        c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
     };
     int i = 0;
-    for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
-    if (i < nsteps) step(i, A, B);
+    if (PMM_OUT_PIPE1) {
+        for (; i < nsteps; i++) step(i, A, A);
+    } else {
+        for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
+        if (i < nsteps) step(i, A, B);
+    }
     grid_launch_dependents();
     // R~ of this (warp, clade)
 #pragma unroll
