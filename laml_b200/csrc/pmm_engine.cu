@@ -519,7 +519,7 @@ void make_lumped_schedule(int N, int n, const int *L, const int *R, const int *P
             const Bin &bin = bins[t][bi];
             const int begin = (int)out_steps.size();
             for (int r : bin.roots) {
-                stk2.clear(); stk2.push_back({r, Pa[r] < 0 ? 0 : KIND_LOAD});
+                stk2.clear(); stk2.push_back({r, KIND_LOAD});      // a root's out-record is stored by the inside pass
                 while (!stk2.empty()) {
                     const int u = stk2.back().first, how = stk2.back().second;
                     stk2.pop_back();
@@ -573,8 +573,8 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     if ((int)in_steps.size() != h->n_int || (int)out_steps.size() != h->n_int) return fail(h, "internal error: clade schedule does not cover the tree");
     // algorithmic bytes per site: 32-byte inside / 40-byte outside records written once and read where not chained, 4-byte leaf codes,
     // 40 bytes of expected counts per (branch, 32 sites)
-    h->l_in_bytes_per_site = 32 * (int64_t)h->n_int + 32 * in_loads + 4 * (int64_t)N + 16 * (int64_t)h->n_roots;
-    h->l_out_bytes_per_site = 32 * (int64_t)(h->n_int) /* inside records of internal children and roots */ + 4 * (int64_t)N +
+    h->l_in_bytes_per_site = 32 * (int64_t)h->n_int + 32 * in_loads + 4 * (int64_t)N + (16 + 40) * (int64_t)h->n_roots;
+    h->l_out_bytes_per_site = 32 * (int64_t)(h->n_int - h->n_roots) /* inside records of internal children */ + 4 * (int64_t)N +
                               40 * (out_loads + out_stores) + 8 * (int64_t)h->n_roots + (40 * (int64_t)n) / 32;
     // device copies (capacity n_int for every array, so that a new topology over the same counts reuses them)
     const size_t cap = (size_t)std::max(h->n_int, 1);

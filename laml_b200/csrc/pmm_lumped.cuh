@@ -322,14 +322,35 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
         prev.r.z = (hu >= 0) ? (bv ? v.qh : w.qh) : xm * sc;
         prev.r.w = pack_hc(hu, v.cum + w.cum + e);
         st_xrec(P.X, rec_index(P, d0.x, sr), prev);               // idle lanes write their own padding column
-        if (valid) {
-            if (d0.w & 16) {
-                // root: site likelihood L = E[root]_0 (the root's own branch starts in state 0, EM_solver.py:140)
-                Child r;
-                decode(r, prev, ld_bc(P.bc, d0.x), qsum);
-                const double L = r.E0;
-                P.invL[(size_t)cl.z * P.K + s] = (L > 0.0) ? 1.0 / L : 0.0;
+        if (d0.w & 16) {
+            // root: site likelihood L = E[root]_0 (the root's own branch starts in state 0, EM_solver.py:140) ...
+            const double4 cr = ld_bc(P.bc, d0.x);
+            Child r;
+            decode(r, prev, cr, qsum);
+            const double L = r.E0, iL = (valid && L > 0.0) ? 1.0 / L : 0.0;
+            if (valid) {
+                P.invL[(size_t)cl.z * P.K + s] = iL;
                 P.root_site_llh[(size_t)cl.z * P.K + s] = (L > 0.0) ? log(L) + (double)r.cum * 0.693147180559945309417232121458 : -INFINITY;
+            }
+            // ... and everything the outside pass needs to know about a root, so that a root is an ordinary step there:
+            // out[root] = (a, g, b q) (EM_solver.py:151-158) as a stored out-record, and the counts of the root's own
+            // branch (:282-286), summed over the warp's sites (a rare step: plain shuffles)
+            Opd seed;
+            seed.r = make_double4(cr.x, cr.w, cr.y, 0.0); seed.ri = make_int2(-1, -r.cum);
+            st_orec(P.O, P.OI, rec_index(P, d0.x, sr), seed);
+            double t0 = r.t0 * iL, t1 = r.t1 * iL, t2 = r.gm * iL;
+            if (P.post0 && valid) {
+                const size_t gp = (size_t)d0.x * P.K_total + P.site0 + s;
+                P.post0[gp] = (t0 > 0.0) ? log(t0) : -INFINITY;
+                P.post1[gp] = (t2 > 0.0) ? log(t2) : -INFINITY;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            }
+            if ((threadIdx.x & 31) < 5) {
+                const int j = threadIdx.x & 31;
+                P.Spart[((size_t)(sr >> 5) * P.n_nodes + d0.x) * 5 + j] = (j == 0) ? t0 : (j == 1) ? t1 : (j == 2) ? t2 : 0.0;
             }
         }
         d0 = d1; d1 = d2; c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
@@ -572,7 +593,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
                 else { const unsigned o = rec_index(P, dp.z, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
             }
         }
-        const int u = d0.x, f = d0.w;
+        const int f = d0.w;
         const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
 #if PMM_LOUT_SHAPES
         // one straight-line body per step shape (which children are leaves): big basic blocks for the scheduler,
@@ -585,30 +606,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         Child v, w;
         if (vleaf) decode_leaf(v, c0v, cur.v.r.z, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
         if (wleaf) decode_leaf(w, c0w, cur.w.r.z, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
-        const int how = f & 3;
-        if (how == 0) {
-            // u is a root: out[root] = (a, g, b q) (EM_solver.py:151-158); its own branch's counts (:282-286)
-            const unsigned ou = rec_index(P, u, s_raw);
-            Opd pr;
-            ld_xrec(pr, P.X, ou);
-            const double4 cr = ld_bc(P.bc, u);
-            Child r;
-            decode(r, pr, cr, qsum);
-            chain.r = make_double4(cr.x, cr.w, cr.y, 0.0); chain.ri = make_int2(-1, -r.cum);
-            if (P.store_all) st_orec(P.O, P.OI, ou, chain);      // the NNI scorer reads out[root] too
-            const double t0 = r.t0 * invL, t2 = r.gm * invL;
-            double r10[10];
-#pragma unroll
-            for (int q = 0; q < 10; q++) r10[q] = 0.0;
-            r10[0] = t0; r10[1] = r.t1 * invL; r10[2] = t2;
-            const double tot = warp_sum10(r10, red, lane);
-            if (lane < 10 && !(lane & 1)) Sg[(size_t)u * 5 + (lane >> 1)] = tot;
-            if (POST && valid) {
-                const size_t gp = (size_t)u * P.K_total + P.site0 + s;
-                P.post0[gp] = (t0 > 0.0) ? log(t0) : -INFINITY;
-                P.post1[gp] = (t2 > 0.0) ? log(t2) : -INFINITY;
-            }
-        }
+        const int how = f & 3;                           // a root's out-record and own counts were written by the inside pass
         if (!PMM_OUT_OCHAIN && how == KIND_LOAD) chain = cur.o;
         // single register set: its contents are decoded, so the loads of step i + 1 can land in it while this step computes
         if (PMM_OUT_PIPE1 && (PMM_OUT_BRFREE || i + 1 < nsteps)) fetch(d1, c1v, c1w, cur);
@@ -644,7 +642,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
         if (!wleaf) {
             normalise_out(ow, F + v.cum);
-            if ((f & 32) || P.store_all) st_orec(P.O, P.OI, rec_index(P, d0.z, s_raw), ow);
+            st_orec(P.O, P.OI, rec_index(P, d0.z, s_raw), ow);      // an internal w is never the chained child: always stored
         }
         if (!vleaf) {
             normalise_out(ov, F + w.cum);

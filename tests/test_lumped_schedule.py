@@ -9,7 +9,7 @@ topologies for several clade capacities:
     (then, and only then, its "earlier launch" bit is set);
   * outside: a step whose out-record is chained (how = 2) follows the step of its parent, which lists it first and
     has the keep bit; a loaded out-record (how = 1) was stored (store bit) by the parent's step at least two steps
-    earlier in the same clade or in an earlier launch; roots have how = 0;
+    earlier in the same clade or in an earlier launch; a root loads too (the inside pass stored its out-record);
   * leaves are flagged as leaves.
 """
 import numpy as np
@@ -90,7 +90,8 @@ def check(N, parent, left, right, cap, top):
             else:
                 how = f & 3
                 assert bool(f & 4) == (v < N) and bool(f & 8) == (w < N)
-                assert (how == 0) == (parent[u] < 0)
+                if parent[u] < 0:
+                    assert how == KIND_LOAD                    # a root's out-record is stored by the inside pass' root step
                 if parent[u] >= 0:
                     j = step_pos[int(parent[u])]
                     pf = steps[j, 3]
