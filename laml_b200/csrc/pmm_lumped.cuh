@@ -62,38 +62,12 @@ constexpr int STEP_PAD = 8;              // entries past the end of the staged s
 #define PMM_PF_DIST 6                    // L2 prefetch distance in steps for operands of earlier launches (0 = off)
 #endif
 constexpr int PF_DIST = PMM_PF_DIST;
-#ifndef PMM_LOUT_SHAPES
-#define PMM_LOUT_SHAPES 1                // 1: one specialised step body per (v leaf?, w leaf?) shape
-#endif
 #ifndef PMM_PF_DIST_OUT
 #define PMM_PF_DIST_OUT 3
 #endif
 constexpr int PF_DIST_OUT = PMM_PF_DIST_OUT;
-// tuning switches of the outside kernel (scripts/build_variants.sh builds one library per setting; defaults = the shipped kernel)
 #ifndef PMM_LD256
-#define PMM_LD256 1                      // records move as one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256) instead of two 128-bit ones
-#endif
-#ifndef PMM_RED_TREE
-#define PMM_RED_TREE 0                   // count reduction: pairwise adds (depth 4) instead of two serial chains of 8
-#endif
-#ifndef PMM_OUT_REGPF
-#define PMM_OUT_REGPF 1                  // 1: the next step's operands are loaded into a second register set one step ahead
-#endif
-#ifndef PMM_PF_O
-#define PMM_PF_O 0                       // 1: out-records a later step loads are pulled into L2 like its children's records
-#endif
-#ifndef PMM_OUT_BRFREE
-#define PMM_OUT_BRFREE 1                 // 1: the per-step fetch / prefetch / leaf-code prologue of the outside kernel is straight-line code:
-                                         //    predicated loads, clamped rows, a step list padded past its end -- no branches
-#endif
-#ifndef PMM_OUT_DESC_RELOAD
-#define PMM_OUT_DESC_RELOAD 1            // 1: step descriptors are re-read from shared memory every step instead of rotating through registers
-#endif
-#ifndef PMM_OUT_OCHAIN
-#define PMM_OUT_OCHAIN 0                 // 1: a loaded out[u] goes straight into the chain registers (they are dead once both T records exist)
-#endif
-#ifndef PMM_OUT_PIPE1
-#define PMM_OUT_PIPE1 0                  // 1: ONE operand register set, refilled for step i + 1 as soon as step i has decoded it
+#define PMM_LD256 1                      // records move as one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256): -3 % on both passes
 #endif
 
 struct LParams {
@@ -425,32 +399,16 @@ __device__ __forceinline__ void red_put5(const double *__restrict__ v, double *_
 }
 __device__ __forceinline__ double red_finish(const double *__restrict__ red, int lane) {
     __syncwarp();
-    double sum = 0.0;
-#if PMM_OUT_BRFREE
-    {   // every lane adds up half a row (lanes 20-31 repeat row 9): no divergent region in the step
-        const double2 *row = reinterpret_cast<const double2 *>(red + min(lane >> 1, 9) * RED_ROW + (lane & 1) * 18);
-#else
-    if (lane < 20) {
-        const double2 *row = reinterpret_cast<const double2 *>(red + (lane >> 1) * RED_ROW + (lane & 1) * 18);
-#endif
-#if PMM_RED_TREE
-        // 16 values, pairwise: dependent depth 4 (the serial form below has two chains of 8 at the end of every step)
-        double2 x[8];
+    // every lane adds up half a row (lanes 20-31 repeat row 9): no divergent region in the step.  Two serial chains
+    // of eight adds -- a pairwise tree was measured slower (more live registers at the end of the step)
+    const double2 *row = reinterpret_cast<const double2 *>(red + min(lane >> 1, 9) * RED_ROW + (lane & 1) * 18);
+    double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int t = 0; t < 8; t++) x[t] = row[t];
-        const double s0 = x[0].x + x[0].y, s1 = x[1].x + x[1].y, s2 = x[2].x + x[2].y, s3 = x[3].x + x[3].y;
-        const double s4 = x[4].x + x[4].y, s5 = x[5].x + x[5].y, s6 = x[6].x + x[6].y, s7 = x[7].x + x[7].y;
-        sum = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-#else
-        double a = 0.0, b = 0.0;
-#pragma unroll
-        for (int t = 0; t < 8; t += 2) {
-            const double2 x = row[t], y = row[t + 1];
-            a += x.x; b += x.y; a += y.x; b += y.y;
-        }
-        sum = a + b;
-#endif
+    for (int t = 0; t < 8; t += 2) {
+        const double2 x = row[t], y = row[t + 1];
+        a += x.x; b += x.y; a += y.x; b += y.y;
     }
+    const double sum = a + b;
     const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
     __syncwarp();                                    // readers done before the next step's writers
     return tot;
@@ -461,173 +419,141 @@ __device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__re
     return red_finish(red, lane);
 }
 
-// step flags: bits 0-1 where out[u] comes from (0 = u is a root, 1 = load, 2 = chained in registers),
-//             bit 2 / 3: v / w is a leaf, bit 4 / 5: store out[v] / out[w],
+// step flags: bits 0-1 where out[u] comes from (1 = load, 2 = chained in registers; a root loads the record the inside
+//             pass' root step stored), bit 2 / 3: v / w is a leaf, bit 4 / 5: store out[v] / out[w],
 //             bit 6: out[v] is chained into the next step (the host orders the children accordingly)
 struct OutSlot { Opd v, w, o; };
 
-__device__ __forceinline__ void outside_fetch(const LParams &P, const int4 d, int cv, int cw, OutSlot &n, const double *__restrict__ prior_site,
-                                              int s, int N) {
-    if (d.w & 4) n.v.r.z = (cv > 0) ? __ldg(prior_site + (cv - 1)) : 0.0;
-    else { const unsigned o = rec_index(P, d.y, s); ld_xrec(n.v, P.X, o); }
-    if (d.w & 8) n.w.r.z = (cw > 0) ? __ldg(prior_site + (cw - 1)) : 0.0;
-    else { const unsigned o = rec_index(P, d.z, s); ld_xrec(n.w, P.X, o); }
-    if (!PMM_OUT_OCHAIN && (d.w & 3) == KIND_LOAD) { const unsigned o = rec_index(P, d.x, s); ld_orec(n.o, P.O, P.OI, o); }
-}
-
-// The same without branches: which access a child needs is a warp-uniform predicate (descriptor flag) or a per-lane one
-// (a leaf's code), so every load is issued under a predicate and the addresses are formed unconditionally.
-// pl: lane gathers the prior of its leaf's state into r.z; pi: lane loads the 32-byte inside record
-__device__ __forceinline__ void fetch_child_pred(Opd &n, bool leaf, int code, const double *__restrict__ prior_site,
-                                                 const double2 *__restrict__ X, unsigned o) {
+// ---- predicated accesses.  The per-step prologue (operands of step i + 1, leaf codes of step i + 2, L2 prefetch of
+// step i + PF) is straight-line code: which access a child needs is a warp-uniform predicate (a descriptor flag) or a
+// per-lane one (a leaf's code), so every access is issued under a predicate and its address is formed unconditionally.
+// ncu on the branching version of this prologue: 18 branches per step, 40 % of the stall samples on the control flow.
 #ifdef PMM_HOST_EMU
-    if (leaf) { if (code > 0) n.r.z = prior_site[code - 1]; }
-    else ld_xrec(n, X, o);
+__device__ __forceinline__ void ld_code_pred(int &c, bool p, const int *a) { if (p) c = *a; }
+__device__ __forceinline__ void ld_child_pred(Opd &n, bool leaf, int code, const double *q, const double2 *x) {
+    if (leaf) { if (code > 0) n.r.z = *q; }
+    else n.r = ld256(x);
+}
+__device__ __forceinline__ void ld_orec_pred(Opd &n, bool p, const double4 *o, const int2 *oi) { if (p) { n.r = ld256(o); n.ri = *oi; } }
+__device__ __forceinline__ void prefetch_l2_either(bool first, const void *, const void *) { (void)first; }
 #else
+__device__ __forceinline__ void ld_code_pred(int &c, bool p, const int *a) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p ld.global.nc.s32 %0, [%2];\n\t}" : "+r"(c) : "r"((int)p), "l"(a));
+}
+// leaf: the prior of the leaf's state (lanes with an edited state only) into r.z; internal child: its 32-byte inside record
+__device__ __forceinline__ void ld_child_pred(Opd &n, bool leaf, int code, const double *q, const double2 *x) {
     const int pl = (leaf && code > 0) ? 1 : 0, pi = leaf ? 0 : 1;
-    const double *pq = prior_site + (code - 1);                   // dereferenced only under pl
-    const double2 *px = X + 2 * (size_t)o;                          // dereferenced only under pi
     asm volatile("{\n\t.reg .pred pl, pi;\n\tsetp.ne.s32 pl, %4, 0;\n\tsetp.ne.s32 pi, %5, 0;\n\t"
                  "@pl ld.global.nc.f64 %2, [%6];\n\t"
                  "@pi ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t}"
-                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(pl), "r"(pi), "l"(pq), "l"(px));
-#endif
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(pl), "r"(pi), "l"(q), "l"(x));
 }
-__device__ __forceinline__ void fetch_orec_pred(Opd &n, bool load, const double4 *__restrict__ O, const int2 *__restrict__ OI, unsigned o) {
-#ifdef PMM_HOST_EMU
-    if (load) ld_orec(n, O, OI, o);
-#else
-    const int p = load ? 1 : 0;
+__device__ __forceinline__ void ld_orec_pred(Opd &n, bool p, const double4 *o, const int2 *oi) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %6, 0;\n\t"
                  "@p ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t"
                  "@p ld.global.v2.s32 {%4,%5}, [%8];\n\t}"
-                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+r"(n.ri.x), "+r"(n.ri.y) : "r"(p), "l"(O + o), "l"(OI + o));
-#endif
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+r"(n.ri.x), "+r"(n.ri.y) : "r"((int)p), "l"(o), "l"(oi));
 }
-__device__ __forceinline__ void outside_fetch_brfree(const LParams &P, const int4 d, int cv, int cw, OutSlot &n,
-                                                     const double *__restrict__ prior_site, int s) {
-    // record index of a leaf id would be negative: the address is formed anyway and never used
-    fetch_child_pred(n.v, d.w & 4, cv, prior_site, P.X, rec_index(P, d.y, s));
-    fetch_child_pred(n.w, d.w & 8, cw, prior_site, P.X, rec_index(P, d.z, s));
-    if (!PMM_OUT_OCHAIN) fetch_orec_pred(n.o, (d.w & 3) == KIND_LOAD, P.O, P.OI, rec_index(P, d.x, s));
+__device__ __forceinline__ void prefetch_l2_either(bool first, const void *a, const void *b) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p prefetch.global.L2 [%1];\n\t@!p prefetch.global.L2 [%2];\n\t}"
+                 ::"r"((int)first), "l"(a), "l"(b));
+}
+#endif
+
+// Look-ahead form of the clade's steps, staged once per CTA next to the descriptors: record / code ROWS premultiplied
+// (32-bit, unsigned), so that an address in the prologue is one add and one multiply-add:
+//   x = (u - N) Kp: row of u's records;  y, z = per child: leaf -> leaf id * code_stride (its code row),
+//   internal -> (c - N) Kp (its record row);  w = the step's flags
+__device__ __forceinline__ void stage_rows(uint4 *s_rows, const int4 *s_steps, const LParams &P, int nsteps) {
+    const unsigned N = (unsigned)P.n_leaves, Kp = (unsigned)P.Kp, cs = (unsigned)P.code_stride;
+    for (int i = threadIdx.x; i < nsteps + STEP_PAD; i += LT) {
+        const int4 d = s_steps[i];
+        auto row = [&](int c) { return ((unsigned)c < N) ? (unsigned)c * cs : ((unsigned)c - N) * Kp; };
+        s_rows[i] = make_uint4(((unsigned)d.x - N) * Kp, row(d.y), row(d.z), (unsigned)d.w);
+    }
+    __syncthreads();
 }
 
 template <bool POST>
 __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
     __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
+    __shared__ uint4 s_rows[STEP_CAP + STEP_PAD];
     __shared__ double4 s_bc[2 * STEP_CAP];
     __shared__ double4 s_lut[4];
     __shared__ __align__(16) double s_red[(LT / 32) * 10 * RED_ROW];
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z, clade id w
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
+    stage_rows(s_rows, s_steps, P, nsteps);
     grid_dependency_wait();
-    const int N = P.n_leaves;
-    const int s_raw = (blockIdx.y + P.sblk0) * LT + threadIdx.x;
-    const bool valid = s_raw < P.K;
-    const int s = min(s_raw, P.K - 1);
+    const unsigned s_raw = (blockIdx.y + P.sblk0) * LT + threadIdx.x;     // record column (idle lanes of the last warp own padding columns)
+    const bool valid = (int)s_raw < P.K;
+    const int s = min((int)s_raw, P.K - 1);
     const int gs = P.site0 + s;
     const int lane = threadIdx.x & 31;
     const int grp = s_raw >> 5;                          // site group of this warp
     if (grp * 32 >= P.K) return;                         // whole warp beyond the last site
     double *red = s_red + (threadIdx.x >> 5) * 10 * RED_ROW;
-    const double *prior_site = P.prior + __ldg(P.site_ptr + gs);
+    const double *prior_m1 = P.prior + __ldg(P.site_ptr + gs) - 1;       // prior of state a at [a]
     const double qsum = __ldg(P.qsum + gs);
     const int *codes_s = P.codes + gs;
     const double invL = valid ? P.invL[(size_t)cl.z * P.K + s] : 0.0;
     double *Sg = P.Spart + (size_t)grp * P.n_nodes * 5;
 
-    auto codes_of = [&](const int4 d, int &cv, int &cw) {
-        if (PMM_OUT_BRFREE) {
-            // always load: an internal child reads (and ignores) the code of the last leaf row, a line every lane keeps hot
-            cv = __ldg(codes_s + (size_t)min(d.y, N - 1) * P.code_stride);
-            cw = __ldg(codes_s + (size_t)min(d.z, N - 1) * P.code_stride);
-        } else {
-            if (d.w & 4) cv = __ldg(codes_s + (size_t)d.y * P.code_stride);
-            if (d.w & 8) cw = __ldg(codes_s + (size_t)d.z * P.code_stride);
-        }
+    // leaf codes of a step (two steps ahead: the prior of a leaf's state is a dependent gather)
+    auto codes_of = [&](const uint4 r, int &cv, int &cw) {
+        ld_code_pred(cv, r.w & 4, codes_s + r.y);
+        ld_code_pred(cw, r.w & 8, codes_s + r.z);
     };
-    auto fetch = [&](const int4 d, int cv, int cw, OutSlot &n) {
-        if (PMM_OUT_BRFREE) outside_fetch_brfree(P, d, cv, cw, n, prior_site, s_raw);
-        else outside_fetch(P, d, cv, cw, n, prior_site, s_raw, N);
+    // operands of a step (one step ahead, into the other register set)
+    auto fetch = [&](const uint4 r, int cv, int cw, OutSlot &n) {
+        ld_child_pred(n.v, r.w & 4, cv, prior_m1 + cv, P.X + 2 * (size_t)(r.y + s_raw));
+        ld_child_pred(n.w, r.w & 8, cw, prior_m1 + cw, P.X + 2 * (size_t)(r.z + s_raw));
+        const unsigned o = r.x + s_raw;
+        ld_orec_pred(n.o, (r.w & 3) == KIND_LOAD, P.O + o, P.OI + o);
     };
     Opd chain;                                           // out-record kept in registers for the next step
     chain.r = make_double4(0.0, 0.0, 0.0, 0.0); chain.ri = make_int2(-1, 0);
     OutSlot A, B;
     A.v = A.w = A.o = B.v = B.w = B.o = chain;
     double rt = 0.0;
-    int4 d0 = s_steps[0], d1 = (nsteps > 1) ? s_steps[1] : d0;
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
-    codes_of(d0, c0v, c0w);
-    if (PMM_OUT_BRFREE || nsteps > 1) codes_of(d1, c1v, c1w);
-    if (PMM_OUT_REGPF) fetch(d0, c0v, c0w, A);
-    if (PMM_OUT_OCHAIN && (d0.w & 3) == KIND_LOAD) ld_orec(chain, P.O, P.OI, rec_index(P, d0.x, s_raw));
+    codes_of(s_rows[0], c0v, c0w);
+    codes_of(s_rows[1], c1v, c1w);                       // the staged lists are padded with copies of the last step
+    fetch(s_rows[0], c0v, c0w, A);
 
     auto step = [&](int i, OutSlot &cur, OutSlot &nxt) {
-        if (PMM_OUT_DESC_RELOAD) { d0 = s_steps[i]; d1 = s_steps[i + 1]; }       // s_steps has two entries of slack
-        int4 d2 = d1;
+        // ---- prologue: look-ahead past the end of the clade re-reads the last step's operands (padding), no guards
         int c2v = 0, c2w = 0;
-        // the staged step list is padded with copies of its last step: looking ahead past the end re-reads that step's operands
-        if (PMM_OUT_BRFREE || i + 2 < nsteps) { d2 = s_steps[i + 2]; codes_of(d2, c2v, c2w); }
-        if (PMM_OUT_PIPE1) {}                                                   // refilled inside the step body, after the decode
-        else if (PMM_OUT_REGPF) { if (PMM_OUT_BRFREE || i + 1 < nsteps) fetch(d1, c1v, c1w, nxt); }
-        else fetch(d0, c0v, c0w, cur);                                          // no second register set: more warps hide the latency
-        if (PF_DIST_OUT > 0 && (PMM_OUT_BRFREE || i + PF_DIST_OUT < nsteps)) {
-            const int4 dp = s_steps[i + PF_DIST_OUT];
-            if (PMM_OUT_BRFREE) {
-                // one prefetch per child, its address chosen by the (uniform) leaf flag
-                const char *cvp = reinterpret_cast<const char *>(codes_s + (size_t)min(dp.y, N - 1) * P.code_stride);
-                const char *cwp = reinterpret_cast<const char *>(codes_s + (size_t)min(dp.z, N - 1) * P.code_stride);
-                const char *xvp = reinterpret_cast<const char *>(P.X + 2 * (size_t)rec_index(P, max(dp.y, N), s_raw));
-                const char *xwp = reinterpret_cast<const char *>(P.X + 2 * (size_t)rec_index(P, max(dp.z, N), s_raw));
-                prefetch_l2((dp.w & 4) ? cvp : xvp);
-                prefetch_l2((dp.w & 8) ? cwp : xwp);
-                if (PMM_PF_O) {      // a loaded out[u] may come from an earlier launch; otherwise repeat a line just asked for
-                    const char *op = reinterpret_cast<const char *>(P.O + rec_index(P, dp.x, s_raw));
-                    prefetch_l2(((dp.w & 3) == KIND_LOAD) ? op : ((dp.w & 4) ? cvp : xvp));
-                }
-            } else {
-                if (dp.w & 4) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
-                else { const unsigned o = rec_index(P, dp.y, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
-                if (dp.w & 8) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
-                else { const unsigned o = rec_index(P, dp.z, s_raw); prefetch_l2(P.X + 2 * (size_t)o); }
-            }
+        codes_of(s_rows[i + 2], c2v, c2w);
+        fetch(s_rows[i + 1], c1v, c1w, nxt);
+        if (PF_DIST_OUT > 0) {
+            // operands written by earlier launches (every inside record, leaf codes) are pulled into L2 a few steps ahead
+            const uint4 rp = s_rows[i + PF_DIST_OUT];
+            prefetch_l2_either(rp.w & 4, codes_s + rp.y, P.X + 2 * (size_t)(rp.y + s_raw));
+            prefetch_l2_either(rp.w & 8, codes_s + rp.z, P.X + 2 * (size_t)(rp.z + s_raw));
         }
+        const int4 d0 = s_steps[i];                      // node ids of this step: count rows, posteriors
+        const uint4 r0 = s_rows[i];
         const int f = d0.w;
         const double4 bcv = s_bc[2 * i], bcw = s_bc[2 * i + 1];
-#if PMM_LOUT_SHAPES
         // one straight-line body per step shape (which children are leaves): big basic blocks for the scheduler,
         // and everything a leaf does not need (out-record, normalisation, store) is compiled out
         auto core = [&](auto VL, auto WL) {
         constexpr bool vleaf = decltype(VL)::value, wleaf = decltype(WL)::value;
-#else
-        const bool vleaf = f & 4, wleaf = f & 8;
-#endif
         Child v, w;
         if (vleaf) decode_leaf(v, c0v, cur.v.r.z, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
         if (wleaf) decode_leaf(w, c0w, cur.w.r.z, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
-        const int how = f & 3;                           // a root's out-record and own counts were written by the inside pass
-        if (!PMM_OUT_OCHAIN && how == KIND_LOAD) chain = cur.o;
-        // single register set: its contents are decoded, so the loads of step i + 1 can land in it while this step computes
-        if (PMM_OUT_PIPE1 && (PMM_OUT_BRFREE || i + 1 < nsteps)) fetch(d1, c1v, c1w, cur);
+        if ((f & 3) == KIND_LOAD) chain = cur.o;         // otherwise out[u] is what the previous step left in the registers
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
         const int F = chain.ri.y;
         const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
         double c5[5];
         Opd ov, ow;
-#if PMM_LOUT_SHAPES
         child_outside<!wleaf>(chain, w, v, bcw, qsum, fac, ow, c5);
         red_put5(c5, red, lane, 5);                      // counts leave the registers at once
         child_outside<!vleaf>(chain, v, w, bcv, qsum, fac, ov, c5);
         red_put5(c5, red, lane, 0);
-        // out[u] is dead: if the next step loads its out-record, it lands in the chain registers while this step finishes
-        if (PMM_OUT_OCHAIN && !PMM_OUT_BRFREE && i + 1 < nsteps && (d1.w & 3) == KIND_LOAD) ld_orec(chain, P.O, P.OI, rec_index(P, d1.x, s_raw));
-#else
-        child_outside(chain, w, v, bcw, qsum, fac, ow, c5);
-        red_put5(c5, red, lane, 5);                      // counts leave the registers at once
-        child_outside(chain, v, w, bcv, qsum, fac, ov, c5);
-        red_put5(c5, red, lane, 0);
-#endif
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
         if (vleaf && valid && c0v == -1) rt += 1.0 - ov.r.y * fac;
         if (wleaf && valid && c0w == -1) rt += 1.0 - ow.r.y * fac;
@@ -642,22 +568,19 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         // F_child = F_u + cum_sibling + (exponent taken out of the child's record)
         if (!wleaf) {
             normalise_out(ow, F + v.cum);
-            st_orec(P.O, P.OI, rec_index(P, d0.z, s_raw), ow);      // an internal w is never the chained child: always stored
+            st_orec(P.O, P.OI, r0.z + s_raw, ow);        // an internal w is never the chained child: always stored
         }
         if (!vleaf) {
             normalise_out(ov, F + w.cum);
-            if ((f & 16) || P.store_all) st_orec(P.O, P.OI, rec_index(P, d0.y, s_raw), ov);
-            if (!PMM_OUT_OCHAIN || PMM_OUT_BRFREE || (f & 64)) chain = ov;
+            if ((f & 16) || P.store_all) st_orec(P.O, P.OI, r0.y + s_raw, ov);
+            chain = ov;
         }
-        // a step that loads its out-record gets it straight into the chain registers, under a predicate: nothing to select
-        if (PMM_OUT_OCHAIN && PMM_OUT_BRFREE) fetch_orec_pred(chain, (d1.w & 3) == KIND_LOAD, P.O, P.OI, rec_index(P, d1.x, s_raw));
         // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
         const double tot = red_finish(red, lane);
         if (lane < 20 && !(lane & 1)) {
             const int j = lane >> 1;
             Sg[(size_t)((j < 5) ? d0.y : d0.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
         }
-#if PMM_LOUT_SHAPES
         };
         switch ((f >> 2) & 3) {
             case 0: core(std::false_type{}, std::false_type{}); break;
@@ -665,17 +588,11 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             case 2: core(std::false_type{}, std::true_type{}); break;
             default: core(std::true_type{}, std::true_type{}); break;
         }
-#endif
-        if (!PMM_OUT_DESC_RELOAD) { d0 = d1; d1 = d2; }
         c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
     };
     int i = 0;
-    if (PMM_OUT_PIPE1) {
-        for (; i < nsteps; i++) step(i, A, A);
-    } else {
-        for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
-        if (i < nsteps) step(i, A, B);
-    }
+    for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }      // two register sets swap roles: no moves
+    if (i < nsteps) step(i, A, B);
     grid_launch_dependents();
     // R~ of this (warp, clade)
 #pragma unroll
