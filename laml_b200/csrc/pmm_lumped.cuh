@@ -428,35 +428,36 @@ struct OutSlot { Opd v, w, o; };
 // step i + PF) is straight-line code: which access a child needs is a warp-uniform predicate (a descriptor flag) or a
 // per-lane one (a leaf's code), so every access is issued under a predicate and its address is formed unconditionally.
 // ncu on the branching version of this prologue: 18 branches per step, 40 % of the stall samples on the control flow.
+// The predicates are formed inside the asm from the raw flag BITS (and a leaf's code), so that no 0/1 integer is ever
+// materialised: `bit` arguments are masked flag words, non-zero = true.
 #ifdef PMM_HOST_EMU
-__device__ __forceinline__ void ld_code_pred(int &c, bool p, const int *a) { if (p) c = *a; }
-__device__ __forceinline__ void ld_child_pred(Opd &n, bool leaf, int code, const double *q, const double2 *x) {
-    if (leaf) { if (code > 0) n.r.z = *q; }
+__device__ __forceinline__ void ld_code_pred(int &c, unsigned bit, const int *a) { if (bit) c = *a; }
+__device__ __forceinline__ void ld_child_pred(Opd &n, unsigned leafbit, int code, const double *q, const double2 *x) {
+    if (leafbit) { if (code > 0) n.r.z = *q; }
     else n.r = ld256(x);
 }
-__device__ __forceinline__ void ld_orec_pred(Opd &n, bool p, const double4 *o, const int2 *oi) { if (p) { n.r = ld256(o); n.ri = *oi; } }
-__device__ __forceinline__ void prefetch_l2_either(bool first, const void *, const void *) { (void)first; }
+__device__ __forceinline__ void ld_orec_pred(Opd &n, unsigned bit, const double4 *o, const int2 *oi) { if (bit) { n.r = ld256(o); n.ri = *oi; } }
+__device__ __forceinline__ void prefetch_l2_either(unsigned, const void *, const void *) {}
 #else
-__device__ __forceinline__ void ld_code_pred(int &c, bool p, const int *a) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p ld.global.nc.s32 %0, [%2];\n\t}" : "+r"(c) : "r"((int)p), "l"(a));
+__device__ __forceinline__ void ld_code_pred(int &c, unsigned bit, const int *a) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.s32 %0, [%2];\n\t}" : "+r"(c) : "r"(bit), "l"(a));
 }
 // leaf: the prior of the leaf's state (lanes with an edited state only) into r.z; internal child: its 32-byte inside record
-__device__ __forceinline__ void ld_child_pred(Opd &n, bool leaf, int code, const double *q, const double2 *x) {
-    const int pl = (leaf && code > 0) ? 1 : 0, pi = leaf ? 0 : 1;
-    asm volatile("{\n\t.reg .pred pl, pi;\n\tsetp.ne.s32 pl, %4, 0;\n\tsetp.ne.s32 pi, %5, 0;\n\t"
-                 "@pl ld.global.nc.f64 %2, [%6];\n\t"
-                 "@pi ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t}"
-                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(pl), "r"(pi), "l"(q), "l"(x));
+__device__ __forceinline__ void ld_child_pred(Opd &n, unsigned leafbit, int code, const double *q, const double2 *x) {
+    asm volatile("{\n\t.reg .pred pleaf, pq;\n\tsetp.ne.u32 pleaf, %4, 0;\n\tsetp.gt.and.s32 pq, %5, 0, pleaf;\n\t"
+                 "@pq ld.global.nc.f64 %2, [%6];\n\t"
+                 "@!pleaf ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t}"
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(leafbit), "r"(code), "l"(q), "l"(x));
 }
-__device__ __forceinline__ void ld_orec_pred(Opd &n, bool p, const double4 *o, const int2 *oi) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %6, 0;\n\t"
+__device__ __forceinline__ void ld_orec_pred(Opd &n, unsigned bit, const double4 *o, const int2 *oi) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %6, 0;\n\t"
                  "@p ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t"
                  "@p ld.global.v2.s32 {%4,%5}, [%8];\n\t}"
-                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+r"(n.ri.x), "+r"(n.ri.y) : "r"((int)p), "l"(o), "l"(oi));
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+r"(n.ri.x), "+r"(n.ri.y) : "r"(bit), "l"(o), "l"(oi));
 }
-__device__ __forceinline__ void prefetch_l2_either(bool first, const void *a, const void *b) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p prefetch.global.L2 [%1];\n\t@!p prefetch.global.L2 [%2];\n\t}"
-                 ::"r"((int)first), "l"(a), "l"(b));
+__device__ __forceinline__ void prefetch_l2_either(unsigned bit, const void *a, const void *b) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p prefetch.global.L2 [%1];\n\t@!p prefetch.global.L2 [%2];\n\t}"
+                 ::"r"(bit), "l"(a), "l"(b));
 }
 #endif
 
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         ld_child_pred(n.v, r.w & 4, cv, prior_m1 + cv, P.X + 2 * (size_t)(r.y + s_raw));
         ld_child_pred(n.w, r.w & 8, cw, prior_m1 + cw, P.X + 2 * (size_t)(r.z + s_raw));
         const unsigned o = r.x + s_raw;
-        ld_orec_pred(n.o, (r.w & 3) == KIND_LOAD, P.O + o, P.OI + o);
+        ld_orec_pred(n.o, r.w & 1, P.O + o, P.OI + o);       // how is 1 (load) or 2 (chained): bit 0
     };
     Opd chain;                                           // out-record kept in registers for the next step
     chain.r = make_double4(0.0, 0.0, 0.0, 0.0); chain.ri = make_int2(-1, 0);
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         Child v, w;
         if (vleaf) decode_leaf(v, c0v, cur.v.r.z, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
         if (wleaf) decode_leaf(w, c0w, cur.w.r.z, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
-        if ((f & 3) == KIND_LOAD) chain = cur.o;         // otherwise out[u] is what the previous step left in the registers
+        if (f & 1) chain = cur.o;                       // how = 1: loaded; otherwise out[u] is what the previous step left in the registers
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
         const int F = chain.ri.y;
         const double fac = invL * pow2i(max(-1000, min(1000, F + v.cum + w.cum)));
