@@ -145,6 +145,7 @@ void *pmm_stats_dev_ptr(pmm_handle *h);           /* device pointer, (5*n_nodes+
 int64_t pmm_stats_len(const pmm_handle *h);
 int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu,
                   int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu);
+int pmm_read_llh(pmm_handle *h, double *llh);      /* the llh slot of the statistics (after pmm_estep_dev / pmm_inside_dev) */
 int pmm_sync(pmm_handle *h);
 
 /*
@@ -217,6 +218,28 @@ int pmm_set_option(pmm_handle *h, const char *name, int64_t value);
 int pmm_ultrametric_solve(int32_t n, const int32_t *parent, const int8_t *kind, const double *fixed_len, double lo,
                           double hi, const double *S, double nu, double eps_nu, const double *H0, double mu_final,
                           double warm_theta, double warm_mu, double *d_out, double *H_out, int32_t *newton_iters);
+
+/*
+ * The same program ON THE DEVICE, fed by the statistics the E-step left there (pmm_estep_dev, or an all-reduce of them):
+ * EM_solver.Mstep with ultra_constr_cache (EM_solver.py:307-459) -- lengths under the equalities by one cooperative
+ * launch that runs the whole barrier Newton method (laml_b200/csrc/pmm_ultrametric_dev.cuh: level-synchronous tree
+ * sweeps, ~45 grid barriers per Newton step at 100k cells), then nu given the new lengths and phi in closed form.
+ * kind[n] / fixed_len[n] as for pmm_ultrametric_solve.  warm != 0: start the barrier path from the heights of the
+ * previous call on this handle (same problem).  *status: 0 optimal, 1 infeasible ("d_infeasible": nothing is updated),
+ * 2 failed ("failed_d").  Results equal the host routine's to its stopping tolerance (summation orders differ).
+ */
+int pmm_mstep_ultra_dev(pmm_handle *h, double R, int32_t n_cells, const int8_t *kind, const double *fixed_len,
+                        int32_t optimize_nu, int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu,
+                        int32_t warm, int32_t *status, int32_t *newton_iters);
+
+/*
+ * EM_solver.EM_optimization with ultra_constr=True (EM_solver.py:461-512) with every step on the device: E-step,
+ * constrained M-step (above, warm-started from the previous iteration), one log-likelihood read per iteration for the
+ * convergence test.  status: 0 "optimal", 1 "d_infeasible" (nllh / parameters of the last feasible iterate), 2 "failed_d".
+ */
+int pmm_em_ultra(pmm_handle *h, double *d, double *nu, double *phi, const int8_t *kind, const double *fixed_len,
+                 int32_t optimize_nu, int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax,
+                 double conv_eps, int32_t max_iter, double *nllh, int32_t *iters, int32_t *status);
 
 /*
  * Test hook, pure host code (works without a GPU): the clade schedule the lumped-state engine derives for a

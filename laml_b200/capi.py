@@ -22,6 +22,7 @@ SYMBOLS = [
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
     "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep", "pmm_em_step",
+    "pmm_mstep_ultra_dev", "pmm_em_ultra", "pmm_read_llh",
 ]
 
 
@@ -85,6 +86,8 @@ def load_library():
     L.pmm_mstep.argtypes = [vp, vp, f64, f64, i32, vp, i32, i32, f64, f64, f64, f64, vp, P(f64), P(f64)]
     L.pmm_em.argtypes = [vp, vp, P(f64), P(f64), vp, i32, i32, f64, i32, f64, f64, f64, i32, P(f64), P(i32), P(i32)]
     L.pmm_em_step.argtypes = [vp, vp, P(f64), P(f64), vp, i32, i32, f64, i32, f64, f64, P(f64)]
+    L.pmm_mstep_ultra_dev.argtypes = [vp, f64, i32, vp, vp, i32, i32, f64, f64, f64, f64, i32, P(i32), P(i32)]
+    L.pmm_em_ultra.argtypes = [vp, vp, P(f64), P(f64), vp, vp, i32, i32, f64, i32, f64, f64, f64, i32, P(f64), P(i32), P(i32)]
     L.pmm_set_total_sites.argtypes = [vp, i32]
     L.pmm_upload_params.argtypes = [vp, vp, f64, f64]
     L.pmm_download_params.argtypes = [vp, vp, P(f64), P(f64)]
@@ -99,6 +102,7 @@ def load_library():
     L.pmm_score_nni_batch_ultra.argtypes = [vp, i32, vp, vp, vp, f64, f64, f64, f64, f64, i32, vp, vp, vp, vp]
     L.pmm_debug_nni_ultra_mstep.argtypes = [vp, f64, f64, f64, f64, f64, f64, f64, f64, i32, i32, vp, vp, P(i32)]
     L.pmm_sync.argtypes = [vp]
+    L.pmm_read_llh.argtypes = [vp, P(f64)]
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
     L.pmm_ultrametric_solve.argtypes = [i32, vp, vp, vp, f64, f64, vp, f64, f64, vp, f64, f64, f64, vp, vp, P(i32)]
@@ -304,8 +308,40 @@ class Engine:
         self._ck(self._L.pmm_mstep_dev(self._h, float(R), int(n_cells), fm.ctypes.data if fm is not None else None,
                                        int(optimize_nu), int(optimize_phi), dmin, dmax, eps_s, eps_nu))
 
+    UM_STATUS = {0: "optimal", 1: "infeasible", 2: "failed_d"}
+
+    def mstep_ultra_dev(self, R, n_cells, kind, fixed_len, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
+                        eps_s=1e-6, eps_nu=1e-5, warm=True):
+        """``pmm_mstep_ultra_dev``: the ultrametric-constrained M-step on the statistics the device holds;
+        returns ``(status, newton_iters)``; the parameters stay on the device (``download_params``)."""
+        kind = np.ascontiguousarray(kind, np.int8); fixed_len = _f64(fixed_len)
+        st, it = C.c_int32(), C.c_int32()
+        self._ck(self._L.pmm_mstep_ultra_dev(self._h, float(R), int(n_cells), kind.ctypes.data, fixed_len.ctypes.data,
+                                             int(optimize_nu), int(optimize_phi), dmin, dmax, eps_s, eps_nu, int(bool(warm)),
+                                             C.byref(st), C.byref(it)))
+        return self.UM_STATUS[st.value], it.value
+
+    def em_ultra(self, d, nu, phi, R, n_cells, kind, fixed_len, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
+                 conv_eps=1e-8, max_iter=1000):
+        """``pmm_em_ultra``: EM under the ultrametric constraint, device-resident"""
+        d = np.array(d, np.float64, copy=True)
+        kind = np.ascontiguousarray(kind, np.int8); fixed_len = _f64(fixed_len)
+        nu_c, phi_c, nllh = C.c_double(nu), C.c_double(phi), C.c_double()
+        iters, status = C.c_int32(), C.c_int32()
+        self._ck(self._L.pmm_em_ultra(self._h, d.ctypes.data, C.byref(nu_c), C.byref(phi_c), kind.ctypes.data, fixed_len.ctypes.data,
+                                      int(optimize_nu), int(optimize_phi), float(R), int(n_cells), dmin, dmax, conv_eps,
+                                      int(max_iter), C.byref(nllh), C.byref(iters), C.byref(status)))
+        return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
+                "status": {0: "optimal", 1: "d_infeasible", 2: "failed_d"}[status.value]}
+
     def stats_ptr(self):
         return int(self._L.pmm_stats_dev_ptr(self._h)), int(self._L.pmm_stats_len(self._h))
+
+    def read_llh(self) -> float:
+        """the log-likelihood the last ``estep_dev`` / ``inside_dev`` left on the device"""
+        x = C.c_double()
+        self._ck(self._L.pmm_read_llh(self._h, C.byref(x)))
+        return x.value
 
     def sync(self):
         self._ck(self._L.pmm_sync(self._h))

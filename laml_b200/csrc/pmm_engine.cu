@@ -8,6 +8,7 @@
 #include "pmm_nni.cuh"
 #include "pmm_lumped.cuh"
 #include "pmm_nni_lumped.cuh"
+#include "pmm_ultrametric_dev.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -75,6 +76,17 @@ struct pmm_handle {
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
     std::vector<unsigned char> free_host;   // the mask d_free holds (empty = all branches free)
+    // ---- ultrametric M-step on the device (pmm_ultrametric_dev.cuh): scratch and level phases, built on first use
+    bool um_ready = false, um_warm = false;
+    std::vector<signed char> um_kind_host;
+    std::vector<double> um_fixed_host;
+    signed char *um_kind = nullptr;
+    double *um_fixed = nullptr, *um_scratch = nullptr, *um_Hprev = nullptr, *um_dnew = nullptr, *um_partial = nullptr;
+    unsigned char *um_grounded = nullptr;
+    int *um_up_ptr = nullptr, *um_dn_ptr = nullptr, *um_result = nullptr;
+    UmPhase *um_up_ph = nullptr, *um_dn_ph = nullptr;
+    int um_n_up_ph = 0, um_n_dn_ph = 0;
+    unsigned *um_bar = nullptr;
     // pinned staging for the parameter vectors (d | nu | phi): uploads and downloads of the per-iteration protocol
     // (pmm_upload_params / pmm_download_params, i.e. ShardedEngine.em_step) are one DMA each, no pageable bounce
     double *pin_up = nullptr, *pin_down = nullptr;
@@ -168,6 +180,9 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
     dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
     dfree(h->d_LSpart); dfree(h->d_LRpart);
+    dfree(h->um_kind); dfree(h->um_fixed); dfree(h->um_scratch); dfree(h->um_Hprev); dfree(h->um_dnew); dfree(h->um_partial);
+    dfree(h->um_grounded); dfree(h->um_up_ptr); dfree(h->um_dn_ptr); dfree(h->um_result); dfree(h->um_up_ph); dfree(h->um_dn_ph); dfree(h->um_bar);
+    h->um_ready = false; h->um_warm = false; h->um_kind_host.clear(); h->um_fixed_host.clear();
     h->full_ready = false;
     free_chunks(h);
 }
@@ -1035,6 +1050,9 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
 
     if (build_lumped_schedule(h, order, root_index)) return 1;
     if (reuse) {
+        // the level phases of the device ultrametric solver belong to the old topology, and so do its warm-start heights
+        dfree(h->um_up_ptr); dfree(h->um_dn_ptr); dfree(h->um_up_ph); dfree(h->um_dn_ph);
+        h->um_ready = false; h->um_warm = false; h->um_kind_host.clear(); h->um_fixed_host.clear();
         // node ids mean something else under the new topology: a mask of the old one must not survive
         CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1160,6 +1178,14 @@ int pmm_estep_dev(pmm_handle *h) {
 void *pmm_stats_dev_ptr(pmm_handle *h) { return h ? (void *)h->d_stats : nullptr; }
 int64_t pmm_stats_len(const pmm_handle *h) { return h ? (int64_t)5 * h->n + 2 : 0; }
 
+int pmm_read_llh(pmm_handle *h, double *llh) {
+    if (check_ready(h)) return 1;
+    if (!llh) return fail(h, "pmm_read_llh: llh is NULL");
+    CK(cudaMemcpyAsync(llh, h->d_stats + (size_t)5 * h->n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int pmm_sync(pmm_handle *h) {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
@@ -1201,12 +1227,14 @@ int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double
 
 // the M-step on the device with the mask d_free holds
 static int mstep_dev_impl(pmm_handle *h, double R, int32_t n_cells, int32_t optimize_nu, int32_t optimize_phi,
-                          double dmin, double dmax, double eps_s, double eps_nu) {
+                          double dmin, double dmax, double eps_s, double eps_nu, bool lengths_done = false) {
     const int n = h->n;
     const int K_total = h->K_total > 0 ? h->K_total : h->K;
-    pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
-                                                               dmin, dmax, eps_s, eps_nu);
-    h->launches += 1;
+    if (!lengths_done) {      // (under the ultrametric constraint the lengths and the normalised statistics exist already)
+        pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
+                                                                   dmin, dmax, eps_s, eps_nu);
+        h->launches += 1;
+    }
     if (optimize_nu) {
         const bool multi = env_int("PMM_NU_MULTI_LAUNCH", 0) != 0;
         const int iters = env_int("PMM_NU_ITERS", multi ? 24 : 60);
@@ -1252,6 +1280,145 @@ int pmm_mstep(pmm_handle *h, const double *S, double Rtilde, double R, int32_t n
     CK(cudaMemcpyAsync(h->d_stats + n5, &Rtilde, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (pmm_mstep_dev(h, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax, eps_s, eps_nu)) return 1;
+    return pmm_download_params(h, d, nu, phi);
+}
+
+// ---- ultrametric-constrained M-step on the device (pmm_ultrametric_dev.cuh) -------------------------------------
+// level phases: a wide level is one phase on the whole grid; a run of narrow levels is one phase on CTA 0
+static void um_phases(const std::vector<int> &ptr, std::vector<UmPhase> &ph) {
+    ph.clear();
+    const int nl = (int)ptr.size() - 1;
+    for (int l = 0; l < nl;) {
+        if (ptr[l + 1] - ptr[l] > UM_NARROW) { ph.push_back(UmPhase{l, l + 1, 1, 0}); l++; continue; }
+        int e = l;
+        while (e < nl && ptr[e + 1] - ptr[e] <= UM_NARROW) e++;
+        ph.push_back(UmPhase{l, e, 0, 0});
+        l = e;
+    }
+}
+
+static int ensure_um(pmm_handle *h) {
+    if (h->um_ready) return 0;
+    const size_t n1 = (size_t)h->n + 1;
+    if (!h->um_scratch) {
+        if (dalloc(h, &h->um_kind, n1) || dalloc(h, &h->um_fixed, n1) || dalloc(h, &h->um_scratch, 11 * n1) || dalloc(h, &h->um_Hprev, n1) ||
+            dalloc(h, &h->um_dnew, n1) || dalloc(h, &h->um_partial, (size_t)2 * 1024 * 4) || dalloc(h, &h->um_grounded, n1) ||
+            dalloc(h, &h->um_result, 2) || dalloc(h, &h->um_bar, 1))
+            return 1;
+    }
+    std::vector<UmPhase> up, dn;
+    um_phases(h->in_ptr, up);
+    um_phases(h->out_ptr, dn);
+    dfree(h->um_up_ptr); dfree(h->um_dn_ptr); dfree(h->um_up_ph); dfree(h->um_dn_ph);
+    if (dalloc(h, &h->um_up_ptr, h->in_ptr.size()) || dalloc(h, &h->um_dn_ptr, h->out_ptr.size()) || dalloc(h, &h->um_up_ph, up.size()) ||
+        dalloc(h, &h->um_dn_ph, dn.size()))
+        return 1;
+    CK(cudaMemcpy(h->um_up_ptr, h->in_ptr.data(), sizeof(int) * h->in_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->um_dn_ptr, h->out_ptr.data(), sizeof(int) * h->out_ptr.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->um_up_ph, up.data(), sizeof(UmPhase) * up.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->um_dn_ph, dn.data(), sizeof(UmPhase) * dn.size(), cudaMemcpyHostToDevice));
+    h->um_n_up_ph = (int)up.size(); h->um_n_dn_ph = (int)dn.size();
+    h->um_ready = true; h->um_warm = false;
+    return 0;
+}
+
+// kinds / fixed lengths of the branches: uploaded when they change (the EM loop repeats them every iteration)
+static int um_set_problem(pmm_handle *h, const int8_t *kind, const double *fixed_len) {
+    const size_t n = (size_t)h->n;
+    if (h->um_kind_host.size() == n && memcmp(h->um_kind_host.data(), kind, n) == 0 &&
+        memcmp(h->um_fixed_host.data(), fixed_len, n * sizeof(double)) == 0)
+        return 0;
+    for (size_t v = 0; v < n; v++)
+        if (kind[v] < 0 || kind[v] > 2) return fail(h, "branch kind of node %zu is %d; need 0 (free), 1 (fixed) or 2 (counts as zero)", v, (int)kind[v]);
+    h->um_kind_host.assign(kind, kind + n);
+    h->um_fixed_host.assign(fixed_len, fixed_len + n);
+    CK(cudaMemcpyAsync(h->um_kind, h->um_kind_host.data(), n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->um_fixed, h->um_fixed_host.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->um_warm = false;              // heights of another problem are no warm start
+    return 0;
+}
+
+// one M-step under the constraint from the statistics on the device; *status: 0 optimal, 1 infeasible, 2 failed
+static int mstep_ultra_impl(pmm_handle *h, double R, int32_t n_cells, int32_t optimize_nu, int32_t optimize_phi, double dmin, double dmax,
+                            double eps_s, double eps_nu, int32_t *status, int32_t *newton_iters) {
+    const int n = h->n;
+    const size_t n1 = (size_t)n + 1;
+    UmArgs A;
+    A.n = n; A.n_roots = h->n_roots; A.n_int = h->n_int;
+    A.parent = h->d_parent; A.left = h->d_left; A.roots = h->d_roots;
+    A.up_items = h->d_in_items; A.dn_items = h->d_out_items; A.up_ptr = h->um_up_ptr; A.dn_ptr = h->um_dn_ptr;
+    A.up_ph = h->um_up_ph; A.dn_ph = h->um_dn_ph; A.n_up_ph = h->um_n_up_ph; A.n_dn_ph = h->um_n_dn_ph;
+    A.kind = h->um_kind; A.fixed_len = h->um_fixed; A.stats = h->d_stats; A.Snorm = h->d_Snorm; A.params = h->d_params;
+    A.lo = dmin; A.hi = dmax; A.eps_s = eps_s; A.eps_nu = eps_nu; A.mu_final = 1e-11; A.warm_theta = 1e-6; A.warm_mu = 1e-9;
+    A.K_total = h->K_total > 0 ? h->K_total : h->K; A.warm = h->um_warm ? 1 : 0;
+    A.H_prev = h->um_Hprev;
+    double *sc = h->um_scratch;
+    A.H = sc; A.Hint = sc + n1; A.g = sc + 2 * n1; A.a = sc + 3 * n1; A.b = sc + 4 * n1; A.alpha = sc + 5 * n1; A.beta = sc + 6 * n1;
+    A.delta = sc + 7 * n1; A.k = sc + 8 * n1; A.S1 = sc + 9 * n1; A.S24 = sc + 10 * n1;
+    A.grounded = h->um_grounded; A.partial = h->um_partial; A.bar = h->um_bar; A.d_out = h->um_dnew; A.result = h->um_result;
+    CK(cudaMemsetAsync(h->um_bar, 0, sizeof(unsigned), h->stream));
+    // one CTA per SM (all co-resident: the kernel synchronises the grid itself), fewer for small trees
+    int G = std::max(1, std::min(h->n_sms, (n + UM_THREADS - 1) / UM_THREADS));
+    void *args[] = {&A};
+    CK(cudaLaunchCooperativeKernel((void *)pmm_um_solve, dim3((unsigned)G), dim3(UM_THREADS), args, 0, h->stream));
+    pmm_um_apply<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->um_kind, h->um_dnew, h->um_result, h->d_d);
+    h->launches += 2;
+    int res[2] = {0, 0};
+    CK(cudaMemcpyAsync(res, h->um_result, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (status) *status = res[0];
+    if (newton_iters) *newton_iters = res[1];
+    if (res[0] == 1) return 0;                       // infeasible: nothing is updated (EM_solver.py:425-426)
+    h->um_warm = true;
+    // nu with the new lengths fixed (:427-433), phi in closed form (:318-326); the free branches are those of kind 0
+    std::vector<uint8_t> fm(n);
+    for (int v = 0; v < n; v++) fm[v] = h->um_kind_host[v] == UM_FREE;
+    if (set_free_mask(h, fm.data())) return 1;
+    return mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, eps_s, eps_nu, true);
+}
+
+int pmm_mstep_ultra_dev(pmm_handle *h, double R, int32_t n_cells, const int8_t *kind, const double *fixed_len, int32_t optimize_nu,
+                        int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu, int32_t warm, int32_t *status,
+                        int32_t *newton_iters) {
+    if (check_ready(h)) return 1;
+    if (!kind || !fixed_len) return fail(h, "pmm_mstep_ultra_dev: kind / fixed_len are NULL");
+    if (ensure_um(h) || um_set_problem(h, kind, fixed_len)) return 1;
+    if (!warm) h->um_warm = false;
+    return mstep_ultra_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, eps_s, eps_nu, status, newton_iters);
+}
+
+int pmm_em_ultra(pmm_handle *h, double *d, double *nu, double *phi, const int8_t *kind, const double *fixed_len, int32_t optimize_nu,
+                 int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax, double conv_eps, int32_t max_iter,
+                 double *nllh, int32_t *iters, int32_t *status) {
+    if (!nu || !phi) return fail(h, "pmm_em_ultra: nu / phi are NULL");
+    if (pmm_upload_params(h, d, *nu, *phi)) return 1;
+    if (!kind || !fixed_len) return fail(h, "pmm_em_ultra: kind / fixed_len are NULL");
+    if (ensure_um(h) || um_set_problem(h, kind, fixed_len)) return 1;
+    h->um_warm = false;                                  // every EM run starts its barrier path from the interior point
+    const size_t n5 = (size_t)5 * h->n;
+    double pre = 0, cur = 0;
+    // EM_solver.py:467 pre_llh, then per iteration E, M, llh (:475-505); as in pmm_em the inside pass that yields
+    // llh(p_k) is the one the next E-step needs, so one E-step per iteration serves both
+    if (run_passes(h, true, false)) return 1;
+    CK(cudaMemcpyAsync(&pre, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cur = pre;
+    int it = 1, st = 0, last = 0;
+    while (it <= max_iter) {
+        if (mstep_ultra_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5, &st, nullptr)) return 1;
+        if (st == 1) break;                              // "d_infeasible": the parameters of the previous iterate stand (:497-499)
+        last = st;
+        if (run_passes(h, true, false)) return 1;
+        CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (std::fabs((cur - pre) / pre) < conv_eps) break;
+        pre = cur;
+        it++;
+    }
+    if (nllh) *nllh = (st == 1) ? -pre : -cur;
+    if (iters) *iters = it;
+    if (status) *status = (st == 1) ? 1 : last;
     return pmm_download_params(h, d, nu, phi);
 }
 

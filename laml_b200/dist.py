@@ -75,6 +75,7 @@ class ShardedEngine:
             stats_tensor = torch.as_tensor(_DeviceArray(ptr, n), device="cuda:%d" % engine.device)
         self.stats = stats_tensor
         self._host_stats = None
+        self._llh_pin = None
         self.n_nodes = engine.n_nodes
 
     def _on_stream(self):
@@ -129,9 +130,18 @@ class ShardedEngine:
             return self.eng.em_step(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)   # pmm_em_step
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
+        if self.stream is not None:
+            # the log-likelihood rides along with the parameters: queued on the stream before the M-step (which does not
+            # touch that slot), read after the one synchronisation of the step
+            if self._llh_pin is None:
+                import torch
+                self._llh_pin = torch.empty(1, dtype=self.stats.dtype).pin_memory()
+            with self._on_stream():
+                self._llh_pin.copy_(self.stats[5 * self.n_nodes + 1:5 * self.n_nodes + 2], non_blocking=True)
         self.eng.mstep_dev(R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)
         d_out, nu_out, phi_out = self.eng.download_params()        # the one synchronisation of the step
-        return d_out, nu_out, phi_out, self.llh()
+        llh = float(self._llh_pin[0]) if self.stream is not None else self.llh()
+        return d_out, nu_out, phi_out, llh
 
     def em(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0,
            conv_eps=1e-8, max_iter=1000):
@@ -166,6 +176,29 @@ class ShardedEngine:
         fm = np.asarray(free_mask, np.uint8)
         free = fm.astype(bool)
         d = np.array(d, np.float64, copy=True)
+        if hasattr(self.eng, "mstep_ultra_dev") and self.eng.info()["inside_levels"] <= 1024:
+            # the constrained M-step on the device (pmm_mstep_ultra_dev: one cooperative launch, fixed-order reductions --
+            # the same bits on every rank from the same all-reduced statistics): parameters and statistics never leave
+            # the GPUs, one all-reduce and one log-likelihood read per iteration
+            self.eng.upload_params(d, nu, phi)
+            self.estep_dev()
+            pre = cur = self.llh()
+            it, status = 1, "optimal"
+            while it <= max_iter:
+                status_d, _ = self.eng.mstep_ultra_dev(R, n_cells, problem.kind, problem.fixed_len, optimize_nu, optimize_phi,
+                                                       problem.lo, problem.hi, eps_s, eps_nu, warm=it > 1)
+                if status_d == "infeasible":
+                    d, nu, phi = self.eng.download_params()
+                    return {"nllh": -pre, "d": d, "nu": nu, "phi": phi, "iters": it, "status": "d_infeasible"}
+                status = "optimal" if status_d == "optimal" else "failed_d"
+                self.estep_dev()
+                cur = self.llh()
+                if abs((cur - pre) / pre) < conv_eps:
+                    break
+                pre = cur
+                it += 1
+            d, nu, phi = self.eng.download_params()
+            return {"nllh": -cur, "d": d, "nu": nu, "phi": phi, "iters": it, "status": status, "converged": it <= max_iter}
         self.eng.upload_params(d, nu, phi)
         self.inside_dev()
         pre = cur = self.llh()

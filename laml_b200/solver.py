@@ -21,6 +21,7 @@ program exactly with a tree-structured barrier Newton method on node heights
 """
 from __future__ import annotations
 
+import os
 from copy import deepcopy
 from math import exp, log
 from random import random, seed
@@ -38,6 +39,7 @@ eps = 1e-10
 conv_eps = 1e-8
 dmin = 0.005
 dmax = 10
+MAX_DEVICE_ULTRA_LEVELS = 1024     # deeper trees take the host solver for the constrained M-step (the device one is level-synchronous)
 DEFAULT_STRATEGY = {'resolve_search_only': False, 'only_marked': False, 'ultra_constr': False, 'fixed_phi': None,
                     'fixed_nu': None, 'local_brlen_opt': True, 'nodes_to_recompute': None}
 
@@ -378,29 +380,62 @@ class GPU_EM_solver:
             if verbose >= 0 and res["iters"] > maxIter:
                 print("Warning: exceeded maximum number of EM iterations (" + str(maxIter) + " iters)!")
             return res["nllh"], res["iters"], res["status"]
-        # the ultrametric loop keeps lengths and parameters in arrays (no per-node Python work per iteration);
-        # node objects and self.params are written once at the end -- same sequence of engine calls as
-        # Estep / Mstep / lineage_llh (EM_solver.py:495-507)
+        # ---- ultra_constr: the same loop with the branch-length program under the ultrametric equalities (:349-366)
         eng = self._engine
         d, fm = self._d(), self._free_mask(True)
         nu, phi = self.params.nu, self.params.phi
-        pre_llh = eng.inside(d, nu, phi)
+        cache = self._ultrametric_problem(local_brlen_opt=True)
+        n_cells = len(self.charMtrx)
+        on_device = (hasattr(eng, "em_ultra") and os.environ.get("PMM_ULTRA_HOST", "0") != "1"
+                     and eng.info()["inside_levels"] <= MAX_DEVICE_ULTRA_LEVELS)
+        if on_device and verbose <= 0:
+            # everything on the device: E-step, the constrained M-step as one cooperative launch (pmm_em_ultra)
+            res = eng.em_ultra(d, nu, phi, self._R, n_cells, cache.kind, cache.fixed_len, optimize_nu, optimize_phi,
+                               self.dmin, self.dmax, conv_eps, maxIter)
+            for nd, length in zip(self._forest.nodes, res["d"].tolist()):
+                nd.edge_length = length
+            self.params.nu, self.params.phi = res["nu"], res["phi"]
+            if res["status"] == "d_infeasible":
+                if verbose >= 0:
+                    print("Warning: EM failed to optimize parameters in one Mstep due to infeasible constraints")
+            elif verbose >= 0 and res["iters"] > maxIter:
+                print("Warning: exceeded maximum number of EM iterations (" + str(maxIter) + " iters)!")
+            return res["nllh"], res["iters"], res["status"]
+        # host-driven loop: progress output (verbose), the CPU stand-in of the tests, very deep trees (the device solver is
+        # level-synchronous).  One E-step per iteration: the E-step at p_k also yields llh(p_k), the convergence test of
+        # iteration k (the reference runs a separate inside pass for it, :500).  With the engine's device M-step the
+        # statistics and parameters stay on the device; otherwise they go through the host solver (laml_b200/ultrametric.py).
+        if on_device:
+            eng.upload_params(d, nu, phi)
+            eng.estep_dev()
+            pre_llh = eng.read_llh()
+        else:
+            est = eng.estep(d, nu, phi)
+            self._stats = est
+            pre_llh = est["llh"]
         if verbose >= 0:
             print("Initial phi: " + str(phi) + ". Initial nu: " + str(nu) + ". Initial nllh: " + str(-pre_llh))
-        cache = self._ultrametric_problem(local_brlen_opt=True)
         em_iter, converged, status, curr_llh = 1, False, "optimal", pre_llh
         infeasible = False
         while em_iter <= maxIter:
-            est = eng.estep(d, nu, phi)
-            self._stats = est
-            d_new, nu, phi, status_d = self._mstep_arrays(est["S"], est["Rtilde"], fm, d, nu, phi, optimize_phi, optimize_nu,
-                                                          1e-5, 1e-6, cache)
+            if on_device:
+                status_d, _ = eng.mstep_ultra_dev(self._R, n_cells, cache.kind, cache.fixed_len, optimize_nu, optimize_phi,
+                                                  self.dmin, self.dmax, warm=em_iter > 1)
+            else:
+                d_new, nu, phi, status_d = self._mstep_arrays(est["S"], est["Rtilde"], fm, d, nu, phi, optimize_phi, optimize_nu,
+                                                              1e-5, 1e-6, cache)
             if status_d == "infeasible":
                 infeasible = True
                 break
             status = "optimal" if status_d == "optimal" else "failed_d"
-            d = np.where(fm.astype(bool), d_new, d)
-            curr_llh = eng.inside(d, nu, phi)
+            if on_device:
+                eng.estep_dev()
+                curr_llh = eng.read_llh()
+            else:
+                d = np.where(fm.astype(bool), d_new, d)
+                est = eng.estep(d, nu, phi)
+                self._stats = est
+                curr_llh = est["llh"]
             if verbose > 0:
                 print("Finished EM iter: " + str(em_iter) + ". Current nllh: " + str(-curr_llh))
             if abs((curr_llh - pre_llh) / pre_llh) < conv_eps:
@@ -408,6 +443,8 @@ class GPU_EM_solver:
                 break
             pre_llh = curr_llh
             em_iter += 1
+        if on_device:
+            d, nu, phi = eng.download_params()
         self.params.nu, self.params.phi = nu, phi
         for nd, length in zip(self._forest.nodes, d.tolist()):
             nd.edge_length = length

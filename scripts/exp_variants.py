@@ -44,7 +44,7 @@ def worker(workloads):
             eng.estep_dev()
             ts.append(eng.last_timing())
         ins, out, tot = (float(np.median([t[k] for t in ts])) for k in ("inside_ms", "outside_ms", "total_ms"))
-        eng.set_option("slices", 2)
+        eng.set_option("slices", int(os.environ.get("EXP_SLICES", "2")))
         for _ in range(2):
             eng.estep_dev()
         t2 = []
