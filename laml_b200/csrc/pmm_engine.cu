@@ -730,14 +730,12 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
             for (int j = 0; j < nslice; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_s[j][2], 0));
             CK(cudaEventRecord(h->ev[2], h->stream));
         }
-        pmm_site_llh<<<(P.K + 255) / 256, 256, 0, h->stream>>>(h->d_Lroot_llh, h->n_roots, P.K, h->d_site_llh + P.site0);
-        pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_site_llh + P.site0, P.K, d_llh, ci > 0);
-        h->launches += 2;
-        if (outside) {
-            pmm_reduce_S<<<(5 * n + 255) / 256, 256, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0);
-            pmm_reduce_S<<<(h->n_clades + 255) / 256, 256, 0, h->stream>>>(h->d_LRpart, G, h->n_clades, h->d_Rnode, 0);
-            pmm_reduce_sum<<<1, 1024, 0, h->stream>>>(h->d_Rnode, h->n_clades, d_Rt, ci > 0);
-            h->launches += 3;
+        {   // per-site and total log-likelihood, counts summed over the site groups, R~: one launch
+            const unsigned nb = outside ? (unsigned)((5 * n + 1023) / 1024) : 0u;
+            pmm_lumped_finish<<<nb + 1, 1024, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0, h->d_Lroot_llh, h->n_roots, P.K,
+                                                             h->d_site_llh + P.site0, d_llh, h->d_LRpart, h->n_clades, h->d_Rnode, d_Rt,
+                                                             outside ? 1 : 0);
+            h->launches += 1;
         }
         CK(cudaEventRecord(h->ev[3], h->stream));
         if (nchunks > 1) {

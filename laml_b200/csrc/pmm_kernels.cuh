@@ -723,6 +723,58 @@ __global__ void pmm_site_llh(const double *__restrict__ root_site_llh, int n_roo
     site_llh[s] = sum;
 }
 
+// Everything that follows the passes of the lumped engine, in ONE launch (five before): blocks 0 .. nb-1 sum the count
+// partials over the site groups (pmm_reduce_S), the last block forms the per-site log-likelihoods and their sum
+// (pmm_site_llh + pmm_reduce_sum) and, after an outside pass, R~ from the per-(warp, clade) partials (pmm_reduce_S +
+// pmm_reduce_sum).  Same summation orders as the separate kernels (1024-thread strided sums, then a tree): same bits.
+__global__ void __launch_bounds__(1024) pmm_lumped_finish(const double *__restrict__ Spart, int G, int n5, double *__restrict__ S, int accumulate,
+                                                          const double *__restrict__ root_site_llh, int n_roots, int K,
+                                                          double *__restrict__ site_llh, double *__restrict__ llh_out,
+                                                          const double *__restrict__ Rpart, int n_clades, double *__restrict__ Rnode,
+                                                          double *__restrict__ Rt_out, int with_counts) {
+    __shared__ double sh[1024];
+    const int tid = threadIdx.x;
+    if (blockIdx.x + 1 < gridDim.x) {
+        if (!with_counts) return;
+        const int i = blockIdx.x * 1024 + tid;
+        if (i >= n5) return;
+        double sum = 0.0;
+        for (int t = 0; t < G; t++) sum += Spart[(size_t)t * n5 + i];
+        S[i] = accumulate ? S[i] + sum : sum;
+        return;
+    }
+    auto block_sum = [&](double v) {
+        sh[tid] = v;
+        __syncthreads();
+        for (int o = 512; o > 0; o >>= 1) {
+            if (tid < o) sh[tid] += sh[tid + o];
+            __syncthreads();
+        }
+        const double r = sh[0];
+        __syncthreads();
+        return r;
+    };
+    double acc = 0.0;
+    for (int s = tid; s < K; s += 1024) {
+        double sum = 0.0;
+        for (int r = 0; r < n_roots; r++) sum += root_site_llh[(size_t)r * K + s];
+        site_llh[s] = sum;
+        acc += sum;
+    }
+    const double llh = block_sum(acc);
+    if (tid == 0) llh_out[0] = accumulate ? llh_out[0] + llh : llh;
+    if (!with_counts) return;
+    acc = 0.0;
+    for (int c = tid; c < n_clades; c += 1024) {
+        double sum = 0.0;
+        for (int t = 0; t < G; t++) sum += Rpart[(size_t)t * n_clades + c];
+        Rnode[c] = sum;
+        acc += sum;
+    }
+    const double rt = block_sum(acc);
+    if (tid == 0) Rt_out[0] = accumulate ? Rt_out[0] + rt : rt;
+}
+
 // ---------------------------------------------------------------- K3: M-step
 // stats = [S(n*5) | Rtilde | llh].  EM_solver.py:318-348 (phi, clamp, rescale),
 // :351-357 (per-branch concave problem in d), :394-407 (1-D problem in nu).
