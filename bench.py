@@ -220,6 +220,10 @@ class Ranks:
         torch.cuda.set_device(local_rank)
         self.dev = "cuda:%d" % local_rank
         if world > 1:
+            # the one collective of the path is an 8 MB fp64 all-reduce (5 n + 2 doubles): on 8 B200s over NVSwitch ring + LL128
+            # takes 54.5 us, NCCL's own choice (NVLS) 68 us (profiles/r2b_nccl_variants_n8.log); an explicit setting wins
+            os.environ.setdefault("NCCL_ALGO", "Ring")
+            os.environ.setdefault("NCCL_PROTO", "LL128")
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier(self):

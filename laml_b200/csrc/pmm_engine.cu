@@ -1059,12 +1059,13 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
     }
     // small per-node buffers first, then the records against what is left
     if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
-        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 8) || dalloc(h, &h->d_nu_bar, 1) || dalloc(h, &h->d_Rnode, h->n_int) ||
+        dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 8) || dalloc(h, &h->d_nu_bar, 2) || dalloc(h, &h->d_Rnode, h->n_int) ||
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
     if (alloc_lumped(h)) return 1;
     if (h->engine == 1 && ensure_fullstate(h)) return 1;
     CK(cudaMemsetAsync(h->d_free, 1, n, h->stream));
+    CK(cudaMemsetAsync(h->d_nu_bar, 0, 2 * sizeof(unsigned), h->stream));    // pmm_mstep_fused leaves its barrier counters at zero
     CK(cudaStreamSynchronize(h->stream));
     h->free_host.clear();
     h->n = n;
@@ -1228,6 +1229,19 @@ static int mstep_dev_impl(pmm_handle *h, double R, int32_t n_cells, int32_t opti
                           double dmin, double dmax, double eps_s, double eps_nu, bool lengths_done = false) {
     const int n = h->n;
     const int K_total = h->K_total > 0 ? h->K_total : h->K;
+    if (!env_int("PMM_NU_MULTI_LAUNCH", 0) && !env_int("PMM_MSTEP_SPLIT", 0)) {
+        // ONE cooperative launch: per-branch Newton, grid barrier, the nu iteration, phi (pmm_mstep_fused)
+        int G = std::max(1, std::min({2 * h->n_sms, NU_BLOCKS, (n + 255) / 256}));
+        const double *stats = h->d_stats; const unsigned char *fm = h->d_free; int nn = n, kt = K_total; double *prm = h->d_params, *dd = h->d_d;
+        double *sn = h->d_Snorm; int db = lengths_done ? 0 : 1, dn = optimize_nu ? 1 : 0, dp = optimize_phi ? 1 : 0;
+        double cs = (double)K_total * (double)n_cells; double *part = h->d_nu_partial; unsigned *bar = h->d_nu_bar; NuState *st = h->d_nu_state;
+        int mi = env_int("PMM_NU_ITERS", 60);
+        void *args[] = {&stats, &fm, &nn, &kt, &prm, &dd, &sn, &dmin, &dmax, &eps_s, &eps_nu, &db, &dn, &dp, &R, &cs, &part, &bar, &st, &mi};
+        CK(cudaLaunchCooperativeKernel((void *)pmm_mstep_fused, dim3((unsigned)G), dim3(256), args, 0, h->stream));
+        h->launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (!lengths_done) {      // (under the ultrametric constraint the lengths and the normalised statistics exist already)
         pmm_mstep_branches<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_stats, h->d_free, n, K_total, h->d_params, h->d_d, h->d_Snorm,
                                                                    dmin, dmax, eps_s, eps_nu);
@@ -1252,6 +1266,7 @@ static int mstep_dev_impl(pmm_handle *h, double R, int32_t n_cells, int32_t opti
             double *part = h->d_nu_partial; unsigned *bar = h->d_nu_bar; NuState *st = h->d_nu_state; double *prm = h->d_params; int mi = iters;
             void *args[] = {&fm, &nn, &sn, &dd, &part, &bar, &st, &prm, &mi};
             CK(cudaLaunchCooperativeKernel((void *)pmm_nu_solve, dim3((unsigned)G), dim3(256), args, 0, h->stream));
+            CK(cudaMemsetAsync(h->d_nu_bar, 0, 2 * sizeof(unsigned), h->stream));     // the fused kernel expects zeroed counters
             h->launches += 1;
         }
     }

@@ -963,6 +963,129 @@ __global__ void __launch_bounds__(256) pmm_nu_solve(const unsigned char *__restr
     if (blockIdx.x == 0 && tid == 0) { *st_out = s; params[0] = s.x; }
 }
 
+// The whole unconstrained M-step in ONE cooperative launch (four launches and a memset before): phase 0 = pmm_mstep_branches
+// grid-strided (every thread later re-reads, in the nu phase, exactly the branches it wrote), a grid barrier, the Newton
+// iteration of pmm_nu_solve, phi by one thread.  The barrier counter is reset by the last CTA to leave, so the next launch
+// needs no memset.  bar[0] = arrivals, bar[1] = CTAs that have left.
+__global__ void __launch_bounds__(256) pmm_mstep_fused(const double *__restrict__ stats, const unsigned char *__restrict__ free_mask, int n,
+                                                        int K_total, double *__restrict__ params, double *__restrict__ d,
+                                                        double *__restrict__ Snorm, double dmin, double dmax, double eps_s, double eps_nu,
+                                                        int do_branches, int do_nu, int do_phi, double R, double cells_times_sites,
+                                                        double *__restrict__ partial, unsigned *bar, NuState *__restrict__ st_out, int max_iter) {
+    __shared__ double sh[4][256];
+    __shared__ double s_end[4];
+    const int tid = threadIdx.x, G = gridDim.x;
+    const double nu_cur = params[0];         // read by every CTA before the first barrier; written after the last one
+    unsigned epoch = 0;
+    auto grid_barrier = [&]() {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const unsigned target = (epoch + 1u) * (unsigned)G;
+            while (*((volatile unsigned *)bar) < target) {}
+            __threadfence();
+        }
+        epoch++;
+        __syncthreads();
+    };
+    if (do_branches) {
+        const bool use_nu = nu_cur > eps_nu;
+        if (tid < 4) s_end[tid] = mstep_end_const(tid, nu_cur, use_nu, dmin, dmax);
+        __syncthreads();
+        for (int v = blockIdx.x * 256 + tid; v < n; v += G * 256) {
+            if (!free_mask[v]) continue;
+            double s[5], tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) { s[k] = fmax(stats[(size_t)v * 5 + k], eps_s); }
+#pragma unroll
+            for (int k = 0; k < 5; k++) tot += s[k];
+#pragma unroll
+            for (int k = 0; k < 5; k++) { s[k] = s[k] / tot * (double)K_total; Snorm[(size_t)v * 5 + k] = s[k]; }
+            d[v] = mstep_branch_length(s, nu_cur, use_nu, dmin, dmax, d[v], s_end);
+        }
+    }
+    NuState s;
+    s.x = 1.0; s.lo = 0.0; s.hi = 1.0; s.lin = 0.0; s.wsum = 0.0; s.done = 0; s.iters = 0;
+    if (do_nu) {
+        for (int it = 0; it <= max_iter; it++) {
+            const bool first = it == 0;
+            const double x = s.x;
+            double f = 0.0, fp = 0.0, lin = 0.0, ws = 0.0;
+            for (int v = blockIdx.x * 256 + tid; v < n; v += G * 256)
+                if (free_mask[v]) {
+                    const double dv = d[v], w = Snorm[(size_t)v * 5 + 2] + Snorm[(size_t)v * 5 + 4];
+                    const double em = expm1(x * dv);
+                    const double r = dv / em;
+                    f += w * r;
+                    fp -= w * r * r * (em + 1.0);
+                    if (first) { lin += (Snorm[(size_t)v * 5] + Snorm[(size_t)v * 5 + 1] + Snorm[(size_t)v * 5 + 3]) * dv; ws += w; }
+                }
+            sh[0][tid] = f; sh[1][tid] = fp; sh[2][tid] = lin; sh[3][tid] = ws;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
+                }
+                __syncthreads();
+            }
+            double *pb = partial + (size_t)(it & 1) * G * 4;
+            if (tid < 4) pb[blockIdx.x * 4 + tid] = sh[tid][0];
+            grid_barrier();
+            // every CTA: fixed-order sum of the G partials (G <= 256), same step everywhere
+#pragma unroll
+            for (int k = 0; k < 4; k++) sh[k][tid] = (tid < G) ? __ldcg(pb + tid * 4 + k) : 0.0;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) sh[k][tid] += sh[k][tid + o];
+                }
+                __syncthreads();
+            }
+            const double F = sh[0][0], FP = sh[1][0];
+            if (first) {
+                s.lin = sh[2][0]; s.wsum = sh[3][0];
+                if (F - s.lin >= 0.0 || !(s.lin > 0.0)) { s.x = 1.0; s.done = 1; }          // upper bound active (EM_solver.py:402)
+                else {
+                    s.lo = 0.0; s.hi = 1.0;
+                    s.x = (nu_cur > 0.0 && nu_cur < 1.0) ? nu_cur : fmin(0.5, s.wsum / s.lin);
+                }
+            } else {
+                const double g = F - s.lin, xo = s.x;
+                if (g > 0.0) s.lo = xo; else s.hi = xo;
+                s.iters++;
+                if (g == 0.0) s.done = 1;
+                else {
+                    double xn = xo - g / FP;
+                    if (fabs(xn - xo) <= 4e-16 * xo) { s.done = 1; xn = fmin(fmax(xn, s.lo), s.hi); }
+                    else if (!(xn > s.lo && xn < s.hi)) xn = (s.lo > 0.0) ? 0.5 * (s.lo + s.hi) : 0.5 * s.hi;
+                    if (xn < 1e-300) { xn = 0.0; s.done = 1; }
+                    s.x = xn;
+                }
+            }
+            __syncthreads();
+            if (s.done) break;          // identical on every CTA: all leave together
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        if (do_nu) { *st_out = s; params[0] = s.x; }
+        if (do_phi) {
+            const double Rt = stats[(size_t)n * 5];
+            double phi_star = Rt / (R + Rt);
+            if (fabs(phi_star) < 1.0 / cells_times_sites) phi_star = 0.0;
+            params[1] = phi_star;
+        }
+    }
+    // the last CTA to leave resets the counters for the next launch (every CTA has passed every barrier by then)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == (unsigned)G - 1u) { bar[0] = 0u; bar[1] = 0u; __threadfence(); }
+    }
+}
+
 __global__ void pmm_phi_step(const double *__restrict__ stats, int n, double *__restrict__ params, double R, double cells_times_sites) {
     const double Rt = stats[(size_t)n * 5];
     double phi_star = Rt / (R + Rt);

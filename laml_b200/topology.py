@@ -180,10 +180,12 @@ class GPU_Topology_search:
         # ``random`` seed -- the policy is replayed identically everywhere -- and scores 1/world of each
         # neighbourhood (``dist.score_nni_sharded``)
         # batch_ultra: score the neighbourhood in one launch under ``ultra_constr`` too (the two-height M-step of
-        # pmm_nni_ultra.cuh).  Off unless asked for (argument or PMM_NNI_ULTRA_BATCH=1): the kernel variant was written
-        # after this round's GPU budget was spent, so its first GPU run is tests/test_zzz_gpu_nni_ultra.py
+        # pmm_nni_ultra.cuh).  On by default since it has been verified and timed on a B200 (tests/test_zzz_gpu_nni_ultra.py;
+        # BASELINE config 5: 9 996 constrained candidates in 22.9 ms on one GPU, 5.1 ms on eight,
+        # profiles/r2a_config5_nni_n1.json / r2b_config5_nni_n8.json); PMM_NNI_ULTRA_BATCH=0 or batch_ultra=False restores
+        # the reference's candidate-by-candidate sequence
         import os
-        self.batch_ultra = bool(int(os.environ.get("PMM_NNI_ULTRA_BATCH", "0"))) if batch_ultra is None else bool(batch_ultra)
+        self.batch_ultra = bool(int(os.environ.get("PMM_NNI_ULTRA_BATCH", "1"))) if batch_ultra is None else bool(batch_ultra)
         self.clamp_start = clamp_start
         self.shard_candidates, self.group, self.gather_device = shard_candidates, group, gather_device
         self.treeTopoList = list(treeTopoList)
