@@ -387,36 +387,39 @@ __device__ __forceinline__ void normalise_out(Opd &n, int F) {
     n.ri.y = F + e;
 }
 
-// Sum of 10 per-lane values over the warp through shared memory: lane l stores its values
-// transposed (row j = value j, 36 doubles per row: lanes 0-15, 2 pad, lanes 16-31, 2 pad --
-// conflict-free for both the 8-byte stores and the 16-byte loads); lanes 0..19 each add up half a
-// row and one shuffle joins the halves.  Returns the total of value (lane >> 1) on lanes < 20.
-constexpr int RED_ROW = 36;
+// Expected counts: a step yields 10 values per lane (5 per child branch) that must be summed over the warp's 32 sites.
+// They are buffered for RED_STEPS steps in a shared-memory tile, one ROW per (step, value), lane l in column l -- the
+// stores of a warp are 256 contiguous bytes, conflict-free -- and then every lane adds up ONE whole row (16 LDS.128 at a
+// row stride of 34 doubles = 4 banks mod 32: conflict-free per quarter-warp; four independent chains of eight adds) and
+// writes its sum straight to Spart.  ncu on the previous form (ten rows reduced at the end of EVERY step by twenty lanes,
+// two chains of eight adds behind the loads): a fifth of the kernel's stall samples sat on those dependent adds.
+#ifndef PMM_RED_STEPS
+#define PMM_RED_STEPS 2                 // measured on config 4: 1 -> 3.29 ms, 2 -> 2.83 ms, 3 -> 2.86 ms (outside pass)
+#endif
+constexpr int RED_STEPS = PMM_RED_STEPS;
+constexpr int RED_ROWS = 10 * RED_STEPS;             // <= 32: one lane per row
+constexpr int RED_ROW = 34;
 __device__ __forceinline__ void red_put5(const double *__restrict__ v, double *__restrict__ red, int lane, int first) {
-    const int col = lane + ((lane >> 4) << 1);
 #pragma unroll
-    for (int j = 0; j < 5; j++) red[(first + j) * RED_ROW + col] = v[j];
+    for (int j = 0; j < 5; j++) red[(first + j) * RED_ROW + lane] = v[j];
 }
-__device__ __forceinline__ double red_finish(const double *__restrict__ red, int lane) {
+// sums of the rows of the `cnt` buffered steps (the last of them is step i_last of the staged list) -> Spart
+__device__ __forceinline__ void red_flush(const double *__restrict__ red, int lane, int cnt, int i_last, const int4 *__restrict__ s_steps,
+                                          double *__restrict__ Sg) {
     __syncwarp();
-    // every lane adds up half a row (lanes 20-31 repeat row 9): no divergent region in the step.  Two serial chains
-    // of eight adds -- a pairwise tree was measured slower (more live registers at the end of the step)
-    const double2 *row = reinterpret_cast<const double2 *>(red + min(lane >> 1, 9) * RED_ROW + (lane & 1) * 18);
-    double a = 0.0, b = 0.0;
+    const int r = min(lane, 10 * cnt - 1);            // idle lanes repeat the last row: no divergent region
+    const double2 *row = reinterpret_cast<const double2 *>(red + r * RED_ROW);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int t = 0; t < 8; t += 2) {
+    for (int t = 0; t < 16; t += 2) {
         const double2 x = row[t], y = row[t + 1];
-        a += x.x; b += x.y; a += y.x; b += y.y;
+        a0 += x.x; a1 += x.y; a2 += y.x; a3 += y.y;
     }
-    const double sum = a + b;
-    const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
+    const double tot = (a0 + a1) + (a2 + a3);
+    const int a = r / 10, j = r - 10 * a;              // buffered step, value (0-4: branch above v, 5-9: above w)
+    const int4 d = s_steps[i_last - (cnt - 1) + a];
+    if (lane < 10 * cnt) Sg[(size_t)((j < 5) ? d.y : d.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
     __syncwarp();                                    // readers done before the next step's writers
-    return tot;
-}
-__device__ __forceinline__ double warp_sum10(const double (&v)[10], double *__restrict__ red, int lane) {
-    red_put5(v, red, lane, 0);
-    red_put5(v + 5, red, lane, 5);
-    return red_finish(red, lane);
 }
 
 // step flags: bits 0-1 where out[u] comes from (1 = load, 2 = chained in registers; a root loads the record the inside
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     __shared__ uint4 s_rows[STEP_CAP + STEP_PAD];
     __shared__ double4 s_bc[2 * STEP_CAP];
     __shared__ double4 s_lut[4];
-    __shared__ __align__(16) double s_red[(LT / 32) * 10 * RED_ROW];
+    __shared__ __align__(16) double s_red[(LT / 32) * RED_ROWS * RED_ROW];
     const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z, clade id w
     const int nsteps = cl.y - cl.x;
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
@@ -494,7 +497,8 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     const int lane = threadIdx.x & 31;
     const int grp = s_raw >> 5;                          // site group of this warp
     if (grp * 32 >= P.K) return;                         // whole warp beyond the last site
-    double *red = s_red + (threadIdx.x >> 5) * 10 * RED_ROW;
+    double *red = s_red + (threadIdx.x >> 5) * RED_ROWS * RED_ROW;
+    int nbuf = 0;                                        // steps whose counts sit in the tile
     const double *prior_m1 = P.prior + __ldg(P.site_ptr + gs) - 1;       // prior of state a at [a]
     const double qsum = __ldg(P.qsum + gs);
     const int *codes_s = P.codes + gs;
@@ -552,9 +556,9 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         double c5[5];
         Opd ov, ow;
         child_outside<!wleaf>(chain, w, v, bcw, qsum, fac, ow, c5);
-        red_put5(c5, red, lane, 5);                      // counts leave the registers at once
+        red_put5(c5, red, lane, 10 * nbuf + 5);          // counts leave the registers at once
         child_outside<!vleaf>(chain, v, w, bcv, qsum, fac, ov, c5);
-        red_put5(c5, red, lane, 0);
+        red_put5(c5, red, lane, 10 * nbuf);
         // phi statistic: 1 - P(leaf silenced | D) on '?' entries (EM_solver.py:323)
         if (vleaf && valid && c0v == -1) rt += 1.0 - ov.r.y * fac;
         if (wleaf && valid && c0w == -1) rt += 1.0 - ow.r.y * fac;
@@ -576,12 +580,6 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             if ((f & 16) || P.store_all) st_orec(P.O, P.OI, r0.y + s_raw, ov);
             chain = ov;
         }
-        // counts: sum over the warp's sites, one 40-byte write per (warp, branch)
-        const double tot = red_finish(red, lane);
-        if (lane < 20 && !(lane & 1)) {
-            const int j = lane >> 1;
-            Sg[(size_t)((j < 5) ? d0.y : d0.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
-        }
         };
         switch ((f >> 2) & 3) {
             case 0: core(std::false_type{}, std::false_type{}); break;
@@ -589,11 +587,14 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
             case 2: core(std::false_type{}, std::true_type{}); break;
             default: core(std::true_type{}, std::true_type{}); break;
         }
+        // counts: summed over the warp's sites once RED_STEPS steps are buffered
+        if (++nbuf == RED_STEPS) { red_flush(red, lane, RED_STEPS, i, s_steps, Sg); nbuf = 0; }
         c0v = c1v; c0w = c1w; c1v = c2v; c1w = c2w;
     };
     int i = 0;
     for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }      // two register sets swap roles: no moves
     if (i < nsteps) step(i, A, B);
+    if (nbuf) red_flush(red, lane, nbuf, nsteps - 1, s_steps, Sg);
     grid_launch_dependents();
     // R~ of this (warp, clade)
 #pragma unroll
