@@ -425,7 +425,7 @@ __device__ __forceinline__ void red_flush(const double *__restrict__ red, int la
 // step flags: bits 0-1 where out[u] comes from (1 = load, 2 = chained in registers; a root loads the record the inside
 //             pass' root step stored), bit 2 / 3: v / w is a leaf, bit 4 / 5: store out[v] / out[w],
 //             bit 6: out[v] is chained into the next step (the host orders the children accordingly)
-struct OutSlot { Opd v, w, o; };
+struct OutSlot { Opd v, w, o; double qv, qw; };      // qv / qw: the prior of a leaf child's state (own registers: see ld_child_pred)
 
 // ---- predicated accesses.  The per-step prologue (operands of step i + 1, leaf codes of step i + 2, L2 prefetch of
 // step i + PF) is straight-line code: which access a child needs is a warp-uniform predicate (a descriptor flag) or a
@@ -435,8 +435,8 @@ struct OutSlot { Opd v, w, o; };
 // materialised: `bit` arguments are masked flag words, non-zero = true.
 #ifdef PMM_HOST_EMU
 __device__ __forceinline__ void ld_code_pred(int &c, unsigned bit, const int *a) { if (bit) c = *a; }
-__device__ __forceinline__ void ld_child_pred(Opd &n, unsigned leafbit, int code, const double *q, const double2 *x) {
-    if (leafbit) { if (code > 0) n.r.z = *q; }
+__device__ __forceinline__ void ld_child_pred(Opd &n, double &ql, unsigned leafbit, int code, const double *q, const double2 *x) {
+    if (leafbit) { if (code > 0) ql = *q; }
     else n.r = ld256(x);
 }
 __device__ __forceinline__ void ld_orec_pred(Opd &n, unsigned bit, const double4 *o, const int2 *oi) { if (bit) { n.r = ld256(o); n.ri = *oi; } }
@@ -445,12 +445,14 @@ __device__ __forceinline__ void prefetch_l2_either(unsigned, const void *, const
 __device__ __forceinline__ void ld_code_pred(int &c, unsigned bit, const int *a) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.global.nc.s32 %0, [%2];\n\t}" : "+r"(c) : "r"(bit), "l"(a));
 }
-// leaf: the prior of the leaf's state (lanes with an edited state only) into r.z; internal child: its 32-byte inside record
-__device__ __forceinline__ void ld_child_pred(Opd &n, unsigned leafbit, int code, const double *q, const double2 *x) {
-    asm volatile("{\n\t.reg .pred pleaf, pq;\n\tsetp.ne.u32 pleaf, %4, 0;\n\tsetp.gt.and.s32 pq, %5, 0, pleaf;\n\t"
-                 "@pq ld.global.nc.f64 %2, [%6];\n\t"
-                 "@!pleaf ld.global.v4.f64 {%0,%1,%2,%3}, [%7];\n\t}"
-                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w) : "r"(leafbit), "r"(code), "l"(q), "l"(x));
+// leaf: the prior of the leaf's state (lanes with an edited state only) into ql; internal child: its 32-byte inside record.
+// The two loads write DIFFERENT registers: predicated loads into overlapping registers serialise on the scoreboard even
+// though only one of them ever executes (ncu: the record load waited for the gather, 12 % of the stall samples)
+__device__ __forceinline__ void ld_child_pred(Opd &n, double &ql, unsigned leafbit, int code, const double *q, const double2 *x) {
+    asm volatile("{\n\t.reg .pred pleaf, pq;\n\tsetp.ne.u32 pleaf, %5, 0;\n\tsetp.gt.and.s32 pq, %6, 0, pleaf;\n\t"
+                 "@pq ld.global.nc.f64 %4, [%7];\n\t"
+                 "@!pleaf ld.global.v4.f64 {%0,%1,%2,%3}, [%8];\n\t}"
+                 : "+d"(n.r.x), "+d"(n.r.y), "+d"(n.r.z), "+d"(n.r.w), "+d"(ql) : "r"(leafbit), "r"(code), "l"(q), "l"(x));
 }
 __device__ __forceinline__ void ld_orec_pred(Opd &n, unsigned bit, const double4 *o, const int2 *oi) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %6, 0;\n\t"
@@ -512,8 +514,8 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     };
     // operands of a step (one step ahead, into the other register set)
     auto fetch = [&](const uint4 r, int cv, int cw, OutSlot &n) {
-        ld_child_pred(n.v, r.w & 4, cv, prior_m1 + cv, P.X + 2 * (size_t)(r.y + s_raw));
-        ld_child_pred(n.w, r.w & 8, cw, prior_m1 + cw, P.X + 2 * (size_t)(r.z + s_raw));
+        ld_child_pred(n.v, n.qv, r.w & 4, cv, prior_m1 + cv, P.X + 2 * (size_t)(r.y + s_raw));
+        ld_child_pred(n.w, n.qw, r.w & 8, cw, prior_m1 + cw, P.X + 2 * (size_t)(r.z + s_raw));
         const unsigned o = r.x + s_raw;
         ld_orec_pred(n.o, r.w & 1, P.O + o, P.OI + o);       // how is 1 (load) or 2 (chained): bit 0
     };
@@ -521,6 +523,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     chain.r = make_double4(0.0, 0.0, 0.0, 0.0); chain.ri = make_int2(-1, 0);
     OutSlot A, B;
     A.v = A.w = A.o = B.v = B.w = B.o = chain;
+    A.qv = A.qw = B.qv = B.qw = 0.0;
     double rt = 0.0;
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(s_rows[0], c0v, c0w);
@@ -547,8 +550,8 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
         auto core = [&](auto VL, auto WL) {
         constexpr bool vleaf = decltype(VL)::value, wleaf = decltype(WL)::value;
         Child v, w;
-        if (vleaf) decode_leaf(v, c0v, cur.v.r.z, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
-        if (wleaf) decode_leaf(w, c0w, cur.w.r.z, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
+        if (vleaf) decode_leaf(v, c0v, cur.qv, bcv, qsum, s_lut); else decode(v, cur.v, bcv, qsum);
+        if (wleaf) decode_leaf(w, c0w, cur.qw, bcw, qsum, s_lut); else decode(w, cur.w, bcw, qsum);
         if (f & 1) chain = cur.o;                       // how = 1: loaded; otherwise out[u] is what the previous step left in the registers
         // everything is relative to the site likelihood: fac = 2^(F_u + cum_v + cum_w) / L
         const int F = chain.ri.y;
