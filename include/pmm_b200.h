@@ -253,6 +253,15 @@ int pmm_debug_lumped_schedule(int32_t n_leaves, int32_t n_nodes, const int32_t *
                               int32_t *out_steps, int32_t *in_clades, int32_t *out_clades, int32_t *in_phase_ptr,
                               int32_t *out_phase_ptr, int32_t *n_clades, int32_t *n_phases);
 
+/* The waits of the dataflow launches of the same schedule (laml_b200/csrc/pmm_lumped.cuh, "dataflow launches"): CSR
+ * lists over clade POSITIONS in in_clades / out_clades -- for the inside pass the clades whose records a clade loads,
+ * for the outside pass the clades that store the out-records of its subtree roots.  in_dep_ptr / out_dep_ptr hold
+ * n_clades + 1 entries, in_deps at most 2 (n_nodes - n_leaves), out_deps at most n_nodes - n_leaves.  Pure host code.
+ */
+int pmm_debug_lumped_deps(int32_t n_leaves, int32_t n_nodes, const int32_t *parent, const int32_t *left, const int32_t *right,
+                          int32_t clade_cap, int32_t clade_cap_top, int32_t *in_dep_ptr, int32_t *in_deps,
+                          int32_t *out_dep_ptr, int32_t *out_deps);
+
 /* ---- introspection for benchmarks ------------------------------------------------- */
 typedef struct {
     int64_t n_nodes, n_leaves, n_sites;

@@ -22,7 +22,7 @@ SYMBOLS = [
     "pmm_upload_params", "pmm_download_params", "pmm_estep_dev", "pmm_inside_dev", "pmm_stats_dev_ptr",
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
     "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep", "pmm_em_step",
-    "pmm_mstep_ultra_dev", "pmm_em_ultra", "pmm_read_llh",
+    "pmm_mstep_ultra_dev", "pmm_em_ultra", "pmm_read_llh", "pmm_debug_lumped_deps",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library():
     L.pmm_read_llh.argtypes = [vp, P(f64)]
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
+    L.pmm_debug_lumped_deps.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.pmm_ultrametric_solve.argtypes = [i32, vp, vp, vp, f64, f64, vp, f64, f64, vp, f64, f64, f64, vp, vp, P(i32)]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
@@ -154,8 +155,16 @@ def lumped_schedule(n_leaves, parent, left, right, clade_cap=16, clade_cap_top=1
     if rc:
         raise PMMError("pmm_debug_lumped_schedule: invalid tree arrays")
     k, p = ncl.value, nph.value
+    # the waits of the dataflow launches: per clade position, the positions of its producer clades (CSR)
+    idp, odp = np.zeros(n_int + 1, np.int32), np.zeros(n_int + 1, np.int32)
+    idd, odd = np.zeros(2 * n_int + 1, np.int32), np.zeros(n_int + 1, np.int32)
+    rc = L.pmm_debug_lumped_deps(int(n_leaves), n, parent.ctypes.data, left.ctypes.data, right.ctypes.data, int(clade_cap),
+                                 int(clade_cap_top), idp.ctypes.data, idd.ctypes.data, odp.ctypes.data, odd.ctypes.data)
+    if rc:
+        raise PMMError("pmm_debug_lumped_deps: invalid tree arrays")
     return {"in_steps": ins, "out_steps": outs, "in_clades": inc[:k], "out_clades": outc[:k],
-            "in_phase_ptr": ipp[:p + 1], "out_phase_ptr": opp[:p + 1], "n_clades": k, "n_phases": p}
+            "in_phase_ptr": ipp[:p + 1], "out_phase_ptr": opp[:p + 1], "n_clades": k, "n_phases": p,
+            "in_dep_ptr": idp[:k + 1], "in_deps": idd[:idp[k]], "out_dep_ptr": odp[:k + 1], "out_deps": odd[:odp[k]]}
 
 
 class Engine:

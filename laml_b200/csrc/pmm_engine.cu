@@ -103,7 +103,18 @@ struct pmm_handle {
     bool last_full = false;         // which engine ran the last pass (for pmm_last_timing)
     bool full_ready = false;        // full-state buffers are allocated on first use (NNI batch, PMM_ENGINE=fullstate)
     int clade_target = 0, n_clades = 0;
-    std::vector<int> lin_phase_ptr, lout_phase_ptr;     // launch -> first clade
+    std::vector<int> lin_phase_ptr, lout_phase_ptr;     // tier -> first clade (inside: tier 0 first; outside: top tier first)
+    // launches of a pass: groups of consecutive tiers; a group of several tiers is ONE dataflow launch (pmm_lumped.cuh)
+    struct LGroup { int c0, c1, n1, n2, df; };
+    std::vector<LGroup> lin_groups, lout_groups;
+    int df_mode = 0;                // 0: one launch per tier; 1: tier 0 | all top tiers (dataflow); 2: all tiers in one dataflow launch
+    int *d_df_dep_ptr_in = nullptr, *d_df_deps_in = nullptr, *d_df_dep_ptr_out = nullptr, *d_df_deps_out = nullptr;
+    int *d_df_flags = nullptr;      // [2][n_clades][df_stride]
+    unsigned *d_df_tickets = nullptr;
+    int *d_df_err = nullptr;
+    unsigned df_ticket_host[64] = {};
+    int df_epoch = 0, df_stride = 0;
+    size_t df_deps_cap_in = 0, df_deps_cap_out = 0;
     int4 *d_lin_steps = nullptr, *d_lout_steps = nullptr, *d_lin_clades = nullptr, *d_lout_clades = nullptr;
     int lKc = 0, lG = 0;            // sites per chunk, site groups (warps) per chunk
     // site slices: the sites of a chunk are split into `slices` ranges whose launches go to separate streams,
@@ -178,6 +189,9 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
     dfree(h->d_post0); dfree(h->d_post1);
     dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
+    dfree(h->d_df_dep_ptr_in); dfree(h->d_df_deps_in); dfree(h->d_df_dep_ptr_out); dfree(h->d_df_deps_out);
+    dfree(h->d_df_flags); dfree(h->d_df_tickets); dfree(h->d_df_err);
+    h->df_deps_cap_in = h->df_deps_cap_out = 0;
     dfree(h->d_LX); dfree(h->d_LO); dfree(h->d_LOI); dfree(h->d_LinvL); dfree(h->d_Lroot_llh);
     dfree(h->d_LSpart); dfree(h->d_LRpart);
     dfree(h->um_kind); dfree(h->um_fixed); dfree(h->um_scratch); dfree(h->um_Hprev); dfree(h->um_dnew); dfree(h->um_partial);
@@ -428,6 +442,8 @@ struct LumpedSchedule {
     std::vector<int4> in_steps, out_steps, in_clades, out_clades;
     std::vector<int> in_phase_ptr, out_phase_ptr;       // launch -> first clade
     std::vector<size_t> tier_clades;
+    // dataflow launches: per clade POSITION in in_clades / out_clades, the positions of the clades it waits for (CSR)
+    std::vector<int> in_dep_ptr, in_deps, out_dep_ptr, out_deps;
     int n_clades = 0, n_tiers = 0;
     int64_t in_loads = 0, out_loads = 0, out_stores = 0;
 };
@@ -492,6 +508,15 @@ void make_lumped_schedule(int N, int n, const int *L, const int *R, const int *P
     int ncl = 0;
     std::vector<std::vector<int>> bin_id(n_tiers);
     std::vector<std::pair<int, int>> stk;
+    std::vector<int> clade_of(n, -1), prod;             // internal node -> clade id (= position in in_clades)
+    S.in_dep_ptr.assign(1, 0); S.in_deps.clear(); S.out_dep_ptr.assign(1, 0); S.out_deps.clear();
+    auto close_deps = [&](std::vector<int> &ptr, std::vector<int> &deps) {
+        std::sort(prod.begin(), prod.end());
+        prod.erase(std::unique(prod.begin(), prod.end()), prod.end());
+        deps.insert(deps.end(), prod.begin(), prod.end());
+        ptr.push_back((int)deps.size());
+        prod.clear();
+    };
     // ---- inside: post-order; of two open internal children the bigger subtree goes first, the one
     // visited last stays in registers (KIND_PREV), everything else is loaded
     for (int t = 0; t < n_tiers; t++) {
@@ -519,8 +544,16 @@ void make_lumped_schedule(int N, int n, const int *L, const int *R, const int *P
                     // bits 5 / 6: the loaded record belongs to a lower tier, i.e. an earlier launch wrote it
                     const int far = ((kv == KIND_LOAD && tier[cv] != t) ? 32 : 0) | ((kw == KIND_LOAD && tier[cw] != t) ? 64 : 0);
                     in_steps.push_back(make_int4(u, cv, cw, kv | (kw << 2) | (Pa[u] < 0 ? 16 : 0) | far));
+                    clade_of[u] = ncl;
                 }
             }
+            // producers: the clades (of lower tiers, numbered earlier) that hold the children marked "far"
+            for (int i = begin; i < (int)in_steps.size(); i++) {
+                const int4 d = in_steps[i];
+                if (d.w & 32) prod.push_back(clade_of[d.y]);
+                if (d.w & 64) prod.push_back(clade_of[d.z]);
+            }
+            close_deps(S.in_dep_ptr, S.in_deps);
             in_clades.push_back(make_int4(begin, (int)in_steps.size(), bin.root_index, ncl));
             ncl++;
         }
@@ -529,10 +562,15 @@ void make_lumped_schedule(int N, int n, const int *L, const int *R, const int *P
     // ---- outside: pre-order, top tiers first; of two open internal children the smaller subtree
     // goes first and its out-record stays in registers, the other one is stored and loaded later
     std::vector<std::pair<int, int>> stk2;
+    std::vector<int> out_pos(ncl, -1);                 // clade id -> position in out_clades (top tiers first)
     for (int t = n_tiers - 1; t >= 0; t--) {
         for (size_t bi = 0; bi < bins[t].size(); bi++) {
             const Bin &bin = bins[t][bi];
             const int begin = (int)out_steps.size();
+            out_pos[bin_id[t][bi]] = (int)out_clades.size();
+            // producers: the (higher-tier, hence earlier) clades whose steps store the out-records of this clade's subtree roots
+            for (int r : bin.roots) if (Pa[r] >= 0) prod.push_back(out_pos[clade_of[Pa[r]]]);
+            close_deps(S.out_dep_ptr, S.out_deps);
             for (int r : bin.roots) {
                 stk2.clear(); stk2.push_back({r, KIND_LOAD});      // a root's out-record is stored by the inside pass
                 while (!stk2.empty()) {
@@ -576,7 +614,13 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
         C0 = std::max(16, std::min(120, C0));
     }
     C0 = std::max(1, std::min(C0, STEP_CAP - 1));      // the kernels stage a clade's steps in shared memory
-    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", 16), STEP_CAP - 1));
+    // dataflow launches (pmm_lumped.cuh): worth it when a pass is a few waves of CTAs at most, i.e. when the latency-bound
+    // top tiers are a visible share of it -- site shards of a multi-GPU run, small trees.  PMM_DF = 0 / 1 / 2 forces a mode.
+    const int site_blocks = (h->K + LT - 1) / LT;
+    h->df_mode = env_int("PMM_DF", -1);
+    if (h->df_mode < 0 || h->df_mode > 2) h->df_mode = (site_blocks <= env_int("PMM_DF_MAX_BLOCKS", 4)) ? 2 : 0;
+    // without launch boundaries between the tiers the top clades can be short: a hand-over costs about as much as four steps
+    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", h->df_mode ? 6 : 16), STEP_CAP - 1));
     h->clade_target = C0;
     LumpedSchedule S;
     make_lumped_schedule(N, n, h->left.data(), h->right.data(), h->parent.data(), order, root_index, C0, Ctop, S);
@@ -600,10 +644,55 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     CK(cudaMemcpy(h->d_lout_steps, out_steps.data(), sizeof(int4) * out_steps.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_lin_clades, in_clades.data(), sizeof(int4) * in_clades.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_lout_clades, out_clades.data(), sizeof(int4) * out_clades.size(), cudaMemcpyHostToDevice));
+    // ---- launch groups: consecutive tiers per launch
+    h->lin_groups.clear(); h->lout_groups.clear();
+    {
+        const int nt0 = (int)S.tier_clades[0];
+        if (h->df_mode == 0 || n_tiers == 1) {
+            for (int t = 0; t < n_tiers; t++) {
+                h->lin_groups.push_back({S.in_phase_ptr[t], S.in_phase_ptr[t + 1], 0, 0, 0});
+                h->lout_groups.push_back({S.out_phase_ptr[t], S.out_phase_ptr[t + 1], 0, 0, 0});
+            }
+        } else if (h->df_mode == 1) {
+            h->lin_groups.push_back({0, nt0, 0, 0, 0});
+            h->lin_groups.push_back({nt0, ncl, 0, ncl - nt0, 1});
+            h->lout_groups.push_back({0, ncl - nt0, ncl - nt0, 0, 1});
+            h->lout_groups.push_back({ncl - nt0, ncl, 0, 0, 0});
+        } else {
+            h->lin_groups.push_back({0, ncl, nt0, ncl - nt0, 1});
+            h->lout_groups.push_back({0, ncl, ncl - nt0, nt0, 1});
+        }
+    }
+    if (h->df_mode) {
+        if (!h->d_df_dep_ptr_in) {
+            if (dalloc(h, &h->d_df_dep_ptr_in, cap + 1) || dalloc(h, &h->d_df_dep_ptr_out, cap + 1) || dalloc(h, &h->d_df_tickets, 64) ||
+                dalloc(h, &h->d_df_err, 1))
+                return 1;
+            CK(cudaMemset(h->d_df_tickets, 0, 64 * sizeof(unsigned)));
+            memset(h->df_ticket_host, 0, sizeof h->df_ticket_host);
+        }
+        if (S.in_deps.size() > h->df_deps_cap_in) {
+            dfree(h->d_df_deps_in);
+            h->df_deps_cap_in = S.in_deps.size() + S.in_deps.size() / 4 + 64;
+            if (dalloc(h, &h->d_df_deps_in, h->df_deps_cap_in)) return 1;
+        }
+        if (S.out_deps.size() > h->df_deps_cap_out) {
+            dfree(h->d_df_deps_out);
+            h->df_deps_cap_out = S.out_deps.size() + S.out_deps.size() / 4 + 64;
+            if (dalloc(h, &h->d_df_deps_out, h->df_deps_cap_out)) return 1;
+        }
+        CK(cudaMemcpy(h->d_df_dep_ptr_in, S.in_dep_ptr.data(), sizeof(int) * S.in_dep_ptr.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_df_dep_ptr_out, S.out_dep_ptr.data(), sizeof(int) * S.out_dep_ptr.size(), cudaMemcpyHostToDevice));
+        if (!S.in_deps.empty()) CK(cudaMemcpy(h->d_df_deps_in, S.in_deps.data(), sizeof(int) * S.in_deps.size(), cudaMemcpyHostToDevice));
+        if (!S.out_deps.empty()) CK(cudaMemcpy(h->d_df_deps_out, S.out_deps.data(), sizeof(int) * S.out_deps.size(), cudaMemcpyHostToDevice));
+        // tickets count up from wherever they are, and the marks of an old topology can never equal a future epoch
+        CK(cudaMemset(h->d_df_err, 0, sizeof(int)));
+    }
     if (env_int("PMM_VERBOSE", 0)) {
         fprintf(stderr, "[pmm] lumped schedule: clade capacity %d (top %d), %d clades in %d tiers:", C0, Ctop, ncl, n_tiers);
         for (int t = 0; t < n_tiers; t++) fprintf(stderr, " %zu", S.tier_clades[t]);
-        fprintf(stderr, "; %lld inside loads, %lld outside loads, %lld outside stores\n", (long long)in_loads, (long long)out_loads, (long long)out_stores);
+        fprintf(stderr, "; %lld inside loads, %lld outside loads, %lld outside stores; dataflow mode %d (%zu + %zu waits)\n", (long long)in_loads,
+                (long long)out_loads, (long long)out_stores, h->df_mode, S.in_deps.size(), S.out_deps.size());
     }
     return 0;
 }
@@ -641,11 +730,16 @@ int alloc_lumped(pmm_handle *h) {
         dalloc(h, &h->d_LinvL, (size_t)h->n_roots * Kc) || dalloc(h, &h->d_Lroot_llh, (size_t)h->n_roots * Kc) ||
         dalloc(h, &h->d_LSpart, (size_t)h->lG * n * 5) || dalloc(h, &h->d_LRpart, (size_t)h->lG * std::max(h->n_int, 1)))
         return 1;
+    // completion marks of the dataflow launches: (pass, clade position, site block of the chunk)
+    h->df_stride = (Kc + LT - 1) / LT;
+    const size_t nflags = (size_t)2 * std::max(h->n_int, 1) * h->df_stride;
+    if (dalloc(h, &h->d_df_flags, nflags)) return 1;
+    CK(cudaMemset(h->d_df_flags, 0, nflags * sizeof(int)));
     return 0;
 }
 
 LParams make_lparams(pmm_handle *h, int ci, bool with_post) {
-    LParams P;
+    LParams P{};
     P.site0 = ci * h->lKc; P.K = std::min(h->lKc, h->K - P.site0); P.Kp = (h->lKc + 31) & ~31; P.code_stride = h->K;
     P.n_leaves = h->n_leaves; P.n_nodes = h->n; P.n_clades = h->n_clades;
     P.codes = h->d_codes; P.site_ptr = h->d_site_ptr; P.prior = h->d_prior; P.qsum = h->d_qsum;
@@ -686,19 +780,42 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
             cudaLaunchKernelEx(&cfg, kern, Q, cl, steps);
             h->launches++;
         };
+        // a dataflow group: one 1-D launch over (clades of the group) x (site blocks), with its own ticket counter
+        int cur_slice = 0;
+        auto df_setup = [&](LParams &Q, const pmm_handle::LGroup &g, int pass, size_t p, unsigned gyq) {
+            const int slot = pass * 32 + cur_slice * 8 + (int)std::min<size_t>(p, 7);
+            Q.df_ticket = h->d_df_tickets + slot; Q.df_base = h->df_ticket_host[slot];
+            h->df_ticket_host[slot] += (unsigned)(g.c1 - g.c0) * gyq;
+            Q.df_flags = h->d_df_flags + (size_t)pass * std::max(h->n_int, 1) * h->df_stride;
+            Q.df_dep_ptr = pass ? h->d_df_dep_ptr_out : h->d_df_dep_ptr_in; Q.df_deps = pass ? h->d_df_deps_out : h->d_df_deps_in;
+            Q.df_lo = g.c0; Q.df_n1 = g.n1; Q.df_n2 = g.n2; Q.df_nblk = (int)gyq; Q.df_stride = h->df_stride;
+            Q.df_epoch = ++h->df_epoch; Q.df_err = h->d_df_err;
+            if (h->df_epoch == 0x7fffffff) h->df_epoch = 0;     // (marks are compared for equality; a wrap after 2^31 launches is harmless)
+        };
         auto launch_in = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq, bool pdl) {
-            const int c0 = h->lin_phase_ptr[p], c1 = h->lin_phase_ptr[p + 1];
-            if (c1 <= c0) return;
-            launch_k(pmm_lumped_inside, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lin_clades + c0), (const int4 *)h->d_lin_steps);
+            const pmm_handle::LGroup &g = h->lin_groups[p];
+            if (g.c1 <= g.c0) return;
+            const int4 *cl = (const int4 *)(h->d_lin_clades + g.c0), *steps = (const int4 *)h->d_lin_steps;
+            if (g.df) { df_setup(Q, g, 0, p, gyq); launch_k(pmm_lumped_inside<true>, st, dim3((unsigned)(g.c1 - g.c0) * gyq), pdl, Q, cl, steps); }
+            else launch_k(pmm_lumped_inside<false>, st, dim3((unsigned)(g.c1 - g.c0), gyq), pdl, Q, cl, steps);
         };
         auto launch_out = [&](cudaStream_t st, size_t p, LParams Q, unsigned gyq, bool pdl) {
-            const int c0 = h->lout_phase_ptr[p], c1 = h->lout_phase_ptr[p + 1];
-            if (c1 <= c0) return;
-            if (with_post) launch_k(pmm_lumped_outside<true>, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lout_clades + c0), (const int4 *)h->d_lout_steps);
-            else launch_k(pmm_lumped_outside<false>, st, dim3((unsigned)(c1 - c0), gyq), pdl, Q, (const int4 *)(h->d_lout_clades + c0), (const int4 *)h->d_lout_steps);
+            const pmm_handle::LGroup &g = h->lout_groups[p];
+            if (g.c1 <= g.c0) return;
+            const int4 *cl = (const int4 *)(h->d_lout_clades + g.c0), *steps = (const int4 *)h->d_lout_steps;
+            const dim3 grid = g.df ? dim3((unsigned)(g.c1 - g.c0) * gyq) : dim3((unsigned)(g.c1 - g.c0), gyq);
+            if (g.df) df_setup(Q, g, 1, p, gyq);
+            if (g.df) {
+                if (with_post) launch_k(pmm_lumped_outside<true, true>, st, grid, pdl, Q, cl, steps);
+                else launch_k(pmm_lumped_outside<false, true>, st, grid, pdl, Q, cl, steps);
+            } else {
+                if (with_post) launch_k(pmm_lumped_outside<true, false>, st, grid, pdl, Q, cl, steps);
+                else launch_k(pmm_lumped_outside<false, false>, st, grid, pdl, Q, cl, steps);
+            }
         };
-        const size_t n_in = h->lin_phase_ptr.size() - 1, n_out = h->lout_phase_ptr.size() - 1;
-        const int nslice = std::max(1, std::min({h->slices, (int)gy, 4}));
+        const size_t n_in = h->lin_groups.size(), n_out = h->lout_groups.size();
+        // a dataflow launch over all tiers interleaves the site blocks itself: no site slices
+        const int nslice = (h->df_mode == 2) ? 1 : std::max(1, std::min({h->slices, (int)gy, 4}));
         h->last_sliced = nslice > 1;
         if (nslice == 1) {
             for (size_t p = 0; p < n_in; p++) launch_in(h->stream, p, P, gy, p > 0);      // the first follows pmm_branch_consts
@@ -711,6 +828,7 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
             for (int j = 0; j < nslice; j++) {
                 cudaStream_t sn = h->aux[2 * j], sh = h->aux[2 * j + 1];
                 LParams Q = P;
+                cur_slice = j;
                 Q.sblk0 = (int)((uint64_t)gy * j / nslice);
                 const unsigned gyq = (unsigned)((uint64_t)gy * (j + 1) / nslice) - (unsigned)Q.sblk0;
                 CK(cudaStreamWaitEvent(sn, h->ev_fork, 0));
@@ -734,7 +852,7 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
             const unsigned nb = outside ? (unsigned)((5 * n + 1023) / 1024) : 0u;
             pmm_lumped_finish<<<nb + 1, 1024, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0, h->d_Lroot_llh, h->n_roots, P.K,
                                                              h->d_site_llh + P.site0, d_llh, h->d_LRpart, h->n_clades, h->d_Rnode, d_Rt,
-                                                             outside ? 1 : 0);
+                                                             outside ? 1 : 0, h->df_mode ? h->d_df_err : nullptr);
             h->launches += 1;
         }
         CK(cudaEventRecord(h->ev[3], h->stream));
@@ -1096,6 +1214,31 @@ int pmm_debug_lumped_schedule(int32_t n_leaves, int32_t n_nodes, const int32_t *
     if (out_phase_ptr) memcpy(out_phase_ptr, S.out_phase_ptr.data(), sizeof(int) * S.out_phase_ptr.size());
     if (n_clades) *n_clades = S.n_clades;
     if (n_phases) *n_phases = S.n_tiers;
+    return 0;
+}
+
+int pmm_debug_lumped_deps(int32_t n_leaves, int32_t n_nodes, const int32_t *parent, const int32_t *left, const int32_t *right,
+                          int32_t clade_cap, int32_t clade_cap_top, int32_t *in_dep_ptr, int32_t *in_deps, int32_t *out_dep_ptr,
+                          int32_t *out_deps) {
+    const int N = n_leaves, n = n_nodes;
+    if (N < 2 || n <= N || n > 2 * N - 1 || !parent || !left || !right || !in_dep_ptr || !in_deps || !out_dep_ptr || !out_deps) return 1;
+    std::vector<int> order, root_index(n, 0);
+    order.reserve(n);
+    int nr = 0;
+    for (int v = 0; v < n; v++) if (parent[v] < 0) { root_index[v] = nr++; order.push_back(v); }
+    for (size_t i = 0; i < order.size(); i++) {
+        const int v = order[i];
+        if (left[v] >= 0) for (int c : {left[v], right[v]}) { if (c < 0 || c >= n) return 1; root_index[c] = root_index[v]; order.push_back(c); }
+        if ((int)order.size() > n) return 1;
+    }
+    if ((int)order.size() != n) return 1;
+    LumpedSchedule S;
+    make_lumped_schedule(N, n, left, right, parent, order, root_index, std::max(1, std::min((int)clade_cap, STEP_CAP - 1)),
+                         std::max(1, std::min((int)clade_cap_top, STEP_CAP - 1)), S);
+    memcpy(in_dep_ptr, S.in_dep_ptr.data(), sizeof(int) * S.in_dep_ptr.size());
+    memcpy(out_dep_ptr, S.out_dep_ptr.data(), sizeof(int) * S.out_dep_ptr.size());
+    if (!S.in_deps.empty()) memcpy(in_deps, S.in_deps.data(), sizeof(int) * S.in_deps.size());
+    if (!S.out_deps.empty()) memcpy(out_deps, S.out_deps.data(), sizeof(int) * S.out_deps.size());
     return 0;
 }
 
@@ -1693,7 +1836,7 @@ int pmm_get_info(const pmm_handle *h, pmm_info *info) {
     info->n_chunks = h->engine == 0 ? (int64_t)((h->K + std::max(h->lKc, 1) - 1) / std::max(h->lKc, 1)) : (int64_t)h->chunks.size();
     info->n_tiles = h->max_tiles; info->tile_slots = h->TS;
     info->engine = h->engine; info->clades = h->n_clades; info->clade_target = h->clade_target;
-    info->launches_per_pass = (int64_t)h->lin_phase_ptr.size() - 1;
+    info->launches_per_pass = (int64_t)h->lin_groups.size();
     info->inside_bytes_per_site = h->l_in_bytes_per_site; info->outside_bytes_per_site = h->l_out_bytes_per_site;
     info->inside_levels = (int64_t)h->in_ptr.size() - 1; info->outside_levels = (int64_t)h->out_ptr.size() - 1;
     info->device_bytes = (int64_t)h->device_bytes; info->kernel_launches = h->launches;

@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(1024) pmm_lumped_finish(const double *__restri
                                                           const double *__restrict__ root_site_llh, int n_roots, int K,
                                                           double *__restrict__ site_llh, double *__restrict__ llh_out,
                                                           const double *__restrict__ Rpart, int n_clades, double *__restrict__ Rnode,
-                                                          double *__restrict__ Rt_out, int with_counts) {
+                                                          double *__restrict__ Rt_out, int with_counts, const int *__restrict__ df_err) {
     __shared__ double sh[1024];
     const int tid = threadIdx.x;
     if (blockIdx.x + 1 < gridDim.x) {
@@ -761,7 +761,8 @@ __global__ void __launch_bounds__(1024) pmm_lumped_finish(const double *__restri
         site_llh[s] = sum;
         acc += sum;
     }
-    const double llh = block_sum(acc);
+    double llh = block_sum(acc);
+    if (df_err && *df_err) llh = NAN;            // a dataflow launch gave up waiting (pmm_lumped.cuh: df_spin): no result, loudly
     if (tid == 0) llh_out[0] = accumulate ? llh_out[0] + llh : llh;
     if (!with_counts) return;
     acc = 0.0;

@@ -94,6 +94,18 @@ struct LParams {
     int K_total;
     int store_all;           // outside pass: also store the out-records that are chained in registers
     int sblk0;               // first site block (of LT sites) this launch covers: site slices run on separate streams
+    // ---- dataflow launches (several tiers of the clade schedule in ONE launch; "dataflow" below).  Unused otherwise.
+    unsigned *df_ticket;     // ticket counter of this launch site ...
+    unsigned df_base;        // ... and its value when the launch starts: a CTA's item is its ticket minus this
+    int *df_flags;           // [clade position][df_stride] completion marks of (clade, site block): == df_epoch once done
+    const int *df_dep_ptr;   // CSR over clade positions: the clades whose records (inside) / out-records (outside) a clade loads
+    const int *df_deps;
+    int df_lo;               // clade position of the launch's first clade; producers below it ran in earlier launches
+    int df_n1, df_n2;        // clades in the launch's first / second segment (inside: tier 0 | top tiers, outside: top tiers | tier 0)
+    int df_nblk;             // site blocks the launch covers (from sblk0)
+    int df_stride;           // row stride of df_flags = site blocks of a chunk
+    int df_epoch;            // value that marks "done" for this launch (the host counts launches)
+    int *df_err;             // set when a wait gives up (a schedule bug must not hang the GPU)
 };
 
 enum { KIND_LEAF = 0, KIND_LOAD = 1, KIND_PREV = 2 };
@@ -156,6 +168,69 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+
+// ---------------------------------------------------------------- dataflow launches
+// The tiers of the clade schedule depend on each other only clade by clade: a clade of the inside pass needs the records
+// of the lower-tier clades it loads from, a clade of the outside pass the out-records its parent clade stored.  One
+// launch per tier turns that into grid-wide barriers -- a handful of latency-bound launches whose chains of <= 16 steps
+// do not shrink with the site shard (8 GPUs: a fifth of the E-step) or with the tree (1k cells: all of it).  A DATAFLOW
+// launch covers several tiers at once: its work items are (clade, site block) pairs in an order in which every producer
+// precedes its consumers; a CTA takes the next item with an atomic ticket (so the order holds whatever order the
+// hardware starts CTAs in: every earlier item is held by a CTA that is running or done, hence no deadlock), stages its
+// clade, waits until the marks of its producer clades show this launch's epoch, walks the clade, and publishes its own
+// mark (bar.sync, then fence + release store by one thread).  Item order, for n1 clades in the launch's first segment
+// and n2 in its second (inside: tier 0 | top tiers; outside: top tiers | tier 0) over B site blocks:
+//     first(0), [first(1), second(0)], [first(2), second(1)], ..., second(B-1)
+// so that the latency-bound top tiers of one site block run beside the bulk of the next.
+template <bool DF> __device__ __forceinline__ void df_item(const LParams &P, int &cl, int &blk) {
+    if (!DF) { cl = blockIdx.x; blk = blockIdx.y; return; }
+    __shared__ int s_item;
+    if (threadIdx.x == 0) s_item = (int)(atomicAdd(P.df_ticket, 1u) - P.df_base);
+    __syncthreads();
+    const int i = s_item, n1 = P.df_n1, n12 = P.df_n1 + P.df_n2;
+    if (i < n1) { cl = i; blk = 0; return; }
+    const int j = i - n1, g = j / n12, r = j - g * n12;
+    if (g < P.df_nblk - 1) { cl = r; blk = (r < n1) ? g + 1 : g; }
+    else { cl = n1 + r; blk = P.df_nblk - 1; }
+}
+__device__ __forceinline__ void df_spin(const int *flag, int epoch, int *err) {
+#ifdef PMM_HOST_EMU
+    if (*flag != epoch) *err = 1;            // CTAs run one after another in ticket order: a producer that has not run is a schedule bug
+#else
+    const long long t0 = clock64();
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) break;
+        if (clock64() - t0 > (1ll << 31)) { *err = 1; break; }      // ~1 s: give up, flag the error (the finishing kernel turns it into NaN)
+        __nanosleep(40);
+    }
+#endif
+}
+// wait for the producers of the clade at position `pos` (site block `blk` of the chunk); all threads of the CTA call it
+template <bool DF> __device__ __forceinline__ void df_wait(const LParams &P, int pos, int blk) {
+    if (!DF) return;
+    const int b = P.df_dep_ptr[pos], e = P.df_dep_ptr[pos + 1];
+    for (int t = b + (int)threadIdx.x; t < e; t += LT) {
+        const int dp = P.df_deps[t];
+        if (dp >= P.df_lo) df_spin(P.df_flags + (size_t)dp * P.df_stride + blk, P.df_epoch, P.df_err);
+    }
+    __syncthreads();
+}
+// every thread's records are written: publish the mark of (pos, blk)
+template <bool DF> __device__ __forceinline__ void df_done(const LParams &P, int pos, int blk) {
+    if (!DF) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int *flag = P.df_flags + (size_t)pos * P.df_stride + blk;
+#ifdef PMM_HOST_EMU
+        *flag = P.df_epoch;
+#else
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(P.df_epoch) : "memory");
+#endif
+    }
+}
 
 // the clade's steps, the branch constants of every step's two children and the four leaf vectors
 // (EM_solver.py:103-116 in full-state form, indexed by min(code, 1) + 2:
@@ -234,16 +309,12 @@ __device__ __forceinline__ void inside_fetch(const LParams &P, const int4 d, int
     else if (kw == KIND_LOAD) { const unsigned o = rec_index(P, d.z, s); ld_xrec(n.w, P.X, o); }
 }
 
-__global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
-    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
-    __shared__ double4 s_bc[2 * STEP_CAP];
-    __shared__ double4 s_lut[4];
-    const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z
+// one thread's walk through the clade `cl` (steps [x, y), root index z) at its site of block `blk`
+__device__ __forceinline__ void inside_walk(const LParams &P, const int4 cl, int blk, const int4 *s_steps, const double4 *s_bc,
+                                            const double4 *s_lut) {
     const int nsteps = cl.y - cl.x;
-    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
-    grid_dependency_wait();
     const int N = P.n_leaves;
-    const int sr = (blockIdx.y + P.sblk0) * LT + threadIdx.x;     // record column (idle lanes own padding columns)
+    const int sr = (blk + P.sblk0) * LT + threadIdx.x;            // record column (idle lanes own padding columns)
     if ((sr & ~31) >= P.K) return;                                   // whole warp beyond the last site
     const bool valid = sr < P.K;
     const int s = min(sr, P.K - 1);                                   // inputs of an idle lane: those of the last site
@@ -333,6 +404,22 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     for (; i + 1 < nsteps; i += 2) { step(i, A, B); step(i + 1, B, A); }
     if (i < nsteps) step(i, A, B);
     grid_launch_dependents();
+}
+
+// grid = (clades of the tier, site blocks); DF: a dataflow launch over several tiers, grid = clades x site blocks in one dimension
+template <bool DF = false>
+__global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
+    __shared__ double4 s_bc[2 * STEP_CAP];
+    __shared__ double4 s_lut[4];
+    int ci, blk;
+    df_item<DF>(P, ci, blk);
+    const int4 cl = clades[ci];
+    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, cl.y - cl.x);
+    grid_dependency_wait();
+    df_wait<DF>(P, P.df_lo + ci, blk + P.sblk0);
+    inside_walk(P, cl, blk, s_steps, s_bc, s_lut);
+    df_done<DF>(P, P.df_lo + ci, blk + P.sblk0);
 }
 
 // ---------------------------------------------------------------- outside pass + expected counts
@@ -480,19 +567,12 @@ __device__ __forceinline__ void stage_rows(uint4 *s_rows, const int4 *s_steps, c
     __syncthreads();
 }
 
+// one thread's walk through the clade `cl` (steps [x, y), root index z, clade id w) at its site of block `blk`
 template <bool POST>
-__global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
-    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
-    __shared__ uint4 s_rows[STEP_CAP + STEP_PAD];
-    __shared__ double4 s_bc[2 * STEP_CAP];
-    __shared__ double4 s_lut[4];
-    __shared__ __align__(16) double s_red[(LT / 32) * RED_ROWS * RED_ROW];
-    const int4 cl = clades[blockIdx.x];                 // steps [x, y), root index z, clade id w
+__device__ __forceinline__ void outside_walk(const LParams &P, const int4 cl, int blk, const int4 *s_steps, const uint4 *s_rows,
+                                             const double4 *s_bc, const double4 *s_lut, double *s_red) {
     const int nsteps = cl.y - cl.x;
-    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, nsteps);
-    stage_rows(s_rows, s_steps, P, nsteps);
-    grid_dependency_wait();
-    const unsigned s_raw = (blockIdx.y + P.sblk0) * LT + threadIdx.x;     // record column (idle lanes of the last warp own padding columns)
+    const unsigned s_raw = (blk + P.sblk0) * LT + threadIdx.x;           // record column (idle lanes of the last warp own padding columns)
     const bool valid = (int)s_raw < P.K;
     const int s = min((int)s_raw, P.K - 1);
     const int gs = P.site0 + s;
@@ -603,6 +683,24 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);
     if (lane == 0) P.Rpart[(size_t)grp * P.n_clades + cl.w] = rt;
+}
+
+template <bool POST, bool DF = false>
+__global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams P, const int4 *__restrict__ clades, const int4 *__restrict__ steps) {
+    __shared__ int4 s_steps[STEP_CAP + STEP_PAD];
+    __shared__ uint4 s_rows[STEP_CAP + STEP_PAD];
+    __shared__ double4 s_bc[2 * STEP_CAP];
+    __shared__ double4 s_lut[4];
+    __shared__ __align__(16) double s_red[(LT / 32) * RED_ROWS * RED_ROW];
+    int ci, blk;
+    df_item<DF>(P, ci, blk);
+    const int4 cl = clades[ci];
+    stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, cl.y - cl.x);
+    stage_rows(s_rows, s_steps, P, cl.y - cl.x);
+    grid_dependency_wait();
+    df_wait<DF>(P, P.df_lo + ci, blk + P.sblk0);
+    outside_walk<POST>(P, cl, blk, s_steps, s_rows, s_bc, s_lut, s_red);
+    df_done<DF>(P, P.df_lo + ci, blk + P.sblk0);
 }
 
 }  // namespace pmm

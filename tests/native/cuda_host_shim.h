@@ -59,6 +59,7 @@ inline double __shfl_xor_sync(unsigned, double x, int lane_mask) {
     return r;
 }
 template <class T> inline T __ldg(const T *p) { return *p; }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }
 inline int __double2loint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffll); }
 inline double __hiloint2double(int hi, int lo) {

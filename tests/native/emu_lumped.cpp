@@ -50,13 +50,16 @@ extern "C" int emu_nni_lumped(int ultra, int n_cand, const int *cand8 /* [n_cand
 }
 
 // The E-step kernels themselves: pmm_lumped_inside, then pmm_lumped_outside<false>, phase by phase as
-// pmm_engine.cu: run_lumped launches them (one launch per tier of the clade schedule, grid = clades x site blocks).
+// pmm_engine.cu: run_lumped launches them (one launch per tier of the clade schedule, grid = clades x site blocks; or the
+// dataflow launches over several tiers, df_mode 1 / 2).
 extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_clades, const int *codes, const int *site_ptr,
                                 const double *prior, const double *qsum, double nu, double phi, const double *d /* [n] */,
                                 const int *in_steps, const int *in_clades, const int *in_phase_ptr, int n_in_phases,
                                 const int *out_steps, const int *out_clades, const int *out_phase_ptr, int n_out_phases, int store_all,
                                 double *X, double *O, int *OI, double *invL, double *root_site_llh, double *Spart, double *Rpart,
-                                double *bc_out /* [n][4] */, double *post0 /* [n][K] or null: the annotation variant */, double *post1) {
+                                double *bc_out /* [n][4] */, double *post0 /* [n][K] or null: the annotation variant */, double *post1,
+                                int df_mode /* 0: a launch per tier; 1: tier 0 | top tiers as one dataflow launch; 2: one dataflow launch per pass */,
+                                const int *in_dep_ptr, const int *in_deps, const int *out_dep_ptr, const int *out_deps) {
     LParams P;
     memset(&P, 0, sizeof(P));
     P.K = K; P.Kp = Kp; P.site0 = 0; P.code_stride = K; P.n_leaves = n_leaves; P.n_nodes = n_nodes; P.n_clades = n_clades;
@@ -73,17 +76,50 @@ extern "C" int emu_lumped_estep(int K, int Kp, int n_leaves, int n_nodes, int n_
     P.K_total = K; P.store_all = store_all; P.sblk0 = 0;
     P.post0 = post0; P.post1 = post1;
     const unsigned gy = (unsigned)((K + LT - 1) / LT);
+    if (df_mode) {
+        // as pmm_engine.cu: run_lumped groups the tiers; the CTAs of a launch run one after another here, in ticket order
+        const int ncl = in_phase_ptr[n_in_phases], nt0 = in_phase_ptr[1];
+        std::vector<int> flags((size_t)2 * ncl * gy, 0);
+        unsigned ticket = 0;
+        int err = 0, epoch = 0;
+        struct G { int c0, c1, n1, n2, df; };
+        std::vector<G> gin, gout;
+        if (df_mode == 1) { gin = {{0, nt0, 0, 0, 0}, {nt0, ncl, 0, ncl - nt0, 1}}; gout = {{0, ncl - nt0, ncl - nt0, 0, 1}, {ncl - nt0, ncl, 0, 0, 0}}; }
+        else { gin = {{0, ncl, nt0, ncl - nt0, 1}}; gout = {{0, ncl, ncl - nt0, nt0, 1}}; }
+        auto run = [&](const G &g, int pass) {
+            if (g.c1 <= g.c0) return;
+            LParams Q = P;
+            const int4 *cl = reinterpret_cast<const int4 *>(pass ? out_clades : in_clades) + g.c0;
+            const int4 *st = reinterpret_cast<const int4 *>(pass ? out_steps : in_steps);
+            if (g.df) {
+                Q.df_ticket = &ticket; Q.df_base = ticket; Q.df_flags = flags.data() + (size_t)pass * ncl * gy;
+                Q.df_dep_ptr = pass ? out_dep_ptr : in_dep_ptr; Q.df_deps = pass ? out_deps : in_deps;
+                Q.df_lo = g.c0; Q.df_n1 = g.n1; Q.df_n2 = g.n2; Q.df_nblk = (int)gy; Q.df_stride = (int)gy; Q.df_epoch = ++epoch; Q.df_err = &err;
+                const unsigned total = (unsigned)(g.c1 - g.c0) * gy;
+                if (!pass) emu::launch(total, LT, pmm_lumped_inside<true>, Q, cl, st);
+                else if (post0) emu::launch(total, LT, pmm_lumped_outside<true, true>, Q, cl, st);
+                else emu::launch(total, LT, pmm_lumped_outside<false, true>, Q, cl, st);
+            } else {
+                if (!pass) emu::launch2((unsigned)(g.c1 - g.c0), gy, LT, pmm_lumped_inside<false>, Q, cl, st);
+                else if (post0) emu::launch2((unsigned)(g.c1 - g.c0), gy, LT, pmm_lumped_outside<true, false>, Q, cl, st);
+                else emu::launch2((unsigned)(g.c1 - g.c0), gy, LT, pmm_lumped_outside<false, false>, Q, cl, st);
+            }
+        };
+        for (const G &g : gin) run(g, 0);
+        for (const G &g : gout) run(g, 1);
+        return err ? 2 : 0;              // 2: a CTA found a producer's mark missing -- the item order is wrong
+    }
     for (int p = 0; p < n_in_phases; p++) {
         const int c0 = in_phase_ptr[p], c1 = in_phase_ptr[p + 1];
-        if (c1 > c0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_inside, P, reinterpret_cast<const int4 *>(in_clades) + c0,
+        if (c1 > c0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_inside<false>, P, reinterpret_cast<const int4 *>(in_clades) + c0,
                                   reinterpret_cast<const int4 *>(in_steps));
     }
     for (int p = 0; p < n_out_phases; p++) {
         const int c0 = out_phase_ptr[p], c1 = out_phase_ptr[p + 1];
         if (c1 <= c0) continue;
-        if (post0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<true>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
+        if (post0) emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<true, false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
                                 reinterpret_cast<const int4 *>(out_steps));
-        else emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
+        else emu::launch2((unsigned)(c1 - c0), gy, LT, pmm_lumped_outside<false, false>, P, reinterpret_cast<const int4 *>(out_clades) + c0,
                           reinterpret_cast<const int4 *>(out_steps));
     }
     return 0;

@@ -157,7 +157,7 @@ def test_constrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi, step):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the E-step kernels themselves (pmm_lumped_inside / pmm_lumped_outside), on the clade schedule the library derives
-def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0, posteriors=False):
+def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0, posteriors=False, df_mode=0):
     from laml_b200.capi import lumped_schedule
     f = w.forest
     N, n, K = f.n_leaves, f.n_nodes, w.codes.shape[1]
@@ -172,15 +172,17 @@ def run_estep_kernels(emu, w, d, nu, phi, clade_cap, clade_cap_top, store_all=0,
     codes = np.ascontiguousarray(w.codes, np.int32)
     site_ptr = np.ascontiguousarray(w.qptr, np.int32); prior = np.ascontiguousarray(w.qval, np.float64)
     dd = np.ascontiguousarray(d, np.float64)
-    arrs = {k: np.ascontiguousarray(sch[k], np.int32) for k in ("in_steps", "in_clades", "in_phase_ptr", "out_steps", "out_clades", "out_phase_ptr")}
+    arrs = {k: np.ascontiguousarray(sch[k], np.int32) for k in ("in_steps", "in_clades", "in_phase_ptr", "out_steps", "out_clades", "out_phase_ptr",
+                                                                "in_dep_ptr", "in_deps", "out_dep_ptr", "out_deps")}
     post0 = np.full((n, K), np.nan) if posteriors else None
     post1 = np.full((n, K), np.nan) if posteriors else None
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)   # noqa: E731
     rc = emu.emu_lumped_estep(K, Kp, N, n, sch["n_clades"], p(codes), p(site_ptr), p(prior), p(qsum), C.c_double(nu), C.c_double(phi),
                               p(dd), p(arrs["in_steps"]), p(arrs["in_clades"]), p(arrs["in_phase_ptr"]), len(arrs["in_phase_ptr"]) - 1,
                               p(arrs["out_steps"]), p(arrs["out_clades"]), p(arrs["out_phase_ptr"]), len(arrs["out_phase_ptr"]) - 1,
-                              store_all, p(X), p(O), p(OI), p(invL), p(rllh), p(Spart), p(Rpart), p(bc), p(post0), p(post1))
-    assert rc == 0
+                              store_all, p(X), p(O), p(OI), p(invL), p(rllh), p(Spart), p(Rpart), p(bc), p(post0), p(post1),
+                              df_mode, p(arrs["in_dep_ptr"]), p(arrs["in_deps"]), p(arrs["out_dep_ptr"]), p(arrs["out_deps"]))
+    assert rc == 0, "a dataflow CTA found a producer's mark missing" if rc == 2 else rc
     return {"S": Spart.sum(axis=0), "llh": float(rllh.sum()), "Rtilde": float(Rpart.sum()), "site_llh": rllh.sum(axis=0),
             "n_phases": sch["n_phases"], "n_clades": sch["n_clades"], "X": X, "O": O, "OI": OI, "invL": invL, "root_llh": rllh,
             "bc": bc, "qsum": qsum, "post0": post0, "post1": post1}
@@ -202,6 +204,34 @@ def test_estep_kernels_on_the_host(emu, seed, n, K, amax, nu, phi, caps):
     np.testing.assert_allclose(got["site_llh"], ref["site_llh"], rtol=1e-9, atol=1e-12)
     if caps[0] < 10:
         assert got["n_phases"] > 1 and got["n_clades"] > 3
+
+
+@pytest.mark.parametrize("seed,n,K,caps,forest", [(34, 60, 300, (5, 3), False), (35, 33, 40, (2, 2), False), (36, 90, 150, (16, 4), False),
+                                                   (37, 24, 130, (3, 2), True)])
+def test_dataflow_launches_on_the_host(emu, seed, n, K, caps, forest):
+    """the dataflow variants of both kernels (several tiers in ONE launch: atomic tickets, waits on the producers'
+    marks) against the launch-per-tier run of the same schedule: every record, count partial and likelihood to the
+    bit, for the launch over all tiers (mode 2) and over the top tiers only (mode 1), one to three site blocks"""
+    w = make_workload(n, K, 1, 14, 0.2, 0.15, seed=seed)
+    if forest:
+        from types import SimpleNamespace
+        from laml_b200.flatten import forest_from_parent
+        from test_lumped_schedule import forest_of
+        from laml_b200.synth import random_tree
+        trees = [random_tree(m, seed=seed + i) for i, m in enumerate((n - 10, 3, 7))]
+        N, parent, left, right = forest_of(trees)
+        f = forest_from_parent(parent, left, right)
+        w = SimpleNamespace(forest=f, codes=w.codes[:N], qptr=w.qptr, qval=w.qval, d=np.resize(w.d, f.n_nodes))
+    base = run_estep_kernels(emu, w, w.d, 0.2, 0.15, *caps)
+    assert base["n_phases"] >= 2
+    for mode in (2, 1):
+        got = run_estep_kernels(emu, w, w.d, 0.2, 0.15, *caps, df_mode=mode)
+        for key in ("X", "O", "OI", "invL", "root_llh", "S"):
+            assert got[key].tobytes() == base[key].tobytes(), (mode, key)      # (packed h | cum words may look like NaN)
+        assert got["llh"] == base["llh"] and got["Rtilde"] == base["Rtilde"]
+    post = run_estep_kernels(emu, w, w.d, 0.2, 0.15, *caps, posteriors=True)
+    got = run_estep_kernels(emu, w, w.d, 0.2, 0.15, *caps, posteriors=True, df_mode=2)
+    assert np.array_equal(got["post0"], post["post0"]) and np.array_equal(got["post1"], post["post1"])
 
 
 def test_posterior_variant_on_the_host(emu):

@@ -10,7 +10,10 @@ topologies for several clade capacities:
   * outside: a step whose out-record is chained (how = 2) follows the step of its parent, which lists it first and
     has the keep bit; a loaded out-record (how = 1) was stored (store bit) by the parent's step at least two steps
     earlier in the same clade or in an earlier launch; a root loads too (the inside pass stored its out-record);
-  * leaves are flagged as leaves.
+  * leaves are flagged as leaves;
+  * dataflow launches (several tiers in one launch): the wait list of a clade holds exactly the clades that produce
+    what it loads from other clades, every one of them at an earlier position of the pass; and the item order of a
+    launch (a re-statement of ``df_item``) visits every (clade, site block) once, producers before consumers.
 """
 import numpy as np
 import pytest
@@ -107,7 +110,60 @@ def check(N, parent, left, right, cap, top):
                 for c, bit in ((v, 16), (w, 32)):
                     if c >= N and not ((f & 64) and c == v):
                         assert f & bit                                                 # everything not chained is stored
+    # ---- dataflow waits: exactly the other clades a clade loads from, all at earlier positions
+    for which in ("in", "out"):
+        steps, clades = S[which + "_steps"], S[which + "_clades"]
+        ptr, deps = S[which + "_dep_ptr"], S[which + "_deps"]
+        sizes = clades[:, 1] - clades[:, 0]
+        step_clade = np.repeat(np.arange(ncl), sizes)
+        pos_of_node = {int(u): int(step_clade[i]) for i, u in enumerate(steps[:, 0])}
+        assert len(ptr) == ncl + 1 and ptr[0] == 0 and ptr[-1] == len(deps)
+        for ci in range(ncl):
+            want = set()
+            for u, v, w, f in steps[clades[ci, 0]:clades[ci, 1]].tolist():
+                if which == "in":
+                    want |= {pos_of_node[c] for c, far in ((v, f & 32), (w, f & 64)) if far}
+                elif parent[u] >= 0 and pos_of_node[int(parent[u])] != ci:
+                    want.add(pos_of_node[int(parent[u])])
+            got = deps[ptr[ci]:ptr[ci + 1]].tolist()
+            assert sorted(got) == sorted(want) and len(set(got)) == len(got)
+            assert all(p < ci for p in got)
     return S
+
+
+def df_item(i, n1, n2, nblk):
+    """the item order of a dataflow launch, as laml_b200/csrc/pmm_lumped.cuh: df_item"""
+    if i < n1:
+        return i, 0
+    j = i - n1
+    g, r = divmod(j, n1 + n2)
+    if g < nblk - 1:
+        return r, (g + 1 if r < n1 else g)
+    return n1 + r, nblk - 1
+
+
+@pytest.mark.parametrize("cap,top", [(3, 2), (16, 6), (40, 8)])
+def test_dataflow_item_order(cap, top):
+    """every (clade, site block) of a dataflow launch is visited once, and after all of its producers -- for the launch
+    over all tiers (mode 2) and for the launch over the top tiers alone (mode 1), both passes, 1 to 5 site blocks"""
+    t = random_tree(300, seed=8)
+    S = lumped_schedule(t.n_leaves, t.parent, t.left, t.right, cap, top)
+    ncl, nt0 = S["n_clades"], int(S["in_phase_ptr"][1])
+    assert S["n_phases"] >= 3
+    for which, groups in (("in", ((0, ncl, nt0, ncl - nt0), (nt0, ncl, 0, ncl - nt0))),
+                          ("out", ((0, ncl, ncl - nt0, nt0), (0, ncl - nt0, ncl - nt0, 0)))):
+        ptr, deps = S[which + "_dep_ptr"], S[which + "_deps"]
+        for c0, c1, n1, n2 in groups:
+            assert n1 + n2 == c1 - c0
+            for nblk in (1, 2, 5):
+                seen = {}
+                for i in range((c1 - c0) * nblk):
+                    cl, blk = df_item(i, n1, n2, nblk)
+                    assert 0 <= cl < c1 - c0 and 0 <= blk < nblk and (cl, blk) not in seen
+                    for p in deps[ptr[c0 + cl]:ptr[c0 + cl + 1]].tolist():
+                        assert p < c0 or (p - c0, blk) in seen           # produced by an earlier launch, or earlier in this one
+                    seen[(cl, blk)] = i
+                assert len(seen) == (c1 - c0) * nblk
 
 
 @pytest.mark.parametrize("cap,top", [(1, 1), (2, 3), (7, 2), (16, 16), (40, 8), (127, 127)])
