@@ -614,13 +614,12 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
         C0 = std::max(16, std::min(120, C0));
     }
     C0 = std::max(1, std::min(C0, STEP_CAP - 1));      // the kernels stage a clade's steps in shared memory
-    // dataflow launches (pmm_lumped.cuh): worth it when a pass is a few waves of CTAs at most, i.e. when the latency-bound
-    // top tiers are a visible share of it -- site shards of a multi-GPU run, small trees.  PMM_DF = 0 / 1 / 2 forces a mode.
-    const int site_blocks = (h->K + LT - 1) / LT;
-    h->df_mode = env_int("PMM_DF", -1);
-    if (h->df_mode < 0 || h->df_mode > 2) h->df_mode = (site_blocks <= env_int("PMM_DF_MAX_BLOCKS", 4)) ? 2 : 0;
-    // without launch boundaries between the tiers the top clades can be short: a hand-over costs about as much as four steps
-    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", h->df_mode ? 6 : 16), STEP_CAP - 1));
+    // dataflow launches (pmm_lumped.cuh), PMM_DF = 1 / 2: several tiers per launch.  Off by default: measured on a B200
+    // (profiles/r2_dataflow.md) a hand-over between clades through a mark costs about as much as six steps, and with
+    // programmatic dependent launch a tier boundary costs no more -- 1k x 30: 70 us either way, 10k x 500: 218 -> 256 us,
+    // a 250-site shard of the 100k-cell tree: 667 -> 720 us
+    h->df_mode = std::max(0, std::min(2, env_int("PMM_DF", 0)));
+    const int Ctop = std::max(1, std::min(env_int("PMM_CLADE_TOP", 16), STEP_CAP - 1));
     h->clade_target = C0;
     LumpedSchedule S;
     make_lumped_schedule(N, n, h->left.data(), h->right.data(), h->parent.data(), order, root_index, C0, Ctop, S);

@@ -198,11 +198,13 @@ __device__ __forceinline__ void df_spin(const int *flag, int epoch, int *err) {
     if (*flag != epoch) *err = 1;            // CTAs run one after another in ticket order: a producer that has not run is a schedule bug
 #else
     const long long t0 = clock64();
-    for (;;) {
+    for (unsigned polls = 1;; polls++) {
         int v;
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v == epoch) break;
-        if (clock64() - t0 > (1ll << 31)) { *err = 1; break; }      // ~1 s: give up, flag the error (the finishing kernel turns it into NaN)
+        // ~1 s without the mark: give up and flag the error (the finishing kernel turns it into a NaN likelihood); once
+        // one wait has given up the others follow at once
+        if ((polls & 1023u) == 0 && (clock64() - t0 > (1ll << 31) || *(volatile int *)err)) { *err = 1; break; }
         __nanosleep(40);
     }
 #endif
