@@ -428,6 +428,10 @@ def run_ours(args, rank, local_rank, world):
         parity["ok"] = bool(parity["llh_rel"] <= 1e-9 and parity["S_max_err_over_tol"] <= 1.0 and parity["Rtilde_rel"] <= 1e-8
                             and parity["site_llh_max_rel_whole_run_vs_oracle"] <= 1e-9)
 
+    exchange = ("peer memory: count reduction + reduce-scatter + all-gather over NVLink inside the E-step's finishing kernel "
+                "(pmm_finish_peer; estep_ms includes it, allreduce_ms is what is left: nothing)" if sh.peer else
+                ("NCCL all_reduce on the engine's statistics buffer" if world > 1 else "none (one GPU)"))
+    sh.close()
     if rank != 0:
         rk.close()
         return
@@ -509,7 +513,8 @@ def run_ours(args, rank, local_rank, world):
         "engine": {"kind": "lumped-state records" if lumped else "full-state rows",
                    "l2": ("per-node state far exceeds L2: %.1f GB per pass per GPU" %
                           ((40e-9 * (hi - lo) if lumped else 8e-9 * info["row_stride"]) * n_int)),
-                   "site_chunks": info["n_chunks"], "clades": info["clades"], "launches_per_pass": info["launches_per_pass"]},
+                   "site_chunks": info["n_chunks"], "clades": info["clades"], "launches_per_pass": info["launches_per_pass"],
+                   "exchange": exchange},
         "em_iter_per_s": 1e3 / ms_step, "estep_ms": estep_ms, "inside_ms": inside_ms, "outside_ms": outside_ms,
         "allreduce_ms": allreduce_ms, "mstep_ms": mstep_ms,
         "estep_cell_site_per_s": N * Ktot / (estep_ms * 1e-3),
@@ -588,9 +593,11 @@ def run_em_convergence(args, rank, local_rank, world):
                        "cell_site_per_s": N * Ktot * res["iters"] / dt},
                 "oracle_em": oracle,
                 "note": "a step = one whole EM run (ShardedEngine.em: EM_solver.EM_optimization on site shards, one llh read-back "
-                        "per iteration); iterations / nllh / nu / phi / d_sum must be equal across n_gpus"}
+                        "per iteration); iterations / nllh / nu / phi / d_sum must be equal across n_gpus",
+                "exchange": "peer memory (pmm_finish_peer), device-resident loop pmm_em on every rank" if sh.peer else ("NCCL all_reduce" if world > 1 else "none")}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
+    sh.close()
     rk.close()
 
 

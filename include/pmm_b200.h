@@ -145,6 +145,23 @@ void *pmm_stats_dev_ptr(pmm_handle *h);           /* device pointer, (5*n_nodes+
 int64_t pmm_stats_len(const pmm_handle *h);
 int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_mask, int32_t optimize_nu,
                   int32_t optimize_phi, double dmin, double dmax, double eps_s, double eps_nu);
+/* ---- the exchange over peer memory (site shards on the GPUs of one NVSwitch domain; laml_b200/csrc/pmm_peer.cuh) ----
+ * The reference sums the expected counts over all sites in one loop (EM_solver.py:247-305); site shards need that sum
+ * across ranks.  After pmm_peer_setup the kernel that finishes an E-step / inside pass also reduces the statistics over
+ * the ranks -- loads from and stores to the peers' buffers over NVLink -- so that pmm_estep_dev / pmm_inside_dev /
+ * pmm_estep / pmm_em / pmm_em_step leave the SAME all-reduced statistics (to the bit) on every rank, with no NCCL call.
+ * Every rank must then make the same sequence of those calls (as with any collective).  Lumped-state engine only.
+ *   pmm_peer_export      64 opaque bytes (a CUDA IPC handle of this rank's exchange buffer); call after pmm_set_tree
+ *   pmm_peer_setup       handles = world x 64 bytes, indexed by rank (own entry ignored); world = 1 drops the peers
+ *   pmm_peer_setup_local the same for ranks that are handles of ONE process (peers[rank] may be NULL)
+ *   pmm_peer_close       unmap the peers (call on every rank before any of them destroys its handle)
+ * A pmm_set_tree that changes the node count frees the exchange buffer: export / set up again afterwards.
+ */
+#define PMM_PEER_HANDLE_BYTES 64
+int pmm_peer_export(pmm_handle *h, void *handle_out);
+int pmm_peer_setup(pmm_handle *h, int32_t rank, int32_t world, const void *handles);
+int pmm_peer_setup_local(pmm_handle *h, int32_t rank, int32_t world, pmm_handle *const *peers);
+int pmm_peer_close(pmm_handle *h);
 int pmm_read_llh(pmm_handle *h, double *llh);      /* the llh slot of the statistics (after pmm_estep_dev / pmm_inside_dev) */
 int pmm_sync(pmm_handle *h);
 

@@ -23,7 +23,9 @@ SYMBOLS = [
     "pmm_stats_len", "pmm_mstep_dev", "pmm_sync", "pmm_get_info", "pmm_last_timing", "pmm_score_nni_batch", "pmm_set_option", "pmm_debug_lumped_schedule",
     "pmm_ultrametric_solve", "pmm_score_nni_batch_ultra", "pmm_debug_nni_ultra_mstep", "pmm_em_step",
     "pmm_mstep_ultra_dev", "pmm_em_ultra", "pmm_read_llh", "pmm_debug_lumped_deps",
+    "pmm_peer_export", "pmm_peer_setup", "pmm_peer_setup_local", "pmm_peer_close",
 ]
+PEER_HANDLE_BYTES = 64
 
 
 def nni_ultra_mstep(S25, nu, lo, hi, hA, hB, hC, hTop, top_free=False, H=None, eps_nu=1e-5):
@@ -106,6 +108,10 @@ def load_library():
     L.pmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.pmm_debug_lumped_schedule.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, P(i32), P(i32)]
     L.pmm_debug_lumped_deps.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.pmm_peer_export.argtypes = [vp, vp]
+    L.pmm_peer_setup.argtypes = [vp, i32, i32, vp]
+    L.pmm_peer_setup_local.argtypes = [vp, i32, i32, vp]
+    L.pmm_peer_close.argtypes = [vp]
     L.pmm_ultrametric_solve.argtypes = [i32, vp, vp, vp, f64, f64, vp, f64, f64, vp, f64, f64, f64, vp, vp, P(i32)]
     L.pmm_get_info.argtypes = [vp, P(PMMInfo)]
     L.pmm_last_timing.argtypes = [vp, P(f64), P(f64), P(f64)]
@@ -342,6 +348,28 @@ class Engine:
                                       int(max_iter), C.byref(nllh), C.byref(iters), C.byref(status)))
         return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
                 "status": {0: "optimal", 1: "d_infeasible", 2: "failed_d"}[status.value]}
+
+    # ---- the exchange over peer memory (site shards on several GPUs): after ``peer_setup`` every E-step / inside pass
+    # leaves the statistics all-reduced over the ranks, computed by the finishing kernel itself over NVLink
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._ck(self._L.pmm_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_setup(self, rank: int, world: int, handles: bytes):
+        """``handles``: the ranks' ``peer_export()`` results concatenated in rank order"""
+        if len(handles) != world * PEER_HANDLE_BYTES:
+            raise PMMError("peer_setup: need %d bytes of handles, got %d" % (world * PEER_HANDLE_BYTES, len(handles)))
+        self._ck(self._L.pmm_peer_setup(self._h, int(rank), int(world), C.c_char_p(handles)))
+
+    def peer_setup_local(self, rank: int, engines):
+        """ranks that are handles of this process (tests; several GPUs driven by one process)"""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        self._ck(self._L.pmm_peer_setup_local(self._h, int(rank), len(engines), arr))
+
+    def peer_close(self):
+        if self._h:
+            self._ck(self._L.pmm_peer_close(self._h))
 
     def stats_ptr(self):
         return int(self._L.pmm_stats_dev_ptr(self._h)), int(self._L.pmm_stats_len(self._h))

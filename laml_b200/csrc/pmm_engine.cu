@@ -9,6 +9,7 @@
 #include "pmm_lumped.cuh"
 #include "pmm_nni_lumped.cuh"
 #include "pmm_ultrametric_dev.cuh"
+#include "pmm_peer.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -72,7 +73,16 @@ struct pmm_handle {
     double *d_Spart = nullptr, *d_Rpart = nullptr, *d_Rnode = nullptr;
     double *d_site_llh = nullptr;   // [K]
     double *d_bc = nullptr, *d_d = nullptr, *d_params = nullptr;
-    double *d_stats = nullptr;      // [5n | Rtilde | llh]
+    double *d_stats = nullptr;      // [5n | Rtilde | llh]: the `red` part of the exchange block d_xb (not a separate allocation)
+    // ---- exchange over peer memory (site shards on several GPUs; pmm_peer.cuh).  d_xb = [loc | red | flags], one allocation
+    double *d_xb = nullptr, *d_xloc = nullptr;
+    int *d_xflags = nullptr;
+    size_t xL = 0;                  // doubles per part (5n + 2 rounded up to even)
+    int peer_world = 1, peer_rank = 0, peer_epoch = 0;
+    PeerArgs peer = {};
+    void *peer_mapped[PEER_MAX] = {};    // bases opened through CUDA IPC (to be closed again)
+    unsigned *d_peer_bar = nullptr;
+    int *d_peer_err = nullptr;
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
     std::vector<unsigned char> free_host;   // the mask d_free holds (empty = all branches free)
@@ -172,6 +182,13 @@ int env_int(const char *name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
+// forget the peers (their buffers are unmapped; ours stays): back to a single-GPU handle
+void peer_drop(pmm_handle *h) {
+    for (auto &m : h->peer_mapped) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    h->peer_world = 1; h->peer_rank = 0; h->peer_epoch = 0;
+    h->peer = PeerArgs{};
+}
+
 void free_chunks(pmm_handle *h) {
     for (auto &c : h->chunks) {
         dfree(c.d_site_off); dfree(c.d_site_len); dfree(c.d_tile_site); dfree(c.d_tile_off); dfree(c.d_ent); dfree(c.d_q); dfree(c.d_qsum);
@@ -186,7 +203,9 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp); dfree(h->d_eX); dfree(h->d_eO); dfree(h->d_sqX);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
-    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_stats); dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
+    peer_drop(h);
+    dfree(h->d_bc); dfree(h->d_d); dfree(h->d_xb); h->d_stats = h->d_xloc = nullptr; h->d_xflags = nullptr; dfree(h->d_peer_bar); dfree(h->d_peer_err);
+    dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
     dfree(h->d_post0); dfree(h->d_post1);
     dfree(h->d_lin_steps); dfree(h->d_lout_steps); dfree(h->d_lin_clades); dfree(h->d_lout_clades);
     dfree(h->d_df_dep_ptr_in); dfree(h->d_df_deps_in); dfree(h->d_df_dep_ptr_out); dfree(h->d_df_deps_out);
@@ -756,8 +775,12 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
     CK(cudaEventRecord(h->ev[0], h->stream));
     pmm_branch_consts<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_d, h->d_params, n, h->d_bc);
     h->launches++;
-    double *d_llh = h->d_stats + (size_t)5 * n + 1;
-    double *d_Rt = h->d_stats + (size_t)5 * n;
+    // with peers the rank's own sums go to the `loc` part of the exchange block; the last chunk's finishing kernel is
+    // then pmm_finish_peer, which also reduces over the ranks into every rank's statistics
+    const bool peers = h->peer_world > 1;
+    double *stats_out = peers ? h->d_xloc : h->d_stats;
+    double *d_llh = stats_out + (size_t)5 * n + 1;
+    double *d_Rt = stats_out + (size_t)5 * n;
     const int nchunks = (h->K + h->lKc - 1) / h->lKc;
     float acc_in = 0, acc_out = 0;
     for (int ci = 0; ci < nchunks; ci++) {
@@ -847,9 +870,21 @@ int run_lumped(pmm_handle *h, bool outside, bool with_post) {
             for (int j = 0; j < nslice; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_s[j][2], 0));
             CK(cudaEventRecord(h->ev[2], h->stream));
         }
-        {   // per-site and total log-likelihood, counts summed over the site groups, R~: one launch
+        if (peers && ci == nchunks - 1) {
+            // the same sums, then the exchange over peer memory: ONE cooperative launch (at most one CTA per SM)
+            const double *sp = h->d_LSpart, *rl = h->d_Lroot_llh, *rp = h->d_LRpart;
+            int gg = G, n5 = 5 * n, acc = ci > 0, nr = h->n_roots, kk = P.K, ncl = h->n_clades, wc = outside ? 1 : 0;
+            double *sl = h->d_site_llh + P.site0, *rn = h->d_Rnode;
+            const int *de = h->df_mode ? h->d_df_err : nullptr;
+            PeerArgs A = h->peer;
+            A.epoch = ++h->peer_epoch;
+            void *args[] = {&sp, &gg, &n5, &acc, &rl, &nr, &kk, &sl, &rp, &ncl, &rn, &wc, &de, &A};
+            const int nblk = std::max(1, std::min(h->n_sms, (n5 + 2 * PEER_THREADS - 1) / (2 * PEER_THREADS)));
+            CK(cudaLaunchCooperativeKernel((void *)pmm_finish_peer, dim3((unsigned)nblk), dim3(PEER_THREADS), args, 0, h->stream));
+            h->launches += 1;
+        } else {   // per-site and total log-likelihood, counts summed over the site groups, R~: one launch
             const unsigned nb = outside ? (unsigned)((5 * n + 1023) / 1024) : 0u;
-            pmm_lumped_finish<<<nb + 1, 1024, 0, h->stream>>>(h->d_LSpart, G, 5 * n, h->d_stats, ci > 0, h->d_Lroot_llh, h->n_roots, P.K,
+            pmm_lumped_finish<<<nb + 1, 1024, 0, h->stream>>>(h->d_LSpart, G, 5 * n, stats_out, ci > 0, h->d_Lroot_llh, h->n_roots, P.K,
                                                              h->d_site_llh + P.site0, d_llh, h->d_LRpart, h->n_clades, h->d_Rnode, d_Rt,
                                                              outside ? 1 : 0, h->df_mode ? h->d_df_err : nullptr);
             h->launches += 1;
@@ -915,6 +950,7 @@ int set_free_mask(pmm_handle *h, const uint8_t *free_mask) {
 // inside (+ optionally outside/counts) over all chunks, parameters already on the device
 int run_passes(pmm_handle *h, bool outside, bool with_post, bool force_full = false) {
     if (h->engine == 0 && !force_full) { h->last_full = false; return run_lumped(h, outside, with_post); }
+    if (h->peer_world > 1) return fail(h, "the exchange over peer memory belongs to the lumped-state engine (PMM_ENGINE=fullstate: all-reduce the statistics yourself)");
     if (ensure_fullstate(h)) return 1;
     h->last_full = true;
     const int n = h->n;
@@ -1175,7 +1211,13 @@ int pmm_set_tree(pmm_handle *h, int32_t n_nodes, const int32_t *parent, const in
         return 0;
     }
     // small per-node buffers first, then the records against what is left
-    if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) || dalloc(h, &h->d_stats, (size_t)5 * n + 2) ||
+    h->xL = ((size_t)5 * n + 2 + 1) & ~(size_t)1;
+    if (dalloc(h, &h->d_xb, 2 * h->xL + PEER_MAX) || dalloc(h, &h->d_peer_bar, 2) || dalloc(h, &h->d_peer_err, 1)) return 1;
+    CK(cudaMemset(h->d_xb, 0, sizeof(double) * (2 * h->xL + PEER_MAX)));
+    CK(cudaMemset(h->d_peer_bar, 0, 2 * sizeof(unsigned)));
+    CK(cudaMemset(h->d_peer_err, 0, sizeof(int)));
+    h->d_xloc = h->d_xb; h->d_stats = h->d_xb + h->xL; h->d_xflags = reinterpret_cast<int *>(h->d_xb + 2 * h->xL);
+    if (dalloc(h, &h->d_bc, (size_t)4 * n) || dalloc(h, &h->d_d, n) ||
         dalloc(h, &h->d_Snorm, (size_t)5 * n) || dalloc(h, &h->d_free, n) || dalloc(h, &h->d_nu_state, 1) || dalloc(h, &h->d_nu_partial, NU_BLOCKS * 8) || dalloc(h, &h->d_nu_bar, 2) || dalloc(h, &h->d_Rnode, h->n_int) ||
         dalloc(h, &h->d_site_llh, h->K))
         return 1;
@@ -1246,6 +1288,88 @@ int pmm_set_option(pmm_handle *h, const char *name, int64_t value) {
     const std::string k(name);
     if (k == "slices") { h->slices = (int)std::max<int64_t>(1, std::min<int64_t>(4, value)); return 0; }
     return fail(h, "pmm_set_option: unknown option '%s'", name);
+}
+
+// ---- exchange over peer memory (pmm_peer.cuh)
+static int peer_finish_setup(pmm_handle *h, int rank, int world, double *const *bases) {
+    PeerArgs A = {};
+    A.world = world; A.rank = rank;
+    for (int p = 0; p < world; p++) {
+        A.loc[p] = bases[p]; A.red[p] = bases[p] + h->xL; A.flags[p] = reinterpret_cast<int *>(bases[p] + 2 * h->xL);
+    }
+    A.err = h->d_peer_err; A.bar = h->d_peer_bar;
+    CK(cudaMemsetAsync(h->d_xflags, 0, sizeof(int) * 2 * PEER_MAX, h->stream));
+    CK(cudaMemsetAsync(h->d_peer_err, 0, sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->peer = A; h->peer_world = world; h->peer_rank = rank; h->peer_epoch = 0;
+    return 0;
+}
+
+int pmm_peer_export(pmm_handle *h, void *handle_out) {
+    if (check_ready(h)) return 1;
+    if (!handle_out) return fail(h, "pmm_peer_export: handle_out is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PMM_PEER_HANDLE_BYTES, "PMM_PEER_HANDLE_BYTES");
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->d_xb));
+    memcpy(handle_out, &mh, sizeof mh);
+    return 0;
+}
+
+int pmm_peer_setup(pmm_handle *h, int32_t rank, int32_t world, const void *handles) {
+    if (check_ready(h)) return 1;
+    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || !handles) return fail(h, "pmm_peer_setup: need 1 <= world <= %d, 0 <= rank < world", PEER_MAX);
+    if (h->engine != 0) return fail(h, "pmm_peer_setup: the exchange over peer memory belongs to the lumped-state engine");
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));
+    peer_drop(h);
+    if (world == 1) return 0;
+    double *bases[PEER_MAX] = {};
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { bases[p] = h->d_xb; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char *)handles + (size_t)p * sizeof mh, sizeof mh);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            peer_drop(h);
+            return fail(h, "pmm_peer_setup: cannot map the exchange buffer of rank %d (%s); is there a peer-to-peer path?", p, cudaGetErrorString(e));
+        }
+        h->peer_mapped[p] = ptr;
+        bases[p] = (double *)ptr;
+    }
+    return peer_finish_setup(h, rank, world, bases);
+}
+
+int pmm_peer_setup_local(pmm_handle *h, int32_t rank, int32_t world, pmm_handle *const *peers) {
+    if (check_ready(h)) return 1;
+    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || !peers) return fail(h, "pmm_peer_setup_local: need 1 <= world <= %d, 0 <= rank < world", PEER_MAX);
+    if (h->engine != 0) return fail(h, "pmm_peer_setup_local: the exchange over peer memory belongs to the lumped-state engine");
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));
+    peer_drop(h);
+    if (world == 1) return 0;
+    double *bases[PEER_MAX] = {};
+    for (int p = 0; p < world; p++) {
+        const pmm_handle *q = (p == rank) ? h : peers[p];
+        if (!q || q->n != h->n || !q->d_xb) return fail(h, "pmm_peer_setup_local: rank %d has no tree of %d nodes", p, h->n);
+        if (q->device != h->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, h->device, q->device));
+            if (!can) return fail(h, "pmm_peer_setup_local: device %d cannot access device %d", h->device, q->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+        }
+        bases[p] = q->d_xb;
+    }
+    return peer_finish_setup(h, rank, world, bases);
+}
+
+int pmm_peer_close(pmm_handle *h) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));
+    peer_drop(h);
+    return 0;
 }
 
 int pmm_set_total_sites(pmm_handle *h, int32_t n_sites_total) {
@@ -1617,6 +1741,7 @@ int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *fre
         if (run_passes(h, true, false)) return 1;
         CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (std::isnan(cur)) return fail(h, "pmm_em: the E-step gave no likelihood (a wait of a dataflow launch or of the exchange over peer memory gave up)");
         if (std::fabs((cur - pre) / pre) < conv_eps) break;
         pre = cur;
         it++;

@@ -2,13 +2,15 @@
 
 Sites are conditionally independent given the tree and the parameters (every
 loop of the reference is ``for site in range(numsites)``, ``EM_solver.py:101,177,263``),
-so the path shards on the site axis with ONE exchange per E-step: an
-``all_reduce(sum, fp64)`` of ``[S(n,5) | Rtilde | llh]`` -- (5n+2)*8 bytes, 8 MB
-at 100k cells.  The M-step is deterministic given the reduced statistics and is
-replicated on every rank (no second exchange).  SURVEY.md 8(e).
-
-``torch.distributed`` is plumbing only: the statistics live in the engine's own
-device buffer, which is wrapped (not copied) as a tensor for the collective.
+so the path shards on the site axis with ONE exchange per E-step: the sum over
+ranks of ``[S(n,5) | Rtilde | llh]`` -- (5n+2)*8 bytes, 8 MB at 100k cells.  On
+GPUs that can map each other's memory the engine's own finishing kernel does it
+(``laml_b200/csrc/pmm_peer.cuh``: count reduction, reduce-scatter and all-gather
+over NVLink peer memory in one cooperative launch; handles exchanged once through
+``torch.distributed``); otherwise it is an NCCL ``all_reduce(sum, fp64)`` on the
+engine's statistics buffer (wrapped, not copied).  The M-step is deterministic
+given the reduced statistics and is replicated on every rank (no second
+exchange).  SURVEY.md 8(e).
 """
 from __future__ import annotations
 
@@ -55,7 +57,7 @@ class ShardedEngine:
     ``inside_dev``, ``mstep_dev``, ``download_params``, ``stats`` access), which
     is what lets the world_size-2 gloo tests drive this class on CPU."""
 
-    def __init__(self, engine, n_sites_total: int, group=None, stats_tensor=None):
+    def __init__(self, engine, n_sites_total: int, group=None, stats_tensor=None, peer=None):
         import torch.distributed as dist
         self.eng = engine
         self.dist = dist
@@ -74,9 +76,53 @@ class ShardedEngine:
             ptr, n = engine.stats_ptr()
             stats_tensor = torch.as_tensor(_DeviceArray(ptr, n), device="cuda:%d" % engine.device)
         self.stats = stats_tensor
+        # the exchange over peer memory (laml_b200/csrc/pmm_peer.cuh): the engine's finishing kernel reduces the
+        # statistics over the ranks itself, through NVLink loads / stores on the peers' buffers -- no NCCL call on the
+        # path.  Set up when every rank can map every other rank's buffer; otherwise the NCCL all-reduce stays.
+        self.peer = False
+        if self.stream is not None and self.world > 1 and peer != 0:
+            self.peer = self._setup_peers()
         self._host_stats = None
         self._llh_pin = None
         self.n_nodes = engine.n_nodes
+
+    def _setup_peers(self) -> bool:
+        import os
+        import torch
+        if os.environ.get("PMM_PEER", "1") == "0" or not hasattr(self.eng, "peer_export"):
+            return False
+        dist, dev = self.dist, "cuda:%d" % self.eng.device
+        rank = dist.get_rank(self.group)
+        try:
+            mine, ok = self.eng.peer_export(), 1.0
+        except Exception:                                           # noqa: BLE001  (e.g. PMM_ENGINE=fullstate)
+            mine, ok = bytes(64), 0.0
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local, group=self.group)
+        handles = b"".join(bytes(p.cpu().tolist()) for p in parts)
+        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if float(flag.item()) > 0.5:
+            try:
+                self.eng.peer_setup(rank, self.world, handles)
+            except Exception:                                       # noqa: BLE001
+                ok = 0.0
+        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if float(flag.item()) < 0.5:                                # all or none: a rank that cannot map a peer sends everybody to NCCL
+            self.eng.peer_close()
+            dist.barrier(group=self.group)
+            return False
+        dist.barrier(group=self.group)                              # nobody starts exchanging before everybody has cleared its flags
+        return True
+
+    def close(self):
+        """unmap the peers on every rank before any rank frees its buffers"""
+        if self.peer:
+            self.eng.peer_close()
+            self.dist.barrier(group=self.group)
+            self.peer = False
 
     def _on_stream(self):
         import contextlib
@@ -86,7 +132,7 @@ class ShardedEngine:
         return torch.cuda.stream(self.stream)
 
     def _allreduce(self):
-        if self.world > 1:
+        if self.world > 1 and not self.peer:                       # with peers the E-step's finishing kernel has done it
             with self._on_stream():
                 self.dist.all_reduce(self.stats, op=self.dist.ReduceOp.SUM, group=self.group)
 
@@ -126,7 +172,7 @@ class ShardedEngine:
         ``Estep`` then ``Mstep``) with the statistics left on the device: parameters up, E-step + all-reduce,
         M-step, parameters down.  Returns ``(d, nu, phi, llh)``; ``llh`` is the log-likelihood AT THE INPUT point
         (what the E-step's inside pass evaluates)."""
-        if self.world == 1 and hasattr(self.eng, "em_step"):
+        if (self.world == 1 or self.peer) and hasattr(self.eng, "em_step"):
             return self.eng.em_step(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)   # pmm_em_step
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
@@ -147,6 +193,10 @@ class ShardedEngine:
            conv_eps=1e-8, max_iter=1000):
         """``EM_solver.EM_optimization`` (EM_solver.py:461-512, ultra_constr=False) on
         site shards: every rank runs the same loop; one all-reduce per E-step."""
+        if self.peer:
+            # the exchange is part of the engine's E-step: the device-resident loop of the library (pmm_em) runs as on one
+            # GPU, every rank reading the same log-likelihood bits and taking the same decisions
+            return self.eng.em(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax, conv_eps, max_iter)
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
         pre = cur = self.llh()

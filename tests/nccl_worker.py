@@ -1,5 +1,6 @@
 """Worker of tests/test_zz_gpu_nccl.py, launched by ``torch.distributed.run`` with one process per GPU: the N > 1 data
-plane on real hardware -- site shards + NCCL all-reduce of ``[S | R~ | llh]``, the replicated M-step, EM to
+plane on real hardware -- site shards + the exchange of ``[S | R~ | llh]`` (over peer memory inside the engine's
+finishing kernel, or with ``PMM_PEER=0`` as an NCCL all-reduce), the replicated M-step, EM to
 convergence on shards, candidate-sharded NNI scoring -- against ONE engine holding the whole problem.  Every rank
 checks its own results; rank 0 writes the summary the test reads."""
 import json
@@ -40,7 +41,7 @@ def main(out_path):
     sh = ShardedEngine(eng, K)
     est = sh.estep(d0, w.nu, w.phi)
     S = np.array(est["S"], copy=True)
-    res = {"rank": rank, "world": world}
+    res = {"rank": rank, "world": world, "peer": bool(sh.peer)}
     res["llh_rel"] = abs(est["llh"] - ref["llh"]) / abs(ref["llh"])
     res["S_max_err"] = float(np.max(np.abs(S - ref["S"]) / (1e-10 * np.abs(ref["S"]) + 1e-12 * K)))
     res["Rtilde_rel"] = abs(est["Rtilde"] - ref["Rtilde"]) / abs(ref["Rtilde"])
@@ -70,6 +71,7 @@ def main(out_path):
     if rank == 0:
         with open(out_path, "w") as fh:
             json.dump(allres, fh)
+    sh.close()
     eng.close(); whole.close()
     dist.destroy_process_group()
 
