@@ -275,9 +275,16 @@ class Engine:
         return {"nllh": nllh.value, "d": d, "nu": nu_c.value, "phi": phi_c.value, "iters": iters.value,
                 "status": "optimal" if status.value == 0 else "failed"}
 
-    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0):
-        """``pmm_em_step``: one EM iteration, host parameters in / out: ``(d, nu, phi, llh at the input point)``"""
-        d = np.array(d, np.float64, copy=True)
+    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0, out=None):
+        """``pmm_em_step``: one EM iteration, host parameters in / out: ``(d, nu, phi, llh at the input point)``.
+        ``out``: a float64 array for the new lengths (may be ``d`` itself); if it is page-locked (``torch``'s
+        ``pin_memory``), the copy engines read and write it in place -- no staging copy in either direction."""
+        if out is None:
+            d = np.array(d, np.float64, copy=True)
+        else:
+            if out is not d:
+                np.copyto(out, d)
+            d = out
         fm = np.ascontiguousarray(free_mask, np.uint8) if free_mask is not None else None
         nu_c, phi_c, llh = C.c_double(nu), C.c_double(phi), C.c_double()
         self._ck(self._L.pmm_em_step(self._h, d.ctypes.data, C.byref(nu_c), C.byref(phi_c),

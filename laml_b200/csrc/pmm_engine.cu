@@ -1393,7 +1393,16 @@ static int ensure_pinned(pmm_handle *h) {
     return 0;
 }
 
-int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi) {
+// is `p` page-locked host memory the copy engines can read and write directly?
+static bool host_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// direct: the caller's array is page-locked and stays untouched until the stream has been synchronised (the synchronous
+// entry points): the DMA reads it in place, no staging copy
+static int upload_impl(pmm_handle *h, const double *d, double nu, double phi, bool direct) {
     if (check_ready(h)) return 1;
     if (!d) return fail(h, "pmm_upload_params: d is NULL");
     if (!(nu >= 0.0) || !(phi >= 0.0) || phi > 1.0) return fail(h, "need nu >= 0 and 0 <= phi <= 1 (got nu=%g phi=%g)", nu, phi);
@@ -1404,17 +1413,26 @@ int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi) {
     // array is free), the DMA itself is ordered on the handle's stream like every kernel
     const int n = h->n;
     double *st = h->pin_up;
-    for (int v = 0; v < n; v++) {
-        const double x = d[v];
-        if (!(x >= 0.0) || !std::isfinite(x)) return fail(h, "branch length of node %d is %g; need finite, non-negative", v, x);
-        st[v] = x;
-    }
+    int bad = 0;                                             // branch-free (vectorised): 200k lengths are staged in ~30 us
+    if (direct)
+        for (int v = 0; v < n; v++) bad |= !(d[v] >= 0.0 && d[v] <= 1.79769313486231570815e308);
+    else
+        for (int v = 0; v < n; v++) {
+            const double x = d[v];
+            bad |= !(x >= 0.0 && x <= 1.79769313486231570815e308);
+            st[v] = x;
+        }
+    if (bad)
+        for (int v = 0; v < n; v++)
+            if (!(d[v] >= 0.0) || !std::isfinite(d[v])) return fail(h, "branch length of node %d is %g; need finite, non-negative", v, d[v]);
     st[n] = nu; st[n + 1] = phi;
-    CK(cudaMemcpyAsync(h->d_d, st, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_d, direct ? d : st, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_params, st + n, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev_up, h->stream));
     return 0;
 }
+
+int pmm_upload_params(pmm_handle *h, const double *d, double nu, double phi) { return upload_impl(h, d, nu, phi, false); }
 
 int pmm_download_params(pmm_handle *h, double *d, double *nu, double *phi) {
     if (check_ready(h)) return 1;
@@ -1704,18 +1722,20 @@ int pmm_em_ultra(pmm_handle *h, double *d, double *nu, double *phi, const int8_t
 int pmm_em_step(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *free_mask, int32_t optimize_nu,
                 int32_t optimize_phi, double R, int32_t n_cells, double dmin, double dmax, double *llh) {
     if (!nu || !phi) return fail(h, "pmm_em_step: nu / phi are NULL");
-    if (pmm_upload_params(h, d, *nu, *phi)) return 1;
+    // a page-locked d (cudaHostAlloc / cudaHostRegister, e.g. torch's pin_memory) is read and written in place by the copy engines
+    const bool direct = d && host_pinned(d);
+    if (upload_impl(h, d, *nu, *phi, direct)) return 1;
     if (set_free_mask(h, free_mask)) return 1;
     if (run_passes(h, true, false)) return 1;
     if (mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
     // one synchronisation for everything that comes back: d | nu | phi | llh (at the INPUT point)
     const int n = h->n;
     double *st = h->pin_down;
-    CK(cudaMemcpyAsync(st, h->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(direct ? d : st, h->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(st + n, h->d_params, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(st + n + 2, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    memcpy(d, st, sizeof(double) * n);
+    if (!direct) memcpy(d, st, sizeof(double) * n);
     *nu = st[n]; *phi = st[n + 1];
     if (llh) *llh = st[n + 2];
     return 0;

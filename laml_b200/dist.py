@@ -167,13 +167,14 @@ class ShardedEngine:
         with self._on_stream():
             return float(self.stats[5 * self.n_nodes + 1].item())
 
-    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0):
+    def em_step(self, d, nu, phi, R, n_cells, free_mask=None, optimize_nu=True, optimize_phi=True, dmin=0.005, dmax=10.0, out=None):
         """ONE EM iteration from host parameters to host parameters (the body of the loop at EM_solver.py:483-499:
         ``Estep`` then ``Mstep``) with the statistics left on the device: parameters up, E-step + all-reduce,
         M-step, parameters down.  Returns ``(d, nu, phi, llh)``; ``llh`` is the log-likelihood AT THE INPUT point
         (what the E-step's inside pass evaluates)."""
         if (self.world == 1 or self.peer) and hasattr(self.eng, "em_step"):
-            return self.eng.em_step(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax)   # pmm_em_step
+            kw = {} if out is None else {"out": out}         # (a page-locked ``out`` is read and written in place by the copy engines)
+            return self.eng.em_step(d, nu, phi, R, n_cells, free_mask, optimize_nu, optimize_phi, dmin, dmax, **kw)   # pmm_em_step
         self.eng.upload_params(d, nu, phi)
         self.estep_dev()
         if self.stream is not None:

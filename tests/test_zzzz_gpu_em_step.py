@@ -68,3 +68,33 @@ def test_verbose_em_runs_on_em_step_and_equals_the_device_loop(capsys):
     assert abs(quiet[4] - loud[4]) <= 1e-14 and abs(quiet[5] - loud[5]) <= 1e-14
     assert "Initial phi: 0.2. Initial nu: 0.15. Initial nllh: " in text
     assert text.count("Finished EM iter: ") == loud[1] and ("Finished EM iter: %d. Current nllh: " % loud[1]) in text
+
+
+def test_em_step_in_place_on_page_locked_memory():
+    """``em_step(out=...)``: a page-locked array is read and written in place by the copy engines (no staging copies);
+    a pageable one goes through the staging buffers.  Both give the bits of the default call; bad lengths are refused
+    on either path."""
+    import torch
+    from laml_b200.capi import PMMError
+    w = make_workload(n_leaves=400, n_sites=50, a_lo=1, a_hi=20, nu=0.2, phi=0.2, seed=9)
+    f = w.forest
+    eng = Engine(400, w.qptr, w.qval, w.codes, device=0)
+    eng.set_tree(f.parent, f.left, f.right)
+    R = float((w.codes != -1).sum())
+    d0 = np.maximum(w.d, 0.01)
+    want = eng.em_step(d0, 0.2, 0.2, R, 400)
+    want2 = eng.em_step(want[0], want[1], want[2], R, 400)
+    pinned = torch.from_numpy(d0.copy()).pin_memory().numpy()
+    pageable = d0.copy()
+    for buf in (pinned, pageable):
+        a = eng.em_step(buf, 0.2, 0.2, R, 400, out=buf)
+        assert a[0] is buf and a[0].tobytes() == want[0].tobytes() and a[1:] == want[1:]
+        b = eng.em_step(buf, a[1], a[2], R, 400, out=buf)                # twice: the output of a step is the next one's input
+        assert b[0].tobytes() == want2[0].tobytes() and b[1:] == want2[1:]
+        buf[3] = np.nan
+        with pytest.raises(PMMError):
+            eng.em_step(buf, 0.2, 0.2, R, 400, out=buf)
+    other = torch.empty(len(d0), dtype=torch.float64).pin_memory().numpy()
+    c = eng.em_step(d0, 0.2, 0.2, R, 400, out=other)                     # out of place into a page-locked array
+    assert c[0] is other and other.tobytes() == want[0].tobytes() and (d0 == np.maximum(w.d, 0.01)).all()
+    eng.close()
