@@ -478,7 +478,7 @@ __device__ __forceinline__ void normalise_out(Opd &n, int F) {
 
 // Expected counts: a step yields 10 values per lane (5 per child branch) that must be summed over the warp's 32 sites.
 // They are buffered for RED_STEPS steps in a shared-memory tile, one ROW per (step, value), lane l in column l -- the
-// stores of a warp are 256 contiguous bytes, conflict-free -- and then every lane adds up ONE whole row (16 LDS.128 at a
+// stores of a warp are 256 contiguous bytes, conflict-free -- and then every lane that has a row adds it up (16 LDS.128 at a
 // row stride of 34 doubles = 4 banks mod 32: conflict-free per quarter-warp; four independent chains of eight adds) and
 // writes its sum straight to Spart.  ncu on the previous form (ten rows reduced at the end of EVERY step by twenty lanes,
 // two chains of eight adds behind the loads): a fifth of the kernel's stall samples sat on those dependent adds.
@@ -496,18 +496,23 @@ __device__ __forceinline__ void red_put5(const double *__restrict__ v, double *_
 __device__ __forceinline__ void red_flush(const double *__restrict__ red, int lane, int cnt, int i_last, const int4 *__restrict__ s_steps,
                                           double *__restrict__ Sg) {
     __syncwarp();
-    const int r = min(lane, 10 * cnt - 1);            // idle lanes repeat the last row: no divergent region
-    const double2 *row = reinterpret_cast<const double2 *>(red + r * RED_ROW);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int r = min(lane, 10 * cnt - 1);
+    // lanes without a row sit the flush out: a quarter fewer shared-memory wavefronts (ncu: the L1 data pipe is this kernel's
+    // busiest unit, 87 %, two thirds of it shared memory).  Measured against it, both slower: pairs of lanes added with a
+    // shuffle before a 16-column tile (2.93 ms), three steps per flush (2.80); this form 2.78, all lanes loading 2.81
+    if (lane < 10 * cnt) {
+        const double2 *row = reinterpret_cast<const double2 *>(red + r * RED_ROW);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int t = 0; t < 16; t += 2) {
-        const double2 x = row[t], y = row[t + 1];
-        a0 += x.x; a1 += x.y; a2 += y.x; a3 += y.y;
+        for (int t = 0; t < 16; t += 2) {
+            const double2 x = row[t], y = row[t + 1];
+            a0 += x.x; a1 += x.y; a2 += y.x; a3 += y.y;
+        }
+        const double tot = (a0 + a1) + (a2 + a3);
+        const int a = r / 10, j = r - 10 * a;          // buffered step, value (0-4: branch above v, 5-9: above w)
+        const int4 d = s_steps[i_last - (cnt - 1) + a];
+        Sg[(size_t)((j < 5) ? d.y : d.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
     }
-    const double tot = (a0 + a1) + (a2 + a3);
-    const int a = r / 10, j = r - 10 * a;              // buffered step, value (0-4: branch above v, 5-9: above w)
-    const int4 d = s_steps[i_last - (cnt - 1) + a];
-    if (lane < 10 * cnt) Sg[(size_t)((j < 5) ? d.y : d.z) * 5 + ((j < 5) ? j : j - 5)] = tot;
     __syncwarp();                                    // readers done before the next step's writers
 }
 
