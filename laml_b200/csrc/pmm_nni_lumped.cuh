@@ -20,7 +20,8 @@
 
 namespace pmm {
 
-// out of line: the barrier Newton loop must not compete for registers with the site loop of the kernel
+// out of line: the barrier Newton loop must not compete for registers with the site loop of the kernel.
+// Called by all 32 lanes of a warp with the same arguments (pmm_nni_ultra.cuh: lanes 0-4 evaluate one edge each).
 __device__ __noinline__ int ultra2_solve_dev(const NniUltra *c, const double *S, double nu, double eps_nu, double lo, double hi,
                                              bool warm, double *H, double *d5) {
     return ultra2_solve(*c, S, nu, eps_nu, lo, hi, warm, H, d5, nullptr);
@@ -178,13 +179,16 @@ __global__ void __launch_bounds__(NNIL_THREADS, 3) pmm_nni_lumped(LParams P, con
                 for (int k = 0; k < 5; k++) s_S[tid * 5 + k] = s_S[tid * 5 + k] / tot * (double)K_total;
             }
             __syncthreads();
-            if (tid == 0) {
+            if (tid < 32) {                                 // the first warp: lanes 0-4 take one edge each inside the solve
                 double d5[5];
-                const int rc = ultra2_solve_dev(ultra + ci, s_S, nu, eps_nu, dmin, dmax, st.iters > 1, s_H, d5);   // first M-step cold
-                if (rc != 0) s_done = 2;
-                else {
+                const bool warm = __shfl_sync(0xffffffffu, (int)(st.iters > 1), 0) != 0;       // first M-step cold (st lives in thread 0)
+                const int rc = ultra2_solve_dev(ultra + ci, s_S, nu, eps_nu, dmin, dmax, warm, s_H, d5);
+                if (tid == 0) {
+                    if (rc != 0) s_done = 2;
+                    else {
 #pragma unroll
-                    for (int b = 0; b < 5; b++) s_d[b] = d5[b];
+                        for (int b = 0; b < 5; b++) s_d[b] = d5[b];
+                    }
                 }
             }
             __syncthreads();

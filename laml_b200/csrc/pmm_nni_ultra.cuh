@@ -13,6 +13,10 @@
 // tests -- so a candidate scored in the batch kernel walks the same EM trajectory as one scored by the
 // host M-step on the whole tree.  Plain fp64 arithmetic, __host__ __device__: the host instance is exported as
 // pmm_debug_nni_ultra_mstep and tested against pmm_ultrametric_solve on CPU (tests/test_nni_ultra_host.py).
+// On the device the routine is called by a WHOLE WARP with the same arguments: the per-edge work of a Newton step
+// (derivatives) and of a line-search trial (values, barrier terms) -- all the transcendental calls -- is done by lanes
+// 0-4, one edge each, and handed to every lane by shuffles; the sums are then formed by every lane in the serial
+// order e = 0..4, so the device instance takes bit for bit the decisions of the host instance, five edges at a time.
 #pragma once
 #include <math.h>
 
@@ -48,6 +52,15 @@ PMM_HD void ultra2_grad_hess(const Ultra2Stats &T, int e, double x, double &g, d
     }
 }
 
+#if defined(__CUDA_ARCH__) && !defined(PMM_HOST_EMU)
+#define PMM_ULTRA2_WARP 1
+// lane e < 5 owns edge e (the other lanes repeat edge 4 and are ignored)
+PMM_HD int ultra2_my_edge() { return min((int)(threadIdx.x & 31u), 4); }
+PMM_HD double ultra2_pick(const double *x, int e) { return e == 0 ? x[0] : e == 1 ? x[1] : e == 2 ? x[2] : e == 3 ? x[3] : x[4]; }
+#else
+#define PMM_ULTRA2_WARP 0
+#endif
+
 // edge lengths (v, u, C, A, B) of heights H = (Hu, Hv, Ht)
 PMM_HD void ultra2_edges(const NniUltra &c, const double *H, double *x) {
     x[0] = H[2] - H[1]; x[1] = H[1] - H[0]; x[2] = H[1] - c.hC; x[3] = H[0] - c.hA; x[4] = H[0] - c.hB;
@@ -61,11 +74,25 @@ PMM_HD Ultra2Obj ultra2_objective(const NniUltra &c, const Ultra2Stats &T, const
     Ultra2Obj o;
     o.fsum = 0.0; o.bsum = 0.0; o.inside = true;
     ultra2_edges(c, H, x);
+#if PMM_ULTRA2_WARP
+    const int me = ultra2_my_edge();
+    const double xe = ultra2_pick(x, me);
+    const bool in = !(xe <= lo || xe >= hi);
+    const double val = in ? ultra2_value(T, me, xe) : 0.0, bar = in ? log(xe - lo) + log(hi - xe) : 0.0;
+    double v5[5], b5[5];
+    for (int e = 0; e < 5; e++) { v5[e] = __shfl_sync(0xffffffffu, val, e); b5[e] = __shfl_sync(0xffffffffu, bar, e); }
+    for (int e = 0; e < 5; e++) {
+        if (x[e] <= lo || x[e] >= hi) { o.inside = false; return o; }
+        o.fsum += v5[e];
+        o.bsum += b5[e];
+    }
+#else
     for (int e = 0; e < 5; e++) {
         if (x[e] <= lo || x[e] >= hi) { o.inside = false; return o; }
         o.fsum += ultra2_value(T, e, x[e]);
         o.bsum += log(x[e] - lo) + log(hi - x[e]);
     }
+#endif
     return o;
 }
 PMM_HD double ultra2_obj_at(const Ultra2Obj &o, double mu) { return o.inside ? o.fsum + mu * o.bsum : -INFINITY; }
@@ -110,12 +137,24 @@ PMM_HD int ultra2_solve(const NniUltra &c, const double *S, double nu, double ep
         for (int it = 0; it < 60; it++) {
             double g[5], w[5];
             ultra2_edges(c, Hc, x);
+#if PMM_ULTRA2_WARP
+            {
+                const int me = ultra2_my_edge();
+                const double xe = ultra2_pick(x, me);
+                double ge, he;
+                ultra2_grad_hess(T, me, xe, ge, he);
+                const double gm = ge + mu * (1.0 / (xe - lo) - 1.0 / (hi - xe));
+                const double wm = he - mu * (1.0 / ((xe - lo) * (xe - lo)) + 1.0 / ((hi - xe) * (hi - xe)));
+                for (int e = 0; e < 5; e++) { g[e] = __shfl_sync(0xffffffffu, gm, e); w[e] = __shfl_sync(0xffffffffu, wm, e); }
+            }
+#else
             for (int e = 0; e < 5; e++) {
                 double ge, he;
                 ultra2_grad_hess(T, e, x[e], ge, he);
                 g[e] = ge + mu * (1.0 / (x[e] - lo) - 1.0 / (hi - x[e]));
                 w[e] = he - mu * (1.0 / ((x[e] - lo) * (x[e] - lo)) + 1.0 / ((hi - x[e]) * (hi - x[e])));
             }
+#endif
             // Newton direction in (Hu, Hv[, Ht]).  A free top is separable: its edge drops out of the (u, v) system
             const double g0 = c.top_free ? 0.0 : g[0], w0 = c.top_free ? 0.0 : w[0];
             const double gu = -g[1] + g[3] + g[4], gv = -g0 + g[1] + g[2];
@@ -157,6 +196,9 @@ PMM_HD int ultra2_solve(const NniUltra &c, const double *S, double nu, double ep
     }
     ultra2_edges(c, Hc, x);
     for (int e = 0; e < 5; e++) d5[e] = fmin(fmax(x[e], lo), hi);
+#if PMM_ULTRA2_WARP || defined(PMM_HOST_EMU)
+    __syncwarp();                      // (H may be shared by the lanes: every lane has read it before any lane writes it)
+#endif
     for (int i = 0; i < 3; i++) H[i] = Hc[i];
     if (newton_iters) *newton_iters = iters;
     return status;

@@ -58,6 +58,15 @@ inline double __shfl_xor_sync(unsigned, double x, int lane_mask) {
     pthread_barrier_wait(&c->warp_bar[threadIdx.x >> 5]);
     return r;
 }
+inline double __shfl_sync(unsigned, double x, int src_lane) {
+    emu::Cta *c = emu::current();
+    c->xchg[threadIdx.x] = x;
+    pthread_barrier_wait(&c->warp_bar[threadIdx.x >> 5]);
+    const double r = c->xchg[(threadIdx.x & ~31u) + (unsigned)src_lane];
+    pthread_barrier_wait(&c->warp_bar[threadIdx.x >> 5]);
+    return r;
+}
+inline int __shfl_sync(unsigned m, int x, int src_lane) { return (int)__shfl_sync(m, (double)x, src_lane); }
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __double2hiint(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }

@@ -4,7 +4,6 @@
 #include "cuda_host_shim.h"
 #include <atomic>
 template <class T> inline T __ldcg(const T *p) { return *p; }
-inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #include "../../laml_b200/csrc/pmm_ultrametric_dev.cuh"
