@@ -83,6 +83,10 @@ struct pmm_handle {
     void *peer_mapped[PEER_MAX] = {};    // bases opened through CUDA IPC (to be closed again)
     unsigned *d_peer_bar = nullptr;
     int *d_peer_err = nullptr;
+    // scratch of the batch NNI scorer, kept from call to call (a search scores a neighbourhood per iteration; cudaMalloc /
+    // cudaFree per call cost up to 100 ms on a virtualised box)
+    NniCand *d_nni_c = nullptr; NniState *d_nni_s = nullptr; NniUltra *d_nni_u = nullptr; double *d_nni_rsum = nullptr;
+    size_t nni_cap = 0, nni_roots_cap = 0;
     double *d_Snorm = nullptr;
     unsigned char *d_free = nullptr;
     std::vector<unsigned char> free_host;   // the mask d_free holds (empty = all branches free)
@@ -1082,6 +1086,7 @@ void pmm_destroy(pmm_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_tree_state(h);
     dfree(h->d_codes); dfree(h->d_params); dfree(h->d_site_ptr); dfree(h->d_prior); dfree(h->d_qsum);
+    dfree(h->d_nni_c); dfree(h->d_nni_s); dfree(h->d_nni_u); dfree(h->d_nni_rsum);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->pin_up) cudaFreeHost(h->pin_up);
     if (h->pin_down) cudaFreeHost(h->pin_down);
@@ -1861,13 +1866,15 @@ static int score_nni_impl(pmm_handle *h, bool ultra, int32_t n_cand, const int32
         if (rc) return 1;
         double llh_total = 0.0;
         CK(cudaMemcpyAsync(&llh_total, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        NniCand *d_c = nullptr; NniState *d_s = nullptr; double *d_rsum = nullptr; NniUltra *d_u = nullptr;
-        auto cleanup = [&]() { dfree(d_c); dfree(d_s); dfree(d_rsum); dfree(d_u); };
-        const size_t keep = h->device_bytes;
-        if (dalloc(h, &d_c, n_cand) || dalloc(h, &d_s, n_cand) || dalloc(h, &d_rsum, h->n_roots) || (ultra && dalloc(h, &d_u, n_cand))) {
-            cleanup(); h->device_bytes = keep; return 1;
+        if ((size_t)n_cand > h->nni_cap || (size_t)h->n_roots > h->nni_roots_cap) {
+            dfree(h->d_nni_c); dfree(h->d_nni_s); dfree(h->d_nni_u); dfree(h->d_nni_rsum);
+            h->nni_cap = h->nni_roots_cap = 0;
+            const size_t cap = (size_t)n_cand + (size_t)n_cand / 8, rcap = (size_t)h->n_roots;
+            if (dalloc(h, &h->d_nni_c, cap) || dalloc(h, &h->d_nni_s, cap) || dalloc(h, &h->d_nni_u, cap) || dalloc(h, &h->d_nni_rsum, rcap)) return 1;
+            h->nni_cap = cap; h->nni_roots_cap = rcap;
         }
-        h->device_bytes = keep;     // scratch of this call only
+        NniCand *d_c = h->d_nni_c; NniState *d_s = h->d_nni_s; double *d_rsum = h->d_nni_rsum; NniUltra *d_u = h->d_nni_u;
+        auto cleanup = [&]() {};
         cudaError_t e = cudaMemcpyAsync(d_c, cands.data(), sizeof(NniCand) * n_cand, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess && ultra) e = cudaMemcpyAsync(d_u, ultras.data(), sizeof(NniUltra) * n_cand, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, st.data(), sizeof(NniState) * n_cand, cudaMemcpyHostToDevice, h->stream);

@@ -47,6 +47,20 @@ def emu(tmp_path_factory):
     return lib
 
 
+@pytest.fixture(scope="module")
+def emu_warp(tmp_path_factory):
+    """the same kernels with the constrained M-step in its WARP form (pmm_nni_ultra.cuh: the transcendental terms of the
+    five edges spread over twenty lanes, handed round by shuffles) -- on the GPU that is the only form"""
+    so = str(tmp_path_factory.mktemp("emu_warp") / "libemu_nni_warp.so")
+    src = os.path.join(HERE, "native", "emu_lumped.cpp")
+    extra = os.environ.get("PMM_EMU_CXXFLAGS", "").split()
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-DPMM_ULTRA2_EMU_WARP", "-I" + CUDA_INC] + extra + [src, "-o", so],
+                   check=True)
+    lib = C.CDLL(so)
+    lib.emu_nni_lumped.restype = C.c_int
+    return lib
+
+
 def pack_records(forest, m, K):
     """the model's records in the engine's memory layout: X [n_int][Kp] x (x0, xz, t, h|cum), O (o0, om, oB, oD), OI (k, F)"""
     N, n = forest.n_leaves, forest.n_nodes
@@ -153,6 +167,20 @@ def test_constrained_kernel_on_the_host(emu, seed, n, K, amax, nu, phi, step):
     np.testing.assert_allclose(nllh[ok], want["nllh"][ok], rtol=1e-9)
     np.testing.assert_allclose(d5[ok], want["d5"][ok], rtol=1e-5, atol=1e-7)
     assert (np.abs(iters[ok] - want["iters"][ok]) <= 1).all()
+
+
+def test_constrained_kernel_warp_form_on_the_host(emu, emu_warp):
+    """the warp form of the constrained M-step takes the serial form's decisions: same scores, lengths, iteration
+    counts and infeasible candidates, to the bit (the sums are formed in the serial order on every lane)"""
+    seed, n, K, amax, nu, phi, step = 92, 14, 9, 40, 0.0, 0.2, (0.006, 0.012)
+    for nu in (0.0, 0.15):
+        w = make_workload(n, K, 1, amax, max(nu, 0.1), max(phi, 0.1), seed=seed)
+        d, _ = ultrametric_lengths(w.forest, np.random.default_rng(seed), step=step)
+        a = run_kernel(emu, w, d, nu, phi, ultra=True)
+        b = run_kernel(emu_warp, w, d, nu, phi, ultra=True)
+        for x, y in zip(a[3:], b[3:]):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+        assert (a[6] == 2).sum() >= 1 and (a[6] == 1).sum() >= 5
 
 
 # ---------------------------------------------------------------------------------------------------------------------
