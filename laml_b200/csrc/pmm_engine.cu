@@ -1786,6 +1786,9 @@ static int score_nni_impl(pmm_handle *h, bool ultra, int32_t n_cand, const int32
                           double nu, double phi, double dmin, double dmax, double conv_eps, int32_t max_iter, double *out_nllh,
                           double *out_d5, int32_t *out_iters, int32_t *out_nodes) {
     if (n_cand <= 0) return 0;
+    if (h && h->peer_world > 1)
+        return fail(h, "pmm_score_nni_batch scores candidates on ALL sites of a handle: shard the candidates over the ranks "
+                       "(dist.score_nni_sharded), not the sites (this handle exchanges statistics with %d peers)", h->peer_world - 1);
     if (pmm_upload_params(h, d, nu, phi)) return 1;
     const bool lumped_nni = h->engine == 0 && !env_int("PMM_NNI_ROWS", 0);
     if (ultra && !lumped_nni) return fail(h, "pmm_score_nni_batch_ultra runs on the lumped-state engine only");

@@ -97,6 +97,12 @@ def test_ranks_in_one_process(world, n, K):
         assert d.tobytes() == outs[0][0].tobytes() and nu == outs[0][1] and phi == outs[0][2]
     np.testing.assert_allclose(outs[0][0], ref_d, rtol=1e-9, atol=1e-12)
     assert abs(outs[0][1] - ref_nu) <= 1e-9 and abs(outs[0][2] - ref_phi) <= 1e-9
+    # candidate scoring needs all sites on one handle: refused on a handle with peers (candidates shard instead)
+    from laml_b200.capi import PMMError
+    from laml_b200.nni import nni_candidates
+    cu, ck = nni_candidates(w.forest.parent, w.forest.left, N)
+    with pytest.raises(PMMError, match="shard the candidates"):
+        engs[0].score_nni_batch(cu[:4], ck[:4], d0, w.nu, w.phi)
     # dropping the peers gives back a single-GPU handle
     for e in engs:
         e.peer_close()
