@@ -337,6 +337,17 @@ __device__ __forceinline__ void inside_walk(const LParams &P, const int4 cl, int
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(d0, c0v, c0w);
     if (nsteps > 1) codes_of(d1, c1v, c1w);
+    // the first PF_DIST steps have nobody to prefetch for them: pull their far operands into L2 now.  Everything up to
+    // here reads inputs only, so it runs before the dependency wait, while the previous launch drains (a top-tier clade
+    // has a dozen steps: ncu shows its warps waiting for DRAM at the first use of nearly every loaded record)
+    for (int i = 0; i < PF_DIST && i < nsteps; i++) {
+        const int4 dp = s_steps[i];
+        if ((dp.w & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.y * P.code_stride);
+        else if (dp.w & 32) { const unsigned o = rec_index(P, dp.y, sr); prefetch_l2(P.X + 2 * (size_t)o); }
+        if (((dp.w >> 2) & 3) == KIND_LEAF) prefetch_l2(codes_s + (size_t)dp.z * P.code_stride);
+        else if (dp.w & 64) { const unsigned o = rec_index(P, dp.z, sr); prefetch_l2(P.X + 2 * (size_t)o); }
+    }
+    grid_dependency_wait();
     inside_fetch(P, d0, c0v, c0w, A, prior_site, sr, N);
 
     auto step = [&](int i, InSlot &cur, InSlot &nxt) {
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(LT, PMM_LIN_MINB) pmm_lumped_inside(LParams P,
     df_item<DF>(P, ci, blk);
     const int4 cl = clades[ci];
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, cl.y - cl.x);
-    grid_dependency_wait();
+    if (DF) grid_dependency_wait();                     // (otherwise inside the walk, after its look-ahead on the inputs)
     df_wait<DF>(P, P.df_lo + ci, blk + P.sblk0);
     inside_walk(P, cl, blk, s_steps, s_bc, s_lut);
     df_done<DF>(P, P.df_lo + ci, blk + P.sblk0);
@@ -591,7 +602,6 @@ __device__ __forceinline__ void outside_walk(const LParams &P, const int4 cl, in
     const double *prior_m1 = P.prior + __ldg(P.site_ptr + gs) - 1;       // prior of state a at [a]
     const double qsum = __ldg(P.qsum + gs);
     const int *codes_s = P.codes + gs;
-    const double invL = valid ? P.invL[(size_t)cl.z * P.K + s] : 0.0;
     double *Sg = P.Spart + (size_t)grp * P.n_nodes * 5;
 
     // leaf codes of a step (two steps ahead: the prior of a leaf's state is a dependent gather)
@@ -615,6 +625,16 @@ __device__ __forceinline__ void outside_walk(const LParams &P, const int4 cl, in
     int c0v = 0, c0w = 0, c1v = 0, c1w = 0;
     codes_of(s_rows[0], c0v, c0w);
     codes_of(s_rows[1], c1v, c1w);                       // the staged lists are padded with copies of the last step
+    // operands of the first PF_DIST_OUT steps into L2 (nobody prefetches for them), the out-record a step LOADS included;
+    // like everything above this reads inputs or only warms L2, so it precedes the dependency wait
+    for (int i = 0; i < PF_DIST_OUT; i++) {
+        const uint4 rp = s_rows[i];
+        prefetch_l2_either(rp.w & 4, codes_s + rp.y, P.X + 2 * (size_t)(rp.y + s_raw));
+        prefetch_l2_either(rp.w & 8, codes_s + rp.z, P.X + 2 * (size_t)(rp.z + s_raw));
+        if (rp.w & 1) { prefetch_l2(P.O + (rp.x + s_raw)); prefetch_l2(P.OI + (rp.x + s_raw)); }
+    }
+    grid_dependency_wait();
+    const double invL = valid ? P.invL[(size_t)cl.z * P.K + s] : 0.0;
     fetch(s_rows[0], c0v, c0w, A);
 
     auto step = [&](int i, OutSlot &cur, OutSlot &nxt) {
@@ -706,7 +726,7 @@ __global__ void __launch_bounds__(LT, PMM_LOUT_MINB) pmm_lumped_outside(LParams 
     const int4 cl = clades[ci];
     stage_clade(s_steps, s_bc, s_lut, P, steps, cl.x, cl.y - cl.x);
     stage_rows(s_rows, s_steps, P, cl.y - cl.x);
-    grid_dependency_wait();
+    if (DF) grid_dependency_wait();                     // (otherwise inside the walk, after its look-ahead on the inputs)
     df_wait<DF>(P, P.df_lo + ci, blk + P.sblk0);
     outside_walk<POST>(P, cl, blk, s_steps, s_rows, s_bc, s_lut, s_red);
     df_done<DF>(P, P.df_lo + ci, blk + P.sblk0);

@@ -19,7 +19,7 @@ def worker(workloads):
         pass
     for wl in workloads:
         cache = "/tmp/pmm_wl_%s.npz" % wl
-        spec = dict(CONFIGS["config3_10k_x_500" if wl == "config3" else "config4_100k_x_2k"])
+        spec = dict(CONFIGS[{"config3": "config3_10k_x_500", "config2": "config2_1k_x_30", "config5": "config5_5k_x_300"}.get(wl, "config4_100k_x_2k")])
         if wl.startswith("shard"):
             spec["n_sites"] = int(wl[5:])
         if os.path.exists(cache):
