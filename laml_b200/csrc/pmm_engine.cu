@@ -630,9 +630,11 @@ int build_lumped_schedule(pmm_handle *h, const std::vector<int> &order, const st
     const int N = h->n_leaves, n = h->n_int + N;
     int C0 = env_int("PMM_CLADE", 0);
     if (C0 <= 0) {
-        // enough CTAs for ~8 waves over the SMs, chains of 16..120 steps
+        // enough CTAs for ~5.5 waves over the SMs (at four resident CTAs per SM), chains of 16..120 steps; measured on a 250-site
+        // shard of the 100k-cell tree: capacity 42 (8 waves) 0.663 ms per E-step, 52: 0.653, 60: 0.649, 68: 0.642-0.654
+        // (profiles/r2_clade_sweeps.log)
         const double site_blocks = (double)((h->K + LT - 1) / LT);
-        const double want_clades = 8.0 * h->n_sms * 4.0 / site_blocks;
+        const double want_clades = 5.5 * h->n_sms * 4.0 / site_blocks;
         C0 = (int)((double)h->n_int / std::max(want_clades, 1.0));
         C0 = std::max(16, std::min(120, C0));
     }
