@@ -934,6 +934,20 @@ int check_ready(pmm_handle *h) {
     return 0;
 }
 
+// After a synchronisation of the handle's stream: did a wait of the exchange over peer memory (pmm_peer.cuh) or of a
+// dataflow launch give up?  The statistics are then incomplete (a late peer's push may even have replaced the NaN the
+// kernel left in the likelihood slot), so every entry point that hands results to the host asks here first.
+int waits_ok(pmm_handle *h) {
+    int e[2] = {0, 0};
+    if (h->peer_world > 1) CK(cudaMemcpy(&e[0], h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->df_mode) CK(cudaMemcpy(&e[1], h->d_df_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e[0])
+        return fail(h, "the exchange over peer memory gave up waiting for a peer after ~2 s (rank %d of %d): a rank that did not make "
+                       "the same call, or kernels of several ranks sharing one GPU's work queues; set up the peers again", h->peer_rank, h->peer_world);
+    if (e[1]) return fail(h, "a dataflow launch gave up waiting for a producer clade (PMM_DF): please report");
+    return 0;
+}
+
 // free-branch mask of the M-step: NULL means "every branch is free" (never "whatever the last call left"); the
 // handle remembers what the device holds, so repeating a mask costs a memcmp and no copy
 int set_free_mask(pmm_handle *h, const uint8_t *free_mask) {
@@ -1449,6 +1463,7 @@ int pmm_download_params(pmm_handle *h, double *d, double *nu, double *phi) {
     if (d) CK(cudaMemcpyAsync(st, h->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(st + n, h->d_params, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (waits_ok(h)) return 1;
     if (d) memcpy(d, st, sizeof(double) * n);
     if (nu) *nu = st[n];
     if (phi) *phi = st[n + 1];
@@ -1473,14 +1488,14 @@ int pmm_read_llh(pmm_handle *h, double *llh) {
     if (!llh) return fail(h, "pmm_read_llh: llh is NULL");
     CK(cudaMemcpyAsync(llh, h->d_stats + (size_t)5 * h->n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return waits_ok(h);
 }
 
 int pmm_sync(pmm_handle *h) {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return h->n ? waits_ok(h) : 0;
 }
 
 int pmm_inside(pmm_handle *h, const double *d, double nu, double phi, double *site_llh, double *llh) {
@@ -1489,7 +1504,7 @@ int pmm_inside(pmm_handle *h, const double *d, double nu, double phi, double *si
     if (llh) CK(cudaMemcpyAsync(llh, h->d_stats + (size_t)5 * h->n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (site_llh) CK(cudaMemcpyAsync(site_llh, h->d_site_llh, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return waits_ok(h);
 }
 
 int pmm_estep(pmm_handle *h, const double *d, double nu, double phi, double *S, double *Rtilde, double *llh, double *site_llh) {
@@ -1501,7 +1516,7 @@ int pmm_estep(pmm_handle *h, const double *d, double nu, double phi, double *S, 
     if (llh) CK(cudaMemcpyAsync(llh, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (site_llh) CK(cudaMemcpyAsync(site_llh, h->d_site_llh, sizeof(double) * h->K, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return waits_ok(h);
 }
 
 int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double *post0, double *post1) {
@@ -1512,7 +1527,7 @@ int pmm_posteriors(pmm_handle *h, const double *d, double nu, double phi, double
     if (post0) CK(cudaMemcpyAsync(post0, h->d_post0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
     if (post1) CK(cudaMemcpyAsync(post1, h->d_post1, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return waits_ok(h);
 }
 
 // the M-step on the device with the mask d_free holds
@@ -1707,6 +1722,7 @@ int pmm_em_ultra(pmm_handle *h, double *d, double *nu, double *phi, const int8_t
     if (run_passes(h, true, false)) return 1;
     CK(cudaMemcpyAsync(&pre, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (waits_ok(h)) return 1;
     cur = pre;
     int it = 1, st = 0, last = 0;
     while (it <= max_iter) {
@@ -1714,8 +1730,11 @@ int pmm_em_ultra(pmm_handle *h, double *d, double *nu, double *phi, const int8_t
         if (st == 1) break;                              // "d_infeasible": the parameters of the previous iterate stand (:497-499)
         last = st;
         if (run_passes(h, true, false)) return 1;
+        int gave_up = 0;                                 // (rides along with the likelihood: one synchronisation)
+        if (h->peer_world > 1) CK(cudaMemcpyAsync(&gave_up, h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (gave_up && waits_ok(h)) return 1;
         if (std::fabs((cur - pre) / pre) < conv_eps) break;
         pre = cur;
         it++;
@@ -1742,6 +1761,7 @@ int pmm_em_step(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t
     CK(cudaMemcpyAsync(st + n, h->d_params, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(st + n + 2, h->d_stats + (size_t)5 * n + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (waits_ok(h)) return 1;
     if (!direct) memcpy(d, st, sizeof(double) * n);
     *nu = st[n]; *phi = st[n + 1];
     if (llh) *llh = st[n + 2];
@@ -1761,13 +1781,17 @@ int pmm_em(pmm_handle *h, double *d, double *nu, double *phi, const uint8_t *fre
     if (run_passes(h, true, false)) return 1;
     CK(cudaMemcpyAsync(&pre, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (waits_ok(h)) return 1;
     cur = pre;
     int it = 1;
     while (it <= max_iter) {
         if (mstep_dev_impl(h, R, n_cells, optimize_nu, optimize_phi, dmin, dmax, 1e-6, 1e-5)) return 1;
         if (run_passes(h, true, false)) return 1;
+        int gave_up = 0;                                 // (rides along with the likelihood: one synchronisation)
+        if (h->peer_world > 1) CK(cudaMemcpyAsync(&gave_up, h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(&cur, h->d_stats + n5 + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (gave_up && waits_ok(h)) return 1;
         if (std::isnan(cur)) return fail(h, "pmm_em: the E-step gave no likelihood (a wait of a dataflow launch or of the exchange over peer memory gave up)");
         if (std::fabs((cur - pre) / pre) < conv_eps) break;
         pre = cur;

@@ -13,7 +13,9 @@
 // Buffers: one allocation per rank, shared by CUDA IPC (or plain pointers when the ranks live in one process):
 //   [ loc: L doubles | red: L doubles | flags: 2 x PEER_MAX ints ]      L = 5 n + 2 padded to an even count
 // `red` IS the handle's statistics buffer (pmm_stats_dev_ptr).  Flags hold the call count (epoch): nothing is reset.
-// A wait that sees nothing for ~2 s gives up and raises the error word (the likelihood becomes NaN) instead of hanging.
+// A wait that sees nothing for ~2 s gives up and raises the handle's error word instead of hanging the GPU; the host side
+// (pmm_engine.cu: waits_ok) turns it into a failed call at the next synchronisation -- the NaN this kernel leaves in the
+// likelihood slot is only a second line of defence: a late peer's push can replace it.
 #pragma once
 #include "pmm_kernels.cuh"
 

@@ -82,7 +82,11 @@ def run_case(world, n, K):
         for o in own[1:]:
             llh_want, rt_want = llh_want + o["llh"], rt_want + o["Rtilde"]
         assert np.isfinite(st[0][5 * nn + 1])
-        assert S.tobytes() == want.tobytes() and st[0][5 * nn + 1] == llh_want and st[0][5 * nn] == rt_want
+        assert st[0][5 * nn + 1] == llh_want, ("llh", rep, st[0][5 * nn + 1], llh_want)
+        assert st[0][5 * nn] == rt_want, ("Rtilde", rep, st[0][5 * nn], rt_want)
+        if S.tobytes() != want.tobytes():
+            bad = np.argwhere(S != want)
+            raise AssertionError(("S", rep, len(bad), bad[:5].tolist(), S[S != want][:5].tolist(), want[S != want][:5].tolist()))
         np.testing.assert_allclose(S, ref["S"], rtol=1e-10, atol=1e-12 * K)
         assert abs(st[0][5 * nn + 1] - ref["llh"]) <= 1e-12 * abs(ref["llh"])
         assert abs(st[0][5 * nn] - ref["Rtilde"]) <= 1e-12 * abs(ref["Rtilde"])
@@ -133,8 +137,31 @@ def run_case(world, n, K):
 
 
 if __name__ == "__main__":
+    from laml_b200.capi import PMMError
+
+    def guarded(*a):
+        """a wait that gave up surfaces as an error at the next synchronisation (pmm_sync, pmm_download_params, ...)"""
+        try:
+            run_case(*a)
+        except PMMError as exc:
+            if "gave up waiting" in str(exc):
+                raise ExchangeTimeout(str(exc)[:80])
+            raise
+
+    if len(sys.argv) > 4:                                # repetitions: how often does a wait give up on this box?
+        import time
+        gave_up = 0
+        for rep in range(int(sys.argv[4])):
+            t0 = time.perf_counter()
+            try:
+                guarded(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
+            except ExchangeTimeout as exc:
+                gave_up += 1
+                print("run %d: exchange gave up waiting (%s) after %.2f s" % (rep, exc, time.perf_counter() - t0), flush=True)
+        print("%d of %s runs gave up" % (gave_up, sys.argv[4]), flush=True)
+        sys.exit(0)
     try:
-        run_case(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
+        guarded(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
     except ExchangeTimeout as exc:
         print("exchange gave up waiting:", exc, flush=True)
         sys.exit(3)
