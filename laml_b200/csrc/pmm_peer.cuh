@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(PEER_THREADS) pmm_finish_peer(const double *__
     // ---- C: my slice, summed over the ranks in rank order, pushed into every rank's statistics
     const int first = with_counts ? 0 : n5;                      // inside pass only: [R~ | llh] (R~ keeps its value: same local parts)
     const int len = n5 + 2 - first;
-    const int per = (((len + W - 1) / W) + 1) & ~1;              // even slice length: 16-byte accesses stay aligned (first is even or n5...)
+    const int per = (((len + W - 1) / W) + 1) & ~1;              // even slice length: with an even `first` every slice starts 16-byte aligned
     const int lo = first + min(len, me * per), hi = first + min(len, (me + 1) * per);
     const bool vec = ((first & 1) == 0);                         // slices start on even elements of 16-byte aligned buffers
     if (vec) {
