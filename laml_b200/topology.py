@@ -181,8 +181,8 @@ class GPU_Topology_search:
         # neighbourhood (``dist.score_nni_sharded``)
         # batch_ultra: score the neighbourhood in one launch under ``ultra_constr`` too (the two-height M-step of
         # pmm_nni_ultra.cuh).  On by default since it has been verified and timed on a B200 (tests/test_zzz_gpu_nni_ultra.py;
-        # BASELINE config 5: 9 996 constrained candidates in 22.9 ms on one GPU, 5.1 ms on eight,
-        # profiles/r2a_config5_nni_n1.json / r2b_config5_nni_n8.json); PMM_NNI_ULTRA_BATCH=0 or batch_ultra=False restores
+        # BASELINE config 5: 9 996 constrained candidates in 7.0 ms on one GPU, 2.5 ms on eight,
+        # profiles/r2j_config5_nni_n1.json / r2j_config5_nni_n8.json); PMM_NNI_ULTRA_BATCH=0 or batch_ultra=False restores
         # the reference's candidate-by-candidate sequence
         import os
         self.batch_ultra = bool(int(os.environ.get("PMM_NNI_ULTRA_BATCH", "1"))) if batch_ultra is None else bool(batch_ultra)
