@@ -79,6 +79,7 @@ struct pmm_handle {
     int *d_xflags = nullptr;
     size_t xL = 0;                  // doubles per part (5n + 2 rounded up to even)
     int peer_world = 1, peer_rank = 0, peer_epoch = 0;
+    bool peer_lost = false;         // a pmm_set_tree with another node count freed the exchange block the peers had mapped
     PeerArgs peer = {};
     void *peer_mapped[PEER_MAX] = {};    // bases opened through CUDA IPC (to be closed again)
     unsigned *d_peer_bar = nullptr;
@@ -207,6 +208,7 @@ void free_tree_state(pmm_handle *h) {
     dfree(h->d_X); dfree(h->d_O); dfree(h->d_iexp); dfree(h->d_dexp); dfree(h->d_eX); dfree(h->d_eO); dfree(h->d_sqX);
     dfree(h->d_rootInvL); dfree(h->d_root_site_llh);
     dfree(h->d_Spart); dfree(h->d_Rpart); dfree(h->d_Rnode); dfree(h->d_site_llh);
+    if (h->peer_world > 1) h->peer_lost = true;
     peer_drop(h);
     dfree(h->d_bc); dfree(h->d_d); dfree(h->d_xb); h->d_stats = h->d_xloc = nullptr; h->d_xflags = nullptr; dfree(h->d_peer_bar); dfree(h->d_peer_err);
     dfree(h->d_Snorm); dfree(h->d_free); dfree(h->d_nu_state); dfree(h->d_nu_partial); dfree(h->d_nu_bar);
@@ -778,6 +780,9 @@ LParams make_lparams(pmm_handle *h, int ci, bool with_post) {
 
 int run_lumped(pmm_handle *h, bool outside, bool with_post) {
     const int n = h->n;
+    if (h->peer_lost)
+        return fail(h, "this handle exchanged statistics with peers until pmm_set_tree changed the node count and freed the exchange "
+                       "buffer: call pmm_peer_export / pmm_peer_setup again on every rank (or pmm_peer_close to go on alone)");
     CK(cudaEventRecord(h->ev[0], h->stream));
     pmm_branch_consts<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_d, h->d_params, n, h->d_bc);
     h->launches++;
@@ -1323,6 +1328,7 @@ static int peer_finish_setup(pmm_handle *h, int rank, int world, double *const *
     CK(cudaMemsetAsync(h->d_peer_err, 0, sizeof(int), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->peer = A; h->peer_world = world; h->peer_rank = rank; h->peer_epoch = 0;
+    h->peer_lost = false;
     return 0;
 }
 
@@ -1342,6 +1348,7 @@ int pmm_peer_setup(pmm_handle *h, int32_t rank, int32_t world, const void *handl
     if (h->engine != 0) return fail(h, "pmm_peer_setup: the exchange over peer memory belongs to the lumped-state engine");
     if (h->stream) CK(cudaStreamSynchronize(h->stream));
     peer_drop(h);
+    h->peer_lost = false;
     if (world == 1) return 0;
     double *bases[PEER_MAX] = {};
     for (int p = 0; p < world; p++) {
@@ -1367,6 +1374,7 @@ int pmm_peer_setup_local(pmm_handle *h, int32_t rank, int32_t world, pmm_handle 
     if (h->engine != 0) return fail(h, "pmm_peer_setup_local: the exchange over peer memory belongs to the lumped-state engine");
     if (h->stream) CK(cudaStreamSynchronize(h->stream));
     peer_drop(h);
+    h->peer_lost = false;
     if (world == 1) return 0;
     double *bases[PEER_MAX] = {};
     for (int p = 0; p < world; p++) {
@@ -1390,6 +1398,7 @@ int pmm_peer_close(pmm_handle *h) {
     CK(cudaSetDevice(h->device));
     if (h->stream) CK(cudaStreamSynchronize(h->stream));
     peer_drop(h);
+    h->peer_lost = false;
     return 0;
 }
 
