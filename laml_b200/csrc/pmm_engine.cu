@@ -944,8 +944,11 @@ int check_ready(pmm_handle *h) {
 // kernel left in the likelihood slot), so every entry point that hands results to the host asks here first.
 int waits_ok(pmm_handle *h) {
     int e[2] = {0, 0};
-    if (h->peer_world > 1) CK(cudaMemcpy(&e[0], h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (h->df_mode) CK(cudaMemcpy(&e[1], h->d_df_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->peer_world <= 1 && !h->df_mode) return 0;
+    // (on the handle's own stream, which the caller has just synchronised: no implicit join with other streams of the process)
+    if (h->peer_world > 1) CK(cudaMemcpyAsync(&e[0], h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->df_mode) CK(cudaMemcpyAsync(&e[1], h->d_df_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     if (e[0])
         return fail(h, "the exchange over peer memory gave up waiting for a peer after ~2 s (rank %d of %d): a rank that did not make "
                        "the same call, or kernels of several ranks sharing one GPU's work queues; set up the peers again", h->peer_rank, h->peer_world);
