@@ -80,7 +80,7 @@ class ShardedEngine:
         # statistics over the ranks itself, through NVLink loads / stores on the peers' buffers -- no NCCL call on the
         # path.  Set up when every rank can map every other rank's buffer; otherwise the NCCL all-reduce stays.
         self.peer = False
-        if self.stream is not None and self.world > 1 and peer != 0:
+        if self.world > 1 and (peer if peer is not None else self.stream is not None):
             self.peer = self._setup_peers()
         self._host_stats = None
         self._llh_pin = None
@@ -91,7 +91,8 @@ class ShardedEngine:
         import torch
         if os.environ.get("PMM_PEER", "1") == "0" or not hasattr(self.eng, "peer_export"):
             return False
-        dist, dev = self.dist, "cuda:%d" % self.eng.device
+        dist = self.dist
+        dev = "cuda:%d" % self.eng.device if self.stream is not None else "cpu"      # ("cpu": the gloo tests of this protocol)
         rank = dist.get_rank(self.group)
         try:
             mine, ok = self.eng.peer_export(), 1.0

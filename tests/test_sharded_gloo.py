@@ -251,3 +251,66 @@ def test_candidate_sharded_ultrametric_search_matches_single_process():
     assert ret2[0][0] == ret2[1][0] == ret1[0][0]
     assert ret2[0][1] == ret2[1][1] == ret1[0][1]
     assert ret2[0][2] == ret1[0][2] and ret2[0][3] == ret1[0][3]
+
+
+class _PeerFake:
+    """what ShardedEngine needs of an engine to set up the exchange over peer memory, with scripted failures"""
+    device, n_nodes = 0, 3
+
+    def __init__(self, rank, fail_export=(), fail_setup=()):
+        self.rank, self.fail_export, self.fail_setup = rank, fail_export, fail_setup
+        self.calls = []
+
+    def set_total_sites(self, k):
+        pass
+
+    def peer_export(self):
+        self.calls.append("export")
+        if self.rank in self.fail_export:
+            raise RuntimeError("no exchange buffer")
+        return bytes([self.rank + 1]) * 64
+
+    def peer_setup(self, rank, world, handles):
+        self.calls.append(("setup", rank, world, handles))
+        if self.rank in self.fail_setup:
+            raise RuntimeError("cannot map a peer")
+
+    def peer_close(self):
+        self.calls.append("close")
+
+
+def _peer_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laml_b200.dist import ShardedEngine
+    out = {}
+    for name, kw in (("ok", {}), ("export_fails_on_1", {"fail_export": (1,)}), ("setup_fails_on_0", {"fail_setup": (0,)})):
+        eng = _PeerFake(rank, **kw)
+        sh = ShardedEngine(eng, 10, stats_tensor=torch.zeros(17, dtype=torch.float64), peer=True)
+        out[name] = (sh.peer, [c if isinstance(c, str) else c[0] for c in eng.calls],
+                     [c[3] for c in eng.calls if not isinstance(c, str)])
+        sh.close()
+        out[name + "_after_close"] = [c if isinstance(c, str) else c[0] for c in eng.calls]
+    os.environ.pop("PMM_PEER", None)
+    os.environ["PMM_PEER"] = "0"
+    eng = _PeerFake(rank)
+    out["env_off"] = (ShardedEngine(eng, 10, stats_tensor=torch.zeros(17, dtype=torch.float64), peer=True).peer, list(eng.calls))
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_peer_setup_is_all_or_none():
+    """ShardedEngine._setup_peers: handles are all-gathered in rank order and every rank maps them; if ANY rank cannot
+    export or map, EVERY rank drops the peers and keeps the NCCL all-reduce (no rank may exchange alone)"""
+    port = 29800 + os.getpid() % 150
+    ret = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(2, port, ret), nprocs=2, join=True)
+    want_handles = bytes([1]) * 64 + bytes([2]) * 64
+    for rank in (0, 1):
+        r = ret[rank]
+        assert r["ok"][0] is True and r["ok"][1] == ["export", "setup"] and r["ok"][2] == [want_handles]
+        assert r["ok_after_close"] == ["export", "setup", "close"]
+        assert r["export_fails_on_1"][0] is False and "setup" not in r["export_fails_on_1"][1] and "close" in r["export_fails_on_1"][1]
+        assert r["setup_fails_on_0"][0] is False and r["setup_fails_on_0"][1].count("close") == 1
+        assert r["setup_fails_on_0_after_close"].count("close") == 1            # close() of a ShardedEngine without peers does nothing
+        assert r["env_off"] == (False, [])
