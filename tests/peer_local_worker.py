@@ -47,6 +47,16 @@ def _shards(w, world):
     return engs
 
 
+def on_every_rank(engs, fn):
+    """``fn(engine)`` for all ranks at once, one host thread per rank as in the production layout (one process per rank):
+    a call that synchronises with the device inside -- a rank that walks its sites in several chunks does -- must not keep
+    the other ranks from being launched (ctypes releases the GIL for the duration of the C call)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(engs)) as pool:
+        for f in [pool.submit(fn, e) for e in engs]:
+            f.result()
+
+
 def run_case(world, n, K):
     from laml_b200.capi import Engine
     from laml_b200.synth import make_workload
@@ -65,10 +75,8 @@ def run_case(world, n, K):
     for e in engs:
         e.upload_params(d0, w.nu, w.phi)
     for rep in range(3):                           # flags and barrier counters carry over from call to call
-        for e in engs:
-            e.estep_dev()                           # asynchronous: the ranks' kernels wait for each other on the device
-        for e in engs:
-            e.sync()
+        on_every_rank(engs, lambda e: e.estep_dev())    # the ranks' kernels wait for each other on the device
+        on_every_rank(engs, lambda e: e.sync())
         st = [_stats(e) for e in engs]
         if any(np.isnan(s[5 * nn + 1]) for s in st):
             raise ExchangeTimeout("E-step %d" % rep)
@@ -91,10 +99,8 @@ def run_case(world, n, K):
         assert abs(st[0][5 * nn + 1] - ref["llh"]) <= 1e-12 * abs(ref["llh"])
         assert abs(st[0][5 * nn] - ref["Rtilde"]) <= 1e-12 * abs(ref["Rtilde"])
     # inside pass only: just the likelihood is exchanged, the counts stay
-    for e in engs:
-        e.inside_dev()
-    for e in engs:
-        e.sync()
+    on_every_rank(engs, lambda e: e.inside_dev())
+    on_every_rank(engs, lambda e: e.sync())
     st2 = [_stats(e) for e in engs]
     if any(np.isnan(s[5 * nn + 1]) for s in st2):
         raise ExchangeTimeout("inside pass")
@@ -107,9 +113,7 @@ def run_case(world, n, K):
     for it in range(4):
         est = whole.estep(ref_d, ref_nu, ref_phi)
         ref_d, ref_nu, ref_phi = whole.mstep(est["S"], est["Rtilde"], R, N, ref_d, ref_nu, ref_phi)
-        for e in engs:
-            e.estep_dev()
-            e.mstep_dev(R, N)
+        on_every_rank(engs, lambda e: (e.estep_dev(), e.mstep_dev(R, N)))
     outs = [e.download_params() for e in engs]
     if any(np.isnan(_stats(e)[5 * nn + 1]) for e in engs):
         raise ExchangeTimeout("EM iterations")

@@ -20,9 +20,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 
-@pytest.mark.parametrize("world,n,K", [(2, 700, 300), (3, 90, 50), (4, 2000, 520), (8, 300, 64)])
-def test_ranks_in_one_process(world, n, K):
+@pytest.mark.parametrize("world,n,K,chunks", [(2, 700, 300, 0), (3, 90, 50, 0), (4, 2000, 520, 0), (8, 300, 64, 0), (2, 500, 400, 3)])
+def test_ranks_in_one_process(world, n, K, chunks):
+    """chunks > 0: every rank walks its sites in that many chunks (PMM_CHUNKS: what a rank does when its records do not
+    fit the memory budget) -- the earlier chunks' sums accumulate in the rank's own buffer, the last chunk's finishing
+    kernel adds its part and exchanges"""
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", PMM_SLICES="1")
+    if chunks:
+        env["PMM_CHUNKS"] = str(chunks)
     cmd = [sys.executable, os.path.join(HERE, "peer_local_worker.py"), str(world), str(n), str(K)]
     for attempt in range(4):
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=500, env=env)
