@@ -156,7 +156,8 @@ int pmm_mstep_dev(pmm_handle *h, double R, int32_t n_cells, const uint8_t *free_
  *   pmm_peer_setup_local the same for ranks that are handles of ONE process (peers[rank] may be NULL)
  *   pmm_peer_close       unmap the peers (call on every rank before any of them destroys its handle)
  * A pmm_set_tree that changes the node count frees the exchange buffer: export / set up again afterwards.
- * A rank that waits ~2 s for a peer in vain gives up instead of hanging the GPU: its statistics are then incomplete, and
+ * A rank that waits for a peer in vain (PMM_PEER_TIMEOUT_MS, read at set-up, default 30 s: ranks may drift apart between two
+ * calls) gives up instead of hanging the GPU: its statistics are then incomplete, and
  * the next entry point that synchronises with the host (pmm_sync, pmm_read_llh, pmm_download_params, pmm_estep, pmm_inside,
  * pmm_em, pmm_em_step, ...) fails with an error that names the rank.  One rank per GPU: kernels of several ranks that wait
  * for each other on ONE GPU can block each other in the device's work queues (tests only; CUDA_DEVICE_MAX_CONNECTIONS=32).

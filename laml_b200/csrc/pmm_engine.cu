@@ -950,8 +950,9 @@ int waits_ok(pmm_handle *h) {
     if (h->df_mode) CK(cudaMemcpyAsync(&e[1], h->d_df_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (e[0])
-        return fail(h, "the exchange over peer memory gave up waiting for a peer after ~2 s (rank %d of %d): a rank that did not make "
-                       "the same call, or kernels of several ranks sharing one GPU's work queues; set up the peers again", h->peer_rank, h->peer_world);
+        return fail(h, "the exchange over peer memory gave up waiting for a peer (rank %d of %d; PMM_PEER_TIMEOUT_MS, default 30 s): a rank "
+                       "that did not make the same call, or kernels of several ranks sharing one GPU's work queues; set up the peers again",
+                    h->peer_rank, h->peer_world);
     if (e[1]) return fail(h, "a dataflow launch gave up waiting for a producer clade (PMM_DF): please report");
     return 0;
 }
@@ -1327,6 +1328,11 @@ static int peer_finish_setup(pmm_handle *h, int rank, int world, double *const *
         A.loc[p] = bases[p]; A.red[p] = bases[p] + h->xL; A.flags[p] = reinterpret_cast<int *>(bases[p] + 2 * h->xL);
     }
     A.err = h->d_peer_err; A.bar = h->d_peer_bar;
+    {   // how long a rank waits for its peers before it gives up, in SM cycles
+        int khz = 1900000;
+        (void)cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+        A.patience = (long long)std::max(1, env_int("PMM_PEER_TIMEOUT_MS", 30000)) * (long long)khz;
+    }
     CK(cudaMemsetAsync(h->d_xflags, 0, sizeof(int) * 2 * PEER_MAX, h->stream));
     CK(cudaMemsetAsync(h->d_peer_err, 0, sizeof(int), h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -13,7 +13,8 @@
 // Buffers: one allocation per rank, shared by CUDA IPC (or plain pointers when the ranks live in one process):
 //   [ loc: L doubles | red: L doubles | flags: 2 x PEER_MAX ints ]      L = 5 n + 2 padded to an even count
 // `red` IS the handle's statistics buffer (pmm_stats_dev_ptr).  Flags hold the call count (epoch): nothing is reset.
-// A wait that sees nothing for ~2 s gives up and raises the handle's error word instead of hanging the GPU; the host side
+// A wait that sees nothing for PMM_PEER_TIMEOUT_MS (default 30 s: ranks may drift apart between two calls -- one writes a
+// checkpoint, another is descheduled) gives up and raises the handle's error word instead of hanging the GPU; the host side
 // (pmm_engine.cu: waits_ok) turns it into a failed call at the next synchronisation -- the NaN this kernel leaves in the
 // likelihood slot is only a second line of defence: a late peer's push can replace it.
 #pragma once
@@ -30,6 +31,7 @@ struct PeerArgs {
     double *red[PEER_MAX];                // every rank's statistics buffer
     int *flags[PEER_MAX];                 // every rank's flags: [2][PEER_MAX]
     int epoch;                            // this call's number (the host counts; ranks call in lockstep, as with any collective)
+    long long patience;                   // SM cycles a wait may last before it gives up (PMM_PEER_TIMEOUT_MS, default 30 s)
     int *err;
     unsigned *bar;                        // grid barrier of this rank: [0] arrivals, [1] CTAs that have left (both zero between launches)
 };
@@ -37,13 +39,13 @@ struct PeerArgs {
 __device__ __forceinline__ void peer_signal(int *flag, int epoch) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ void peer_wait(const int *flag, int epoch, int *err) {
+__device__ __forceinline__ void peer_wait(const int *flag, int epoch, long long patience, int *err) {
     const long long t0 = clock64();
     for (unsigned polls = 1;; polls++) {
         int v;
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v - epoch >= 0) break;        // (a peer that is already one call ahead has passed this point too)
-        if ((polls & 255u) == 0 && (clock64() - t0 > (1ll << 32) || *(volatile int *)err)) { *err = 2; break; }
+        if ((polls & 255u) == 0 && (clock64() - t0 > patience || *(volatile int *)err)) { *err = 2; break; }
         __nanosleep(100);
     }
 }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(PEER_THREADS) pmm_finish_peer(const double *__
     // ---- B: "my sums are there" to every peer; wait for every peer's
     const int W = A.world, me = A.rank;
     if (blockIdx.x == 0 && tid < W && tid != me) peer_signal(A.flags[tid] + me, A.epoch);
-    if (tid < W && tid != me) peer_wait(A.flags[me] + tid, A.epoch, A.err);
+    if (tid < W && tid != me) peer_wait(A.flags[me] + tid, A.epoch, A.patience, A.err);
     __syncthreads();
     // ---- C: my slice, summed over the ranks in rank order, pushed into every rank's statistics
     const int first = with_counts ? 0 : n5;                      // inside pass only: [R~ | llh] (R~ keeps its value: same local parts)
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(PEER_THREADS) pmm_finish_peer(const double *__
     if (blockIdx.x == 0) {
         if (tid < W && tid != me) {
             peer_signal(A.flags[tid] + PEER_MAX + me, A.epoch);
-            peer_wait(A.flags[me] + PEER_MAX + tid, A.epoch, A.err);
+            peer_wait(A.flags[me] + PEER_MAX + tid, A.epoch, A.patience, A.err);
         }
         __syncthreads();
         if (tid == 0 && *(volatile int *)A.err) A.red[me][n5 + 1] = NAN;      // an exchange that gave up must not look like a result

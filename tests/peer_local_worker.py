@@ -6,7 +6,7 @@ The ranks' finishing kernels wait for each other ON the device, so they -- and t
 still computing -- must really run concurrently.  Between GPUs (one process per GPU, the production layout) nothing can
 prevent that; on one GPU the streams of all the handles share the device's hardware work queues
 (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and a kernel that lands behind a waiting kernel in the same queue cannot
-start: the wait then gives up after two seconds (NaN likelihood instead of a hung GPU).  The test therefore runs this
+start: the wait then gives up (PMM_PEER_TIMEOUT_MS; a failed call instead of a hung GPU).  The test therefore runs this
 worker with 32 queues and one site slice (one busy stream per handle) and repeats it if it reports exactly that."""
 import os
 import sys

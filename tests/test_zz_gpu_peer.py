@@ -6,8 +6,9 @@ ranks' own statistics taken in rank order; they agree with one engine holding al
 the single engine's iterations (tests/peer_local_worker.py).  (Two GPUs, two processes, CUDA IPC: tests/test_zz_gpu_nccl.py.)
 
 The worker runs in its own process with 32 hardware work queues: kernels of different handles that wait for each other
-must not share a queue (see the worker's header).  If a wait nevertheless gives up (exit code 3: a NaN likelihood, by
-design, instead of a hung GPU) the case is repeated; any wrong NUMBER fails at once."""
+must not share a queue (see the worker's header), and with a patience of 2 s instead of the default 30.  If a wait
+nevertheless gives up (exit code 3: a failed call, by design, instead of a hung GPU) the case is repeated; any wrong
+NUMBER fails at once."""
 import os
 import subprocess
 import sys
@@ -25,7 +26,7 @@ def test_ranks_in_one_process(world, n, K, chunks):
     """chunks > 0: every rank walks its sites in that many chunks (PMM_CHUNKS: what a rank does when its records do not
     fit the memory budget) -- the earlier chunks' sums accumulate in the rank's own buffer, the last chunk's finishing
     kernel adds its part and exchanges"""
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", PMM_SLICES="1")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", PMM_SLICES="1", PMM_PEER_TIMEOUT_MS="2000")
     if chunks:
         env["PMM_CHUNKS"] = str(chunks)
     cmd = [sys.executable, os.path.join(HERE, "peer_local_worker.py"), str(world), str(n), str(K)]
