@@ -54,8 +54,20 @@ def main(out_path):
     one_ref = whole.mstep(ref["S"], ref["Rtilde"], R, N, d0, w.nu, w.phi)
     res["em_step_d_max_abs"] = float(np.max(np.abs(one[0] - one_ref[0])))
     res["em_step_llh_rel"] = abs(one[3] - ref["llh"]) / abs(ref["llh"])
+    # EM under the ultrametric constraint (the runner's default mode) on shards: the device M-step (pmm_mstep_ultra_dev) is a
+    # pure function of the exchanged statistics, so the shards must walk the single engine's iterations (pmm_em_ultra)
+    from laml_b200 import ultrametric as um
+    kind, fixed_len = np.zeros(n, np.int8), np.zeros(n)
+    prob = um.UltrametricProblem(w.forest.parent, kind, fixed_len, 0.005, 10.0)
+    ref_u = whole.em_ultra(d0, w.nu, w.phi, R, N, kind, fixed_len, max_iter=12)
+    em_u = sh.em_ultrametric(prob, d0, w.nu, w.phi, R, N, np.ones(n, np.uint8), max_iter=12)
+    res["ultra_iters"] = [int(em_u["iters"]), int(ref_u["iters"])]
+    res["ultra_status"] = [em_u["status"], ref_u["status"]]
+    res["ultra_nllh_rel"] = abs(em_u["nllh"] - ref_u["nllh"]) / abs(ref_u["nllh"])
+    res["ultra_d_max_abs"] = float(np.max(np.abs(em_u["d"] - ref_u["d"])))
     # every rank must hold bit-identical results (replicated M-step on identical all-reduced statistics)
-    mine = torch.tensor(np.concatenate([em["d"], [em["nu"], em["phi"], em["nllh"]], S.reshape(-1)]), device="cuda:%d" % local)
+    mine = torch.tensor(np.concatenate([em["d"], [em["nu"], em["phi"], em["nllh"]], S.reshape(-1), em_u["d"], [em_u["nu"], em_u["phi"], em_u["nllh"]]]),
+                        device="cuda:%d" % local)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
     res["ranks_bit_identical"] = bool(all(torch.equal(parts[0], p) for p in parts))

@@ -35,4 +35,6 @@ def test_site_shards_over_nccl_match_one_gpu(world, peer, tmp_path):
         assert r["em_iters"][0] == r["em_iters"][1] and r["em_nllh_rel"] <= 1e-10, r
         assert r["em_d_max_abs"] <= 1e-7 and r["em_nu_abs"] <= 1e-7 and r["em_phi_abs"] <= 1e-7, r
         assert r["em_step_d_max_abs"] <= 1e-9 and r["em_step_llh_rel"] <= 1e-12, r
+        assert r["ultra_iters"][0] == r["ultra_iters"][1] and r["ultra_status"][0] == r["ultra_status"][1] == "optimal", r
+        assert r["ultra_nllh_rel"] <= 1e-9 and r["ultra_d_max_abs"] <= 1e-6, r
         assert r["ranks_bit_identical"] and r["nni_scores_equal"], r
